@@ -1,0 +1,221 @@
+"""Host-side mirror of the reference's entry points for the match -> RANSAC -> warp/blend path,
+implemented on the C ABI of libuavmosaic.so (include/uavm.h).  Names follow the reference:
+
+    match()                <- FlannBasedMatcher().match            M/MosaicWithoutPos.cpp:5108-5110
+    select_match_pairs()   <- std::sort + SelectMatchPairs          :5111, :5146-5153, :4977-5028
+    ransac2d()             <- Ransac2D                              M/mosaicimage.h:1729-2035
+    PairBatch              <- the per-pair body of GetMatchedPairsOneToAllSIFTThread (:5083-5227), batched
+    align_affine()         <- BundleAdjustmentSparse                :6971-7202
+    Canvas                 <- LaplacianPyramidBlending              M/MosaicImage.cpp:2205-2510
+
+numpy arrays are host buffers (copied by the library); torch CUDA tensors are passed as device
+pointers.  There is no CPU fallback anywhere in this module.
+"""
+import ctypes as C
+import numpy as np
+
+from . import _lib as L
+from ._lib import (SfPoint, DMatch, RansacResult, MatchPointPairs, ImageTransform, ChipLayout, CanvasLayout,
+                   f32p, i32p, u32p, u8p)
+
+
+class UavmError(RuntimeError):
+    pass
+
+
+def _is_torch_cuda(x):
+    return hasattr(x, "is_cuda") and x.is_cuda
+
+
+def _ptr(x, ctype):
+    if _is_torch_cuda(x):
+        return C.cast(C.c_void_p(x.data_ptr()), ctype)
+    return x.ctypes.data_as(ctype)
+
+
+class Context:
+    """One per process/GPU (uavm_ctx)."""
+
+    def __init__(self, device=0, stream=None):
+        self._h = C.c_void_p()
+        rc = L.lib().uavm_ctx_create(int(device), C.byref(self._h))
+        if rc != 0:
+            raise UavmError(f"uavm_ctx_create({device}) failed with {rc}: no sm_100 CUDA device (no CPU fallback)")
+        if stream is not None:
+            self.set_stream(stream)
+
+    def set_stream(self, stream):
+        ptr = stream.cuda_stream if hasattr(stream, "cuda_stream") else int(stream)
+        self.check(L.lib().uavm_ctx_set_stream(self._h, C.c_void_p(ptr)))
+
+    def check(self, rc):
+        if rc != 0:
+            raise UavmError(f"uavm error {rc}: {L.lib().uavm_last_error(self._h).decode()}")
+
+    def sync(self):
+        self.check(L.lib().uavm_ctx_sync(self._h))
+
+    @property
+    def launch_count(self):
+        return int(L.lib().uavm_ctx_launch_count(self._h))
+
+    @property
+    def sm_count(self):
+        return int(L.lib().uavm_ctx_sm_count(self._h))
+
+    def close(self):
+        if self._h:
+            L.lib().uavm_ctx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class FeatureSet:
+    """Device-resident descriptors + keypoints of a set of images (uavm_featureset)."""
+
+    def __init__(self, ctx, n_keypoints):
+        self.ctx = ctx
+        self.n = np.ascontiguousarray(n_keypoints, np.int32)
+        self._h = C.c_void_p()
+        ctx.check(L.lib().uavm_featureset_create(ctx._h, len(self.n), _ptr(self.n, i32p), C.byref(self._h)))
+
+    def upload(self, image, desc, kp_xy=None):
+        """desc: (n,128) uint8 or float32 (integer valued) numpy array or torch CUDA tensor; kp_xy: (n,2) f32."""
+        dev = 1 if _is_torch_cuda(desc) else 0
+        if dev:
+            is_u8 = str(desc.dtype) == "torch.uint8"
+            assert desc.is_contiguous()
+            if kp_xy is not None:
+                assert _is_torch_cuda(kp_xy) and kp_xy.is_contiguous()
+        else:
+            is_u8 = desc.dtype == np.uint8
+            desc = np.ascontiguousarray(desc, np.uint8 if is_u8 else np.float32)
+            if kp_xy is not None:
+                kp_xy = np.ascontiguousarray(kp_xy, np.float32)
+        assert desc.shape[0] == self.n[image] and desc.shape[1] == 128
+        kp_ptr = _ptr(kp_xy, f32p) if kp_xy is not None else None
+        if is_u8:
+            rc = L.lib().uavm_featureset_upload_u8(self.ctx._h, self._h, int(image), _ptr(desc, u8p), kp_ptr, dev)
+        else:
+            rc = L.lib().uavm_featureset_upload_f32(self.ctx._h, self._h, int(image), _ptr(desc, f32p), kp_ptr, dev)
+        self.ctx.check(rc)
+        self._keep = (desc, kp_xy)     # keep pageable sources alive until the stream has consumed them
+
+    def close(self):
+        if self._h:
+            L.lib().uavm_featureset_destroy(self.ctx._h, self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class PairBatch:
+    """match -> select -> RANSAC for a list of (query image, train image) pairs (uavm_pairbatch)."""
+
+    def __init__(self, ctx, fs, pairs):
+        self.ctx = ctx
+        self.fs = fs
+        self.pairs = np.ascontiguousarray(pairs, np.int32).reshape(-1, 2)
+        self._h = C.c_void_p()
+        ctx.check(L.lib().uavm_pairbatch_create(ctx._h, fs._h, len(self.pairs), _ptr(self.pairs, i32p), C.byref(self._h)))
+
+    def match(self):
+        self.ctx.check(L.lib().uavm_pairbatch_match(self.ctx._h, self._h))
+
+    def select(self, width, height, grid_x=3, grid_y=3, max_num=400, frac=0.3):
+        self.ctx.check(L.lib().uavm_pairbatch_select(self.ctx._h, self._h, int(width), int(height), grid_x, grid_y,
+                                                     max_num, C.c_double(frac)))
+
+    def ransac(self, ransac_dist=2.5, sample_times=1000, seeds=None, base_seed=0):
+        sp = None
+        if seeds is not None:
+            seeds = np.ascontiguousarray(seeds, np.uint32)
+            assert len(seeds) == len(self.pairs)
+            sp = _ptr(seeds, u32p)
+        self.ctx.check(L.lib().uavm_pairbatch_ransac(self.ctx._h, self._h, C.c_float(ransac_dist), int(sample_times),
+                                                     sp, C.c_uint32(base_seed)))
+
+    def matches(self, pair):
+        nq = int(self.fs.n[self.pairs[pair, 0]])
+        out = (DMatch * max(nq, 1))()
+        n = C.c_int(0)
+        self.ctx.check(L.lib().uavm_pairbatch_get_matches(self.ctx._h, self._h, int(pair), out, nq, C.byref(n)))
+        a = np.frombuffer(out, dtype=np.dtype([("queryIdx", "<i4"), ("trainIdx", "<i4"), ("imgIdx", "<i4"), ("distance", "<f4")]))
+        return a[:n.value].copy()
+
+    def candidates(self, pair, cap=1024):
+        p1 = (SfPoint * cap)(); p2 = (SfPoint * cap)(); n = C.c_int(0)
+        self.ctx.check(L.lib().uavm_pairbatch_get_candidates(self.ctx._h, self._h, int(pair), p1, p2, cap, C.byref(n)))
+        dt = np.dtype([("x", "<f4"), ("y", "<f4"), ("id", "<i4")])
+        return np.frombuffer(p1, dtype=dt)[:n.value].copy(), np.frombuffer(p2, dtype=dt)[:n.value].copy()
+
+    def ransac_result(self, pair, cap=1024):
+        mask = np.zeros(cap, np.uint8); res = RansacResult()
+        self.ctx.check(L.lib().uavm_pairbatch_get_ransac(self.ctx._h, self._h, int(pair), _ptr(mask, u8p), cap, C.byref(res)))
+        return mask, res
+
+    def collect(self, min_inner_points=30, cap=None):
+        n = C.c_int(0); acc = C.c_int(0)
+        self.ctx.check(L.lib().uavm_pairbatch_collect(self.ctx._h, self._h, int(min_inner_points), None, 0, C.byref(n), C.byref(acc)))
+        out = (MatchPointPairs * max(n.value, 1))()
+        self.ctx.check(L.lib().uavm_pairbatch_collect(self.ctx._h, self._h, int(min_inner_points), out, n.value, C.byref(n), C.byref(acc)))
+        return out, n.value, acc.value
+
+    def close(self):
+        if self._h:
+            L.lib().uavm_pairbatch_destroy(self.ctx._h, self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+# ---- single-pair seams (host buffers in, host buffers out) -------------------------------------
+def match(ctx, desc1, desc2):
+    """Exact L2 1-NN of every row of desc1 in desc2 -> structured array (queryIdx, trainIdx, imgIdx, distance)."""
+    d1 = np.ascontiguousarray(desc1, np.float32); d2 = np.ascontiguousarray(desc2, np.float32)
+    out = (DMatch * max(len(d1), 1))()
+    ctx.check(L.lib().uavm_match(ctx._h, _ptr(d1, f32p), len(d1), _ptr(d2, f32p), len(d2), out))
+    a = np.frombuffer(out, dtype=np.dtype([("queryIdx", "<i4"), ("trainIdx", "<i4"), ("imgIdx", "<i4"), ("distance", "<f4")]))
+    return a[:len(d1)].copy()
+
+
+def select_match_pairs(ctx, matches, kp1_xy, kp2_xy, width, height, grid_x=3, grid_y=3, max_num=400, frac=0.3):
+    m = np.ascontiguousarray(matches)
+    kp1 = np.ascontiguousarray(kp1_xy, np.float32); kp2 = np.ascontiguousarray(kp2_xy, np.float32)
+    cap = 1024
+    p1 = (SfPoint * cap)(); p2 = (SfPoint * cap)(); n = C.c_int(0)
+    ctx.check(L.lib().uavm_select(ctx._h, C.cast(m.ctypes.data, C.POINTER(DMatch)), len(m), _ptr(kp1, f32p), len(kp1),
+                                  _ptr(kp2, f32p), len(kp2), int(width), int(height), grid_x, grid_y, max_num,
+                                  C.c_double(frac), p1, p2, cap, C.byref(n)))
+    dt = np.dtype([("x", "<f4"), ("y", "<f4"), ("id", "<i4")])
+    return np.frombuffer(p1, dtype=dt)[:n.value].copy(), np.frombuffer(p2, dtype=dt)[:n.value].copy()
+
+
+def ransac2d(ctx, xy1, xy2, ransac_dist=2.5, sample_times=1000, seed=1):
+    """Ransac2D on candidate pairs (n,2)+(n,2).  Returns (ok, inlier_mask, H[9], RansacResult)."""
+    xy1 = np.ascontiguousarray(xy1, np.float32); xy2 = np.ascontiguousarray(xy2, np.float32)
+    n = len(xy1)
+    a = (SfPoint * max(n, 1))(); b = (SfPoint * max(n, 1))()
+    for i in range(n):
+        a[i].x, a[i].y, a[i].id = float(xy1[i, 0]), float(xy1[i, 1]), i
+        b[i].x, b[i].y, b[i].id = float(xy2[i, 0]), float(xy2[i, 1]), i
+    in1 = (SfPoint * max(n, 1))(); in2 = (SfPoint * max(n, 1))(); res = RansacResult()
+    ctx.check(L.lib().uavm_ransac2d(ctx._h, a, b, n, C.c_float(ransac_dist), int(sample_times), C.c_uint32(seed),
+                                    in1, in2, n, C.byref(res)))
+    mask = np.zeros(n, np.uint8)
+    for k in range(res.n_inliers):
+        mask[in1[k].id] = 1
+    return res.ok, mask, np.array(list(res.H), np.float32), res

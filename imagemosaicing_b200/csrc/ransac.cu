@@ -1,0 +1,338 @@
+// ransac.cu — K4: RANSAC homography, bit-exact with Ransac2D (M/mosaicimage.h:1729-2035).
+//
+// The reference loop is sequential and data dependent, but its 4-index draws depend only on the RNG
+// and on ptNum (the "4 distinct indices" rejection at :1801-1813 never looks at the data, and redraws
+// always consume 4 rand() calls).  So draw group g = rand() calls 4g..4g+3 of the per-pair LCG stream
+// is either a valid 4-tuple or skipped, and every group can be evaluated independently:
+//   k4_ransac_eval      one thread per draw group: 4-point solve + 5 px gate + Gauss-Newton refine
+//                       (ransac_math.cuh) + support count over all candidates (smem broadcast reads)
+//   k4_ransac_finalize  one CTA per pair: replays the reference's sequential rule over the per-group
+//                       results with prefix scans (t counts accepted tuples, realSamTimes counts valid
+//                       tuples, first strict maximum wins, 0.99 early exit), evaluates further groups
+//                       itself if the first pass did not reach sampleTimes, then the final inlier pass
+//                       (division form, :1922-1944) and the final refine on all inliers (:1979-1986)
+//                       with the reference's summation order.
+#include "internal.h"
+#include "ransac_math.cuh"
+
+using namespace uavm::rmath;
+
+namespace {
+
+constexpr int kEvalThreads = 128;
+constexpr int kFinThreads = 256;
+constexpr uint32_t RES_VALID = 0x80000000u, RES_REJ = 0x40000000u, RES_SUP = 0x0000ffffu;
+constexpr int kMaxGroups = 1 << 20;
+
+// evaluate draw group g of a pair whose candidates are staged in shared memory (x1,y1,x2,y2 per point)
+__device__ __forceinline__ uint32_t eval_group(const float4* __restrict__ pts, int n, uint32_t seed, uint32_t g,
+                                               float thr2, float* h_out)
+{
+    int idx[4];
+    if (!draw_group(seed, g, n, idx)) return 0u;
+    float x1[4], y1[4], x2[4], y2[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) { float4 p = pts[idx[i]]; x1[i] = p.x; y1[i] = p.y; x2[i] = p.z; y2[i] = p.w; }
+    float h[9];
+    const int st = hypothesis(x1, y1, x2, y2, h);
+    if (h_out) {
+#pragma unroll
+        for (int i = 0; i < 9; i++) h_out[i] = h[i];
+    }
+    if (st == TUPLE_REJECTED) return RES_VALID | RES_REJ;
+    int sup = 0;
+    for (int i = 0; i < n; i++) {
+        const float4 p = pts[i];
+        float xb, yb;
+        project_mul(p.z, p.w, h, xb, yb);
+        if (dist2(xb, yb, p.x, p.y) < thr2) sup++;
+    }
+    return RES_VALID | (uint32_t)sup;
+}
+
+__device__ __forceinline__ void stage_points(float4* pts, const float* xy1, const float* xy2, int n, int tid, int nthreads) {
+    for (int i = tid; i < n; i += nthreads)
+        pts[i] = make_float4(xy1[2 * i], xy1[2 * i + 1], xy2[2 * i], xy2[2 * i + 1]);
+}
+
+__global__ void __launch_bounds__(kEvalThreads)
+k4_ransac_eval(const PairDesc* __restrict__ pairs, const float* __restrict__ cand_xy1, const float* __restrict__ cand_xy2,
+               const int32_t* __restrict__ cand_n, float thr2, int groups, uint32_t* __restrict__ tuple_res)
+{
+    __shared__ float4 pts[UAVM_CAND_SLOTS];
+    const int p = blockIdx.y;
+    const int n = cand_n[p];
+    const size_t base = (size_t)p * UAVM_CAND_SLOTS;
+    const uint32_t g = blockIdx.x * kEvalThreads + threadIdx.x;
+    if (n < 4) { if (g < (uint32_t)groups) tuple_res[(size_t)p * UAVM_RANSAC_MAX_TUPLES_FIRST + g] = 0u; return; }
+    stage_points(pts, cand_xy1 + base * 2, cand_xy2 + base * 2, n, threadIdx.x, kEvalThreads);
+    __syncthreads();
+    if (g >= (uint32_t)groups) return;
+    tuple_res[(size_t)p * UAVM_RANSAC_MAX_TUPLES_FIRST + g] = eval_group(pts, n, pairs[p].seed, g, thr2, nullptr);
+}
+
+// ---- block-wide helpers (kFinThreads = 256 threads, 8 warps) ----
+__device__ __forceinline__ int block_excl_scan(int v, int* warp_tot /*[8]*/, int* total) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+    __syncthreads();
+    if (lane == 31) warp_tot[wid] = inc;
+    __syncthreads();
+    int off = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < kFinThreads / 32; w++) { int t = warp_tot[w]; if (w < wid) off += t; tot += t; }
+    *total = tot;
+    return off + inc - v;
+}
+__device__ __forceinline__ int block_reduce_max(int v, int* scratch /*[8]*/) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    v = __reduce_max_sync(0xffffffffu, v);
+    __syncthreads();
+    if (lane == 0) scratch[wid] = v;
+    __syncthreads();
+    int m = scratch[0];
+#pragma unroll
+    for (int w = 1; w < kFinThreads / 32; w++) m = max(m, scratch[w]);
+    return m;
+}
+__device__ __forceinline__ int block_reduce_min(int v, int* scratch) { return -block_reduce_max(-v, scratch); }
+
+struct FinSmem {
+    float4 pts[UAVM_CAND_SLOTS];
+    float in_x1[UAVM_CAND_SLOTS], in_y1[UAVM_CAND_SLOTS], in_x2[UAVM_CAND_SLOTS], in_y2[UAVM_CAND_SLOTS];
+    float C[2 * UAVM_CAND_SLOTS];
+    float N1[64], N2[64];
+    float w[8], dx[8];
+    float hbest[9];
+    int scratch[8];
+    int flag;
+};
+
+__global__ void __launch_bounds__(kFinThreads, 1)
+k4_ransac_finalize(const PairDesc* __restrict__ pairs, const float* __restrict__ cand_xy1, const float* __restrict__ cand_xy2,
+                   const int32_t* __restrict__ cand_n, float thr2, int sample_times, int groups_first,
+                   const uint32_t* __restrict__ tuple_res, uint8_t* __restrict__ inlier, uavm_ransac_result* __restrict__ results)
+{
+    extern __shared__ __align__(16) uint8_t fin_raw[];
+    FinSmem& S = *reinterpret_cast<FinSmem*>(fin_raw);
+    float* J = reinterpret_cast<float*>(fin_raw + sizeof(FinSmem));        // [2N][8]
+    float* L = J + 2 * UAVM_CAND_SLOTS * 8;                                // [8][2N]
+
+    const int p = blockIdx.x, tid = threadIdx.x;
+    const int n = cand_n[p];
+    const size_t base = (size_t)p * UAVM_CAND_SLOTS;
+    const uint32_t seed = pairs[p].seed;
+    uavm_ransac_result R;
+    R.ok = 0; R.n_inliers = 0; R.max_support = 0; R.best_tuple = -1; R.n_tuples = 0; R.n_counted = 0;
+#pragma unroll
+    for (int i = 0; i < 9; i++) R.H[i] = 0.0f;
+    for (int i = tid; i < UAVM_CAND_SLOTS; i += kFinThreads) inlier[base + i] = 0;
+    if (n < 4) { if (tid == 0) results[p] = R; return; }
+    stage_points(S.pts, cand_xy1 + base * 2, cand_xy2 + base * 2, n, tid, kFinThreads);
+    __syncthreads();
+
+    // ---------------- replay of the sequential sampling loop (:1785-1920) ----------------
+    const float inv_n = 1.0f / (float)n;
+    int k_valid = 0, t_acc = 0;
+    int best_sup = 0, best_g = -1, best_k = -1, first_acc_g = -1;
+    int n_tuples = 0, n_counted = 0;
+    bool done = false;
+    for (int g0 = 0; !done && g0 < kMaxGroups; g0 += kFinThreads) {
+        const int g = g0 + tid;
+        uint32_t res;
+        if (g < groups_first) res = tuple_res[(size_t)p * UAVM_RANSAC_MAX_TUPLES_FIRST + g];
+        else res = eval_group(S.pts, n, seed, (uint32_t)g, thr2, nullptr);
+        const int v = (res & RES_VALID) ? 1 : 0;
+        const int a = (v && !(res & RES_REJ)) ? 1 : 0;
+        const int sup = (int)(res & RES_SUP);
+        int tot_v, tot_a;
+        const int kx = k_valid + block_excl_scan(v, S.scratch, &tot_v);
+        const int tx = t_acc + block_excl_scan(a, S.scratch, &tot_a);
+        const bool processed = v && (kx + 1 < 5000) && (tx < sample_times);
+        const bool cand = processed && a;
+        const bool early = cand && ((float)sup * inv_n > 0.99f);
+        const int e_tid = block_reduce_min(early ? tid : kFinThreads, S.scratch);     // first early exit in chunk
+        const bool in_range = tid <= e_tid;                                           // tuples after the exit never run
+        // first accepted tuple overall (its matrix sits in pProjectMat[0])
+        const int fa = block_reduce_min((cand && in_range) ? tid : kFinThreads, S.scratch);
+        if (first_acc_g < 0 && fa < kFinThreads) first_acc_g = g0 + fa;
+        // first strict maximum: max support, ties -> lowest index
+        const int key = (cand && in_range) ? ((sup << 8) | (kFinThreads - 1 - tid)) : -1;
+        const int bk = block_reduce_max(key, S.scratch);
+        if (bk >= 0) {
+            const int bsup = bk >> 8, btid = kFinThreads - 1 - (bk & 255);
+            if (bsup > best_sup) {
+                best_sup = bsup; best_g = g0 + btid;
+                // valid-order index of that tuple: broadcast kx of thread btid
+                __syncthreads();
+                if (tid == btid) S.flag = kx;
+                __syncthreads();
+                best_k = S.flag;
+            }
+        }
+        // bookkeeping of realSamTimes / t at loop end
+        const int proc_cnt_tot = block_reduce_max((processed && in_range) ? (kx + 1) : 0, S.scratch);
+        const int acc_cnt_tot = block_reduce_max((cand && in_range) ? (tx + 1) : 0, S.scratch);
+        if (proc_cnt_tot > n_tuples) n_tuples = proc_cnt_tot;
+        if (acc_cnt_tot > n_counted) n_counted = acc_cnt_tot;
+        k_valid += tot_v; t_acc += tot_a;
+        if (e_tid < kFinThreads) done = true;
+        if (t_acc >= sample_times || k_valid + 1 >= 5000) done = true;
+    }
+    R.max_support = best_sup; R.best_tuple = best_k; R.n_tuples = n_tuples; R.n_counted = n_counted;
+
+    // ---------------- winning hypothesis matrix ----------------
+    const int hg = best_g >= 0 ? best_g : first_acc_g;
+    if (tid == 0) {
+        float h[9];
+#pragma unroll
+        for (int i = 0; i < 9; i++) h[i] = 0.0f;
+        if (hg >= 0) eval_group(S.pts, n, seed, (uint32_t)hg, -1.0f, h);
+#pragma unroll
+        for (int i = 0; i < 9; i++) S.hbest[i] = h[i];
+    }
+    __syncthreads();
+
+    // ---------------- final inlier pass, division form (:1922-1944) ----------------
+    int cnt = 0;
+    for (int i0 = 0; i0 < n; i0 += kFinThreads) {
+        const int i = i0 + tid;
+        int f = 0;
+        float4 pt = make_float4(0, 0, 0, 0);
+        if (i < n) {
+            pt = S.pts[i];
+            float xb, yb;
+            project_div(pt.z, pt.w, S.hbest, xb, yb);
+            f = dist2(xb, yb, pt.x, pt.y) < thr2 ? 1 : 0;
+            inlier[base + i] = (uint8_t)f;
+        }
+        int tot;
+        const int pos = cnt + block_excl_scan(f, S.scratch, &tot);
+        if (f) { S.in_x1[pos] = pt.x; S.in_y1[pos] = pt.y; S.in_x2[pos] = pt.z; S.in_y2[pos] = pt.w; }
+        cnt += tot;
+    }
+    __syncthreads();
+    R.n_inliers = cnt;
+    R.ok = cnt >= 4 ? 1 : 0;
+    if (cnt < 4) { if (tid == 0) results[p] = R; return; }
+
+    // ---------------- final refine on all inliers (:1979-1986 -> M/LeastSquare.h:353-531) --------
+    // (the SolveHomographyMatrix result of :1958 is overwritten by this refine and is not computed)
+    const int rows = 2 * cnt;
+    if (tid < 8) S.w[tid] = S.hbest[tid];
+    if (tid < 64) S.N2[tid] = 0.0f;      // reference: uninitialised; defined as zeros (see oracle.c)
+    __syncthreads();
+    for (int it = 0; it < 15; it++) {
+        for (int i = tid; i < cnt; i += kFinThreads) {
+            const float xs = S.in_x2[i], ys = S.in_y2[i];
+            const float d = S.w[6] * xs + S.w[7] * ys + 1.0f;
+            const float u = S.w[0] * xs + S.w[1] * ys + S.w[2];
+            const float v = S.w[3] * xs + S.w[4] * ys + S.w[5];
+            float* j0 = J + (2 * i) * 8; float* j1 = j0 + 8;
+            const float a = xs / d, b = ys / d, c = 1.0f / d;
+            j0[0] = a; j0[1] = b; j0[2] = c; j0[3] = 0.0f; j0[4] = 0.0f; j0[5] = 0.0f;
+            j0[6] = -xs * u / (d * d); j0[7] = -ys * u / (d * d);
+            j1[0] = 0.0f; j1[1] = 0.0f; j1[2] = 0.0f; j1[3] = a; j1[4] = b; j1[5] = c;
+            j1[6] = -xs * v / (d * d); j1[7] = -ys * v / (d * d);
+            S.C[2 * i] = S.in_x1[i] - u / d;
+            S.C[2 * i + 1] = S.in_y1[i] - v / d;
+        }
+        __syncthreads();
+        if (tid < 64) {                      // N1 = J^T J, ascending-k accumulation (M/matrix.h:94-120)
+            const int r = tid >> 3, c = tid & 7;
+            float acc = 0.0f;
+            for (int k = 0; k < rows; k++) acc += J[k * 8 + r] * J[k * 8 + c];
+            S.N1[tid] = acc;
+        }
+        __syncthreads();
+        if (tid == 0) {                      // InverseMatrix, eps 1e-6, return value ignored (:451)
+            float M[8][8];
+#pragma unroll
+            for (int r = 0; r < 8; r++)
+#pragma unroll
+                for (int c = 0; c < 8; c++) M[r][c] = S.N1[r * 8 + c];
+            if (inverse8_fast(M, 1e-6f)) {
+#pragma unroll
+                for (int r = 0; r < 8; r++)
+#pragma unroll
+                    for (int c = 0; c < 8; c++) S.N2[r * 8 + c] = M[r][c];
+            } else {
+                float tmp[64];
+                if (inverse8_generic(S.N1, tmp, 1e-6f) == 1)
+                    for (int i = 0; i < 64; i++) S.N2[i] = tmp[i];
+            }
+        }
+        __syncthreads();
+        for (int e = tid; e < 8 * rows; e += kFinThreads) {   // L = N2 * J^T  (8 x rows)
+            const int r = e / rows, k = e - r * rows;
+            float acc = 0.0f;
+#pragma unroll
+            for (int m = 0; m < 8; m++) acc += S.N2[r * 8 + m] * J[k * 8 + m];
+            L[e] = acc;
+        }
+        __syncthreads();
+        if (tid < 8) {                       // delta = L * C, ascending k
+            float acc = 0.0f;
+            const float* Lr = L + tid * rows;
+            for (int k = 0; k < rows; k++) acc += Lr[k] * S.C[k];
+            S.dx[tid] = acc;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            bool small = true;
+            for (int i = 0; i < 8; i++) { S.w[i] += S.dx[i]; if (!(fabsf(S.dx[i]) < 1e-10f)) small = false; }
+            S.flag = small ? 1 : 0;
+        }
+        __syncthreads();
+        if (S.flag) break;
+    }
+    // out[8] = max residual (float, reciprocal-multiply projection, sqrtf)  (:501-519)
+    float emax = 0.0f;
+    for (int i = tid; i < cnt; i += kFinThreads) {
+        float xb, yb;
+        project_mul(S.in_x2[i], S.in_y2[i], S.w, xb, yb);
+        const float ex = S.in_x1[i] - xb, ey = S.in_y1[i] - yb;
+        const float dist = sqrtf(ex * ex + ey * ey);
+        if (dist > emax) emax = dist;
+    }
+    const int emax_bits = block_reduce_max(__float_as_int(emax), S.scratch);   // emax >= 0: int order == float order
+    if (tid == 0) {
+        for (int i = 0; i < 8; i++) R.H[i] = S.w[i];
+        R.H[8] = __int_as_float(emax_bits);
+        results[p] = R;
+    }
+}
+
+constexpr size_t kFinSmemBytes = sizeof(FinSmem) + (size_t)2 * UAVM_CAND_SLOTS * 8 * 4 * 2;
+
+}  // namespace
+
+int uavm_launch_ransac(uavm_ctx* ctx, uavm_pairbatch* pb, float dist, int sample_times)
+{
+    if (sample_times > 5000) sample_times = 5000;            // maxTimes clamp (:1765-1769)
+    if (sample_times < 0) sample_times = 0;
+    const float thr2 = dist * dist;                          // fRansacDistSquare (:1757)
+    // first pass: enough draw groups that, at the ~35 % gate-rejection rate seen on 4000x3000 data, the
+    // 1000th accepted tuple is usually inside it; the finalize kernel continues past it when needed.
+    int groups = sample_times * 5 / 2 + 128;
+    if (groups > UAVM_RANSAC_MAX_TUPLES_FIRST) groups = UAVM_RANSAC_MAX_TUPLES_FIRST;
+    groups = (groups / kEvalThreads) * kEvalThreads;
+    static bool attr_set = false;
+    if (!attr_set) {
+        UAVM_CUDA(ctx, cudaFuncSetAttribute(k4_ransac_finalize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFinSmemBytes));
+        attr_set = true;
+    }
+    if (groups > 0) {
+        dim3 grid(groups / kEvalThreads, pb->n_pairs);
+        k4_ransac_eval<<<grid, kEvalThreads, 0, ctx->stream>>>(pb->d_pairs, pb->d_cand_xy1, pb->d_cand_xy2, pb->d_cand_n,
+                                                               thr2, groups, pb->d_tuple_res);
+        UAVM_CHECK_LAUNCH(ctx);
+    }
+    k4_ransac_finalize<<<pb->n_pairs, kFinThreads, kFinSmemBytes, ctx->stream>>>(
+        pb->d_pairs, pb->d_cand_xy1, pb->d_cand_xy2, pb->d_cand_n, thr2, sample_times, groups, pb->d_tuple_res,
+        pb->d_inlier, pb->d_res);
+    UAVM_CHECK_LAUNCH(ctx);
+    return UAVM_OK;
+}

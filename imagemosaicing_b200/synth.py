@@ -1,0 +1,93 @@
+"""Seeded synthetic inputs for the hot path: SIFT-like u8 descriptors, keypoints,
+pair geometry with known homographies, band-limited BGR textures.  Used by tests/ and bench.py."""
+import numpy as np
+
+SEED_BASE = 20160308
+
+
+def sift_like_descriptors(rng, n):
+    """gamma(1,30) -> L2 normalise -> clip 0.2 -> renormalise -> x512 -> floor -> saturate 255 (u8)."""
+    d = rng.gamma(1.0, 30.0, size=(n, 128)).astype(np.float32)
+    d /= np.maximum(np.linalg.norm(d, axis=1, keepdims=True), 1e-12)
+    d = np.minimum(d, 0.2)
+    d /= np.maximum(np.linalg.norm(d, axis=1, keepdims=True), 1e-12)
+    return np.minimum(np.floor(d * 512.0), 255).astype(np.uint8)
+
+
+def random_keypoints(rng, n, w, h):
+    return np.stack([rng.uniform(0, w - 1, n), rng.uniform(0, h - 1, n)], 1).astype(np.float32)
+
+
+def pair_homography(rng, w, h, overlap=(0.6, 0.8), max_rot_deg=5.0, scale=(0.95, 1.05), proj=1e-5):
+    """H maps image-2 points to image-1 points (the reference's convention, M/matrix.h:783)."""
+    th = np.deg2rad(rng.uniform(-max_rot_deg, max_rot_deg))
+    s = rng.uniform(*scale)
+    ov = rng.uniform(*overlap)
+    tx = rng.uniform(-0.05, 0.05) * w
+    ty = (1.0 - ov) * h * (1 if rng.random() < 0.5 else -1)
+    c, si = np.cos(th) * s, np.sin(th) * s
+    cx, cy = (w - 1) / 2.0, (h - 1) / 2.0
+    H = np.array([[c, -si, cx - c * cx + si * cy + tx],
+                  [si, c, cy - si * cx - c * cy + ty],
+                  [rng.uniform(-proj, proj), rng.uniform(-proj, proj), 1.0]])
+    return H
+
+
+def apply_h(H, xy):
+    q = np.c_[xy, np.ones(len(xy))] @ H.T
+    return q[:, :2] / q[:, 2:3]
+
+
+def make_strip(n_images, w, h, n_kp, seed=SEED_BASE, true_frac=0.5, desc_noise=4.0, pos_noise=0.5,
+               geom_outlier_frac=0.5):
+    """Sequential-overlap strip: image k+1 overlaps image k.  Returns (descs[u8], kps[f32], Hs) where
+    Hs[k] maps image k+1 -> image k.  A fraction `geom_outlier_frac` of the descriptor-true matches is
+    given a random position (repeated-structure mismatches), so the <=396 candidates that reach RANSAC
+    hold ~50 % inliers like the reference's real runs (32..275 inliers of <=396 in matchPairs.match)
+    and the loop really runs its 1000 counted hypotheses instead of taking the 0.99 early exit."""
+    descs, kps, Hs = [], [], []
+    rng = np.random.default_rng(seed)
+    descs.append(sift_like_descriptors(rng, n_kp)); kps.append(random_keypoints(rng, n_kp, w, h))
+    for k in range(1, n_images):
+        rng = np.random.default_rng(seed + k)
+        H = pair_homography(rng, w, h)
+        Hi = np.linalg.inv(H)
+        p_prev = kps[k - 1].astype(np.float64)
+        p2 = apply_h(Hi, p_prev) + rng.normal(0, pos_noise, size=p_prev.shape)
+        inside = (p2[:, 0] >= 0) & (p2[:, 0] <= w - 1) & (p2[:, 1] >= 0) & (p2[:, 1] <= h - 1)
+        take = inside & (rng.random(len(p2)) < true_frac)
+        idx = np.nonzero(take)[0]
+        bad = rng.random(len(idx)) < geom_outlier_frac
+        p2[idx[bad]] = random_keypoints(rng, int(bad.sum()), w, h)
+        d_true = np.clip(np.rint(descs[k - 1][idx].astype(np.float32) + rng.normal(0, desc_noise, size=(len(idx), 128))), 0, 255).astype(np.uint8)
+        n_rand = n_kp - len(idx)
+        d = np.concatenate([d_true, sift_like_descriptors(rng, n_rand)], 0)
+        p = np.concatenate([p2[idx].astype(np.float32), random_keypoints(rng, n_rand, w, h)], 0)
+        perm = rng.permutation(n_kp)
+        descs.append(np.ascontiguousarray(d[perm])); kps.append(np.ascontiguousarray(p[perm])); Hs.append(H)
+    return descs, kps, Hs
+
+
+def make_candidates(rng, n, w, h, inlier_frac=0.5, noise=0.5):
+    """Candidate point pairs for RANSAC: (xy1, xy2, H) with xy1 ~ H xy2 for inliers."""
+    xy2 = random_keypoints(rng, n, w, h)
+    H = pair_homography(rng, w, h)
+    xy1 = apply_h(H, xy2.astype(np.float64)) + rng.normal(0, noise, size=(n, 2))
+    out = rng.random(n) > inlier_frac
+    xy1[out] = random_keypoints(rng, int(out.sum()), w, h)
+    return xy1.astype(np.float32), xy2, H
+
+
+def texture_image(rng, w, h, n_waves=24):
+    """Band-limited BGR u8 texture: a sum of random sinusoids per channel (deterministic per rng)."""
+    yy, xx = np.mgrid[0:h, 0:w].astype(np.float32)
+    img = np.zeros((h, w, 3), np.float32)
+    for c in range(3):
+        acc = np.zeros((h, w), np.float32)
+        for _ in range(n_waves):
+            fx, fy = rng.uniform(-0.15, 0.15, 2)
+            ph = rng.uniform(0, 2 * np.pi)
+            acc += np.sin(xx * fx + yy * fy + ph).astype(np.float32)
+        acc = (acc - acc.min()) / max(float(acc.max() - acc.min()), 1e-6)
+        img[..., c] = acc * 255.0
+    return img.astype(np.uint8)

@@ -1,0 +1,167 @@
+/* uavm.h — C ABI of libuavmosaic.so, the B200-native (sm_100a) hot path of UAV image mosaicking.
+ *
+ * Drop-in boundary for YuhuaXu/ImageMosaicing ("M/" = code/MosaicingCode/mosaicing/ of the
+ * reference).  Each entry point names the reference call site it replaces.  Plain C types only:
+ * pointers, sizes, PODs; no C++/torch/OpenCV types.  Return codes mirror the reference's
+ * (M/MosaicWithoutPos.h:631): 0 ok, -1 invalid argument, -2 operation failed (CUDA error text via
+ * uavm_last_error()).  There is no CPU fallback: every compute entry point fails with -2 if no
+ * sm_100 device is available.
+ *
+ * Threading: one uavm_ctx per host thread / CUDA stream; objects created from a ctx are used
+ * with that ctx.  All "host" pointers may be pageable; pinned memory makes uploads asynchronous.
+ */
+#ifndef UAVM_H
+#define UAVM_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UAVM_OK 0
+#define UAVM_EINVAL (-1)
+#define UAVM_EFAIL (-2)
+
+#define UAVM_DESC_DIM 128          /* SIFT-128 */
+#define UAVM_MAX_CANDIDATES 400    /* maxNum, M/MosaicWithoutPos.cpp:5146 (9*44 = 396 used) */
+
+/* ---- POD mirrors of the reference's wire types -------------------------------------------- */
+typedef struct { float x, y; int32_t id; } uavm_sfpoint;                 /* SfPoint, M/Point.h:27-47 (12 B) */
+typedef struct { int32_t queryIdx, trainIdx, imgIdx; float distance; } uavm_dmatch; /* cv::DMatch (16 B) */
+typedef struct { float m[9]; } uavm_projectmat;                          /* ProjectMat, M/Bitmap.h:42-45 */
+typedef struct { uavm_projectmat h; int32_t fixed; } uavm_imagetransform;/* ImageTransform, M/MosaicWithoutPos.h:224-228 */
+typedef struct {                                                         /* MatchPointPairs, M/MosaicWithoutPos.h:135-153 (40 B) */
+    uavm_sfpoint ptA; int32_t ptA_i; int32_t ptA_Fixed;
+    uavm_sfpoint ptB; int32_t ptB_i; int32_t ptB_Fixed;
+} uavm_matchpointpairs;
+typedef struct {                                                         /* fields of IplImage the path reads (CV/core/types_c.h:460-493) */
+    int32_t width, height, nChannels, widthStep;
+    uint8_t* imageData;
+} uavm_image;
+typedef struct {                                                         /* UavMatchParam, M/MosaicWithoutPos.h:57-79 (hot-path fields) */
+    float ransacDist;        /* 2.5 */
+    int32_t blending;        /* 2 = multi-band */
+    int32_t loadMatchPairs;  /* 0 */
+    int32_t sampleTimes;     /* 1000 (Ransac2D default, M/mosaicimage.h:1735) */
+    int32_t pairWindow;      /* 182: j in (i, min(n, i+pairWindow)), M/MosaicWithoutPos.cpp:5083 */
+    int32_t minInnerPoints;  /* 30, :5049 */
+    int32_t gridX, gridY;    /* 3, 3, :5041-5042 */
+    int32_t maxNum;          /* 400, :5146 */
+    float matchFrac;         /* 0.3, :5147 */
+    int32_t numBands;        /* 5, :2179 */
+    float overlapT;          /* 0.7, M/MosaicImage.cpp:2228 */
+    uint32_t seed;           /* base seed of the RANSAC sample stream (replaces srand(time(0))) */
+} uavm_param;
+void uavm_param_default(uavm_param* p);
+
+typedef struct {
+    int32_t ok;            /* Ransac2D return value */
+    int32_t n_inliers;
+    int32_t max_support;   /* maxSupport */
+    int32_t best_tuple;    /* index of the winning 4-tuple in the order of valid tuples, -1 none */
+    int32_t n_tuples;      /* valid tuples consumed (realSamTimes) */
+    int32_t n_counted;     /* hypotheses that passed the 5 px gate */
+    float H[9];            /* refined homography, H[8] = max residual (M/LeastSquare.h:519) */
+} uavm_ransac_result;
+
+/* ---- context --------------------------------------------------------------------------------- */
+typedef struct uavm_ctx uavm_ctx;
+int uavm_ctx_create(int device, uavm_ctx** out);
+void uavm_ctx_destroy(uavm_ctx* ctx);
+int uavm_ctx_set_stream(uavm_ctx* ctx, void* cuda_stream);   /* cudaStream_t of the caller (e.g. torch's) */
+int uavm_ctx_sync(uavm_ctx* ctx);
+const char* uavm_last_error(const uavm_ctx* ctx);
+int64_t uavm_ctx_launch_count(const uavm_ctx* ctx);          /* kernels launched so far by this ctx */
+int uavm_ctx_sm_count(const uavm_ctx* ctx);
+
+/* ---- device-resident feature set (replaces keypoint_%d.key / discriptor_%d.xml round trips,
+ *      M/MosaicWithoutPos.cpp:4682-4734, :5073-5103) -------------------------------------------- */
+typedef struct uavm_featureset uavm_featureset;
+int uavm_featureset_create(uavm_ctx* ctx, int n_images, const int32_t* n_keypoints, uavm_featureset** out);
+void uavm_featureset_destroy(uavm_ctx* ctx, uavm_featureset* fs);
+/* desc: n x 128 (row-major); f32 descriptors must be integer-valued 0..255 (OpenCV SIFT output);
+ * kp_xy: n x 2 floats (KeyPoint.pt).  is_device != 0: pointers are device memory. */
+int uavm_featureset_upload_f32(uavm_ctx* ctx, uavm_featureset* fs, int image, const float* desc, const float* kp_xy, int is_device);
+int uavm_featureset_upload_u8(uavm_ctx* ctx, uavm_featureset* fs, int image, const uint8_t* desc, const float* kp_xy, int is_device);
+
+/* ---- batched pair pipeline: match -> select -> RANSAC ------------------------------------------ */
+typedef struct uavm_pairbatch uavm_pairbatch;
+/* pair_ij: n_pairs x 2 (query image i, train image j), host memory. */
+int uavm_pairbatch_create(uavm_ctx* ctx, uavm_featureset* fs, int n_pairs, const int32_t* pair_ij, uavm_pairbatch** out);
+void uavm_pairbatch_destroy(uavm_ctx* ctx, uavm_pairbatch* pb);
+/* K2: exact L2 1-NN of every query descriptor in the train image (replaces FlannBasedMatcher().match,
+ * M/MosaicWithoutPos.cpp:5108-5110).  tcgen05 u8 x u8 -> s32 distance-GEMM with fused arg-min. */
+int uavm_pairbatch_match(uavm_ctx* ctx, uavm_pairbatch* pb);
+/* K3: sort by (d2, queryIdx) + nMatch = Min(maxNum, frac*size) + grid quota (replaces :5111, :5146-5153). */
+int uavm_pairbatch_select(uavm_ctx* ctx, uavm_pairbatch* pb, int width, int height, int grid_x, int grid_y, int max_num, double frac);
+/* K4: Ransac2D (replaces :5169 -> M/mosaicimage.h:1729-2035).  seeds: n_pairs host values, or NULL
+ * for seed[p] = base_seed + p.  Sample stream = MSVC rand() LCG seeded per pair. */
+int uavm_pairbatch_ransac(uavm_ctx* ctx, uavm_pairbatch* pb, float ransac_dist, int sample_times, const uint32_t* seeds, uint32_t base_seed);
+/* results -> host (each call synchronises the ctx stream) */
+int uavm_pairbatch_get_matches(uavm_ctx* ctx, uavm_pairbatch* pb, int pair, uavm_dmatch* out, int cap, int* n_out);
+int uavm_pairbatch_get_candidates(uavm_ctx* ctx, uavm_pairbatch* pb, int pair, uavm_sfpoint* pts1, uavm_sfpoint* pts2, int cap, int* n_out);
+int uavm_pairbatch_get_ransac(uavm_ctx* ctx, uavm_pairbatch* pb, int pair, uint8_t* inlier_mask, int cap, uavm_ransac_result* res);
+/* accept rule nInliers > minInnerPoints and MatchPointPairs assembly (:5201-5221): appends the inliers of
+ * every accepted pair in pair order.  Returns the number written in *n_out. */
+int uavm_pairbatch_collect(uavm_ctx* ctx, uavm_pairbatch* pb, int min_inner_points, uavm_matchpointpairs* out, int cap, int* n_out, int* n_accepted_pairs);
+
+/* ---- single-pair host-buffer seams (the calls the retained C++ host makes instead of OpenCV/own loops) */
+/* replaces matcher.match(descriptors1, descriptors2, matches), :5108-5110 */
+int uavm_match(uavm_ctx* ctx, const float* desc1, int n1, const float* desc2, int n2, uavm_dmatch* matches);
+/* replaces std::sort + SelectMatchPairs, :5111, :5146-5153.  kp*_xy: n x 2. */
+int uavm_select(uavm_ctx* ctx, const uavm_dmatch* matches, int n_matches, const float* kp1_xy, int n1, const float* kp2_xy, int n2,
+                int width, int height, int grid_x, int grid_y, int max_num, double frac,
+                uavm_sfpoint* pts1, uavm_sfpoint* pts2, int cap, int* n_out);
+/* replaces Ransac2D(vecMatch1, vecMatch2, vecInner1, vecInner2, homo, ransacDist), :5169 */
+int uavm_ransac2d(uavm_ctx* ctx, const uavm_sfpoint* pts1, const uavm_sfpoint* pts2, int n, float ransac_dist, int sample_times,
+                  uint32_t seed, uavm_sfpoint* inner1, uavm_sfpoint* inner2, int cap, uavm_ransac_result* res);
+
+/* ---- K8 global affine alignment (host; replaces BundleAdjustmentSparse, :6971-7202) ----------- */
+int uavm_align_affine(const uavm_matchpointpairs* pairs, int n_pairs, const uavm_imagetransform* init, int n_images,
+                      int n_fixed, uavm_imagetransform* out);
+/* largest connected component of the pair graph (Select_Connected_Matched_Images, :2754-2796) */
+int uavm_connected_images(const uavm_matchpointpairs* pairs, int n_pairs, int n_images, int32_t* label);
+
+/* ---- warp + seam masks + multi-band blend (replaces LaplacianPyramidBlending, M/MosaicImage.cpp:2205-2510) */
+typedef struct uavm_canvas uavm_canvas;
+typedef struct {
+    int32_t keep; int32_t beg_x, beg_y, chip_w, chip_h;
+    float sx, sy; float quad[8]; float inv[9];
+} uavm_chip_layout;
+typedef struct { int32_t canvas_w, canvas_h; float dgx, dgy; } uavm_canvas_layout;
+/* canvas sizing + per-image chip boxes (:2233-2348); H: n x 9 (already scaled), keep: n (1 = use) or NULL */
+int uavm_canvas_layout_compute(const float* H, const int32_t* keep, int n, int img_w, int img_h,
+                               uavm_canvas_layout* canvas, uavm_chip_layout* chips);
+/* overlap filter (ResampleByOverlap, :2070-2201): keep[n] out */
+int uavm_resample_by_overlap(const float* H, int n, int img_w, int img_h, float overlap_t, int32_t* keep);
+
+int uavm_canvas_create(uavm_ctx* ctx, int n_images, int img_w, int img_h, const float* H, const int32_t* keep, uavm_canvas** out);
+void uavm_canvas_destroy(uavm_ctx* ctx, uavm_canvas* cv);
+int uavm_canvas_get_layout(uavm_canvas* cv, uavm_canvas_layout* canvas, uavm_chip_layout* chips);
+/* source frame n (BGR u8 interleaved, `step` bytes per row); is_device != 0: device pointer */
+int uavm_canvas_set_image(uavm_ctx* ctx, uavm_canvas* cv, int image, const uint8_t* bgr, int step, int is_device);
+/* K5: bilinear warp of every kept frame into its chip + validity mask (:2350-2448) */
+int uavm_canvas_warp(uavm_ctx* ctx, uavm_canvas* cv);
+/* K6: FindMasksByDistMap (:1761-1881) */
+int uavm_canvas_seam_masks(uavm_ctx* ctx, uavm_canvas* cv);
+/* K7: MultiBandBlender prepare/feed/blend + convertTo(CV_8U) (:2296-2299, :2476-2486) */
+int uavm_canvas_blend(uavm_ctx* ctx, uavm_canvas* cv, int num_bands);
+/* blending != 2 variant (MosaicImagesRefined, M/MosaicWithoutPos.cpp:2194-2352): last image wins */
+int uavm_canvas_paste(uavm_ctx* ctx, uavm_canvas* cv);
+/* copies -> host */
+int uavm_canvas_get_chip(uavm_ctx* ctx, uavm_canvas* cv, int image, uint8_t* chip_bgr, int chip_step, uint8_t* mask, int mask_step);
+int uavm_canvas_get_result(uavm_ctx* ctx, uavm_canvas* cv, uint8_t* bgr, int step, uint8_t* mask, int mask_step);
+
+/* ---- top-level shim with the shape of MosaicVavImages (M/MosaicWithoutPos.h:638-645,
+ *      M/MosaicWithoutPos.cpp:10148-10214).  Features are supplied by the caller (SIFT extraction is
+ *      upstream of this library): desc[i] n_kp[i] x 128 f32, kp_xy[i] n_kp[i] x 2.
+ *      result is allocated by the library (uavm_free); returns 0 / -1 / -2 like the reference. */
+int uavm_mosaic_images(uavm_ctx* ctx, const uavm_image* images, int n_images,
+                       const float* const* desc, const float* const* kp_xy, const int32_t* n_kp,
+                       const uavm_param* param, float scale,
+                       uavm_image* result, int* num_mosaiced, uavm_imagetransform* transforms_out);
+void uavm_free(void* p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

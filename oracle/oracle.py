@@ -94,7 +94,7 @@ def select(train_idx, d2, kp1, kp2, width, height, grid_x=3, grid_y=3, max_num=4
     train_idx = np.ascontiguousarray(train_idx, np.int32); d2 = np.ascontiguousarray(d2, np.int32)
     kp1 = _f32(kp1); kp2 = _f32(kp2)
     n = len(train_idx)
-    cap = max(max_num, 1) + 16
+    cap = 2048
     xy1 = np.zeros((cap, 2), np.float32); xy2 = np.zeros((cap, 2), np.float32)
     id1 = np.zeros(cap, np.int32); id2 = np.zeros(cap, np.int32)
     cnt = lib().orc_select(_p(train_idx, i32p), _p(d2, i32p), n, _p(kp1, f32p), _p(kp2, f32p),

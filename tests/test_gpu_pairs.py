@@ -1,0 +1,162 @@
+"""GPU parity tests (through the C ABI) of K2 match, K3 select and K4 RANSAC against the CPU oracle.
+
+Bar (BASELINE.json north_star): match indices, candidate lists and RANSAC inlier masks bit-exact;
+homography parameters within 1e-4 relative (they are in fact compared bit for bit first).
+"""
+import numpy as np
+import pytest
+
+from imagemosaicing_b200 import api, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _rand_desc(rng, n):
+    return synth.sift_like_descriptors(rng, n)
+
+
+@pytest.mark.parametrize("na,nb", [(1, 1), (5, 3), (127, 129), (128, 128), (256, 255), (257, 1000), (300, 2048), (2048, 2048), (1000, 4097)])
+def test_match_parity_sizes(ctx, oracle, na, nb):
+    rng = np.random.default_rng(na * 100003 + nb)
+    A = _rand_desc(rng, na); B = _rand_desc(rng, nb)
+    m = api.match(ctx, A.astype(np.float32), B.astype(np.float32))
+    idx, d2 = oracle.match_l2(A, B)
+    assert np.array_equal(m["queryIdx"], np.arange(na))
+    assert np.array_equal(m["trainIdx"], idx)
+    assert np.array_equal(m["distance"].view(np.uint32), np.sqrt(d2.astype(np.float32)).view(np.uint32))
+
+
+def test_match_ties_duplicates_and_extremes(ctx, oracle):
+    rng = np.random.default_rng(7)
+    B = _rand_desc(rng, 700)
+    B[100] = B[5]; B[650] = B[5]; B[300] = 0; B[301] = 0; B[400] = 255; B[401] = 255     # duplicates, zero rows, max rows
+    A = np.concatenate([B[[5, 100, 300, 400, 699]], np.zeros((1, 128), np.uint8), np.full((1, 128), 255, np.uint8), _rand_desc(rng, 50)])
+    fs = api.FeatureSet(ctx, [len(A), len(B)])
+    fs.upload(0, A); fs.upload(1, B)
+    pb = api.PairBatch(ctx, fs, [[0, 1]])
+    pb.match()
+    m = pb.matches(0)
+    idx, d2 = oracle.match_l2(A, B)
+    assert np.array_equal(m["trainIdx"], idx)          # lowest index wins ties: 5 (not 100/650), 300, 400
+    assert m["trainIdx"][0] == 5 and m["trainIdx"][1] == 5 and m["trainIdx"][2] == 300 and m["trainIdx"][3] == 400
+    assert np.array_equal((m["distance"].astype(np.float64) ** 2).round().astype(np.int64), d2.astype(np.int64))
+
+
+def test_match_batched_pairs_full_size(ctx, oracle):
+    """BASELINE config sizes: 8192 keypoints per image, several pairs in one launch; checked against the
+    oracle on two pairs and by a size-independent property on the rest (d2 recomputed from the indices)."""
+    descs, kps, _ = synth.make_strip(5, 4000, 3000, 8192, seed=11)
+    fs = api.FeatureSet(ctx, [len(d) for d in descs])
+    for i, (d, k) in enumerate(zip(descs, kps)):
+        fs.upload(i, d, k)
+    pairs = [[0, 1], [1, 2], [2, 3], [3, 4], [4, 0], [2, 2]]
+    pb = api.PairBatch(ctx, fs, pairs)
+    pb.match()
+    for p, (i, j) in enumerate(pairs):
+        m = pb.matches(p)
+        A = descs[i].astype(np.int64); B = descs[j].astype(np.int64)
+        d2 = ((A - B[m["trainIdx"]]) ** 2).sum(1)
+        assert np.array_equal(np.rint(m["distance"].astype(np.float64) ** 2).astype(np.int64), d2)
+        if i == j:
+            assert np.array_equal(m["trainIdx"], np.arange(len(A))) or (d2 == 0).all()
+        if p < 2:
+            idx, od2 = oracle.match_l2(descs[i], descs[j])
+            assert np.array_equal(m["trainIdx"], idx)
+            assert np.array_equal(d2, od2.astype(np.int64))
+
+
+@pytest.mark.parametrize("n,w,h", [(2048, 512, 512), (8192, 4000, 3000), (2000, 1000, 750), (30, 512, 512), (1335, 4000, 3000)])
+def test_select_parity(ctx, oracle, n, w, h):
+    rng = np.random.default_rng(n + w)
+    kp1 = synth.random_keypoints(rng, n, w, h); kp2 = synth.random_keypoints(rng, n + 17, w, h)
+    kp1[:5, 0] = w - 0.25          # exercises the nX == gridX quirk column (M/MosaicWithoutPos.cpp:4993-5010)
+    train = rng.integers(0, n + 17, n).astype(np.int32)
+    d2 = rng.integers(0, 60000, n).astype(np.int32)
+    d2[rng.integers(0, n, n // 4)] = 12345           # many equal distances: (d2, queryIdx) order must hold
+    m = np.zeros(n, dtype=np.dtype([("queryIdx", "<i4"), ("trainIdx", "<i4"), ("imgIdx", "<i4"), ("distance", "<f4")]))
+    m["queryIdx"] = np.arange(n); m["trainIdx"] = train; m["distance"] = np.sqrt(d2.astype(np.float32))
+    p1, p2 = api.select_match_pairs(ctx, m, kp1, kp2, w, h)
+    o1, oi1, o2, oi2 = oracle.select(train, d2, kp1, kp2, w, h)
+    assert len(p1) == len(oi1)
+    assert np.array_equal(p1["id"], oi1) and np.array_equal(p2["id"], oi2)
+    assert np.array_equal(np.c_[p1["x"], p1["y"]], o1) and np.array_equal(np.c_[p2["x"], p2["y"]], o2)
+
+
+def _check_ransac(ctx, oracle, xy1, xy2, seed, sample_times=1000, dist=2.5):
+    ok, mask, H, res = api.ransac2d(ctx, xy1, xy2, dist, sample_times, seed)
+    o_ok, o_mask, o_H, o_n, st = oracle.ransac2d(xy1, xy2, dist, sample_times, seed)
+    assert ok == o_ok
+    assert res.n_inliers == o_n
+    assert np.array_equal(mask, o_mask)
+    assert res.max_support == st.max_support
+    assert res.best_tuple == st.best_tuple
+    assert res.n_tuples == st.n_tuples
+    assert res.n_counted == st.n_counted
+    if o_n >= 4:
+        assert np.allclose(H, o_H, rtol=1e-4, atol=0), (H, o_H)       # north_star tolerance
+        assert np.array_equal(H.view(np.uint32), o_H.view(np.uint32)) or np.array_equal(H, o_H), (H, o_H)
+    return st
+
+
+def test_ransac_parity_many_pairs(ctx, oracle):
+    rng = np.random.default_rng(42)
+    n_early = 0
+    for trial in range(60):
+        w, h = [(4000, 3000), (1000, 750), (512, 512)][trial % 3]
+        n = int(rng.integers(4, 397))
+        inl = 1.0 if trial % 10 == 9 else float(rng.uniform(0.15, 1.0))      # every 10th: all inliers -> early exit
+        noise = float(rng.choice([0.0, 0.3, 0.5]))
+        xy1, xy2, _ = synth.make_candidates(rng, n, w, h, inl, noise)
+        st = _check_ransac(ctx, oracle, xy1, xy2, int(rng.integers(0, 2 ** 32)))
+        n_early += st.early_exit
+    assert n_early > 0          # the 0.99 early exit was exercised
+
+
+def test_ransac_edge_cases(ctx, oracle):
+    rng = np.random.default_rng(5)
+    for n in (0, 1, 3, 4, 5, 8):
+        xy1, xy2, _ = synth.make_candidates(rng, max(n, 1), 1000, 750, 1.0, 0.0)
+        _check_ransac(ctx, oracle, xy1[:n], xy2[:n], 99)
+    # pure noise: (almost) no consensus, loop runs until 5000 draws or 1000 counted
+    xy1 = synth.random_keypoints(rng, 200, 4000, 3000); xy2 = synth.random_keypoints(rng, 200, 4000, 3000)
+    _check_ransac(ctx, oracle, xy1, xy2, 1234)
+    # all points collinear / duplicated: singular systems, exercises the slow path and the gates
+    xy2 = np.stack([np.linspace(0, 999, 100), np.linspace(0, 500, 100)], 1).astype(np.float32)
+    _check_ransac(ctx, oracle, xy2 + 3.0, xy2, 77)
+    xy2 = np.repeat(synth.random_keypoints(rng, 10, 1000, 750), 10, 0)
+    _check_ransac(ctx, oracle, xy2 * 1.01, xy2, 78)
+    # small sample_times and the 5000 clamp
+    xy1, xy2, _ = synth.make_candidates(rng, 300, 4000, 3000, 0.5, 0.5)
+    _check_ransac(ctx, oracle, xy1, xy2, 5, sample_times=10)
+    _check_ransac(ctx, oracle, xy1, xy2, 6, sample_times=7000)
+
+
+def test_pipeline_match_select_ransac_strip(ctx, oracle):
+    """End to end on a synthetic strip (C2-shaped, fewer images): every stage's output equals the oracle's."""
+    w, h, nk = 4000, 3000, 8192
+    descs, kps, Hs = synth.make_strip(4, w, h, nk, seed=20160308)
+    fs = api.FeatureSet(ctx, [nk] * 4)
+    for i in range(4):
+        fs.upload(i, descs[i], kps[i])
+    pairs = [[0, 1], [1, 2], [2, 3]]
+    pb = api.PairBatch(ctx, fs, pairs)
+    pb.match(); pb.select(w, h); pb.ransac(2.5, 1000, base_seed=1000)
+    for p, (i, j) in enumerate(pairs):
+        idx, d2 = oracle.match_l2(descs[i], descs[j])
+        m = pb.matches(p)
+        assert np.array_equal(m["trainIdx"], idx)
+        o1, oi1, o2, oi2 = oracle.select(idx, d2, kps[i], kps[j], w, h)
+        c1, c2 = pb.candidates(p)
+        assert np.array_equal(c1["id"], oi1) and np.array_equal(c2["id"], oi2)
+        o_ok, o_mask, o_H, o_n, st = oracle.ransac2d(o1, o2, 2.5, 1000, 1000 + p)
+        mask, res = pb.ransac_result(p)
+        assert res.n_inliers == o_n and np.array_equal(mask[:len(o_mask)], o_mask)
+        assert res.best_tuple == st.best_tuple and res.max_support == st.max_support
+        Hg = np.array(list(res.H), np.float32)
+        assert np.allclose(Hg, o_H, rtol=1e-4, atol=0)
+        # the recovered homography maps image j -> image i like the ground truth
+        assert o_n > 100
+        Ht = Hs[i] / Hs[i][2, 2]
+        assert np.allclose(Hg[:8], Ht.reshape(-1)[:8], rtol=0.05, atol=2.0)
+    out, n, acc = pb.collect(30)
+    assert acc == 3 and n == sum(pb.ransac_result(p)[1].n_inliers for p in range(3))
