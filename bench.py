@@ -1,0 +1,338 @@
+#!/usr/bin/env python
+"""bench.py — image-pairs/s through match + select + RANSAC + warp (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (config.workload): BASELINE configs[1] — a 50-image UAV strip of 4000x3000 frames with 8192
+SIFT-128 keypoints per image, sequential-overlap pair graph (49 pairs).  One *step* = one pass of the hot
+path over the strip: 49 x { 8192x8192x128 L2 1-NN match, candidate selection, Ransac2D (<=396 candidates,
+1000 counted hypotheses), one 4000x3000 frame warped into its chip + mask }.  With N GPUs every rank
+processes its own strip (weak scaling, no data-path collective: pairs are independent units).
+
+`value`  = pairs/s with inputs resident in HBM, timed with CUDA events on the launching stream.
+`e2e`    = pairs/s through the host-buffer API: every step copies the strip's descriptors, keypoints and
+           frames from pinned host memory, runs the path and reads the inlier match list back.
+`roofline` = the dominant kernel of the step (K5 warp: HBM bound; algorithmic 7 B per source pixel).
+`cpu_baseline` = the CPU oracle port timed on this box's host cores on a bounded sample of the same pairs.
+--impl reference times the CPU path only (oracle port; RANSAC through the reference's own compiled
+Ransac2D when oracle/_ref is present).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+W, H, NKP, NIMG = 4000, 3000, 8192, 50
+RANSAC_DIST, SAMPLE_TIMES = 2.5, 1000
+METRIC = "image-pairs/sec (match+RANSAC+warp)"
+UNIT = "pairs/s"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"], "bf16_tflops_sustained": d.get("bf16_tflops_sustained"), "src": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "src": "fallback"}
+
+
+def strip_transforms(Hs):
+    """Affine chain image k -> mosaic frame of image 0 (what BundleAdjustmentSparse produces)."""
+    T = [np.eye(3)]
+    for Hk in Hs:
+        A = Hk / Hk[2, 2]
+        A = A.copy(); A[2, :2] = 0
+        T.append(T[-1] @ A)
+    return np.stack(T).astype(np.float32).reshape(len(T), 9)
+
+
+def make_workload(rank, n_img=NIMG):
+    from imagemosaicing_b200 import synth
+    descs, kps, Hs = synth.make_strip(n_img, W, H, NKP, seed=synth.SEED_BASE + 1000 * rank)
+    T = strip_transforms(Hs)
+    rng = np.random.default_rng(synth.SEED_BASE + 77 + rank)
+    base = synth.texture_image(rng, W, H, 6)
+    return descs, kps, Hs, T, base
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU leg (oracle port) — used for cpu_baseline and for --impl reference
+# ------------------------------------------------------------------------------------------------
+def cpu_pairs(descs, kps, T, frames, pairs, seeds):
+    """Runs the CPU path on the given pairs; returns seconds."""
+    from oracle import oracle as O
+    canvas, chips = O.canvas_layout(T, None, W, H)
+    use_ref = O.ref() is not None
+    t0 = time.perf_counter()
+    for (i, j), seed in zip(pairs, seeds):
+        idx, d2 = O.match_l2(descs[i], descs[j])
+        x1, i1, x2, i2 = O.select(idx, d2, kps[i], kps[j], W, H)
+        if use_ref:
+            O.ref_ransac2d(x1, x2, RANSAC_DIST, SAMPLE_TIMES, seed)
+        else:
+            O.ransac2d(x1, x2, RANSAC_DIST, SAMPLE_TIMES, seed)
+        O.warp_chip(frames[j], canvas, chips[j])
+    return time.perf_counter() - t0
+
+
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n_sample = 4                       # pairs per step (bounded sample of the 49-pair workload)
+    descs, kps, Hs, T, base = make_workload(0, n_img=n_sample + 1)
+    frames = [base] * (n_sample + 1)
+    pairs = [(i, i + 1) for i in range(n_sample)]
+    seeds = [1000 + p for p in range(n_sample)]
+    from oracle import oracle as O
+    O.lib()
+    for _ in range(max(args.warmup, 1) if args.warmup > 0 else 0):
+        cpu_pairs(descs, kps, T, frames, pairs[:1], seeds[:1])
+    t = 0.0
+    for _ in range(args.steps):
+        t += cpu_pairs(descs, kps, T, frames, pairs, seeds)
+    val = n_sample * args.steps / t
+    cores = host_threads()
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1000.0 * t / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u8/int32 match, f32 RANSAC+warp", "data": "synthetic",
+        "config": {"workload": "configs[1]: 50-image strip 4000x3000, 8192 kp/image, sequential pairs",
+                   "pairs_per_step": n_sample},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores,
+                         "kind": "port", "sample": f"{n_sample} of 49 pairs per step; brute-force match + warp on {cores} OpenMP threads, "
+                                                   f"RANSAC 1 thread ({'reference Ransac2D compiled from /root/reference' if O.ref() is not None else 'oracle restatement'})"},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(gpu_index)],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush(); self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        for ln in self.f.read().splitlines():
+            c = [x.strip() for x in ln.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1])); mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if sm:
+            out["sm_mhz"] = float(np.median(sm)); out["sm_max_mhz"] = float(max(mx)); out["samples"] = len(sm)
+        out["reasons"] = sorted(reasons)
+        try:
+            os.unlink(self.f.name)
+        except Exception:
+            pass
+        return out
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from imagemosaicing_b200 import api
+
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    stream = torch.cuda.current_stream()
+    ctx = api.Context(local, stream)
+
+    descs, kps, Hs, T, base = make_workload(rank)
+    n_pairs = NIMG - 1
+    pairs = np.array([[i, i + 1] for i in range(n_pairs)], np.int32)
+    keep = np.ones(NIMG, np.int32); keep[0] = 0            # pair (i, i+1) warps frame i+1: 49 frames per step
+
+    # ---- pinned host copies (e2e inputs) ----
+    h_desc = [torch.from_numpy(d).pin_memory() for d in descs]
+    h_kp = [torch.from_numpy(k).pin_memory() for k in kps]
+    h_frames = []
+    for k in range(NIMG):                                  # distinct frames: circular shifts of one texture
+        h_frames.append(torch.from_numpy(np.roll(base, (37 * k) % H, axis=0)).pin_memory())
+
+    fs = api.FeatureSet(ctx, [NKP] * NIMG)
+    pb = api.PairBatch(ctx, fs, pairs)
+    cv = api.Canvas(ctx, T, W, H, keep)
+
+    def upload_all():
+        for k in range(NIMG):
+            fs.upload(k, h_desc[k], h_kp[k])
+        for k in range(1, NIMG):
+            cv.set_image(k, h_frames[k])
+
+    def compute(ev=None):
+        if ev: ev[0].record()
+        pb.match()
+        if ev: ev[1].record()
+        pb.select(W, H)
+        if ev: ev[2].record()
+        pb.ransac(RANSAC_DIST, SAMPLE_TIMES, base_seed=1000)
+        if ev: ev[3].record()
+        cv.warp()
+        if ev: ev[4].record()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    upload_all()
+    torch.cuda.synchronize()
+
+    # ---- device-resident timing ----
+    for _ in range(args.warmup):
+        compute()
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(args.steps)]
+    l0 = ctx.launch_count
+    t_start = torch.cuda.Event(enable_timing=True); t_end = torch.cuda.Event(enable_timing=True)
+    barrier()
+    t_start.record()
+    for s in range(args.steps):
+        compute(evs[s])
+    t_end.record()
+    barrier()
+    launches = ctx.launch_count - l0
+    ms_total = t_start.elapsed_time(t_end)
+    stage_ms = np.zeros(4)
+    for s in range(args.steps):
+        for k in range(4):
+            stage_ms[k] += evs[s][k].elapsed_time(evs[s][k + 1])
+    stage_ms /= args.steps
+
+    # ---- end-to-end timing (host buffers in, inlier match list out) ----
+    def e2e_step():
+        upload_all()
+        compute()
+        return pb.collect(30)
+    for _ in range(min(args.warmup, 2)):
+        e2e_step()
+    barrier()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e_steps = max(1, min(args.steps, 5))
+    e0.record()
+    n_match_pairs = 0
+    for _ in range(e_steps):
+        out, n_match_pairs, n_acc = e2e_step()
+    e1.record()
+    barrier()
+    e2e_ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if sampler else None
+
+    t = torch.tensor([ms_total, e2e_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total, e2e_ms = float(t[0]), float(t[1])
+
+    if rank == 0:
+        pk = peaks()
+        ms_step = ms_total / args.steps
+        value = world * n_pairs * args.steps / (ms_total / 1000.0)
+        e2e_val = world * n_pairs * e_steps / (e2e_ms / 1000.0)
+        h2d = NIMG * (NKP * 128 + NKP * 8) + n_pairs * W * H * 3
+        d2h = int(n_match_pairs) * 40 + n_pairs * (4 * 16)
+        warp_bytes = 7.0 * W * H * n_pairs                      # 7 B per source pixel
+        match_flop = 2.0 * NKP * NKP * 128 * n_pairs
+        warp_gbs = warp_bytes / (stage_ms[3] / 1000.0) / 1e9
+        match_tf = match_flop / (stage_ms[0] / 1000.0) / 1e12
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8 x u8 -> s32 match (tcgen05 kind::i8), f32 RANSAC + warp", "data": "synthetic",
+            "config": {"workload": "configs[1]: 50-image strip 4000x3000, 8192 kp/image, sequential pairs (49 pair units per step per GPU)",
+                       "pairs_per_step_per_gpu": n_pairs, "ransac": "396 candidates, 1000 counted hypotheses, ~50% inliers",
+                       "l2": "per-step working set 5 GB (frames + chips) >> 126 MB L2; the warp pass evicts the 52 MB descriptor pool between match passes",
+                       "parallelism": f"pairs sharded over {world} GPU(s), no data-path collective"},
+            "roofline": {"kernel": "k5_warp_chips", "bound": "hbm", "achieved": warp_gbs, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                         "frac": warp_gbs / pk["hbm_gbs"], "traffic": None, "peak_src": pk["src"],
+                         "algorithmic_bytes_per_launch": warp_bytes, "ms_per_launch": float(stage_ms[3])},
+            "kernels": {"k2_match_tcgen05": {"ms": float(stage_ms[0]), "bound": "tensor", "achieved_tflops": match_tf,
+                                             "peak_bf16_tflops": pk["bf16_tflops"], "frac_of_bf16_peak": match_tf / pk["bf16_tflops"]},
+                        "k3_select": {"ms": float(stage_ms[1])},
+                        "k4_ransac_eval+finalize": {"ms": float(stage_ms[2]), "hypotheses_per_s": n_pairs * 2628 / (stage_ms[2] / 1000.0)},
+                        "k5_warp_chips": {"ms": float(stage_ms[3]), "achieved_gbs": warp_gbs}},
+            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": e_steps,
+                    "ms_per_step": e2e_ms / e_steps},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+        }
+        # ---- CPU baseline on a bounded sample (rank 0, N=1 only) ----
+        if world == 1 and not args.no_cpu:
+            n_sample = 6
+            frames = [h_frames[k].numpy() for k in range(n_sample + 1)]
+            sp = [(i, i + 1) for i in range(n_sample)]
+            cpu_pairs(descs, kps, T[:n_sample + 1], frames, sp[:1], [1000])       # warm
+            t_cpu = cpu_pairs(descs, kps, T[:n_sample + 1], frames, sp, [1000 + p for p in range(n_sample)])
+            from oracle import oracle as O
+            line["cpu_baseline"] = {"value": n_sample / t_cpu, "unit": UNIT, "cores": host_threads(), "kind": "port",
+                                    "sample": f"{n_sample} of 49 pairs; brute-force match + warp on {host_threads()} OpenMP threads, RANSAC 1 thread "
+                                              f"({'reference Ransac2D compiled from /root/reference' if O.ref() is not None else 'oracle restatement'})"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -27,6 +27,13 @@ def _is_torch_cuda(x):
     return hasattr(x, "is_cuda") and x.is_cuda
 
 
+def _host(x):
+    """torch CPU tensors (e.g. pinned host buffers) are viewed as numpy arrays without a copy."""
+    if hasattr(x, "is_cuda") and not x.is_cuda:
+        return x.numpy()
+    return x
+
+
 def _ptr(x, ctype):
     if _is_torch_cuda(x):
         return C.cast(C.c_void_p(x.data_ptr()), ctype)
@@ -86,6 +93,7 @@ class FeatureSet:
 
     def upload(self, image, desc, kp_xy=None):
         """desc: (n,128) uint8 or float32 (integer valued) numpy array or torch CUDA tensor; kp_xy: (n,2) f32."""
+        desc = _host(desc); kp_xy = _host(kp_xy) if kp_xy is not None else None
         dev = 1 if _is_torch_cuda(desc) else 0
         if dev:
             is_u8 = str(desc.dtype) == "torch.uint8"
@@ -219,3 +227,83 @@ def ransac2d(ctx, xy1, xy2, ransac_dist=2.5, sample_times=1000, seed=1):
     for k in range(res.n_inliers):
         mask[in1[k].id] = 1
     return res.ok, mask, np.array(list(res.H), np.float32), res
+
+
+# ---- warp / seam masks / blend --------------------------------------------------------------------
+def canvas_layout(H, keep, img_w, img_h):
+    """Canvas sizing + chip boxes (M/MosaicImage.cpp:2233-2348), host side."""
+    H = np.ascontiguousarray(H, np.float32).reshape(-1, 9)
+    n = len(H)
+    kp = None
+    if keep is not None:
+        keep = np.ascontiguousarray(keep, np.int32); kp = _ptr(keep, i32p)
+    canvas = CanvasLayout(); chips = (ChipLayout * n)()
+    rc = L.lib().uavm_canvas_layout_compute(_ptr(H, f32p), kp, n, int(img_w), int(img_h), C.byref(canvas), chips)
+    if rc != 0:
+        raise UavmError(f"uavm_canvas_layout_compute failed: {rc}")
+    return canvas, chips
+
+
+class Canvas:
+    """Warp + seam masks + blend of N frames with transforms H (uavm_canvas; LaplacianPyramidBlending)."""
+
+    def __init__(self, ctx, H, img_w, img_h, keep=None):
+        self.ctx = ctx
+        self.H = np.ascontiguousarray(H, np.float32).reshape(-1, 9)
+        self.n = len(self.H); self.img_w = int(img_w); self.img_h = int(img_h)
+        kp = None
+        if keep is not None:
+            keep = np.ascontiguousarray(keep, np.int32); kp = _ptr(keep, i32p)
+        self._h = C.c_void_p()
+        ctx.check(L.lib().uavm_canvas_create(ctx._h, self.n, self.img_w, self.img_h, _ptr(self.H, f32p), kp, C.byref(self._h)))
+        self.layout = CanvasLayout(); self.chips = (ChipLayout * self.n)()
+        ctx.check(L.lib().uavm_canvas_get_layout(self._h, C.byref(self.layout), self.chips))
+
+    def set_image(self, image, bgr):
+        """bgr: (h, w, 3) uint8 numpy array (host) or torch CUDA tensor (device)."""
+        bgr = _host(bgr)
+        dev = 1 if _is_torch_cuda(bgr) else 0
+        if dev:
+            assert bgr.is_contiguous(); step = bgr.stride(0)
+        else:
+            bgr = np.ascontiguousarray(bgr, np.uint8); step = bgr.strides[0]
+        assert bgr.shape[0] == self.img_h and bgr.shape[1] == self.img_w and bgr.shape[2] == 3
+        self.ctx.check(L.lib().uavm_canvas_set_image(self.ctx._h, self._h, int(image), _ptr(bgr, u8p), int(step), dev))
+        self._keep = bgr
+
+    def warp(self):
+        self.ctx.check(L.lib().uavm_canvas_warp(self.ctx._h, self._h))
+
+    def seam_masks(self):
+        self.ctx.check(L.lib().uavm_canvas_seam_masks(self.ctx._h, self._h))
+
+    def blend(self, num_bands=5):
+        self.ctx.check(L.lib().uavm_canvas_blend(self.ctx._h, self._h, int(num_bands)))
+
+    def paste(self):
+        self.ctx.check(L.lib().uavm_canvas_paste(self.ctx._h, self._h))
+
+    def chip(self, image):
+        c = self.chips[image]
+        px = np.zeros((c.chip_h, c.chip_w, 3), np.uint8); mask = np.zeros((c.chip_h, c.chip_w), np.uint8)
+        self.ctx.check(L.lib().uavm_canvas_get_chip(self.ctx._h, self._h, int(image), _ptr(px, u8p), px.strides[0],
+                                                    _ptr(mask, u8p), mask.strides[0]))
+        return px, mask
+
+    def result(self):
+        out = np.zeros((self.layout.canvas_h, self.layout.canvas_w, 3), np.uint8)
+        mask = np.zeros((self.layout.canvas_h, self.layout.canvas_w), np.uint8)
+        self.ctx.check(L.lib().uavm_canvas_get_result(self.ctx._h, self._h, _ptr(out, u8p), out.strides[0],
+                                                      _ptr(mask, u8p), mask.strides[0]))
+        return out, mask
+
+    def close(self):
+        if self._h:
+            L.lib().uavm_canvas_destroy(self.ctx._h, self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,229 @@
+// canvas.cu — device side of the warp stage of LaplacianPyramidBlending (M/MosaicImage.cpp:2205-2510):
+//   K5  k5_warp_chips   bilinear inverse warp of every kept frame into its chip + validity mask (:2350-2448)
+// (K6 seam masks live in masks.cu, K7 multi-band blend in blend.cu.)
+//
+// HBM layout: source frames are stored as BGRA (uchar4) so that one 32-bit load returns a whole pixel
+// (a BGR triple straddles words; 12 byte loads per output pixel would make the kernel LSU-bound);
+// chips are packed BGR u8 with a row step of 3*align4(chip_w) so every thread stores whole 12-byte
+// groups; masks are u8 with a row step of align4(chip_w).
+#include <string.h>
+#include "canvas.h"
+
+namespace {
+
+// BGR (3 B/px, arbitrary step) -> BGRA (4 B/px)
+__global__ void __launch_bounds__(256) k5_bgr_to_bgra(const uint8_t* __restrict__ src, int w, int h, int step,
+                                                       uchar4* __restrict__ dst, int dst_step_px)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y;
+    if (x >= w || y >= h) return;
+    const uint8_t* s = src + (size_t)y * step + 3 * x;
+    dst[(size_t)y * dst_step_px + x] = make_uchar4(s[0], s[1], s[2], 0);
+}
+
+// exact u8 -> f32 without the conversion pipe: byte k of `word` into the mantissa of 2^23, minus 2^23
+template <int K>
+__device__ __forceinline__ float byte_f32(uint32_t word)
+{
+    return __int_as_float(__byte_perm(word, 0x4B000000u, 0x7540 | K)) - 8388608.0f;
+}
+
+// one channel of the reference's bilinear expression (:2398-2410), evaluated left to right in float:
+//   uchar( g1*(1-p)*(1-q) + g2*(1-p)*q + g3*p*(1-q) + g4*p*q )
+template <int K>
+__device__ __forceinline__ uint32_t bilinear_channel(uint32_t t00, uint32_t t01, uint32_t t10, uint32_t t11,
+                                                     float p, float q, float omp, float omq)
+{
+    const float g1 = byte_f32<K>(t00), g2 = byte_f32<K>(t01), g3 = byte_f32<K>(t10), g4 = byte_f32<K>(t11);
+    const float v = g1 * omp * omq + g2 * omp * q + g3 * p * omq + g4 * p * q;
+    return (uint32_t)(int)v;                       // truncation, value in [0, 255]
+}
+
+constexpr int kWarpTileW = 128;   // 32 threads x 4 px
+constexpr int kWarpTileH = 16;    // 8 thread rows x 2
+
+__global__ void __launch_bounds__(256)
+k5_warp_chips(const ChipDesc* __restrict__ descs, int img_w, int img_h, int src_step_px, float dgx, float dgy)
+{
+    const ChipDesc& D = descs[blockIdx.z];
+    if (!D.keep) return;
+    const int x0 = blockIdx.x * kWarpTileW + threadIdx.x * 4;
+    const int ybase = blockIdx.y * kWarpTileH + threadIdx.y;
+    if (x0 >= D.chip_w || blockIdx.y * kWarpTileH >= D.chip_h) return;
+    const float iv0 = D.inv[0], iv1 = D.inv[1], iv2 = D.inv[2], iv3 = D.inv[3], iv4 = D.inv[4], iv5 = D.inv[5];
+    const float iv6 = D.inv[6], iv7 = D.inv[7], iv8 = D.inv[8];
+    const bool affine = D.affine != 0;
+    const float w1 = (float)(img_w - 1), h1 = (float)(img_h - 1);
+    const uchar4* __restrict__ src = D.src;
+    const float fbx = (float)D.beg_x, fby = (float)D.beg_y;
+#pragma unroll
+    for (int ry = 0; ry < kWarpTileH / 8; ry++) {
+        const int yd = ybase + ry * 8;
+        if (yd >= D.chip_h) break;
+        const float yt = (float)yd - dgy - D.sy + fby;             // yTemp (:2357)
+        uint32_t out[4][3];
+        uint32_t mbits = 0;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int xd = x0 + i;
+            const float xt = (float)xd - dgx - D.sx + fbx;         // xTemp (:2356)
+            float xs = xt * iv0 + yt * iv1 + iv2;
+            float ys = xt * iv3 + yt * iv4 + iv5;
+            if (!affine) {                                         // two true divides per coordinate (:2359-2362)
+                const float den = xt * iv6 + yt * iv7 + iv8;
+                xs = xs / den;
+                ys = ys / den;
+            }                                                      // affine: den == 1.0f exactly, x/1 == x
+            const int iy = (int)ys, ix = (int)xs;
+            out[i][0] = 0; out[i][1] = 0; out[i][2] = 0;
+            if ((xs >= 0.0f) && (xs < w1) && (ys >= 0.0f) && (ys < h1)) {
+                const float p = ys - (float)iy, q = xs - (float)ix;
+                const float omp = 1.0f - p, omq = 1.0f - q;
+                const uint32_t* r0 = reinterpret_cast<const uint32_t*>(src + (size_t)iy * src_step_px + ix);
+                const uint32_t* r1 = r0 + src_step_px;
+                const uint32_t t00 = __ldg(r0), t01 = __ldg(r0 + 1), t10 = __ldg(r1), t11 = __ldg(r1 + 1);
+                out[i][0] = bilinear_channel<0>(t00, t01, t10, t11, p, q, omp, omq);
+                out[i][1] = bilinear_channel<1>(t00, t01, t10, t11, p, q, omp, omq);
+                out[i][2] = bilinear_channel<2>(t00, t01, t10, t11, p, q, omp, omq);
+                mbits |= 0xffu << (8 * i);
+            }
+        }
+        uint32_t* crow = reinterpret_cast<uint32_t*>(D.chip + (size_t)yd * D.chip_step + 3 * x0);
+        crow[0] = out[0][0] | (out[0][1] << 8) | (out[0][2] << 16) | (out[1][0] << 24);
+        crow[1] = out[1][1] | (out[1][2] << 8) | (out[2][0] << 16) | (out[2][1] << 24);
+        crow[2] = out[2][2] | (out[3][0] << 8) | (out[3][1] << 16) | (out[3][2] << 24);
+        *reinterpret_cast<uint32_t*>(D.mask + (size_t)yd * D.mask_step + x0) = mbits;
+    }
+}
+
+inline int align4(int v) { return (v + 3) & ~3; }
+
+}  // namespace
+
+int uavm_canvas_upload_desc(uavm_ctx* ctx, uavm_canvas* cv)
+{
+    UAVM_CUDA(ctx, cudaMemcpyAsync(cv->d_desc, cv->desc.data(), cv->desc.size() * sizeof(ChipDesc), cudaMemcpyHostToDevice, ctx->stream));
+    UAVM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return UAVM_OK;
+}
+
+extern "C" int uavm_canvas_create(uavm_ctx* ctx, int n_images, int img_w, int img_h, const float* H, const int32_t* keep, uavm_canvas** out)
+{
+    if (!ctx || !out || n_images <= 0 || img_w < 2 || img_h < 2 || !H) return UAVM_EINVAL;
+    *out = nullptr;
+    uavm_canvas* cv = new uavm_canvas();
+    cv->n = n_images; cv->img_w = img_w; cv->img_h = img_h; cv->src_step_px = img_w;
+    cv->H.assign(H, H + (size_t)n_images * 9);
+    cv->chips.resize(n_images);
+    int rc = uavm_canvas_layout_compute(H, keep, n_images, img_w, img_h, &cv->layout, cv->chips.data());
+    if (rc != UAVM_OK) { delete cv; return rc; }
+    if (cv->layout.canvas_w <= 0 || cv->layout.canvas_h <= 0 || (int64_t)cv->layout.canvas_w * cv->layout.canvas_h > (int64_t)1 << 33) {
+        UAVM_SET_ERR(ctx, "canvas %d x %d out of range", cv->layout.canvas_w, cv->layout.canvas_h);
+        delete cv; return UAVM_EINVAL;
+    }
+    cv->desc.resize(n_images);
+    size_t chip_off = 0, mask_off = 0;
+    std::vector<size_t> coff(n_images), moff(n_images);
+    for (int k = 0; k < n_images; k++) {
+        ChipDesc& d = cv->desc[k]; memset(&d, 0, sizeof(d));
+        const uavm_chip_layout& c = cv->chips[k];
+        d.keep = c.keep;
+        if (!c.keep) continue;
+        if (c.chip_w <= 0 || c.chip_h <= 0 || c.chip_w > (1 << 20) || c.chip_h > (1 << 20)) {
+            UAVM_SET_ERR(ctx, "chip %d has size %d x %d", k, c.chip_w, c.chip_h);
+            delete cv; return UAVM_EINVAL;
+        }
+        d.chip_w = c.chip_w; d.chip_h = c.chip_h;
+        d.mask_step = align4(c.chip_w); d.chip_step = 3 * d.mask_step;
+        d.beg_x = c.beg_x; d.beg_y = c.beg_y; d.sx = c.sx; d.sy = c.sy;
+        memcpy(d.inv, c.inv, sizeof(d.inv)); memcpy(d.quad, c.quad, sizeof(d.quad));
+        d.affine = (c.inv[6] == 0.0f && c.inv[7] == 0.0f && c.inv[8] == 1.0f) ? 1 : 0;
+        coff[k] = chip_off; moff[k] = mask_off;
+        chip_off += (size_t)d.chip_step * d.chip_h; mask_off += (size_t)d.mask_step * d.chip_h;
+        chip_off = (chip_off + 255) & ~(size_t)255; mask_off = (mask_off + 255) & ~(size_t)255;
+        if (c.chip_w > cv->max_chip_w) cv->max_chip_w = c.chip_w;
+        if (c.chip_h > cv->max_chip_h) cv->max_chip_h = c.chip_h;
+    }
+    cv->chips_bytes = chip_off; cv->masks_bytes = mask_off;
+    UAVM_CUDA(ctx, cudaSetDevice(ctx->device));
+    UAVM_CUDA(ctx, cudaMalloc(&cv->d_src, (size_t)n_images * img_h * cv->src_step_px * sizeof(uchar4)));
+    UAVM_CUDA(ctx, cudaMalloc(&cv->d_chips, chip_off + 256));
+    UAVM_CUDA(ctx, cudaMalloc(&cv->d_masks, mask_off + 256));
+    UAVM_CUDA(ctx, cudaMalloc(&cv->d_desc, (size_t)n_images * sizeof(ChipDesc)));
+    cv->stage_bytes = (size_t)img_h * img_w * 3;
+    UAVM_CUDA(ctx, cudaMalloc(&cv->d_stage, cv->stage_bytes));
+    for (int k = 0; k < n_images; k++) {
+        ChipDesc& d = cv->desc[k];
+        d.src = cv->d_src + (size_t)k * img_h * cv->src_step_px;
+        if (!d.keep) continue;
+        d.chip = cv->d_chips + coff[k]; d.mask = cv->d_masks + moff[k];
+    }
+    rc = uavm_canvas_upload_desc(ctx, cv);
+    if (rc != UAVM_OK) { uavm_canvas_destroy(ctx, cv); return rc; }
+    *out = cv;
+    return UAVM_OK;
+}
+
+extern "C" void uavm_canvas_destroy(uavm_ctx* ctx, uavm_canvas* cv)
+{
+    if (!cv) return;
+    if (ctx) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
+    uavm_blend_free(cv);
+    cudaFree(cv->d_src); cudaFree(cv->d_chips); cudaFree(cv->d_masks); cudaFree(cv->d_dist); cudaFree(cv->d_dist_max);
+    cudaFree(cv->d_desc); cudaFree(cv->d_nbr); cudaFree(cv->d_stage); cudaFree(cv->d_result); cudaFree(cv->d_result_mask);
+    delete cv;
+}
+
+extern "C" int uavm_canvas_get_layout(uavm_canvas* cv, uavm_canvas_layout* canvas, uavm_chip_layout* chips)
+{
+    if (!cv) return UAVM_EINVAL;
+    if (canvas) *canvas = cv->layout;
+    if (chips) memcpy(chips, cv->chips.data(), cv->chips.size() * sizeof(uavm_chip_layout));
+    return UAVM_OK;
+}
+
+extern "C" int uavm_canvas_set_image(uavm_ctx* ctx, uavm_canvas* cv, int image, const uint8_t* bgr, int step, int is_device)
+{
+    if (!ctx || !cv || image < 0 || image >= cv->n || !bgr || step < cv->img_w * 3) return UAVM_EINVAL;
+    const uint8_t* src = bgr; int sstep = step;
+    if (!is_device) {
+        UAVM_CUDA(ctx, cudaMemcpy2DAsync(cv->d_stage, (size_t)cv->img_w * 3, bgr, (size_t)step, (size_t)cv->img_w * 3, cv->img_h,
+                                         cudaMemcpyHostToDevice, ctx->stream));
+        src = cv->d_stage; sstep = cv->img_w * 3;
+    }
+    dim3 grid((cv->img_w + 255) / 256, cv->img_h);
+    k5_bgr_to_bgra<<<grid, 256, 0, ctx->stream>>>(src, cv->img_w, cv->img_h, sstep,
+                                                   cv->d_src + (size_t)image * cv->img_h * cv->src_step_px, cv->src_step_px);
+    UAVM_CHECK_LAUNCH(ctx);
+    return UAVM_OK;
+}
+
+extern "C" int uavm_canvas_warp(uavm_ctx* ctx, uavm_canvas* cv)
+{
+    if (!ctx || !cv) return UAVM_EINVAL;
+    if (cv->max_chip_w <= 0) return UAVM_OK;
+    dim3 grid((cv->max_chip_w + kWarpTileW - 1) / kWarpTileW, (cv->max_chip_h + kWarpTileH - 1) / kWarpTileH, cv->n);
+    dim3 block(32, 8);
+    k5_warp_chips<<<grid, block, 0, ctx->stream>>>(cv->d_desc, cv->img_w, cv->img_h, cv->src_step_px, cv->layout.dgx, cv->layout.dgy);
+    UAVM_CHECK_LAUNCH(ctx);
+    cv->warped = true;
+    return UAVM_OK;
+}
+
+extern "C" int uavm_canvas_get_chip(uavm_ctx* ctx, uavm_canvas* cv, int image, uint8_t* chip_bgr, int chip_step, uint8_t* mask, int mask_step)
+{
+    if (!ctx || !cv || image < 0 || image >= cv->n) return UAVM_EINVAL;
+    const ChipDesc& d = cv->desc[image];
+    if (!d.keep) return UAVM_EINVAL;
+    if (chip_bgr) {
+        if (chip_step < d.chip_w * 3) return UAVM_EINVAL;
+        UAVM_CUDA(ctx, cudaMemcpy2DAsync(chip_bgr, (size_t)chip_step, d.chip, (size_t)d.chip_step, (size_t)d.chip_w * 3, d.chip_h, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    if (mask) {
+        if (mask_step < d.chip_w) return UAVM_EINVAL;
+        UAVM_CUDA(ctx, cudaMemcpy2DAsync(mask, (size_t)mask_step, d.mask, (size_t)d.mask_step, (size_t)d.chip_w, d.chip_h, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    UAVM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return UAVM_OK;
+}

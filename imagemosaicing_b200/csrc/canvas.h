@@ -1,0 +1,46 @@
+// canvas.h — internal structures of the warp / seam-mask / blend stage (not part of the C ABI).
+#pragma once
+#include "internal.h"
+
+struct ChipDesc {               // one per image, device-visible
+    const uchar4* src;          // BGRA source frame
+    uint8_t* chip;              // packed BGR, chip_step bytes per row (= 3 * align4(chip_w))
+    uint8_t* mask;              // u8, mask_step bytes per row (= align4(chip_w))
+    float* dist;                // K6 distance map, mask_step floats per row (nullptr until K6 runs)
+    int32_t keep;
+    int32_t chip_w, chip_h, chip_step, mask_step;
+    int32_t beg_x, beg_y;
+    float sx, sy;
+    float inv[9];
+    float quad[8];
+    int32_t affine;             // inv[6] == 0 && inv[7] == 0 && inv[8] == 1: the projective divide is exact identity
+    float lineA[4], lineB[4], lineC[4], lineInv[4];   // K6: quad edges as A x + B y + C = 0 and 1/sqrt(A^2+B^2)
+    int32_t nbr_off, nbr_cnt;   // K6: chips whose boxes intersect this one (indices into the neighbour list)
+};
+
+struct uavm_canvas {
+    int n = 0, img_w = 0, img_h = 0, src_step_px = 0;
+    std::vector<float> H;
+    uavm_canvas_layout layout;
+    std::vector<uavm_chip_layout> chips;
+    std::vector<ChipDesc> desc;
+    uchar4* d_src = nullptr;
+    uint8_t* d_chips = nullptr;
+    uint8_t* d_masks = nullptr;
+    float* d_dist = nullptr;
+    float* d_dist_max = nullptr;     // [n] per-image maximum of the distance map (as uint bits)
+    int32_t* d_nbr = nullptr;        // K6 neighbour lists
+    ChipDesc* d_desc = nullptr;
+    uint8_t* d_stage = nullptr;      // staging for host BGR frames
+    size_t stage_bytes = 0;
+    size_t chips_bytes = 0, masks_bytes = 0;
+    int max_chip_w = 0, max_chip_h = 0;
+    // result canvas (K7 / paste)
+    uint8_t* d_result = nullptr;     // canvas_h x canvas_w x 3
+    uint8_t* d_result_mask = nullptr;
+    bool warped = false, seamed = false, blended = false;
+    void* blend_ws = nullptr;        // opaque workspace owned by blend.cu
+};
+
+int uavm_canvas_upload_desc(uavm_ctx* ctx, uavm_canvas* cv);
+void uavm_blend_free(uavm_canvas* cv);

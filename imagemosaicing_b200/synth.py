@@ -38,19 +38,38 @@ def apply_h(H, xy):
     return q[:, :2] / q[:, 2:3]
 
 
+def strip_poses(rng, n_images, w, h, overlap=(0.6, 0.8), max_rot_deg=5.0, scale=(0.95, 1.05)):
+    """Absolute poses T_k (image k -> mosaic frame): rotation +-5 deg and scale 0.95..1.05 about the image
+    centre, along-track step (1 - overlap) * h, small cross-track jitter.  T_0 = identity."""
+    cx, cy = (w - 1) / 2.0, (h - 1) / 2.0
+    T = [np.eye(3)]
+    ty = 0.0
+    for k in range(1, n_images):
+        th = np.deg2rad(rng.uniform(-max_rot_deg, max_rot_deg)); s = rng.uniform(*scale)
+        ty += (1.0 - rng.uniform(*overlap)) * h
+        tx = rng.uniform(-0.05, 0.05) * w
+        c, si = np.cos(th) * s, np.sin(th) * s
+        T.append(np.array([[c, -si, cx - c * cx + si * cy + tx], [si, c, cy - si * cx - c * cy + ty], [0, 0, 1.0]]))
+    return T
+
+
 def make_strip(n_images, w, h, n_kp, seed=SEED_BASE, true_frac=0.5, desc_noise=4.0, pos_noise=0.5,
-               geom_outlier_frac=0.5):
+               geom_outlier_frac=0.5, proj=1e-5):
     """Sequential-overlap strip: image k+1 overlaps image k.  Returns (descs[u8], kps[f32], Hs) where
-    Hs[k] maps image k+1 -> image k.  A fraction `geom_outlier_frac` of the descriptor-true matches is
-    given a random position (repeated-structure mismatches), so the <=396 candidates that reach RANSAC
-    hold ~50 % inliers like the reference's real runs (32..275 inliers of <=396 in matchPairs.match)
-    and the loop really runs its 1000 counted hypotheses instead of taking the 0.99 early exit."""
+    Hs[k] maps image k+1 -> image k (the reference's convention, M/matrix.h:783) and is
+    inv(T_k) T_{k+1} of the absolute poses plus projective terms <= 1e-5.  A fraction
+    `geom_outlier_frac` of the descriptor-true matches is given a random position (repeated-structure
+    mismatches), so the <=396 candidates that reach RANSAC hold ~50 % inliers like the reference's real
+    runs (32..275 inliers of <=396 in matchPairs.match) and the loop really runs its 1000 counted
+    hypotheses instead of taking the 0.99 early exit."""
     descs, kps, Hs = [], [], []
     rng = np.random.default_rng(seed)
+    poses = strip_poses(np.random.default_rng(seed + 999983), n_images, w, h)
     descs.append(sift_like_descriptors(rng, n_kp)); kps.append(random_keypoints(rng, n_kp, w, h))
     for k in range(1, n_images):
         rng = np.random.default_rng(seed + k)
-        H = pair_homography(rng, w, h)
+        H = np.linalg.inv(poses[k - 1]) @ poses[k]
+        H[2, 0] += rng.uniform(-proj, proj); H[2, 1] += rng.uniform(-proj, proj)
         Hi = np.linalg.inv(H)
         p_prev = kps[k - 1].astype(np.float64)
         p2 = apply_h(Hi, p_prev) + rng.normal(0, pos_noise, size=p_prev.shape)

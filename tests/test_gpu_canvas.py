@@ -1,0 +1,82 @@
+"""GPU parity tests of K5 (chip warp) and K6 (seam masks) against the CPU oracle, through the C ABI.
+Bar: chip bytes and masks identical (the kernels reproduce the reference's float expression order)."""
+import numpy as np
+import pytest
+
+from imagemosaicing_b200 import api, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _transforms(rng, n, w, h, projective=False):
+    """Chain of transforms image k -> mosaic frame (image 0 = identity), affine like BundleAdjustmentSparse's output."""
+    T = [np.eye(3)]
+    for k in range(1, n):
+        H = synth.pair_homography(rng, w, h, overlap=(0.55, 0.8))
+        if not projective:
+            H[2, :2] = 0
+        T.append(T[-1] @ H)
+    out = np.stack([t / t[2, 2] for t in T]).astype(np.float32).reshape(n, 9)
+    return out
+
+
+def _compare_layout(canvas, chips, o_canvas, o_chips, n):
+    assert (canvas.canvas_w, canvas.canvas_h) == (o_canvas.canvas_w, o_canvas.canvas_h)
+    assert canvas.dgx == o_canvas.dgx and canvas.dgy == o_canvas.dgy
+    for k in range(n):
+        a, b = chips[k], o_chips[k]
+        assert (a.keep, a.beg_x, a.beg_y, a.chip_w, a.chip_h) == (b.keep, b.beg_x, b.beg_y, b.chip_w, b.chip_h)
+        assert a.sx == b.sx and a.sy == b.sy
+        assert list(a.quad) == list(b.quad) and list(a.inv) == list(b.inv)
+
+
+@pytest.mark.parametrize("w,h,n,projective", [(512, 512, 2, False), (1000, 750, 4, False), (640, 480, 3, True), (333, 257, 3, False)])
+def test_warp_and_masks_parity(ctx, oracle, w, h, n, projective):
+    rng = np.random.default_rng(w * 7 + n)
+    H = _transforms(rng, n, w, h, projective)
+    imgs = [synth.texture_image(rng, w, h, 8) for _ in range(n)]
+    cv = api.Canvas(ctx, H, w, h)
+    o_canvas, o_chips = oracle.canvas_layout(H, None, w, h)
+    _compare_layout(cv.layout, cv.chips, o_canvas, o_chips, n)
+    for k in range(n):
+        cv.set_image(k, imgs[k])
+    cv.warp()
+    o_masks = []
+    for k in range(n):
+        px, mask = cv.chip(k)
+        o_px, o_mask = oracle.warp_chip(imgs[k], o_canvas, o_chips[k])
+        assert np.array_equal(mask, o_mask)
+        assert np.array_equal(px, o_px), f"chip {k}: {(px != o_px).sum()} differing bytes"
+        o_masks.append(o_mask)
+    cv.seam_masks()
+    o_seam = oracle.seam_masks(o_masks, [o_chips[k] for k in range(n)], o_canvas.canvas_w, o_canvas.canvas_h)
+    for k in range(n):
+        _, mask = cv.chip(k)
+        assert np.array_equal(mask, o_seam[k]), f"seam mask {k}: {(mask != o_seam[k]).sum()} differing pixels"
+    # every covered canvas pixel has exactly one owner at most
+    own = np.zeros((o_canvas.canvas_h, o_canvas.canvas_w), np.int32)
+    for k in range(n):
+        c = o_chips[k]
+        own[c.beg_y:c.beg_y + c.chip_h, c.beg_x:c.beg_x + c.chip_w] += (o_seam[k] > 0)
+    assert own.max() <= 1
+
+
+def test_warp_skip_flags_and_full_frame(ctx, oracle):
+    """keep flags / m[8]==0 sentinel (M/MosaicImage.cpp:2243,2311) and one full-size 4000x3000 frame."""
+    rng = np.random.default_rng(3)
+    w, h = 4000, 3000
+    H = _transforms(rng, 3, w, h)
+    H[1, 8] = 0.0                      # "skip me"
+    keep = np.array([1, 1, 1], np.int32)
+    img = synth.texture_image(rng, w, h, 4)
+    cv = api.Canvas(ctx, H, w, h, keep)
+    o_canvas, o_chips = oracle.canvas_layout(H, keep, w, h)
+    _compare_layout(cv.layout, cv.chips, o_canvas, o_chips, 3)
+    assert cv.chips[1].keep == 0
+    for k in (0, 2):
+        cv.set_image(k, img)
+    cv.warp()
+    for k in (0, 2):
+        px, mask = cv.chip(k)
+        o_px, o_mask = oracle.warp_chip(img, o_canvas, o_chips[k])
+        assert np.array_equal(mask, o_mask) and np.array_equal(px, o_px)
