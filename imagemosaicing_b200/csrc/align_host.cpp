@@ -1,0 +1,152 @@
+// align_host.cpp — host-side stages between RANSAC and warp:
+//   uavm_connected_images  <- Select_Connected_Matched_Images + ClusterMatchNode (M/MosaicWithoutPos.cpp:2673-2796)
+//   uavm_align_affine      <- BundleAdjustmentSparse (:6971-7202) + SolveSparseSystem2 (M/test_cholmod.cpp:180-262)
+// Both are tiny (<= 6(N-1) unknowns) and stay on the host, as SURVEY §8e says ("replicas only"/host).
+// The reference solves x = (A^T A)^-1 A^T b with CHOLMOD in double; here the normal equations are
+// accumulated directly (double) and solved with a dense Cholesky — same system, same precision class.
+#include <math.h>
+#include <string.h>
+#include <vector>
+#include "internal.h"
+
+extern "C" int uavm_connected_images(const uavm_matchpointpairs* pairs, int n_pairs, int n_images, int32_t* label)
+{
+    if (!label || n_images <= 0 || n_pairs < 0 || (n_pairs > 0 && !pairs)) return UAVM_EINVAL;
+    for (int i = 0; i < n_images; i++) label[i] = 0;
+    // adjacency (r = min, c = max) scanned row-major -> edge list (:2756-2785)
+    std::vector<uint8_t> node((size_t)n_images * n_images, 0);
+    for (int i = 0; i < n_pairs; i++) {
+        int a = pairs[i].ptA_i, b = pairs[i].ptB_i;
+        if (a < 0 || a >= n_images || b < 0 || b >= n_images) return UAVM_EINVAL;
+        int r = a < b ? a : b, c = a < b ? b : a;
+        node[(size_t)r * n_images + c] = 255;
+    }
+    const int words = (n_images + 63) / 64;
+    std::vector<std::vector<uint64_t>> clusters;
+    for (int r = 0; r < n_images; r++)
+        for (int c = 0; c < n_images; c++)
+            if (node[(size_t)r * n_images + c]) {
+                std::vector<uint64_t> s(words, 0);
+                s[r >> 6] |= 1ull << (r & 63); s[c >> 6] |= 1ull << (c & 63);
+                clusters.push_back(s);
+            }
+    if (clusters.empty()) return UAVM_OK;
+    // ClusterMatchNode's merge loop with its exact control flow (merge j into i, move the last cluster
+    // into slot j, repeat passes until nothing merges); sets as bitmasks instead of index lists.
+    bool over;
+    do {
+        over = true;
+        for (size_t i = 0; i < clusters.size(); i++) {
+            for (size_t j = i + 1; j < clusters.size();) {
+                bool share = false;
+                for (int w = 0; w < words; w++) if (clusters[i][w] & clusters[j][w]) { share = true; break; }
+                if (share) {
+                    over = false;
+                    for (int w = 0; w < words; w++) clusters[i][w] |= clusters[j][w];
+                    clusters[j] = clusters.back();
+                    clusters.pop_back();
+                } else j++;
+            }
+        }
+    } while (!over);
+    size_t imax = 0; int maxval = 0;
+    for (size_t i = 0; i < clusters.size(); i++) {
+        int cnt = 0;
+        for (int w = 0; w < words; w++) cnt += __builtin_popcountll(clusters[i][w]);
+        if (cnt > maxval) { maxval = cnt; imax = i; }
+    }
+    for (int k = 0; k < n_images; k++)
+        if (clusters[imax][k >> 6] >> (k & 63) & 1ull) label[k] = 1;
+    return UAVM_OK;
+}
+
+static int cholesky_solve(std::vector<double>& N, std::vector<double>& b, int n)
+{
+    for (int j = 0; j < n; j++) {
+        double s = N[(size_t)j * n + j];
+        for (int k = 0; k < j; k++) s -= N[(size_t)j * n + k] * N[(size_t)j * n + k];
+        if (!(s > 0)) return -1;
+        const double l = sqrt(s);
+        N[(size_t)j * n + j] = l;
+        for (int i = j + 1; i < n; i++) {
+            double t = N[(size_t)i * n + j];
+            for (int k = 0; k < j; k++) t -= N[(size_t)i * n + k] * N[(size_t)j * n + k];
+            N[(size_t)i * n + j] = t / l;
+        }
+    }
+    for (int i = 0; i < n; i++) {
+        double t = b[i];
+        for (int k = 0; k < i; k++) t -= N[(size_t)i * n + k] * b[k];
+        b[i] = t / N[(size_t)i * n + i];
+    }
+    for (int i = n - 1; i >= 0; i--) {
+        double t = b[i];
+        for (int k = i + 1; k < n; k++) t -= N[(size_t)k * n + i] * b[k];
+        b[i] = t / N[(size_t)i * n + i];
+    }
+    return 0;
+}
+
+extern "C" int uavm_align_affine(const uavm_matchpointpairs* pairs, int n_pairs, const uavm_imagetransform* init, int n_images,
+                                 int n_fixed, uavm_imagetransform* out)
+{
+    if (!pairs || n_pairs <= 0 || !init || !out) return UAVM_EINVAL;
+    if (n_images <= 1) return UAVM_EFAIL;                 // reference returns -2 (:6978-6981)
+    std::vector<int> acc_fixed(n_images, 0);
+    int nf = 0;
+    for (int i = 0; i < n_images; i++) { acc_fixed[i] = nf; if (init[i].fixed == 1) nf++; }
+    if (n_fixed >= 0 && n_fixed != nf) return UAVM_EINVAL;
+    const int nu = 6 * (n_images - nf);
+    if (nu <= 0) return UAVM_EFAIL;
+    if (nu > 12000) return UAVM_EFAIL;                    // dense normal matrix limit (1.1 GB)
+    std::vector<double> N((size_t)nu * nu, 0.0), g(nu, 0.0);
+    // unknown order inside an image block: a b c d e f with x' = a x + b y + e, y' = c x + d y + f (:7035-7046)
+    static const int slot_x[3] = {0, 1, 4}, slot_y[3] = {2, 3, 5};
+    for (int n = 0; n < n_pairs; n++) {
+        const uavm_matchpointpairs& m = pairs[n];
+        if (m.ptA_i < 0 || m.ptA_i >= n_images || m.ptB_i < 0 || m.ptB_i >= n_images) return UAVM_EINVAL;
+        int cols[6]; double vals[6]; int nc = 0; double rx = 0, ry = 0;
+        const double xa = m.ptA.x, ya = m.ptA.y, xb = m.ptB.x, yb = m.ptB.y;
+        if (m.ptA_Fixed == 0 && m.ptB_Fixed == 0) {
+            const int ca = 6 * (m.ptA_i - acc_fixed[m.ptA_i]), cb = 6 * (m.ptB_i - acc_fixed[m.ptB_i]);
+            cols[0] = ca; vals[0] = xa; cols[1] = ca; vals[1] = ya; cols[2] = ca; vals[2] = 1;
+            cols[3] = cb; vals[3] = -xb; cols[4] = cb; vals[4] = -yb; cols[5] = cb; vals[5] = -1; nc = 6;
+        } else if (m.ptA_Fixed == 1 && m.ptB_Fixed == 0) {
+            const int cb = 6 * (m.ptB_i - acc_fixed[m.ptB_i]);
+            cols[0] = cb; vals[0] = xb; cols[1] = cb; vals[1] = yb; cols[2] = cb; vals[2] = 1; nc = 3;
+            double h[9]; for (int t = 0; t < 9; t++) h[t] = init[m.ptA_i].h.m[t];
+            rx = (h[0] * xa + h[1] * ya + h[2]) / (h[6] * xa + h[7] * ya + h[8]);      // ApplyProject9 (M/MosaicWithoutPos.h:331-336)
+            ry = (h[3] * xa + h[4] * ya + h[5]) / (h[6] * xa + h[7] * ya + h[8]);
+        } else if (m.ptA_Fixed == 0 && m.ptB_Fixed == 1) {
+            const int ca = 6 * (m.ptA_i - acc_fixed[m.ptA_i]);
+            cols[0] = ca; vals[0] = xa; cols[1] = ca; vals[1] = ya; cols[2] = ca; vals[2] = 1; nc = 3;
+            double h[9]; for (int t = 0; t < 9; t++) h[t] = init[m.ptB_i].h.m[t];
+            rx = (h[0] * xb + h[1] * yb + h[2]) / (h[6] * xb + h[7] * yb + h[8]);
+            ry = (h[3] * xb + h[4] * yb + h[5]) / (h[6] * xb + h[7] * yb + h[8]);
+        } else continue;
+        for (int a = 0; a < nc; a++) {
+            if (cols[a] < 0 || cols[a] + 5 >= nu) return UAVM_EINVAL;      // a "free" point on a fixed image
+            const int ax = cols[a] + slot_x[a % 3], ay = cols[a] + slot_y[a % 3];
+            for (int b = 0; b < nc; b++) {
+                N[(size_t)ax * nu + cols[b] + slot_x[b % 3]] += vals[a] * vals[b];
+                N[(size_t)ay * nu + cols[b] + slot_y[b % 3]] += vals[a] * vals[b];
+            }
+            g[ax] += vals[a] * rx;
+            g[ay] += vals[a] * ry;
+        }
+    }
+    if (cholesky_solve(N, g, nu) != 0) return UAVM_EFAIL;
+    int k = 0;
+    for (int i = 0; i < n_images; i++) {
+        if (init[i].fixed == 0) {
+            uavm_imagetransform t; memset(&t, 0, sizeof(t));
+            t.fixed = 0;
+            t.h.m[0] = (float)g[6 * k + 0]; t.h.m[1] = (float)g[6 * k + 1];
+            t.h.m[3] = (float)g[6 * k + 2]; t.h.m[4] = (float)g[6 * k + 3];
+            t.h.m[2] = (float)g[6 * k + 4]; t.h.m[5] = (float)g[6 * k + 5];
+            t.h.m[6] = 0; t.h.m[7] = 0; t.h.m[8] = 1;
+            out[i] = t; k++;
+        } else out[i] = init[i];
+    }
+    return UAVM_OK;
+}
