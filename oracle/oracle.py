@@ -188,3 +188,28 @@ def seam_masks(masks, chips_valid, canvas_w, canvas_h):
     arr = (ChipLayout * n)(*chips_valid)
     lib().orc_seam_masks(ptrs, _p(steps, i32p), arr, n, canvas_w, canvas_h)
     return ms
+
+
+# ---- the reference's own warp loop / FindMasksByDistMap compiled from /root/reference (oracle/_ref) ----
+def ref_warp_chip(img, canvas, chip):
+    """M/MosaicImage.cpp:2350-2448 compiled in place; chip bytes start at zero (the reference leaves
+    invalid pixels uninitialised)."""
+    img = np.ascontiguousarray(img, np.uint8); h, w = img.shape[:2]
+    out = np.zeros((chip.chip_h, chip.chip_w, 3), np.uint8); mask = np.zeros((chip.chip_h, chip.chip_w), np.uint8)
+    inv = np.array(list(chip.inv), np.float32)
+    ref().ref_warp_chip(_p(img, u8p), w, h, img.strides[0], C.c_float(canvas.dgx), C.c_float(canvas.dgy),
+                        C.c_float(chip.sx), C.c_float(chip.sy), chip.beg_x, chip.beg_y, _p(inv, f32p),
+                        chip.chip_w, chip.chip_h, _p(out, u8p), out.strides[0], _p(mask, u8p), mask.strides[0])
+    return out, mask
+
+
+def ref_seam_masks(masks, chips_valid, canvas_w, canvas_h):
+    n = len(masks)
+    ms = [np.ascontiguousarray(m, np.uint8).copy() for m in masks]
+    ptrs = (u8p * n)(*[_p(m, u8p) for m in ms])
+    steps = np.array([m.strides[0] for m in ms], np.int32)
+    cw = np.array([c.chip_w for c in chips_valid], np.int32); chh = np.array([c.chip_h for c in chips_valid], np.int32)
+    quads = np.array([list(c.quad) for c in chips_valid], np.float32)
+    tl = np.array([[c.beg_x, c.beg_y] for c in chips_valid], np.int32)
+    ref().ref_find_masks(ptrs, _p(steps, i32p), _p(cw, i32p), _p(chh, i32p), _p(quads, f32p), _p(tl, i32p), n, canvas_w, canvas_h)
+    return ms

@@ -344,3 +344,26 @@ def test_product_resample_by_overlap():
     # 30 % steps: nothing dropped; the m[8] == 0 sentinel is ignored; the last image is always kept (:2198)
     T = lambda tx, ty: [1, 0, tx, 0, 1, ty, 0, 0, 1]
     assert list(run([T(0, 0), T(0, 225), T(0, 450), T(0, 675)], 1000, 750, L.uavm_resample_by_overlap)) == [1, 1, 1, 1]
+
+
+# ------------------------------------------------------------------------------------------------
+# K5 / K6: oracle restatement == the reference's own warp loop and FindMasksByDistMap
+# ------------------------------------------------------------------------------------------------
+def test_oracle_warp_and_masks_vs_golden_reference_vectors(oracle):
+    """tests/golden/warp_golden.npz was produced by the reference's own code (M/MosaicImage.cpp:2350-2448,
+    :1761-1881) compiled in place; the oracle's restatements must reproduce every byte."""
+    g = np.load(os.path.join(GOLD, "warp_golden.npz"))
+    for ci in range(int(g["n_cases"][0])):
+        w, h, n = [int(v) for v in g[f"whn_{ci}"]]
+        canvas, chips = oracle.canvas_layout(g[f"H_{ci}"], None, w, h)
+        masks = []
+        for k in range(n):
+            px, m = oracle.warp_chip(g[f"img_{ci}_{k}"], canvas, chips[k])
+            assert np.array_equal(px, g[f"chip_{ci}_{k}"]) and np.array_equal(m, g[f"mask_{ci}_{k}"]), (ci, k)
+            masks.append(m)
+            if oracle.ref() is not None:
+                rpx, rm = oracle.ref_warp_chip(g[f"img_{ci}_{k}"], canvas, chips[k])
+                assert np.array_equal(px, rpx) and np.array_equal(m, rm)
+        seam = oracle.seam_masks(masks, [chips[k] for k in range(n)], canvas.canvas_w, canvas.canvas_h)
+        for k in range(n):
+            assert np.array_equal(seam[k], g[f"seam_{ci}_{k}"]), (ci, k)
