@@ -22,78 +22,91 @@ __global__ void __launch_bounds__(256) k5_bgr_to_bgra(const uint8_t* __restrict_
     dst[(size_t)y * dst_step_px + x] = make_uchar4(s[0], s[1], s[2], 0);
 }
 
-// exact u8 -> f32 without the conversion pipe: byte k of `word` into the mantissa of 2^23, minus 2^23
-template <int K>
-__device__ __forceinline__ float byte_f32(uint32_t word)
-{
-    return __int_as_float(__byte_perm(word, 0x4B000000u, 0x7540 | K)) - 8388608.0f;
-}
-
 // one channel of the reference's bilinear expression (:2398-2410), evaluated left to right in float:
 //   uchar( g1*(1-p)*(1-q) + g2*(1-p)*q + g3*p*(1-q) + g4*p*q )
+// u8 -> f32 conversion and the first multiply are ONE exact FFMA off the conversion (XU) pipe: the byte is
+// placed in the mantissa of 2^23 (G = 2^23 + g, PRMT) and fma(G, w, -(2^23 * w)) rounds the infinitely
+// precise value (2^23 + g) w - 2^23 w = g w once — bit-identical to float(g) * w (2^23 * w is exact).
+// The remaining multiplies and adds stay separate instructions (-fmad=false), in the reference's order.
 template <int K>
 __device__ __forceinline__ uint32_t bilinear_channel(uint32_t t00, uint32_t t01, uint32_t t10, uint32_t t11,
-                                                     float p, float q, float omp, float omq)
+                                                     float p, float q, float omp, float omq, float c_omp, float c_p,
+                                                     uint32_t two23)
 {
-    const float g1 = byte_f32<K>(t00), g2 = byte_f32<K>(t01), g3 = byte_f32<K>(t10), g4 = byte_f32<K>(t11);
-    const float v = g1 * omp * omq + g2 * omp * q + g3 * p * omq + g4 * p * q;
-    return (uint32_t)(int)v;                       // truncation, value in [0, 255]
+    const float G1 = __int_as_float(__byte_perm(t00, two23, 0x7540 | K));
+    const float G2 = __int_as_float(__byte_perm(t01, two23, 0x7540 | K));
+    const float G3 = __int_as_float(__byte_perm(t10, two23, 0x7540 | K));
+    const float G4 = __int_as_float(__byte_perm(t11, two23, 0x7540 | K));
+    const float a1 = __fmaf_rn(G1, omp, c_omp), a2 = __fmaf_rn(G2, omp, c_omp);      // g1*(1-p), g2*(1-p)
+    const float a3 = __fmaf_rn(G3, p, c_p), a4 = __fmaf_rn(G4, p, c_p);              // g3*p, g4*p
+    const float v = a1 * omq + a2 * q + a3 * omq + a4 * q;
+    return (uint32_t)__float2int_rz(v);            // truncation, value in [0, 255]
 }
 
 constexpr int kWarpTileW = 128;   // 32 threads x 4 px
-constexpr int kWarpTileH = 16;    // 8 thread rows x 2
+constexpr int kWarpRows = 4;      // rows per thread
+constexpr int kWarpTileH = 8 * kWarpRows;
 
+// AFFINE: inv[6] == inv[7] == 0 and inv[8] == 1, so the reference's denominator is exactly 1.0f for every
+// pixel and x / 1.0f == x: the two divides per coordinate (:2359-2362) are skipped without changing a bit.
+template <bool AFFINE>
 __global__ void __launch_bounds__(256)
-k5_warp_chips(const ChipDesc* __restrict__ descs, int img_w, int img_h, int src_step_px, float dgx, float dgy)
+k5_warp_chips(const ChipDesc* __restrict__ descs, int img_w, int img_h, int src_step_px, float dgx, float dgy,
+              uint32_t two23 /* = 0x4B000000, bits of 2^23: a kernel argument so PRMT takes the SELECTOR as its immediate */)
 {
     const ChipDesc& D = descs[blockIdx.z];
-    if (!D.keep) return;
+    if (!D.keep || (D.affine != 0) != AFFINE) return;
     const int x0 = blockIdx.x * kWarpTileW + threadIdx.x * 4;
     const int ybase = blockIdx.y * kWarpTileH + threadIdx.y;
     if (x0 >= D.chip_w || blockIdx.y * kWarpTileH >= D.chip_h) return;
     const float iv0 = D.inv[0], iv1 = D.inv[1], iv2 = D.inv[2], iv3 = D.inv[3], iv4 = D.inv[4], iv5 = D.inv[5];
     const float iv6 = D.inv[6], iv7 = D.inv[7], iv8 = D.inv[8];
-    const bool affine = D.affine != 0;
     const float w1 = (float)(img_w - 1), h1 = (float)(img_h - 1);
-    const uchar4* __restrict__ src = D.src;
-    const float fbx = (float)D.beg_x, fby = (float)D.beg_y;
+    const uint32_t* __restrict__ src = reinterpret_cast<const uint32_t*>(D.src);
+    const float fbx = (float)D.beg_x, fby = (float)D.beg_y, sx = D.sx, sy = D.sy;
+    // xTemp = xDst - dGx - sx + begBoxX (:2356); (float)(x0 + i) == (float)x0 + i exactly (both < 2^24)
+    float xt[4];
+    const float fx0 = (float)x0;
 #pragma unroll
-    for (int ry = 0; ry < kWarpTileH / 8; ry++) {
+    for (int i = 0; i < 4; i++) xt[i] = (fx0 + (float)i) - dgx - sx + fbx;
+    uint8_t* chip_row = D.chip + (size_t)ybase * D.chip_step + 3 * x0;
+    uint8_t* mask_row = D.mask + (size_t)ybase * D.mask_step + x0;
+#pragma unroll
+    for (int ry = 0; ry < kWarpRows; ry++) {
         const int yd = ybase + ry * 8;
         if (yd >= D.chip_h) break;
-        const float yt = (float)yd - dgy - D.sy + fby;             // yTemp (:2357)
-        uint32_t out[4][3];
+        const float yt = (float)yd - dgy - sy + fby;               // yTemp (:2357)
+        const float ya = yt * iv1, yb = yt * iv4;
+        uint32_t o[12];
         uint32_t mbits = 0;
 #pragma unroll
         for (int i = 0; i < 4; i++) {
-            const int xd = x0 + i;
-            const float xt = (float)xd - dgx - D.sx + fbx;         // xTemp (:2356)
-            float xs = xt * iv0 + yt * iv1 + iv2;
-            float ys = xt * iv3 + yt * iv4 + iv5;
-            if (!affine) {                                         // two true divides per coordinate (:2359-2362)
-                const float den = xt * iv6 + yt * iv7 + iv8;
+            float xs = xt[i] * iv0 + ya + iv2;
+            float ys = xt[i] * iv3 + yb + iv5;
+            if (!AFFINE) {
+                const float den = xt[i] * iv6 + yt * iv7 + iv8;
                 xs = xs / den;
                 ys = ys / den;
-            }                                                      // affine: den == 1.0f exactly, x/1 == x
-            const int iy = (int)ys, ix = (int)xs;
-            out[i][0] = 0; out[i][1] = 0; out[i][2] = 0;
+            }
+            o[3 * i] = 0; o[3 * i + 1] = 0; o[3 * i + 2] = 0;
             if ((xs >= 0.0f) && (xs < w1) && (ys >= 0.0f) && (ys < h1)) {
+                const int iy = __float2int_rz(ys), ix = __float2int_rz(xs);
                 const float p = ys - (float)iy, q = xs - (float)ix;
                 const float omp = 1.0f - p, omq = 1.0f - q;
-                const uint32_t* r0 = reinterpret_cast<const uint32_t*>(src + (size_t)iy * src_step_px + ix);
-                const uint32_t* r1 = r0 + src_step_px;
-                const uint32_t t00 = __ldg(r0), t01 = __ldg(r0 + 1), t10 = __ldg(r1), t11 = __ldg(r1 + 1);
-                out[i][0] = bilinear_channel<0>(t00, t01, t10, t11, p, q, omp, omq);
-                out[i][1] = bilinear_channel<1>(t00, t01, t10, t11, p, q, omp, omq);
-                out[i][2] = bilinear_channel<2>(t00, t01, t10, t11, p, q, omp, omq);
+                const float c_omp = -8388608.0f * omp, c_p = -8388608.0f * p;        // exact (power-of-two scale)
+                const uint32_t* r0 = src + iy * src_step_px + ix;
+                const uint32_t t00 = __ldg(r0), t01 = __ldg(r0 + 1), t10 = __ldg(r0 + src_step_px), t11 = __ldg(r0 + src_step_px + 1);
+                o[3 * i] = bilinear_channel<0>(t00, t01, t10, t11, p, q, omp, omq, c_omp, c_p, two23);
+                o[3 * i + 1] = bilinear_channel<1>(t00, t01, t10, t11, p, q, omp, omq, c_omp, c_p, two23);
+                o[3 * i + 2] = bilinear_channel<2>(t00, t01, t10, t11, p, q, omp, omq, c_omp, c_p, two23);
                 mbits |= 0xffu << (8 * i);
             }
         }
-        uint32_t* crow = reinterpret_cast<uint32_t*>(D.chip + (size_t)yd * D.chip_step + 3 * x0);
-        crow[0] = out[0][0] | (out[0][1] << 8) | (out[0][2] << 16) | (out[1][0] << 24);
-        crow[1] = out[1][1] | (out[1][2] << 8) | (out[2][0] << 16) | (out[2][1] << 24);
-        crow[2] = out[2][2] | (out[3][0] << 8) | (out[3][1] << 16) | (out[3][2] << 24);
-        *reinterpret_cast<uint32_t*>(D.mask + (size_t)yd * D.mask_step + x0) = mbits;
+        uint32_t* crow = reinterpret_cast<uint32_t*>(chip_row + (size_t)ry * 8 * D.chip_step);
+        crow[0] = o[0] | (o[1] << 8) | (o[2] << 16) | (o[3] << 24);
+        crow[1] = o[4] | (o[5] << 8) | (o[6] << 16) | (o[7] << 24);
+        crow[2] = o[8] | (o[9] << 8) | (o[10] << 16) | (o[11] << 24);
+        *reinterpret_cast<uint32_t*>(mask_row + (size_t)ry * 8 * D.mask_step) = mbits;
     }
 }
 
@@ -205,8 +218,17 @@ extern "C" int uavm_canvas_warp(uavm_ctx* ctx, uavm_canvas* cv)
     if (cv->max_chip_w <= 0) return UAVM_OK;
     dim3 grid((cv->max_chip_w + kWarpTileW - 1) / kWarpTileW, (cv->max_chip_h + kWarpTileH - 1) / kWarpTileH, cv->n);
     dim3 block(32, 8);
-    k5_warp_chips<<<grid, block, 0, ctx->stream>>>(cv->d_desc, cv->img_w, cv->img_h, cv->src_step_px, cv->layout.dgx, cv->layout.dgy);
-    UAVM_CHECK_LAUNCH(ctx);
+    bool any_affine = false, any_proj = false;
+    for (int k = 0; k < cv->n; k++)
+        if (cv->desc[k].keep) { if (cv->desc[k].affine) any_affine = true; else any_proj = true; }
+    if (any_affine) {
+        k5_warp_chips<true><<<grid, block, 0, ctx->stream>>>(cv->d_desc, cv->img_w, cv->img_h, cv->src_step_px, cv->layout.dgx, cv->layout.dgy, 0x4B000000u);
+        UAVM_CHECK_LAUNCH(ctx);
+    }
+    if (any_proj) {
+        k5_warp_chips<false><<<grid, block, 0, ctx->stream>>>(cv->d_desc, cv->img_w, cv->img_h, cv->src_step_px, cv->layout.dgx, cv->layout.dgy, 0x4B000000u);
+        UAVM_CHECK_LAUNCH(ctx);
+    }
     cv->warped = true;
     return UAVM_OK;
 }

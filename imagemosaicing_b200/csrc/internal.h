@@ -101,6 +101,7 @@ struct uavm_pairbatch {
     // ransac
     int tuples_first_pass = 0;
     uint32_t* d_tuple_res = nullptr;  // [n_pairs][MAX_TUPLES_FIRST] packed (valid, rejected, support)
+    float* d_tuple_h = nullptr;       // [n_pairs][MAX_TUPLES_FIRST][9] hypotheses of the accepted first-pass tuples
     uint8_t* d_inlier = nullptr;      // [n_pairs][SLOTS]
     uavm_ransac_result* d_res = nullptr;  // [n_pairs]
     bool matched = false, selected = false, ransacked = false;

@@ -46,6 +46,7 @@ extern "C" int uavm_pairbatch_create(uavm_ctx* ctx, uavm_featureset* fs, int n_p
     UAVM_CUDA(ctx, cudaMalloc(&pb->d_cand_id2, np * UAVM_CAND_SLOTS * 4));
     UAVM_CUDA(ctx, cudaMalloc(&pb->d_cand_n, np * 4));
     UAVM_CUDA(ctx, cudaMalloc(&pb->d_tuple_res, np * UAVM_RANSAC_MAX_TUPLES_FIRST * 4));
+    UAVM_CUDA(ctx, cudaMalloc(&pb->d_tuple_h, np * UAVM_RANSAC_MAX_TUPLES_FIRST * 9 * 4));
     UAVM_CUDA(ctx, cudaMalloc(&pb->d_inlier, np * UAVM_CAND_SLOTS));
     UAVM_CUDA(ctx, cudaMalloc(&pb->d_res, np * sizeof(uavm_ransac_result)));
     UAVM_CUDA(ctx, cudaMemcpyAsync(pb->d_pairs, pb->pairs.data(), np * sizeof(PairDesc), cudaMemcpyHostToDevice, ctx->stream));
@@ -66,7 +67,7 @@ extern "C" void uavm_pairbatch_destroy(uavm_ctx* ctx, uavm_pairbatch* pb)
     if (ctx) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
     cudaFree(pb->d_pairs); cudaFree(pb->d_items); cudaFree(pb->d_train_idx); cudaFree(pb->d_d2);
     cudaFree(pb->d_cand_xy1); cudaFree(pb->d_cand_xy2); cudaFree(pb->d_cand_id1); cudaFree(pb->d_cand_id2);
-    cudaFree(pb->d_cand_n); cudaFree(pb->d_tuple_res); cudaFree(pb->d_inlier); cudaFree(pb->d_res);
+    cudaFree(pb->d_cand_n); cudaFree(pb->d_tuple_res); cudaFree(pb->d_tuple_h); cudaFree(pb->d_inlier); cudaFree(pb->d_res);
     delete pb;
 }
 

@@ -12,8 +12,10 @@
 //                       itself if the first pass did not reach sampleTimes, then the final inlier pass
 //                       (division form, :1922-1944) and the final refine on all inliers (:1979-1986)
 //                       with the reference's summation order.
+#include <stdlib.h>
 #include "internal.h"
 #include "ransac_math.cuh"
+#include "ransac_warp.cuh"
 
 using namespace uavm::rmath;
 
@@ -21,24 +23,21 @@ namespace {
 
 constexpr int kEvalThreads = 128;
 constexpr int kFinThreads = 256;
-constexpr uint32_t RES_VALID = 0x80000000u, RES_REJ = 0x40000000u, RES_SUP = 0x0000ffffu;
+constexpr uint32_t RES_VALID = 0x80000000u, RES_REJ = 0x40000000u, RES_DEFER = 0x20000000u, RES_SUP = 0x0000ffffu;
 constexpr int kMaxGroups = 1 << 20;
 
-// evaluate draw group g of a pair whose candidates are staged in shared memory (x1,y1,x2,y2 per point)
-__device__ __forceinline__ uint32_t eval_group(const float4* __restrict__ pts, int n, uint32_t seed, uint32_t g,
-                                               float thr2, float* h_out)
+// per-thread evaluation of draw group g with the fast path only; candidates are staged in shared memory
+// (x1,y1,x2,y2 per point).  Tuples the fast path cannot reproduce come back as RES_VALID | RES_DEFER.
+__device__ __forceinline__ uint32_t eval_group_fast(const float4* __restrict__ pts, int n, uint32_t seed, uint32_t g,
+                                                    float thr2, float h[9])
 {
     int idx[4];
     if (!draw_group(seed, g, n, idx)) return 0u;
     float x1[4], y1[4], x2[4], y2[4];
 #pragma unroll
     for (int i = 0; i < 4; i++) { float4 p = pts[idx[i]]; x1[i] = p.x; y1[i] = p.y; x2[i] = p.z; y2[i] = p.w; }
-    float h[9];
-    const int st = hypothesis(x1, y1, x2, y2, h);
-    if (h_out) {
-#pragma unroll
-        for (int i = 0; i < 9; i++) h_out[i] = h[i];
-    }
+    const int st = hypothesis_fast(x1, y1, x2, y2, h);
+    if (st == TUPLE_NEED_SLOW) return RES_VALID | RES_DEFER;
     if (st == TUPLE_REJECTED) return RES_VALID | RES_REJ;
     int sup = 0;
     for (int i = 0; i < n; i++) {
@@ -50,25 +49,154 @@ __device__ __forceinline__ uint32_t eval_group(const float4* __restrict__ pts, i
     return RES_VALID | (uint32_t)sup;
 }
 
+// Warp-cooperative clean-up: every lane whose result is RES_DEFER gets its tuple evaluated by the whole warp
+// with the generic algorithm (ransac_warp.cuh).  Must be called by all 32 lanes.
+__device__ __forceinline__ void warp_resolve_deferred(const float4* __restrict__ pts, int n, uint32_t seed, uint32_t g,
+                                                      float thr2, uint32_t& res, float h[9])
+{
+    const int lane = threadIdx.x & 31;
+    unsigned m = __ballot_sync(0xffffffffu, (res & RES_DEFER) != 0u);
+    while (m) {
+        const int src = __ffs(m) - 1;
+        m &= m - 1;
+        const uint32_t gs = __shfl_sync(0xffffffffu, g, src);
+        int idx[4];
+        draw_group(seed, gs, n, idx);
+        float x1[4], y1[4], x2[4], y2[4], hh[9];
+#pragma unroll
+        for (int i = 0; i < 4; i++) { float4 p = pts[idx[i]]; x1[i] = p.x; y1[i] = p.y; x2[i] = p.z; y2[i] = p.w; }
+        const int st = uavm::rwarp::warp_hypothesis_generic(x1, y1, x2, y2, hh, lane);
+        uint32_t r = RES_VALID | RES_REJ;
+        if (st != TUPLE_REJECTED) {
+            int sup = 0;
+            for (int i = lane; i < n; i += 32) {
+                const float4 p = pts[i];
+                float xb, yb;
+                project_mul(p.z, p.w, hh, xb, yb);
+                if (dist2(xb, yb, p.x, p.y) < thr2) sup++;
+            }
+            sup = __reduce_add_sync(0xffffffffu, sup);
+            r = RES_VALID | (uint32_t)sup;
+        }
+        if (lane == src) {
+            res = r;
+#pragma unroll
+            for (int i = 0; i < 9; i++) h[i] = hh[i];
+        }
+    }
+}
+
 __device__ __forceinline__ void stage_points(float4* pts, const float* xy1, const float* xy2, int n, int tid, int nthreads) {
     for (int i = tid; i < n; i += nthreads)
         pts[i] = make_float4(xy1[2 * i], xy1[2 * i + 1], xy2[2 * i], xy2[2 * i + 1]);
 }
 
-__global__ void __launch_bounds__(kEvalThreads)
+// support of hypothesis h over all candidates (scoring loop, :1889-1904): reciprocal-multiply projection
+__device__ __forceinline__ int count_support(const float4* __restrict__ pts, int n, const float* h, float thr2)
+{
+    int sup = 0;
+    for (int i = 0; i < n; i++) {
+        const float4 p = pts[i];
+        float xb, yb;
+        project_mul(p.z, p.w, h, xb, yb);
+        if (dist2(xb, yb, p.x, p.y) < thr2) sup++;
+    }
+    return sup;
+}
+
+// First pass over the draw groups of every pair.  One thread per group for the cheap part (draw, 4-point
+// direct solve, 5 px gate; kGroupsPerThread groups per thread); the ~half of the tuples that survive the
+// gate are COMPACTED in shared memory so that the expensive parts — the 15-iteration Gauss-Newton refine
+// and the support count over all candidates — run on full, converged warps.
+constexpr int kGroupsPerThread = 2;
+constexpr int kGroupsPerBlock = kEvalThreads * kGroupsPerThread;
+
+__global__ void __launch_bounds__(kEvalThreads, 3)
 k4_ransac_eval(const PairDesc* __restrict__ pairs, const float* __restrict__ cand_xy1, const float* __restrict__ cand_xy2,
-               const int32_t* __restrict__ cand_n, float thr2, int groups, uint32_t* __restrict__ tuple_res)
+               const int32_t* __restrict__ cand_n, float thr2, int groups, uint32_t* __restrict__ tuple_res,
+               float* __restrict__ tuple_h)
 {
     __shared__ float4 pts[UAVM_CAND_SLOTS];
+    __shared__ float samp[kGroupsPerBlock][17];   // x1[4] y1[4] x2[4] y2[4] of the tuples to refine (+1 pad)
+    __shared__ float hs[kGroupsPerBlock][9];      // hypotheses (indexed by the tuple's position in the block)
+    __shared__ short refine_src[kGroupsPerBlock], score_src[kGroupsPerBlock];
+    __shared__ int n_refine, n_score;
     const int p = blockIdx.y;
     const int n = cand_n[p];
     const size_t base = (size_t)p * UAVM_CAND_SLOTS;
-    const uint32_t g = blockIdx.x * kEvalThreads + threadIdx.x;
-    if (n < 4) { if (g < (uint32_t)groups) tuple_res[(size_t)p * UAVM_RANSAC_MAX_TUPLES_FIRST + g] = 0u; return; }
-    stage_points(pts, cand_xy1 + base * 2, cand_xy2 + base * 2, n, threadIdx.x, kEvalThreads);
+    const int tid = threadIdx.x;
+    const uint32_t g0 = blockIdx.x * kGroupsPerBlock;
+    uint32_t* res_out = tuple_res + (size_t)p * UAVM_RANSAC_MAX_TUPLES_FIRST + g0;
+    float* h_out = tuple_h + ((size_t)p * UAVM_RANSAC_MAX_TUPLES_FIRST + g0) * 9;
+    if (n < 4) {
+        for (int k = tid; k < kGroupsPerBlock; k += kEvalThreads) if (g0 + k < (uint32_t)groups) res_out[k] = 0u;
+        return;
+    }
+    stage_points(pts, cand_xy1 + base * 2, cand_xy2 + base * 2, n, tid, kEvalThreads);
+    if (tid == 0) { n_refine = 0; n_score = 0; }
     __syncthreads();
-    if (g >= (uint32_t)groups) return;
-    tuple_res[(size_t)p * UAVM_RANSAC_MAX_TUPLES_FIRST + g] = eval_group(pts, n, pairs[p].seed, g, thr2, nullptr);
+    const uint32_t seed = pairs[p].seed;
+
+    // ---- phase A: draw + direct solve + gate ----
+    for (int k = tid; k < kGroupsPerBlock; k += kEvalThreads) {
+        if (g0 + k >= (uint32_t)groups) break;
+        int idx[4];
+        uint32_t res = 0u;
+        if (draw_group(seed, g0 + k, n, idx)) {
+            float x1[4], y1[4], x2[4], y2[4], h[9];
+#pragma unroll
+            for (int i = 0; i < 4; i++) { const float4 q = pts[idx[i]]; x1[i] = q.x; y1[i] = q.y; x2[i] = q.z; y2[i] = q.w; }
+            const int st = dlt_fast(x1, y1, x2, y2, h);
+            res = RES_VALID;
+            if (st == TUPLE_NEED_SLOW) res = RES_VALID | RES_DEFER;      // rare: evaluated by the finalize kernel (tiers 2/3)
+            else if (st == TUPLE_REJECTED) res = RES_VALID | RES_REJ;
+            else if (st == TUPLE_NEED_REFINE) {
+                const int slot = atomicAdd(&n_refine, 1);
+                refine_src[slot] = (short)k;
+#pragma unroll
+                for (int i = 0; i < 4; i++) { samp[slot][i] = x1[i]; samp[slot][4 + i] = y1[i]; samp[slot][8 + i] = x2[i]; samp[slot][12 + i] = y2[i]; }
+#pragma unroll
+                for (int i = 0; i < 9; i++) hs[k][i] = h[i];
+            } else {
+                score_src[atomicAdd(&n_score, 1)] = (short)k;
+#pragma unroll
+                for (int i = 0; i < 9; i++) hs[k][i] = h[i];
+            }
+        }
+        res_out[k] = res;
+    }
+    __syncthreads();
+
+    // ---- phase B: Gauss-Newton refine on the compacted survivors ----
+    const int nr = n_refine;
+    for (int t = tid; t < nr; t += kEvalThreads) {
+        const int src = refine_src[t];
+        float x1[4], y1[4], x2[4], y2[4], h[9];
+#pragma unroll
+        for (int i = 0; i < 4; i++) { x1[i] = samp[t][i]; y1[i] = samp[t][4 + i]; x2[i] = samp[t][8 + i]; y2[i] = samp[t][12 + i]; }
+#pragma unroll
+        for (int i = 0; i < 9; i++) h[i] = hs[src][i];
+        const int st = refine_fast(x1, y1, x2, y2, h);
+        if (st == TUPLE_NEED_SLOW) res_out[src] = RES_VALID | RES_DEFER;
+        else {
+#pragma unroll
+            for (int i = 0; i < 9; i++) hs[src][i] = h[i];
+            score_src[atomicAdd(&n_score, 1)] = (short)src;
+        }
+    }
+    __syncthreads();
+
+    // ---- phase C: support count on the compacted accepted hypotheses ----
+    const int ns = n_score;
+    for (int t = tid; t < ns; t += kEvalThreads) {
+        const int src = score_src[t];
+        float h[9];
+#pragma unroll
+        for (int i = 0; i < 9; i++) h[i] = hs[src][i];
+        res_out[src] = RES_VALID | (uint32_t)count_support(pts, n, h, thr2);
+#pragma unroll
+        for (int i = 0; i < 9; i++) h_out[src * 9 + i] = h[i];
+    }
 }
 
 // ---- block-wide helpers (kFinThreads = 256 threads, 8 warps) ----
@@ -113,7 +241,8 @@ struct FinSmem {
 __global__ void __launch_bounds__(kFinThreads, 1)
 k4_ransac_finalize(const PairDesc* __restrict__ pairs, const float* __restrict__ cand_xy1, const float* __restrict__ cand_xy2,
                    const int32_t* __restrict__ cand_n, float thr2, int sample_times, int groups_first,
-                   const uint32_t* __restrict__ tuple_res, uint8_t* __restrict__ inlier, uavm_ransac_result* __restrict__ results)
+                   const uint32_t* __restrict__ tuple_res, float* __restrict__ tuple_h,
+                   uint8_t* __restrict__ inlier, uavm_ransac_result* __restrict__ results)
 {
     extern __shared__ __align__(16) uint8_t fin_raw[];
     FinSmem& S = *reinterpret_cast<FinSmem*>(fin_raw);
@@ -142,8 +271,16 @@ k4_ransac_finalize(const PairDesc* __restrict__ pairs, const float* __restrict__
     for (int g0 = 0; !done && g0 < kMaxGroups; g0 += kFinThreads) {
         const int g = g0 + tid;
         uint32_t res;
+        float hd[9];
+        bool fresh = false;                                      // evaluated here (not by the first pass)
         if (g < groups_first) res = tuple_res[(size_t)p * UAVM_RANSAC_MAX_TUPLES_FIRST + g];
-        else res = eval_group(S.pts, n, seed, (uint32_t)g, thr2, nullptr);
+        else { res = eval_group_fast(S.pts, n, seed, (uint32_t)g, thr2, hd); fresh = true; }
+        if (res & RES_DEFER) fresh = true;
+        warp_resolve_deferred(S.pts, n, seed, (uint32_t)g, thr2, res, hd);   // rare tuples: generic algorithm, whole warp
+        if (fresh && g < UAVM_RANSAC_MAX_TUPLES_FIRST && (res & RES_VALID) && !(res & RES_REJ)) {
+#pragma unroll
+            for (int i = 0; i < 9; i++) tuple_h[((size_t)p * UAVM_RANSAC_MAX_TUPLES_FIRST + g) * 9 + i] = hd[i];
+        }
         const int v = (res & RES_VALID) ? 1 : 0;
         const int a = (v && !(res & RES_REJ)) ? 1 : 0;
         const int sup = (int)(res & RES_SUP);
@@ -185,13 +322,24 @@ k4_ransac_finalize(const PairDesc* __restrict__ pairs, const float* __restrict__
 
     // ---------------- winning hypothesis matrix ----------------
     const int hg = best_g >= 0 ? best_g : first_acc_g;
-    if (tid == 0) {
+    __syncthreads();                                    // tuple_h written above by other threads of this CTA
+    if (tid < 32) {
         float h[9];
 #pragma unroll
         for (int i = 0; i < 9; i++) h[i] = 0.0f;
-        if (hg >= 0) eval_group(S.pts, n, seed, (uint32_t)hg, -1.0f, h);
+        if (hg >= 0 && hg < UAVM_RANSAC_MAX_TUPLES_FIRST) {          // stored by the first pass or by the replay above
+            if (tid == 0) {
 #pragma unroll
-        for (int i = 0; i < 9; i++) S.hbest[i] = h[i];
+                for (int i = 0; i < 9; i++) h[i] = tuple_h[((size_t)p * UAVM_RANSAC_MAX_TUPLES_FIRST + hg) * 9 + i];
+            }
+        } else if (hg >= 0) {                                        // beyond the stored range: evaluate again
+            uint32_t r = (tid == 0) ? eval_group_fast(S.pts, n, seed, (uint32_t)hg, -1.0f, h) : 0u;
+            warp_resolve_deferred(S.pts, n, seed, (uint32_t)hg, -1.0f, r, h);
+        }
+        if (tid == 0) {
+#pragma unroll
+            for (int i = 0; i < 9; i++) S.hbest[i] = h[i];
+        }
     }
     __syncthreads();
 
@@ -316,23 +464,24 @@ int uavm_launch_ransac(uavm_ctx* ctx, uavm_pairbatch* pb, float dist, int sample
     const float thr2 = dist * dist;                          // fRansacDistSquare (:1757)
     // first pass: enough draw groups that, at the ~35 % gate-rejection rate seen on 4000x3000 data, the
     // 1000th accepted tuple is usually inside it; the finalize kernel continues past it when needed.
-    int groups = sample_times * 5 / 2 + 128;
+    int groups = sample_times * 9 / 4 + 64;     // ~2115 +- 50 groups are consumed per 1000 counted tuples at 4000x3000
     if (groups > UAVM_RANSAC_MAX_TUPLES_FIRST) groups = UAVM_RANSAC_MAX_TUPLES_FIRST;
-    groups = (groups / kEvalThreads) * kEvalThreads;
+    groups = ((groups + kGroupsPerBlock - 1) / kGroupsPerBlock) * kGroupsPerBlock;
+    if (groups > UAVM_RANSAC_MAX_TUPLES_FIRST) groups = UAVM_RANSAC_MAX_TUPLES_FIRST;
     static bool attr_set = false;
     if (!attr_set) {
         UAVM_CUDA(ctx, cudaFuncSetAttribute(k4_ransac_finalize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFinSmemBytes));
         attr_set = true;
     }
     if (groups > 0) {
-        dim3 grid(groups / kEvalThreads, pb->n_pairs);
+        dim3 grid(groups / kGroupsPerBlock, pb->n_pairs);
         k4_ransac_eval<<<grid, kEvalThreads, 0, ctx->stream>>>(pb->d_pairs, pb->d_cand_xy1, pb->d_cand_xy2, pb->d_cand_n,
-                                                               thr2, groups, pb->d_tuple_res);
+                                                               thr2, groups, pb->d_tuple_res, pb->d_tuple_h);
         UAVM_CHECK_LAUNCH(ctx);
     }
     k4_ransac_finalize<<<pb->n_pairs, kFinThreads, kFinSmemBytes, ctx->stream>>>(
         pb->d_pairs, pb->d_cand_xy1, pb->d_cand_xy2, pb->d_cand_n, thr2, sample_times, groups, pb->d_tuple_res,
-        pb->d_inlier, pb->d_res);
+        pb->d_tuple_h, pb->d_inlier, pb->d_res);
     UAVM_CHECK_LAUNCH(ctx);
     return UAVM_OK;
 }

@@ -124,7 +124,11 @@ UAVM_HD bool inverse8_fast(float M[8][8], float eps) {
             if (j == i) continue;
             const float f = M[j][i];
             if (fabsf(f) < eps) {
-                if (f != 0.0f) ok = false;       // the reference leaves a non-zero entry behind
+                // The reference skips this row but leaves the non-zero entry f behind in the left block.  For a
+                // row that already served as pivot (j < i) that residue is never read again: column i is done,
+                // and it can only spread to other rows through a LATER pivot row.  For j > i it can (and could
+                // then disturb the exact-1 search of the re-ordering pass), so only that case leaves tier 1.
+                if (f != 0.0f && j > i) ok = false;
                 M[j][i] = 0.0f;
             } else {
                 const float nf = -f;
@@ -142,6 +146,106 @@ UAVM_HD bool inverse8_fast(float M[8][8], float eps) {
         for (int c = 0; c < 8; c++) chk += fabsf(M[r][c]);
     if (!(chk <= 3.0e38f)) ok = false;           // inf/NaN anywhere
     return ok;
+}
+
+// Tier 2: InverseMatrix (M/matrix.h:147-296) with ALL of its quirks (first-unused-row pivoting, small
+// multipliers skipped but not zeroed, row re-ordering by exact-1 search) on the full 8 x 16 augmented
+// matrix, written with static indices only so that it stays in registers: the data-dependent pivot /
+// swap rows are extracted with select chains instead of dynamic indexing (no local memory).
+// Returns 1 ok, 0 when no pivot exists (the reference then leaves its output untouched).
+UAVM_HD int inverse8_generic_reg(const float N[8][8], float eps, float out[8][8]) {
+    float T[8][16];
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+#pragma unroll
+        for (int c = 0; c < 8; c++) { T[i][c] = N[i][c]; T[i][8 + c] = (i == c) ? 1.0f : 0.0f; }
+    unsigned used = 0u;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        int row = -1;
+#pragma unroll
+        for (int j = 0; j < 8; j++)
+            if (row < 0 && !((used >> j) & 1u) && fabsf(T[j][i]) > eps) row = j;
+        if (row < 0) return 0;
+        used |= 1u << row;
+        float e = 0.0f;
+#pragma unroll
+        for (int j = 0; j < 8; j++) e = (j == row) ? T[j][i] : e;
+        float prow[16];
+#pragma unroll
+        for (int c = 0; c < 16; c++) {
+            float v = 0.0f;
+#pragma unroll
+            for (int j = 0; j < 8; j++) v = (j == row) ? T[j][c] : v;
+            prow[c] = v / e;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            if (j == row) {
+#pragma unroll
+                for (int c = 0; c < 16; c++) T[j][c] = prow[c];
+            } else {
+                const float f = T[j][i];
+                if (!(fabsf(f) < eps)) {
+                    const float nf = -f;
+#pragma unroll
+                    for (int c = 0; c < 16; c++) T[j][c] = T[j][c] + nf * prow[c];
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+        int target = -1;
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+            if (target < 0 && T[i][r] == 1.0f) target = i;
+        if (target >= 0 && target != r) {
+            float tr[16];
+#pragma unroll
+            for (int c = 0; c < 16; c++) {
+                float v = 0.0f;
+#pragma unroll
+                for (int i = 0; i < 8; i++) v = (i == target) ? T[i][c] : v;
+                tr[c] = v;
+            }
+#pragma unroll
+            for (int i = 0; i < 8; i++)
+                if (i == target) {
+#pragma unroll
+                    for (int c = 0; c < 16; c++) T[i][c] = T[r][c];
+                }
+#pragma unroll
+            for (int c = 0; c < 16; c++) T[r][c] = tr[c];
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+#pragma unroll
+        for (int c = 0; c < 8; c++) out[i][c] = T[i][8 + c];
+    return 1;
+}
+
+// inverse of the 4-point normal matrix of R.  kGeneric == false: tier 1 (in-place fast inverse; false when
+// its assumptions fail).  kGeneric == true: tier 2 (register-resident generic inverse); false when no pivot
+// exists (the reference then reuses a stale matrix) or the result is not finite (zero-skipping in the
+// sparse products would hide NaNs) — those cases go to the tier-3 generic path.
+template <bool kGeneric>
+UAVM_HD bool normal_inverse(const Rows4& R, float eps, float N[8][8]) {
+    if (!kGeneric) {
+        normal_matrix(R, N);
+        return inverse8_fast(N, eps);
+    } else {
+        float M[8][8];
+        normal_matrix(R, M);
+        if (inverse8_generic_reg(M, eps, N) != 1) return false;
+        float chk = 0.0f;
+#pragma unroll
+        for (int r = 0; r < 8; r++)
+#pragma unroll
+            for (int c = 0; c < 8; c++) chk += fabsf(N[r][c]);
+        return chk <= 3.0e38f;
+    }
 }
 
 // X = (Ninv * R^T) * rhs with the reference association ((A^T A)^-1 A^T) B (M/matrix.h:391-397):
@@ -165,12 +269,13 @@ UAVM_HD void solve_from_inverse(const float Ninv[8][8], const Rows4& R, const fl
 }
 
 // status of a tuple evaluation
-enum { TUPLE_REJECTED = 0, TUPLE_KEPT = 1, TUPLE_REFINED = 2, TUPLE_NEED_SLOW = 3 };
+enum { TUPLE_REJECTED = 0, TUPLE_KEPT = 1, TUPLE_REFINED = 2, TUPLE_NEED_SLOW = 3, TUPLE_NEED_REFINE = 4 };
 
-// 4-point hypothesis, fast path: SolveHomographyMatrix (M/matrix.h:783-877) + gates
-// (M/mosaicimage.h:1864-1876) + NonlinearLeastSquareProjection2 (M/LeastSquare.h:353-531).
-// x1,y1 = points of image 1 (targets), x2,y2 = points of image 2 (sources).
-UAVM_HD int hypothesis_fast(const float x1[4], const float y1[4], const float x2[4], const float y2[4], float h[9]) {
+// 4-point direct solve, fast path: SolveHomographyMatrix (M/matrix.h:783-877) + the gates of the sampling
+// loop (M/mosaicimage.h:1864-1876).  x1,y1 = points of image 1 (targets), x2,y2 = points of image 2
+// (sources).  Returns REJECTED (> 5 px), KEPT (<= 0.01 px, used as is), NEED_REFINE or NEED_SLOW.
+template <bool kGeneric>
+UAVM_HD int dlt_t(const float x1[4], const float y1[4], const float x2[4], const float y2[4], float h[9]) {
     Rows4 R;
     float rhs[8];
 #pragma unroll
@@ -181,8 +286,7 @@ UAVM_HD int hypothesis_fast(const float x1[4], const float y1[4], const float x2
         rhs[2 * i] = x1[i]; rhs[2 * i + 1] = y1[i];
     }
     float N[8][8];
-    normal_matrix(R, N);
-    if (!inverse8_fast(N, 1e-20f)) return TUPLE_NEED_SLOW;
+    if (!normal_inverse<kGeneric>(R, 1e-20f, N)) return TUPLE_NEED_SLOW;
     solve_from_inverse(N, R, rhs, h);
     // max residual: float projection, double distance (M/matrix.h:848-866, M/mvMath.h:186-192)
     double e2max = 0.0;
@@ -194,12 +298,19 @@ UAVM_HD int hypothesis_fast(const float x1[4], const float y1[4], const float x2
         double e2 = dx * dx + dy * dy;
         if (e2 > e2max) e2max = e2;          // sqrt is monotone: max of sqrt == sqrt of max
     }
-    if (!(e2max == e2max)) return TUPLE_NEED_SLOW;   // NaN: let the generic path decide
     h[8] = (float)sqrt(e2max);
     if (h[8] > 5.0f) return TUPLE_REJECTED;
     if (!((h[8] < 5.0f) && (h[8] > 0.01f))) return TUPLE_KEPT;
+    return TUPLE_NEED_REFINE;
+}
 
-    // Gauss-Newton refine, <= 15 iterations, stop when all |delta| < 1e-10
+// Gauss-Newton refine of a 4-point hypothesis, fast path: NonlinearLeastSquareProjection2
+// (M/LeastSquare.h:353-531), <= 15 iterations, stop when all |delta| < 1e-10.  h: in = direct solve,
+// out = refined (h[8] = max residual, float).  Returns REFINED or NEED_SLOW.
+template <bool kGeneric>
+UAVM_HD int refine_t(const float x1[4], const float y1[4], const float x2[4], const float y2[4], float h[9]) {
+    Rows4 R;
+    float N[8][8];
     float w[8];
 #pragma unroll
     for (int i = 0; i < 8; i++) w[i] = h[i];
@@ -218,8 +329,7 @@ UAVM_HD int hypothesis_fast(const float x1[4], const float y1[4], const float x2
             res[2 * i] = x1[i] - u / d;
             res[2 * i + 1] = y1[i] - v / d;
         }
-        normal_matrix(R, N);
-        if (!inverse8_fast(N, 1e-6f)) return TUPLE_NEED_SLOW;
+        if (!normal_inverse<kGeneric>(R, 1e-6f, N)) return TUPLE_NEED_SLOW;
         float dx[8];
         solve_from_inverse(N, R, res, dx);
         bool small = true;
@@ -240,6 +350,24 @@ UAVM_HD int hypothesis_fast(const float x1[4], const float y1[4], const float x2
     }
     h[8] = emax;
     return TUPLE_REFINED;
+}
+
+UAVM_HD int dlt_fast(const float x1[4], const float y1[4], const float x2[4], const float y2[4], float h[9]) {
+    return dlt_t<false>(x1, y1, x2, y2, h);
+}
+UAVM_HD int refine_fast(const float x1[4], const float y1[4], const float x2[4], const float y2[4], float h[9]) {
+    return refine_t<false>(x1, y1, x2, y2, h);
+}
+UAVM_HD int hypothesis_fast(const float x1[4], const float y1[4], const float x2[4], const float y2[4], float h[9]) {
+    int st = dlt_fast(x1, y1, x2, y2, h);
+    if (st == TUPLE_NEED_REFINE) st = refine_fast(x1, y1, x2, y2, h);
+    return st;
+}
+// tier 2: the whole tuple again with the register-resident generic inverse (rare: ~0.3 % of tuples)
+UAVM_HD_NOINLINE int hypothesis_tier2(const float x1[4], const float y1[4], const float x2[4], const float y2[4], float h[9]) {
+    int st = dlt_t<true>(x1, y1, x2, y2, h);
+    if (st == TUPLE_NEED_REFINE) st = refine_t<true>(x1, y1, x2, y2, h);
+    return st;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -369,6 +497,7 @@ UAVM_HD_NOINLINE int hypothesis_slow(const float x1[4], const float y1[4], const
 UAVM_HD int hypothesis(const float x1[4], const float y1[4], const float x2[4], const float y2[4], float h[9],
                        bool* took_slow = nullptr) {
     int st = hypothesis_fast(x1, y1, x2, y2, h);
+    if (st == TUPLE_NEED_SLOW) st = hypothesis_tier2(x1, y1, x2, y2, h);
     if (st == TUPLE_NEED_SLOW) {
         if (took_slow) *took_slow = true;
         st = hypothesis_slow(x1, y1, x2, y2, h);

@@ -160,3 +160,29 @@ def test_pipeline_match_select_ransac_strip(ctx, oracle):
         assert np.allclose(Hg[:8], Ht.reshape(-1)[:8], rtol=0.05, atol=2.0)
     out, n, acc = pb.collect(30)
     assert acc == 3 and n == sum(pb.ransac_result(p)[1].n_inliers for p in range(3))
+
+
+def test_ransac_degenerate_inputs_generic_path(ctx, oracle):
+    """Inputs that push many 4-tuples off the fast path (singular / ill-conditioned normal equations, skipped
+    multipliers, missing pivots): the warp-cooperative generic evaluation must still match the oracle bit for bit."""
+    rng = np.random.default_rng(17)
+    cases = []
+    # integer grid with duplicates and exact collinearities
+    g = np.stack(np.meshgrid(np.arange(0, 1000, 125), np.arange(0, 750, 125)), -1).reshape(-1, 2).astype(np.float32)
+    g = np.concatenate([g, g[:20]])
+    cases.append((g * 1.0 + 2.0, g))
+    # three collinear clusters
+    t = np.linspace(0, 1, 60, dtype=np.float32)[:, None]
+    c = np.concatenate([t * [900, 10] + [5, 5], t * [10, 700] + [5, 5], t * [900, 700] + [50, 20]]).astype(np.float32)
+    cases.append((c + rng.normal(0, 0.2, c.shape).astype(np.float32), c))
+    # everything inside a 3 px window (tiny baselines)
+    s = rng.uniform(100, 103, (80, 2)).astype(np.float32)
+    cases.append((s + 0.5, s))
+    # very large coordinates (float32 normal equations overflow towards 1e20+)
+    b = rng.uniform(0, 2e5, (120, 2)).astype(np.float32)
+    cases.append((b * 0.999 + 30.0, b))
+    # axis-aligned points: many exact zeros in the systems
+    z = np.zeros((100, 2), np.float32); z[:50, 0] = rng.uniform(0, 4000, 50); z[50:, 1] = rng.uniform(0, 3000, 50)
+    cases.append((z + 1.0, z))
+    for k, (xy1, xy2) in enumerate(cases):
+        _check_ransac(ctx, oracle, np.ascontiguousarray(xy1, np.float32), np.ascontiguousarray(xy2, np.float32), 4242 + k)
