@@ -1,23 +1,328 @@
-// blend.cu — K7 multi-band blend (placeholder until the kernels land in this file).
+// blend.cu — K7: multi-band blend.  Replaces detail::MultiBandBlender prepare / feed / blend and the final
+// convertTo(CV_8U) as driven by LaplacianPyramidBlending (M/MosaicImage.cpp:2296-2299, :2476-2486).
+//
+// The blender itself is OpenCV code (third party, not under /root/reference); the arithmetic restated here is
+// the one documented in oracle/oracle_blend.c: int16 Laplacian pyramids ([1 4 6 4 1] pyrDown with
+// (sum+128)>>8, pyrUp with (sum+32)>>6, reflect-101 / replicate borders), f32 Gaussian weight pyramids,
+// dst += short(src * w), wsum += w, dst = short(dst / (wsum + 1e-5)), collapse with saturating adds.
+//
+// HBM layout: the canvas pyramid (int16 x3 interleaved + f32 weights per level, canvas padded to a multiple
+// of 2^bands) stays resident; every fed chip gets a scratch pyramid of its padded ROI that is reused for the
+// next chip.  Images are fed in index order (the f32 weight sums are order dependent), pixels in parallel.
+#include <math.h>
+#include <string.h>
 #include "canvas.h"
 
-void uavm_blend_free(uavm_canvas* cv) { (void)cv; }
+namespace {
+
+constexpr int kMaxBands = 8;
+
+struct BlendWs {
+    int nb = 0, W = 0, H = 0;
+    int lw[kMaxBands + 1], lh[kMaxBands + 1];
+    short* dlap[kMaxBands + 1] = {nullptr};
+    float* dw[kMaxBands + 1] = {nullptr};
+    short* pyr[kMaxBands + 1] = {nullptr};     // scratch pyramid of the chip being fed (capacity of the largest ROI)
+    float* wp[kMaxBands + 1] = {nullptr};
+    size_t roi_cap = 0;
+};
+
+__device__ __forceinline__ int reflect101(int p, int n) {
+    if (n == 1) return 0;
+    while (p < 0 || p >= n) p = (p < 0) ? -p : 2 * n - 2 - p;
+    return p;
+}
+__device__ __forceinline__ int reflect_edge(int p, int n) {     // BORDER_REFLECT
+    if (n == 1) return 0;
+    while (p < 0 || p >= n) p = (p < 0) ? -p - 1 : 2 * n - 1 - p;
+    return p;
+}
+__device__ __forceinline__ short sat16(int v) { return (short)max(-32768, min(32767, v)); }
+
+// level 0 of the fed image: copyMakeBorder(REFLECT) of the chip (u8 -> s16) and mask/255 with a zero border
+__global__ void __launch_bounds__(256)
+k7_feed_level0(const uint8_t* __restrict__ chip, int chip_step, const uint8_t* __restrict__ mask, int mask_step,
+               int cw, int ch, int left, int top, int width, int height, short* __restrict__ pyr0, float* __restrict__ wp0)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= width || y >= height) return;
+    const int ix = x - left, iy = y - top;
+    const int sx = reflect_edge(ix, cw), sy = reflect_edge(iy, ch);
+    const uint8_t* s = chip + (size_t)sy * chip_step + 3 * sx;
+    short* d = pyr0 + ((size_t)y * width + x) * 3;
+    d[0] = s[0]; d[1] = s[1]; d[2] = s[2];
+    float wv = 0.0f;
+    if (ix >= 0 && ix < cw && iy >= 0 && iy < ch) wv = (float)mask[(size_t)iy * mask_step + ix] * (float)(1. / 255.);
+    wp0[(size_t)y * width + x] = wv;
+}
+
+// pyrDown of the int16 x3 image and of the f32 weight map, one output pixel per thread
+__global__ void __launch_bounds__(256)
+k7_pyrdown(const short* __restrict__ src, const float* __restrict__ wsrc, int w, int h,
+           short* __restrict__ dst, float* __restrict__ wdst, int dw, int dh)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= dw || y >= dh) return;
+    int xs[5], ys[5];
+#pragma unroll
+    for (int k = 0; k < 5; k++) { xs[k] = reflect101(2 * x - 2 + k, w); ys[k] = reflect101(2 * y - 2 + k, h); }
+    int acc[3] = {0, 0, 0};
+    float frow[5];
+    const int kw[5] = {1, 4, 6, 4, 1};
+#pragma unroll
+    for (int r = 0; r < 5; r++) {
+        const short* srow = src + (size_t)ys[r] * w * 3;
+        int ra[3] = {0, 0, 0};
+#pragma unroll
+        for (int k = 0; k < 5; k++) {
+            const short* px = srow + xs[k] * 3;
+            ra[0] += kw[k] * px[0]; ra[1] += kw[k] * px[1]; ra[2] += kw[k] * px[2];
+        }
+        acc[0] += kw[r] * ra[0]; acc[1] += kw[r] * ra[1]; acc[2] += kw[r] * ra[2];
+        if (wsrc) {
+            const float* wr = wsrc + (size_t)ys[r] * w;
+            const float s0 = wr[xs[0]], s1 = wr[xs[1]], s2 = wr[xs[2]], s3 = wr[xs[3]], s4 = wr[xs[4]];
+            frow[r] = s2 * 6.0f + (s1 + s3) * 4.0f + s0 + s4;           // row pass, oracle order
+        }
+    }
+    short* d = dst + ((size_t)y * dw + x) * 3;
+    d[0] = sat16((acc[0] + 128) >> 8); d[1] = sat16((acc[1] + 128) >> 8); d[2] = sat16((acc[2] + 128) >> 8);
+    if (wsrc) {
+        const float v = frow[2] * 6.0f + (frow[1] + frow[3]) * 4.0f + frow[0] + frow[4];   // column pass
+        wdst[(size_t)y * dw + x] = v * (1.0f / 256.0f);
+    }
+}
+
+// value of pyrUp(lo) at (x, y) of the 2x larger level; lo is lw x lh, 3 channels
+__device__ __forceinline__ void pyrup_at(const short* __restrict__ lo, int lw, int lh, int x, int y, int out[3])
+{
+    const int cx = x >> 1, cy = y >> 1;
+    const int xm = (cx == 0) ? (lw > 1 ? 1 : 0) : cx - 1, xp = (cx == lw - 1) ? lw - 1 : cx + 1;
+    const int ym = (cy == 0) ? (lh > 1 ? 1 : 0) : cy - 1, yp = (cy == lh - 1) ? lh - 1 : cy + 1;
+    // per axis: even sample s[i-1] + 6 s[i] + s[i+1], odd sample 4 (s[i] + s[i+1])
+    const int wx0 = (x & 1) ? 0 : 1, wx1 = (x & 1) ? 4 : 6, wx2 = (x & 1) ? 4 : 1;
+    const int wy0 = (y & 1) ? 0 : 1, wy1 = (y & 1) ? 4 : 6, wy2 = (y & 1) ? 4 : 1;
+    const int rows[3] = {ym, cy, yp}, wy[3] = {wy0, wy1, wy2};
+    int acc[3] = {0, 0, 0};
+#pragma unroll
+    for (int r = 0; r < 3; r++) {
+        if (wy[r] == 0) continue;
+        const short* row = lo + (size_t)rows[r] * lw * 3;
+        const short* a = row + xm * 3; const short* b = row + cx * 3; const short* c = row + xp * 3;
+#pragma unroll
+        for (int k = 0; k < 3; k++) acc[k] += wy[r] * (wx0 * a[k] + wx1 * b[k] + wx2 * c[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < 3; k++) out[k] = sat16((acc[k] + 32) >> 6);
+}
+
+// Laplacian level (pyr[i] - pyrUp(pyr[i+1]), saturating; the top level is the Gaussian itself) times the
+// weight, accumulated into the canvas pyramid: dst += short(lap * w), wsum += w
+__global__ void __launch_bounds__(256)
+k7_lap_accumulate(const short* __restrict__ cur, const short* __restrict__ next, const float* __restrict__ wcur,
+                  int w, int h, int nw, int nh, short* __restrict__ dlap, float* __restrict__ dwsum, int dst_w, int x_tl, int y_tl)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= w || y >= h) return;
+    const short* c = cur + ((size_t)y * w + x) * 3;
+    int lap[3] = {c[0], c[1], c[2]};
+    if (next) {
+        int up[3];
+        pyrup_at(next, nw, nh, x, y, up);
+#pragma unroll
+        for (int k = 0; k < 3; k++) lap[k] = sat16(lap[k] - up[k]);
+    }
+    const float wv = wcur[(size_t)y * w + x];
+    const size_t di = (size_t)(y + y_tl) * dst_w + (x + x_tl);
+    short* d = dlap + di * 3;
+#pragma unroll
+    for (int k = 0; k < 3; k++) d[k] = (short)(d[k] + (short)__float2int_rz((float)lap[k] * wv));
+    dwsum[di] += wv;
+}
+
+__global__ void __launch_bounds__(256)
+k7_normalize(short* __restrict__ dlap, const float* __restrict__ dwsum, size_t n)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float wv = dwsum[i] + 1e-5f;
+    short* d = dlap + i * 3;
+#pragma unroll
+    for (int k = 0; k < 3; k++) d[k] = (short)__float2int_rz((float)d[k] / wv);
+}
+
+// restoreImageFromLaplacePyr step: hi = sat(pyrUp(lo) + hi)
+__global__ void __launch_bounds__(256)
+k7_collapse(const short* __restrict__ lo, int lw, int lh, short* __restrict__ hi, int w, int h)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= w || y >= h) return;
+    int up[3];
+    pyrup_at(lo, lw, lh, x, y, up);
+    short* d = hi + ((size_t)y * w + x) * 3;
+#pragma unroll
+    for (int k = 0; k < 3; k++) d[k] = sat16(up[k] + d[k]);
+}
+
+// crop, zero where wsum <= 1e-5, convertTo(CV_8U) (saturate)
+__global__ void __launch_bounds__(256)
+k7_output(const short* __restrict__ lap0, const float* __restrict__ w0, int W, int cw, int ch,
+          uint8_t* __restrict__ out, uint8_t* __restrict__ out_mask)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= cw || y >= ch) return;
+    const bool m = w0[(size_t)y * W + x] > 1e-5f;
+    const short* s = lap0 + ((size_t)y * W + x) * 3;
+    uint8_t* d = out + ((size_t)y * cw + x) * 3;
+#pragma unroll
+    for (int k = 0; k < 3; k++) d[k] = m ? (uint8_t)max(0, min(255, (int)s[k])) : 0;
+    out_mask[(size_t)y * cw + x] = m ? 255 : 0;
+}
+
+void free_ws(BlendWs* ws)
+{
+    if (!ws) return;
+    for (int i = 0; i <= kMaxBands; i++) { cudaFree(ws->dlap[i]); cudaFree(ws->dw[i]); cudaFree(ws->pyr[i]); cudaFree(ws->wp[i]); }
+    delete ws;
+}
+
+inline int pad_to(int v, int nb) { return v + ((1 << nb) - v % (1 << nb)) % (1 << nb); }
+
+struct Roi { int tlx, tly, width, height, top, left; };
+Roi feed_roi(int tl_x, int tl_y, int cw, int ch, int W, int H, int nb)
+{
+    // MultiBandBlender::feed: gap = 3 * 2^bands, corners aligned to 2^bands, shifted back inside the canvas
+    const int gap = 3 * (1 << nb);
+    int tlx = tl_x - gap > 0 ? tl_x - gap : 0, tly = tl_y - gap > 0 ? tl_y - gap : 0;
+    int brx = tl_x + cw + gap < W ? tl_x + cw + gap : W, bry = tl_y + ch + gap < H ? tl_y + ch + gap : H;
+    tlx = (tlx >> nb) << nb; tly = (tly >> nb) << nb;
+    int width = pad_to(brx - tlx, nb), height = pad_to(bry - tly, nb);
+    brx = tlx + width; bry = tly + height;
+    const int dy = bry - H > 0 ? bry - H : 0, dx = brx - W > 0 ? brx - W : 0;
+    tlx -= dx; tly -= dy;
+    Roi r; r.tlx = tlx; r.tly = tly; r.width = width; r.height = height; r.top = tl_y - tly; r.left = tl_x - tlx;
+    return r;
+}
+
+}  // namespace
+
+void uavm_blend_free(uavm_canvas* cv)
+{
+    if (cv && cv->blend_ws) { free_ws((BlendWs*)cv->blend_ws); cv->blend_ws = nullptr; }
+}
 
 extern "C" int uavm_canvas_blend(uavm_ctx* ctx, uavm_canvas* cv, int num_bands)
 {
-    (void)cv; (void)num_bands;
-    UAVM_SET_ERR(ctx, "uavm_canvas_blend: not implemented yet");
-    return UAVM_EFAIL;
+    if (!ctx || !cv || num_bands < 0 || num_bands > kMaxBands) return UAVM_EINVAL;
+    if (!cv->warped) { UAVM_SET_ERR(ctx, "blend before warp"); return UAVM_EINVAL; }
+    UAVM_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int cw = cv->layout.canvas_w, ch = cv->layout.canvas_h;
+    // prepare(): crop the band count, pad the canvas
+    const double max_len = (double)(cw > ch ? cw : ch);
+    int nb = (int)ceil(log(max_len) / log(2.0));
+    if (num_bands < nb) nb = num_bands;
+    BlendWs* ws = (BlendWs*)cv->blend_ws;
+    if (ws && ws->nb != nb) { free_ws(ws); ws = nullptr; cv->blend_ws = nullptr; }
+    if (!ws) {
+        ws = new BlendWs();
+        cv->blend_ws = ws;
+        ws->nb = nb; ws->W = pad_to(cw, nb); ws->H = pad_to(ch, nb);
+        size_t roi_cap = 0;
+        for (int k = 0; k < cv->n; k++) {
+            const ChipDesc& d = cv->desc[k];
+            if (!d.keep) continue;
+            Roi r = feed_roi(d.beg_x, d.beg_y, d.chip_w, d.chip_h, ws->W, ws->H, nb);
+            if ((size_t)r.width * r.height > roi_cap) roi_cap = (size_t)r.width * r.height;
+        }
+        ws->roi_cap = roi_cap;
+        ws->lw[0] = ws->W; ws->lh[0] = ws->H;
+        size_t cap = roi_cap;
+        for (int i = 0; i <= nb; i++) {
+            if (i > 0) { ws->lw[i] = (ws->lw[i - 1] + 1) / 2; ws->lh[i] = (ws->lh[i - 1] + 1) / 2; cap = (cap + 3) / 4 + 4096; }
+            const size_t px = (size_t)ws->lw[i] * ws->lh[i];
+            UAVM_CUDA(ctx, cudaMalloc(&ws->dlap[i], px * 3 * sizeof(short)));
+            UAVM_CUDA(ctx, cudaMalloc(&ws->dw[i], px * sizeof(float)));
+            UAVM_CUDA(ctx, cudaMalloc(&ws->pyr[i], (cap + 16) * 3 * sizeof(short)));
+            UAVM_CUDA(ctx, cudaMalloc(&ws->wp[i], (cap + 16) * sizeof(float)));
+        }
+        if (!cv->d_result) {
+            UAVM_CUDA(ctx, cudaMalloc(&cv->d_result, (size_t)cw * ch * 3));
+            UAVM_CUDA(ctx, cudaMalloc(&cv->d_result_mask, (size_t)cw * ch));
+        }
+    }
+    for (int i = 0; i <= nb; i++) {
+        const size_t px = (size_t)ws->lw[i] * ws->lh[i];
+        UAVM_CUDA(ctx, cudaMemsetAsync(ws->dlap[i], 0, px * 3 * sizeof(short), ctx->stream));
+        UAVM_CUDA(ctx, cudaMemsetAsync(ws->dw[i], 0, px * sizeof(float), ctx->stream));
+    }
+    // feed(), image by image in index order
+    for (int k = 0; k < cv->n; k++) {
+        const ChipDesc& d = cv->desc[k];
+        if (!d.keep) continue;
+        const Roi r = feed_roi(d.beg_x, d.beg_y, d.chip_w, d.chip_h, ws->W, ws->H, nb);
+        int pw[kMaxBands + 1], ph[kMaxBands + 1];
+        pw[0] = r.width; ph[0] = r.height;
+        {
+            dim3 grid((r.width + 255) / 256, r.height);
+            k7_feed_level0<<<grid, 256, 0, ctx->stream>>>(d.chip, d.chip_step, d.mask, d.mask_step, d.chip_w, d.chip_h, r.left, r.top,
+                                                           r.width, r.height, ws->pyr[0], ws->wp[0]);
+            UAVM_CHECK_LAUNCH(ctx);
+        }
+        for (int i = 0; i < nb; i++) {
+            pw[i + 1] = (pw[i] + 1) / 2; ph[i + 1] = (ph[i] + 1) / 2;
+            dim3 grid((pw[i + 1] + 255) / 256, ph[i + 1]);
+            k7_pyrdown<<<grid, 256, 0, ctx->stream>>>(ws->pyr[i], ws->wp[i], pw[i], ph[i], ws->pyr[i + 1], ws->wp[i + 1], pw[i + 1], ph[i + 1]);
+            UAVM_CHECK_LAUNCH(ctx);
+        }
+        int x_tl = r.tlx, y_tl = r.tly;
+        for (int i = 0; i <= nb; i++) {
+            dim3 grid((pw[i] + 255) / 256, ph[i]);
+            k7_lap_accumulate<<<grid, 256, 0, ctx->stream>>>(ws->pyr[i], i < nb ? ws->pyr[i + 1] : nullptr, ws->wp[i], pw[i], ph[i],
+                                                              i < nb ? pw[i + 1] : 0, i < nb ? ph[i + 1] : 0, ws->dlap[i], ws->dw[i], ws->lw[i], x_tl, y_tl);
+            UAVM_CHECK_LAUNCH(ctx);
+            x_tl /= 2; y_tl /= 2;
+        }
+    }
+    // blend(): normalise every level, collapse from the top, crop + mask + convertTo(CV_8U)
+    for (int i = 0; i <= nb; i++) {
+        const size_t px = (size_t)ws->lw[i] * ws->lh[i];
+        k7_normalize<<<(unsigned)((px + 255) / 256), 256, 0, ctx->stream>>>(ws->dlap[i], ws->dw[i], px);
+        UAVM_CHECK_LAUNCH(ctx);
+    }
+    for (int i = nb; i > 0; i--) {
+        dim3 grid((ws->lw[i - 1] + 255) / 256, ws->lh[i - 1]);
+        k7_collapse<<<grid, 256, 0, ctx->stream>>>(ws->dlap[i], ws->lw[i], ws->lh[i], ws->dlap[i - 1], ws->lw[i - 1], ws->lh[i - 1]);
+        UAVM_CHECK_LAUNCH(ctx);
+    }
+    {
+        dim3 grid((cw + 255) / 256, ch);
+        k7_output<<<grid, 256, 0, ctx->stream>>>(ws->dlap[0], ws->dw[0], ws->W, cw, ch, cv->d_result, cv->d_result_mask);
+        UAVM_CHECK_LAUNCH(ctx);
+    }
+    cv->blended = true;
+    return UAVM_OK;
 }
+
 extern "C" int uavm_canvas_paste(uavm_ctx* ctx, uavm_canvas* cv)
 {
     (void)cv;
     UAVM_SET_ERR(ctx, "uavm_canvas_paste: not implemented yet");
     return UAVM_EFAIL;
 }
+
 extern "C" int uavm_canvas_get_result(uavm_ctx* ctx, uavm_canvas* cv, uint8_t* bgr, int step, uint8_t* mask, int mask_step)
 {
-    (void)cv; (void)bgr; (void)step; (void)mask; (void)mask_step;
-    UAVM_SET_ERR(ctx, "uavm_canvas_get_result: not implemented yet");
-    return UAVM_EFAIL;
+    if (!ctx || !cv) return UAVM_EINVAL;
+    if (!cv->blended || !cv->d_result) { UAVM_SET_ERR(ctx, "get_result before blend"); return UAVM_EINVAL; }
+    const int cw = cv->layout.canvas_w, ch = cv->layout.canvas_h;
+    if (bgr) {
+        if (step < cw * 3) return UAVM_EINVAL;
+        UAVM_CUDA(ctx, cudaMemcpy2DAsync(bgr, (size_t)step, cv->d_result, (size_t)cw * 3, (size_t)cw * 3, ch, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    if (mask) {
+        if (mask_step < cw) return UAVM_EINVAL;
+        UAVM_CUDA(ctx, cudaMemcpy2DAsync(mask, (size_t)mask_step, cv->d_result_mask, (size_t)cw, (size_t)cw, ch, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    UAVM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return UAVM_OK;
 }

@@ -213,3 +213,40 @@ def ref_seam_masks(masks, chips_valid, canvas_w, canvas_h):
     tl = np.array([[c.beg_x, c.beg_y] for c in chips_valid], np.int32)
     ref().ref_find_masks(ptrs, _p(steps, i32p), _p(cw, i32p), _p(chh, i32p), _p(quads, f32p), _p(tl, i32p), n, canvas_w, canvas_h)
     return ms
+
+
+# ---- K7: multi-band blend ---------------------------------------------------------------------------
+def pyr_down_s16(a):
+    a = np.ascontiguousarray(a, np.int16); h, w = a.shape[:2]; ch = 1 if a.ndim == 2 else a.shape[2]
+    out = np.zeros(((h + 1) // 2, (w + 1) // 2) + (() if a.ndim == 2 else (ch,)), np.int16)
+    lib().orc_pyr_down_s16(_p(a, i16p), w, h, ch, _p(out, i16p))
+    return out
+
+
+def pyr_up_s16(a):
+    a = np.ascontiguousarray(a, np.int16); h, w = a.shape[:2]; ch = 1 if a.ndim == 2 else a.shape[2]
+    out = np.zeros((2 * h, 2 * w) + (() if a.ndim == 2 else (ch,)), np.int16)
+    lib().orc_pyr_up_s16(_p(a, i16p), w, h, ch, _p(out, i16p), 2 * w, 2 * h)
+    return out
+
+
+def pyr_down_f32(a):
+    a = np.ascontiguousarray(a, np.float32); h, w = a.shape
+    out = np.zeros(((h + 1) // 2, (w + 1) // 2), np.float32)
+    lib().orc_pyr_down_f32(_p(a, f32p), w, h, _p(out, f32p))
+    return out
+
+
+def multiband_blend(chips_u8, masks, tls, canvas_w, canvas_h, num_bands=5):
+    """chips_u8: list of (h,w,3) u8 (converted to int16 like Mat::convertTo(CV_16S)); masks: list of (h,w) u8;
+    tls: list of (x, y).  Returns (canvas u8 (H,W,3), mask u8 (H,W))."""
+    n = len(chips_u8)
+    c16 = [np.ascontiguousarray(c, np.uint8).astype(np.int16) for c in chips_u8]
+    ms = [np.ascontiguousarray(m, np.uint8) for m in masks]
+    cp = (i16p * n)(*[_p(c, i16p) for c in c16]); mp = (u8p * n)(*[_p(m, u8p) for m in ms])
+    tx = np.array([t[0] for t in tls], np.int32); ty = np.array([t[1] for t in tls], np.int32)
+    cw = np.array([c.shape[1] for c in c16], np.int32); chh = np.array([c.shape[0] for c in c16], np.int32)
+    out = np.zeros((canvas_h, canvas_w, 3), np.uint8); om = np.zeros((canvas_h, canvas_w), np.uint8)
+    lib().orc_multiband_blend(cp, mp, _p(tx, i32p), _p(ty, i32p), _p(cw, i32p), _p(chh, i32p), n, canvas_w, canvas_h,
+                              num_bands, _p(out, u8p), _p(om, u8p))
+    return out, om

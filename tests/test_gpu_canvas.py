@@ -80,3 +80,40 @@ def test_warp_skip_flags_and_full_frame(ctx, oracle):
         px, mask = cv.chip(k)
         o_px, o_mask = oracle.warp_chip(img, o_canvas, o_chips[k])
         assert np.array_equal(mask, o_mask) and np.array_equal(px, o_px)
+
+
+@pytest.mark.parametrize("w,h,n,bands", [(320, 240, 3, 5), (500, 375, 4, 5), (257, 190, 2, 3), (640, 480, 5, 5)])
+def test_multiband_blend_parity(ctx, oracle, w, h, n, bands):
+    """K7 against the oracle's restatement of MultiBandBlender (bit-exact) and against the cv2 4.13 blender
+    (proxy for the reference's OpenCV 2.4.0 binary: +-1 LSB, flips caused by last-ulp differences of OpenCV's
+    SIMD f32 pyrDown of the weight maps; the flip rate is asserted below 2 %)."""
+    rng = np.random.default_rng(w + n)
+    H = _transforms(rng, n, w, h, False)
+    imgs = [synth.texture_image(rng, w, h, 5) for _ in range(n)]
+    cv = api.Canvas(ctx, H, w, h)
+    for k in range(n):
+        cv.set_image(k, imgs[k])
+    cv.warp(); cv.seam_masks(); cv.blend(bands)
+    out, om = cv.result()
+    o_canvas, o_chips = oracle.canvas_layout(H, None, w, h)
+    chips, masks = [], []
+    for k in range(n):
+        px, m = oracle.warp_chip(imgs[k], o_canvas, o_chips[k]); chips.append(px); masks.append(m)
+    seam = oracle.seam_masks(masks, [o_chips[k] for k in range(n)], o_canvas.canvas_w, o_canvas.canvas_h)
+    tls = [(o_chips[k].beg_x, o_chips[k].beg_y) for k in range(n)]
+    o_out, o_om = oracle.multiband_blend(chips, seam, tls, o_canvas.canvas_w, o_canvas.canvas_h, bands)
+    assert np.array_equal(om, o_om)
+    assert np.array_equal(out, o_out), f"{(out != o_out).sum()} differing bytes"
+    try:
+        import cv2
+    except Exception:
+        return
+    b = cv2.detail_MultiBandBlender(0, bands)
+    b.prepare((0, 0, o_canvas.canvas_w, o_canvas.canvas_h))
+    for k in range(n):
+        b.feed(chips[k].astype(np.int16), seam[k], tls[k])
+    rs, rm = b.blend(None, None)
+    r8 = np.clip(rs, 0, 255).astype(np.uint8)
+    d = np.abs(out.astype(np.int32) - r8.astype(np.int32))
+    assert np.array_equal(om, rm)
+    assert d.max() <= 1 and (d > 0).mean() < 0.02
