@@ -291,8 +291,10 @@ class Canvas:
         return px, mask
 
     def result(self):
-        out = np.zeros((self.layout.canvas_h, self.layout.canvas_w, 3), np.uint8)
-        mask = np.zeros((self.layout.canvas_h, self.layout.canvas_w), np.uint8)
+        rw = C.c_int(0); rh = C.c_int(0)
+        self.ctx.check(L.lib().uavm_canvas_result_size(self._h, C.byref(rw), C.byref(rh)))
+        out = np.zeros((rh.value, rw.value, 3), np.uint8)
+        mask = np.zeros((rh.value, rw.value), np.uint8)
         self.ctx.check(L.lib().uavm_canvas_get_result(self.ctx._h, self._h, _ptr(out, u8p), out.strides[0],
                                                       _ptr(mask, u8p), mask.strides[0]))
         return out, mask
@@ -307,3 +309,31 @@ class Canvas:
             self.close()
         except Exception:
             pass
+
+
+def mosaic_images(ctx, images, descs, kps, param=None, scale=1.0):
+    """MosaicVavImages-shaped entry (uavm_mosaic_images): images = list of (h,w,3) u8 BGR frames, descs = list of
+    (n_i,128) f32/u8 descriptors, kps = list of (n_i,2) f32.  Returns (mosaic u8 (H,W,3), transforms (n,9) f32, fixed (n,))."""
+    n = len(images)
+    ims = [np.ascontiguousarray(i, np.uint8) for i in images]
+    ds = [np.ascontiguousarray(d, np.float32) for d in descs]
+    ks = [np.ascontiguousarray(k, np.float32) for k in kps]
+    arr = (L.Image * n)()
+    for i, im in enumerate(ims):
+        arr[i].width, arr[i].height, arr[i].nChannels, arr[i].widthStep = im.shape[1], im.shape[0], 3, im.strides[0]
+        arr[i].imageData = im.ctypes.data
+    dp = (f32p * n)(*[_ptr(d, f32p) for d in ds]); kp = (f32p * n)(*[_ptr(k, f32p) for k in ks])
+    nk = np.array([len(d) for d in ds], np.int32)
+    P = L.Param()
+    L.lib().uavm_param_default(C.byref(P))
+    for k, v in (param or {}).items():
+        setattr(P, k, v)
+    res = L.Image(); nm = C.c_int(0); tr = (ImageTransform * n)()
+    rc = L.lib().uavm_mosaic_images(ctx._h, arr, n, dp, kp, _ptr(nk, i32p), C.byref(P), C.c_float(scale), C.byref(res), C.byref(nm), tr)
+    ctx.check(rc)
+    buf = (C.c_uint8 * (res.widthStep * res.height)).from_address(res.imageData)
+    out = np.frombuffer(buf, np.uint8).reshape(res.height, res.widthStep)[:, :res.width * 3].reshape(res.height, res.width, 3).copy()
+    L.lib().uavm_free(C.c_void_p(res.imageData))
+    T = np.array([[tr[i].h.m[t] for t in range(9)] for i in range(n)], np.float32)
+    fixed = np.array([tr[i].fixed for i in range(n)], np.int32)
+    return out, T, fixed

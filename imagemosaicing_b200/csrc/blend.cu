@@ -245,10 +245,12 @@ extern "C" int uavm_canvas_blend(uavm_ctx* ctx, uavm_canvas* cv, int num_bands)
             UAVM_CUDA(ctx, cudaMalloc(&ws->pyr[i], (cap + 16) * 3 * sizeof(short)));
             UAVM_CUDA(ctx, cudaMalloc(&ws->wp[i], (cap + 16) * sizeof(float)));
         }
-        if (!cv->d_result) {
-            UAVM_CUDA(ctx, cudaMalloc(&cv->d_result, (size_t)cw * ch * 3));
-            UAVM_CUDA(ctx, cudaMalloc(&cv->d_result_mask, (size_t)cw * ch));
-        }
+    }
+    if (cv->result_w != cw || cv->result_h != ch) {
+        cudaFree(cv->d_result); cudaFree(cv->d_result_mask); cv->d_result = nullptr; cv->d_result_mask = nullptr;
+        UAVM_CUDA(ctx, cudaMalloc(&cv->d_result, (size_t)cw * ch * 3));
+        UAVM_CUDA(ctx, cudaMalloc(&cv->d_result_mask, (size_t)cw * ch));
+        cv->result_w = cw; cv->result_h = ch;
     }
     for (int i = 0; i <= nb; i++) {
         const size_t px = (size_t)ws->lw[i] * ws->lh[i];
@@ -303,18 +305,11 @@ extern "C" int uavm_canvas_blend(uavm_ctx* ctx, uavm_canvas* cv, int num_bands)
     return UAVM_OK;
 }
 
-extern "C" int uavm_canvas_paste(uavm_ctx* ctx, uavm_canvas* cv)
-{
-    (void)cv;
-    UAVM_SET_ERR(ctx, "uavm_canvas_paste: not implemented yet");
-    return UAVM_EFAIL;
-}
-
 extern "C" int uavm_canvas_get_result(uavm_ctx* ctx, uavm_canvas* cv, uint8_t* bgr, int step, uint8_t* mask, int mask_step)
 {
     if (!ctx || !cv) return UAVM_EINVAL;
     if (!cv->blended || !cv->d_result) { UAVM_SET_ERR(ctx, "get_result before blend"); return UAVM_EINVAL; }
-    const int cw = cv->layout.canvas_w, ch = cv->layout.canvas_h;
+    const int cw = cv->result_w, ch = cv->result_h;
     if (bgr) {
         if (step < cw * 3) return UAVM_EINVAL;
         UAVM_CUDA(ctx, cudaMemcpy2DAsync(bgr, (size_t)step, cv->d_result, (size_t)cw * 3, (size_t)cw * 3, ch, cudaMemcpyDeviceToHost, ctx->stream));
@@ -324,5 +319,12 @@ extern "C" int uavm_canvas_get_result(uavm_ctx* ctx, uavm_canvas* cv, uint8_t* b
         UAVM_CUDA(ctx, cudaMemcpy2DAsync(mask, (size_t)mask_step, cv->d_result_mask, (size_t)cw, (size_t)cw, ch, cudaMemcpyDeviceToHost, ctx->stream));
     }
     UAVM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return UAVM_OK;
+}
+
+extern "C" int uavm_canvas_result_size(uavm_canvas* cv, int* w, int* h)
+{
+    if (!cv || !w || !h) return UAVM_EINVAL;
+    *w = cv->result_w; *h = cv->result_h;
     return UAVM_OK;
 }

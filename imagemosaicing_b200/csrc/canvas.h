@@ -38,6 +38,7 @@ struct uavm_canvas {
     // result canvas (K7 / paste)
     uint8_t* d_result = nullptr;     // canvas_h x canvas_w x 3
     uint8_t* d_result_mask = nullptr;
+    int result_w = 0, result_h = 0;  // size of d_result (blend: canvas layout; paste: MosaicImagesRefined's own bbox)
     bool warped = false, seamed = false, blended = false;
     void* blend_ws = nullptr;        // opaque workspace owned by blend.cu
 };

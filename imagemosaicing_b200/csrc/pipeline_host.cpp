@@ -1,16 +1,112 @@
 // pipeline_host.cpp — uavm_mosaic_images: the MosaicVavImages-shaped shim (M/MosaicWithoutPos.cpp:10148-10214
 // -> CMosaicByPose::MosaicWithoutPose :4430-4679) composing the stage entry points of this library.
+// SIFT extraction (SiftExtraction_Thread, :4832-4887) is upstream of this library: the caller passes the
+// descriptors and keypoints it extracted.
+#include <stdlib.h>
 #include <string.h>
 #include <vector>
 #include "internal.h"
 
 extern "C" int uavm_mosaic_images(uavm_ctx* ctx, const uavm_image* images, int n_images,
                                   const float* const* desc, const float* const* kp_xy, const int32_t* n_kp,
-                                  const uavm_param* param, float scale,
+                                  const uavm_param* param_in, float scale,
                                   uavm_image* result, int* num_mosaiced, uavm_imagetransform* transforms_out)
 {
-    (void)images; (void)n_images; (void)desc; (void)kp_xy; (void)n_kp; (void)param; (void)scale; (void)result;
-    (void)num_mosaiced; (void)transforms_out;
-    UAVM_SET_ERR(ctx, "uavm_mosaic_images: not implemented yet");
-    return UAVM_EFAIL;
+    // argument checks of MosaicVavImages (:10157-10165): -1 on invalid input
+    if (!ctx || !images || n_images < 2 || !desc || !kp_xy || !n_kp || !result) return UAVM_EINVAL;
+    memset(result, 0, sizeof(*result));
+    uavm_param P;
+    if (param_in) P = *param_in; else uavm_param_default(&P);
+    const int w = images[0].width, h = images[0].height;              // size taken from image 0 (:10185-10186)
+    for (int i = 0; i < n_images; i++) {
+        if (!images[i].imageData || images[i].nChannels != 3 || images[i].width != w || images[i].height != h ||
+            images[i].widthStep < 3 * w || n_kp[i] < 0 || (n_kp[i] > 0 && (!desc[i] || !kp_xy[i]))) return UAVM_EINVAL;
+    }
+    if (num_mosaiced) *num_mosaiced = 0;
+
+    // ---- [A] feature matching: GetMatchedPairsOneToAllSIFT_MultiThread (:5244) ----
+    uavm_featureset* fs = nullptr; uavm_pairbatch* pb = nullptr; uavm_canvas* cv = nullptr;
+    int rc = uavm_featureset_create(ctx, n_images, n_kp, &fs);
+    for (int i = 0; rc == UAVM_OK && i < n_images; i++) rc = uavm_featureset_upload_f32(ctx, fs, i, desc[i], kp_xy[i], 0);
+    std::vector<int32_t> pair_ij;
+    for (int i = 0; i < n_images; i++)                                // j in (i, min(n, i + 182)) (:5083-5084)
+        for (int j = i + 1; j < n_images && j < i + P.pairWindow; j++) { pair_ij.push_back(i); pair_ij.push_back(j); }
+    const int n_pairs = (int)pair_ij.size() / 2;
+    std::vector<uavm_matchpointpairs> matches;
+    if (rc == UAVM_OK && n_pairs > 0) {
+        rc = uavm_pairbatch_create(ctx, fs, n_pairs, pair_ij.data(), &pb);
+        if (rc == UAVM_OK) rc = uavm_pairbatch_match(ctx, pb);
+        if (rc == UAVM_OK) rc = uavm_pairbatch_select(ctx, pb, w, h, P.gridX, P.gridY, P.maxNum, (double)P.matchFrac);
+        if (rc == UAVM_OK) rc = uavm_pairbatch_ransac(ctx, pb, P.ransacDist, P.sampleTimes, nullptr, P.seed);
+        int n_m = 0, n_acc = 0;
+        if (rc == UAVM_OK) rc = uavm_pairbatch_collect(ctx, pb, P.minInnerPoints, nullptr, 0, &n_m, &n_acc);
+        if (rc == UAVM_OK && n_m > 0) {
+            matches.resize(n_m);
+            rc = uavm_pairbatch_collect(ctx, pb, P.minInnerPoints, matches.data(), n_m, &n_m, &n_acc);
+        }
+    }
+    uavm_pairbatch_destroy(ctx, pb);
+    uavm_featureset_destroy(ctx, fs);
+    if (rc != UAVM_OK) return UAVM_EFAIL;
+
+    // ---- [B] largest connected component, reference image 0 fixed (:4501-4571) ----
+    std::vector<int32_t> label(n_images, 0);
+    if (!matches.empty()) uavm_connected_images(matches.data(), (int)matches.size(), n_images, label.data());
+    for (size_t m = 0; m < matches.size();) {                          // same removal order as the reference (:4512-4523)
+        if (label[matches[m].ptA_i] == 0 || label[matches[m].ptB_i] == 0) { matches[m] = matches.back(); matches.pop_back(); }
+        else m++;
+    }
+    const int ref = 0;
+    std::vector<uavm_imagetransform> init(n_images), refined(n_images);
+    for (int i = 0; i < n_images; i++) {
+        memset(&init[i], 0, sizeof(init[i]));
+        init[i].h.m[0] = init[i].h.m[4] = init[i].h.m[8] = 1.0f;
+    }
+    for (size_t m = 0; m < matches.size(); m++) {
+        if (matches[m].ptA_i == ref) matches[m].ptA_Fixed = 1;
+        if (matches[m].ptB_i == ref) matches[m].ptB_Fixed = 1;
+    }
+    int n_fixed = 0;
+    for (int i = 0; i < n_images; i++) if (label[i] == 0) { init[i].fixed = 1; n_fixed++; }
+    if (init[ref].fixed == 0) { init[ref].fixed = 1; n_fixed++; }
+    else if (!matches.empty()) { UAVM_SET_ERR(ctx, "reference image 0 is not in the largest connected component"); return UAVM_EFAIL; }
+    if (num_mosaiced) *num_mosaiced = n_images;                        // numMosaiced = nImages (:4621)
+    if (matches.empty()) { UAVM_SET_ERR(ctx, "no image pair was accepted"); return UAVM_EFAIL; }
+
+    // ---- [C] global affine alignment: BundleAdjustmentSparse (:4591) ----
+    rc = uavm_align_affine(matches.data(), (int)matches.size(), init.data(), n_images, n_fixed, refined.data());
+    if (rc != UAVM_OK) { UAVM_SET_ERR(ctx, "global alignment failed (%d)", rc); return UAVM_EFAIL; }
+    for (int i = 0; i < n_images; i++) if (label[i] == 0) refined[i].h.m[8] = 0;          // "skip me" (:4646-4652)
+    if (transforms_out) memcpy(transforms_out, refined.data(), sizeof(uavm_imagetransform) * n_images);
+
+    // ---- [D] warp + blend: MergeImagesRefined -> LaplacianPyramidBlending(band = 5, scale) (:4663, :2180) ----
+    std::vector<float> H((size_t)n_images * 9);
+    for (int i = 0; i < n_images; i++) {
+        memcpy(&H[(size_t)i * 9], refined[i].h.m, 36);
+        for (int j = 0; j < 6; j++) H[(size_t)i * 9 + j] *= scale;                         // pImgT[i].m[j] *= scale (M/MosaicImage.cpp:2216-2223)
+    }
+    std::vector<int32_t> keep(n_images, 1);
+    if (P.blending == 2) uavm_resample_by_overlap(H.data(), n_images, w, h, P.overlapT, keep.data());
+    rc = uavm_canvas_create(ctx, n_images, w, h, H.data(), keep.data(), &cv);
+    for (int i = 0; rc == UAVM_OK && i < n_images; i++)
+        if (keep[i] && H[(size_t)i * 9 + 8] != 0) rc = uavm_canvas_set_image(ctx, cv, i, images[i].imageData, images[i].widthStep, 0);
+    if (rc == UAVM_OK) rc = uavm_canvas_warp(ctx, cv);
+    if (rc == UAVM_OK) {
+        if (P.blending == 2) {
+            rc = uavm_canvas_seam_masks(ctx, cv);
+            if (rc == UAVM_OK) rc = uavm_canvas_blend(ctx, cv, P.numBands);
+        } else rc = uavm_canvas_paste(ctx, cv);
+    }
+    if (rc == UAVM_OK) {
+        int rw = 0, rh = 0;
+        uavm_canvas_result_size(cv, &rw, &rh);
+        result->width = rw; result->height = rh; result->nChannels = 3;
+        result->widthStep = (rw * 3 + 3) & ~3;                                             // IplImage row alignment
+        result->imageData = (uint8_t*)calloc((size_t)result->widthStep * result->height, 1);
+        if (!result->imageData) rc = UAVM_EFAIL;
+        else rc = uavm_canvas_get_result(ctx, cv, result->imageData, result->widthStep, nullptr, 0);
+        if (rc != UAVM_OK) { free(result->imageData); memset(result, 0, sizeof(*result)); }
+    }
+    uavm_canvas_destroy(ctx, cv);
+    return rc == UAVM_OK ? UAVM_OK : UAVM_EFAIL;                        // -2: mosaic failed (:4675-4676)
 }

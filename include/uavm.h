@@ -149,6 +149,7 @@ int uavm_canvas_blend(uavm_ctx* ctx, uavm_canvas* cv, int num_bands);
 int uavm_canvas_paste(uavm_ctx* ctx, uavm_canvas* cv);
 /* copies -> host */
 int uavm_canvas_get_chip(uavm_ctx* ctx, uavm_canvas* cv, int image, uint8_t* chip_bgr, int chip_step, uint8_t* mask, int mask_step);
+int uavm_canvas_result_size(uavm_canvas* cv, int* w, int* h);   /* size of the blended / pasted result */
 int uavm_canvas_get_result(uavm_ctx* ctx, uavm_canvas* cv, uint8_t* bgr, int step, uint8_t* mask, int mask_step);
 
 /* ---- top-level shim with the shape of MosaicVavImages (M/MosaicWithoutPos.h:638-645,

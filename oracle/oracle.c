@@ -667,4 +667,76 @@ int orc_seam_masks(uint8_t** masks, const int32_t* mask_step, const orc_chip_lay
     return 0;
 }
 
+/* ------------------------------------------------------------------------------------------ */
+/* MosaicImagesRefined (M/MosaicWithoutPos.cpp:2194-2352): no blending, images pasted in index order */
+/* ------------------------------------------------------------------------------------------ */
+static void apply_project9(const float* h, float x, float y, float* xd, float* yd)
+{   /* ApplyProject9 (M/MosaicWithoutPos.h:331-336): division form with h[8] */
+    *xd = (h[0] * x + h[1] * y + h[2]) / (h[6] * x + h[7] * y + h[8]);
+    *yd = (h[3] * x + h[4] * y + h[5]) / (h[6] * x + h[7] * y + h[8]);
+}
+int orc_paste(const float* H, int n, int img_w, int img_h, const uint8_t** srcs, int src_step,
+              int* out_w, int* out_h, uint8_t* out, int out_step)
+{
+    float minX = (float)(1 << 29), minY = (float)(1 << 29), maxX = (float)(-1 << 29), maxY = (float)(-1 << 29);
+    float cx[4] = {0, (float)(img_w - 1), (float)(img_w - 1), 0}, cy[4] = {0, 0, (float)(img_h - 1), (float)(img_h - 1)};
+    for (int k = 0; k < n; k++) {
+        const float* m = H + (size_t)k * 9;
+        if (m[8] == 0) continue;
+        for (int i = 0; i < 4; i++) {
+            float bx, by;
+            apply_project9(m, cx[i], cy[i], &bx, &by);
+            if (bx < minX) minX = bx;
+            if (bx > maxX) maxX = bx;
+            if (by < minY) minY = by;
+            if (by > maxY) maxY = by;
+        }
+    }
+    int W = (int)(maxX - minX + 1.5f), Hh = (int)(maxY - minY + 1.5f);
+    *out_w = W; *out_h = Hh;
+    if (!out) return 0;
+    for (int y = 0; y < Hh; y++) memset(out + (size_t)y * out_step, 0, (size_t)W * 3);
+    float dgx = -minX, dgy = -minY;
+    int w1 = img_w - 1, h1 = img_h - 1;
+    for (int k = 0; k < n; k++) {
+        const float* m = H + (size_t)k * 9;
+        if (m[8] == 0) continue;
+        float inv[9]; memset(inv, 0, sizeof(inv));
+        orc_inverse_matrix(m, 3, inv, 1e-12f);
+        float bminx = (float)(1 << 29), bminy = (float)(1 << 29), bmaxx = (float)(-1 << 29), bmaxy = (float)(-1 << 29);
+        for (int i = 0; i < 4; i++) {
+            float bx, by;
+            apply_project9(m, cx[i], cy[i], &bx, &by);
+            bx += (0 + dgx); by += (0 + dgy);
+            if (bx < bminx) bminx = bx;
+            if (bx > bmaxx) bmaxx = bx;
+            if (by < bminy) bminy = by;
+            if (by > bmaxy) bmaxy = by;
+        }
+        int begY = (int)(bminy - 0.5f), endY = (int)(bmaxy + 0.5f), begX = (int)(bminx - 0.5f), endX = (int)(bmaxx + 0.5f);
+        const uint8_t* src = srcs[k];
+        for (int yd = begY; yd <= endY; yd++) {
+            if (yd < 0 || yd >= Hh) continue;                     /* the reference would write out of bounds */
+            uint8_t* row = out + (size_t)yd * out_step;
+            for (int xd = begX; xd <= endX; xd++) {
+                if (xd < 0 || xd >= W) continue;
+                float xm = xd - 0 - dgx, ym = yd - 0 - dgy;
+                float xs, ys;
+                apply_project9(inv, xm, ym, &xs, &ys);
+                int ix = (int)xs, iy = (int)ys;
+                float p = ys - iy, q = xs - ix;
+                if ((ys < 0) || (ys >= h1)) continue;
+                if ((xs < 0) || (xs >= w1)) continue;
+                const uint8_t* t = src + (size_t)iy * src_step + 3 * ix;
+                for (int c = 0; c < 3; c++) {
+                    int g1 = t[c], g2 = t[c + 3], g3 = t[c + src_step], g4 = t[c + src_step + 3];
+                    float v = g1 * (1 - p) * (1 - q) + g2 * (1 - p) * q + g3 * p * (1 - q) + g4 * p * q;
+                    row[3 * xd + c] = (uint8_t)(int)v;
+                }
+            }
+        }
+    }
+    return 0;
+}
+
 /* K7 (multi-band blend) lives in oracle_blend.c */

@@ -8,12 +8,13 @@
  * Parity pinning:
  *   - orc_ransac2d and its sub-functions are pinned bit-for-bit against the reference's own
  *     Ransac2D/SolveHomographyMatrix/NonlinearLeastSquareProjection2/InverseMatrix compiled in
- *     place from /root/reference (oracle/_ref/libref_ransac.so, tests/test_oracle_vs_ref.py).
+ *     place from /root/reference (oracle/_ref/libref_ransac.so, tests/test_cpu_oracle.py).
  *   - orc_align is pinned by the reference's golden fixtures matchPairs.txt -> tran0.txt.
  *   - orc_match_l2 is pinned against cv2.BFMatcher(NORM_L2) (the reference's FLANN matcher is
  *     approximate + randomised: parity for FLANN itself is UNPINNED, contract = exact 1-NN).
- *   - orc_warp_chip / orc_seam_masks restate in-repo reference loops; no reference fixture
- *     holds a mosaic image, so they are pinned only by code reading: PARITY UNPINNED.
+ *   - orc_warp_chip / orc_seam_masks / the overlap filter are pinned byte-for-byte against the
+ *     reference's own loops (M/MosaicImage.cpp:2350-2448, :1761-1881, :2070-2201) compiled in place
+ *     (oracle/_ref) and against golden vectors generated from them (tests/golden/*.npz).
  *   - orc_multiband_blend restates OpenCV's detail::MultiBandBlender (third-party, not under
  *     /root/reference; version 2.4.0 per Readme.md:7); pinned against cv2 4.13's blender.
  *
@@ -100,6 +101,11 @@ int orc_canvas_layout_compute(const float* H, const int32_t* keep_in, int n, int
 void orc_warp_chip(const uint8_t* src, int img_w, int img_h, int src_step,
                    const orc_canvas_layout* canvas, const orc_chip_layout* chip,
                    uint8_t* chip_px, int chip_step, uint8_t* mask, int mask_step);
+
+/* blending != 2 variant: MosaicImagesRefined (M/MosaicWithoutPos.cpp:2194-2352), last image wins.
+ * H: n x 9; srcs[n]: img_h x src_step BGR frames.  First call with out == NULL returns the canvas size. */
+int orc_paste(const float* H, int n, int img_w, int img_h, const uint8_t** srcs, int src_step,
+              int* out_w, int* out_h, uint8_t* out, int out_step);
 
 /* ---------------- K6: distance-map seam masks (M/MosaicImage.cpp:1761-1881) ----------------- */
 /* masks[n]: chip_h x mask_step[n] u8, in/out. */

@@ -250,3 +250,16 @@ def multiband_blend(chips_u8, masks, tls, canvas_w, canvas_h, num_bands=5):
     lib().orc_multiband_blend(cp, mp, _p(tx, i32p), _p(ty, i32p), _p(cw, i32p), _p(chh, i32p), n, canvas_w, canvas_h,
                               num_bands, _p(out, u8p), _p(om, u8p))
     return out, om
+
+
+def paste(H, imgs):
+    """MosaicImagesRefined (blending != 2): returns the canvas (h, w, 3) u8."""
+    H = _f32(H).reshape(-1, 9); n = len(H)
+    ims = [np.ascontiguousarray(i, np.uint8) for i in imgs]
+    h, w = ims[0].shape[:2]
+    ptrs = (u8p * n)(*[_p(i, u8p) for i in ims])
+    ow = C.c_int(0); oh = C.c_int(0)
+    lib().orc_paste(_p(H, f32p), n, w, h, ptrs, ims[0].strides[0], C.byref(ow), C.byref(oh), None, 0)
+    out = np.zeros((oh.value, ow.value, 3), np.uint8)
+    lib().orc_paste(_p(H, f32p), n, w, h, ptrs, ims[0].strides[0], C.byref(ow), C.byref(oh), _p(out, u8p), out.strides[0])
+    return out
