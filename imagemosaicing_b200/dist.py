@@ -1,0 +1,47 @@
+"""Multi-GPU plumbing for the pair stage: image pairs are independent units, so ranks take
+disjoint slices of the pair list with NO data-path collective; one gather of the (small) per-pair inlier
+records at the end gives every rank the full MatchPointPairs list, after which the global alignment runs
+identically on every rank ("replicas only").  Works with torch.distributed backends nccl (GPU tensors) and
+gloo (CPU tests)."""
+import numpy as np
+
+MPP_DTYPE = np.dtype([("xa", "<f4"), ("ya", "<f4"), ("ida", "<i4"), ("ia", "<i4"), ("fa", "<i4"),
+                      ("xb", "<f4"), ("yb", "<f4"), ("idb", "<i4"), ("ib", "<i4"), ("fb", "<i4")])   # 40-byte MatchPointPairs
+
+
+def reference_pair_list(n_images, window=182):
+    """j in (i, min(n, i + window)) — the reference's candidate rule (M/MosaicWithoutPos.cpp:5083-5084)."""
+    return np.array([(i, j) for i in range(n_images) for j in range(i + 1, min(n_images, i + window))], np.int32).reshape(-1, 2)
+
+
+def shard_pairs(n_pairs, rank, world):
+    """Round-robin shard: pair p belongs to rank p % world.  Returns the global pair indices of this rank."""
+    return np.arange(rank, n_pairs, world, dtype=np.int64)
+
+
+def gather_match_pairs(local_records, local_pair_ids, n_pairs, group=None, device=None):
+    """local_records: list (one per local pair, aligned with local_pair_ids) of MPP_DTYPE arrays (possibly empty).
+    Returns the concatenation over ALL pairs in global pair order — identical on every rank and identical to
+    what a single process produces."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    counts = torch.zeros(n_pairs, dtype=torch.int64)
+    for pid, rec in zip(local_pair_ids, local_records):
+        counts[int(pid)] = len(rec)
+    dev = device if device is not None else torch.device("cpu")
+    counts = counts.to(dev)
+    if world > 1:
+        dist.all_reduce(counts, op=dist.ReduceOp.SUM, group=group)
+    counts = counts.cpu().numpy()
+    offsets = np.concatenate([[0], np.cumsum(counts)])
+    total = int(offsets[-1])
+    buf = np.zeros(total, MPP_DTYPE)
+    for pid, rec in zip(local_pair_ids, local_records):
+        buf[offsets[int(pid)]:offsets[int(pid) + 1]] = rec
+    if world > 1 and total > 0:
+        # every slot is written by exactly one rank and zero elsewhere: a SUM over the raw int32 words merges them
+        t = torch.from_numpy(buf.view(np.int32).copy()).to(dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+        buf = t.cpu().numpy().view(MPP_DTYPE).copy()
+    return buf

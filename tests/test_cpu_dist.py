@@ -1,0 +1,50 @@
+"""world_size-2 gloo test of the multi-GPU host logic: sharding the pair list over ranks and gathering the
+per-pair inlier records reproduces the single-process MatchPointPairs list (order and bytes)."""
+import os
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from imagemosaicing_b200 import dist as D
+
+
+def _fake_pair_records(pid, i, j):
+    rng = np.random.default_rng(1000 + pid)
+    n = int(rng.integers(0, 60))
+    rec = np.zeros(n, D.MPP_DTYPE)
+    rec["xa"] = rng.uniform(0, 4000, n); rec["ya"] = rng.uniform(0, 3000, n); rec["ida"] = rng.integers(0, 8192, n)
+    rec["xb"] = rng.uniform(0, 4000, n); rec["yb"] = rng.uniform(0, 3000, n); rec["idb"] = rng.integers(0, 8192, n)
+    rec["ia"] = i; rec["ib"] = j
+    return rec
+
+
+def _worker(rank, world, port, pairs, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    mine = D.shard_pairs(len(pairs), rank, world)
+    recs = [_fake_pair_records(int(p), *pairs[int(p)]) for p in mine]
+    full = D.gather_match_pairs(recs, mine, len(pairs))
+    np.save(os.path.join(out_dir, f"full_{rank}.npy"), full)
+    dist.destroy_process_group()
+
+
+def test_pair_sharding_and_gather_world2(tmp_path):
+    pairs = D.reference_pair_list(12, window=4)
+    assert len(pairs) == sum(min(12, i + 4) - i - 1 for i in range(12))
+    world = 2
+    shards = [D.shard_pairs(len(pairs), r, world) for r in range(world)]
+    assert sorted(np.concatenate(shards).tolist()) == list(range(len(pairs)))      # disjoint cover
+    port = 29500 + (os.getpid() % 2000)
+    mp.spawn(_worker, args=(world, port, pairs, str(tmp_path)), nprocs=world, join=True)
+    serial = np.concatenate([_fake_pair_records(p, *pairs[p]) for p in range(len(pairs))])
+    for r in range(world):
+        got = np.load(os.path.join(str(tmp_path), f"full_{r}.npy"))
+        assert got.dtype == D.MPP_DTYPE and got.itemsize == 40
+        assert np.array_equal(got.view(np.uint8), serial.view(np.uint8))
+
+
+def test_reference_pair_window():
+    p = D.reference_pair_list(200, 182)
+    assert len(p) == 19729                       # the reference rule on a 200-image block
+    assert len(D.reference_pair_list(50, 2)) == 49
