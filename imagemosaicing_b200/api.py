@@ -62,6 +62,15 @@ class Context:
     def sync(self):
         self.check(L.lib().uavm_ctx_sync(self._h))
 
+    def fork(self):
+        self.check(L.lib().uavm_ctx_fork(self._h))
+
+    def unfork(self):
+        self.check(L.lib().uavm_ctx_unfork(self._h))
+
+    def join(self):
+        self.check(L.lib().uavm_ctx_join(self._h))
+
     @property
     def launch_count(self):
         return int(L.lib().uavm_ctx_launch_count(self._h))

@@ -35,24 +35,57 @@ extern "C" int uavm_ctx_create(int device, uavm_ctx** out) {
     c->sm_count = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return UAVM_EFAIL; }
     c->own_stream = true;
+    c->main_stream = c->stream;
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);          // side stream = highest priority: its (latency-bound)
+    if (cudaStreamCreateWithPriority(&c->side_stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||   // blocks are placed first
+
+        cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_side, cudaEventDisableTiming) != cudaSuccess) { delete c; return UAVM_EFAIL; }
     *out = c;
     return UAVM_OK;
 }
 extern "C" void uavm_ctx_destroy(uavm_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->own_stream && ctx->main_stream) cudaStreamDestroy(ctx->main_stream);
+    if (ctx->side_stream) cudaStreamDestroy(ctx->side_stream);
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_side) cudaEventDestroy(ctx->ev_side);
     delete ctx;
 }
 extern "C" int uavm_ctx_set_stream(uavm_ctx* ctx, void* s) {
     if (!ctx) return UAVM_EINVAL;
-    if (ctx->own_stream && ctx->stream) { cudaStreamDestroy(ctx->stream); ctx->own_stream = false; }
-    ctx->stream = (cudaStream_t)s;
+    if (ctx->forked) return UAVM_EINVAL;
+    if (ctx->own_stream && ctx->main_stream) { cudaStreamDestroy(ctx->main_stream); ctx->own_stream = false; }
+    ctx->stream = ctx->main_stream = (cudaStream_t)s;
     return UAVM_OK;
 }
 extern "C" int uavm_ctx_sync(uavm_ctx* ctx) {
     if (!ctx) return UAVM_EINVAL;
     UAVM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->side_pending && !ctx->forked) { UAVM_CUDA(ctx, cudaStreamSynchronize(ctx->side_stream)); }
+    return UAVM_OK;
+}
+// fork / unfork / join: run independent stages of one step concurrently.  After fork() every launch of this
+// ctx goes to an internal side stream that first waits for all work queued so far; unfork() switches back to
+// the main stream without waiting; join() makes the main stream wait for the side work.
+extern "C" int uavm_ctx_fork(uavm_ctx* ctx) {
+    if (!ctx || ctx->forked) return UAVM_EINVAL;
+    UAVM_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->main_stream));
+    UAVM_CUDA(ctx, cudaStreamWaitEvent(ctx->side_stream, ctx->ev_fork, 0));
+    ctx->stream = ctx->side_stream; ctx->forked = true; ctx->side_pending = true;
+    return UAVM_OK;
+}
+extern "C" int uavm_ctx_unfork(uavm_ctx* ctx) {
+    if (!ctx || !ctx->forked) return UAVM_EINVAL;
+    UAVM_CUDA(ctx, cudaEventRecord(ctx->ev_side, ctx->side_stream));
+    ctx->stream = ctx->main_stream; ctx->forked = false;
+    return UAVM_OK;
+}
+extern "C" int uavm_ctx_join(uavm_ctx* ctx) {
+    if (!ctx || ctx->forked) return UAVM_EINVAL;
+    if (ctx->side_pending) { UAVM_CUDA(ctx, cudaStreamWaitEvent(ctx->main_stream, ctx->ev_side, 0)); ctx->side_pending = false; }
     return UAVM_OK;
 }
 extern "C" const char* uavm_last_error(const uavm_ctx* ctx) { return ctx ? ctx->err : "null context"; }

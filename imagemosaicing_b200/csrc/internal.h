@@ -11,8 +11,11 @@
 struct uavm_ctx {
     int device = 0;
     int sm_count = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;     // stream every launch of this ctx goes to (main or, between fork/unfork, side)
     bool own_stream = false;
+    cudaStream_t main_stream = nullptr, side_stream = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_side = nullptr;
+    bool forked = false, side_pending = false;
     int64_t launches = 0;
     char err[512] = {0};
 };

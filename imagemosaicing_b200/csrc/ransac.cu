@@ -475,7 +475,19 @@ int uavm_launch_ransac(uavm_ctx* ctx, uavm_pairbatch* pb, float dist, int sample
     }
     if (groups > 0) {
         dim3 grid(groups / kGroupsPerBlock, pb->n_pairs);
-        k4_ransac_eval<<<grid, kEvalThreads, 0, ctx->stream>>>(pb->d_pairs, pb->d_cand_xy1, pb->d_cand_xy2, pb->d_cand_n,
+        // Residency knob (blocks per SM, via dummy dynamic shared memory).  Measured on B200 with RANSAC on the
+        // high-priority side stream next to the warp kernel: 3 blocks/SM (no padding) gives the best step time
+        // (3.20 ms vs 3.50 at 2 and 3.53 at 1), so the default stays 3; the knob is kept for experiments.
+        size_t pad_smem = 0;
+        int bpsm = 3;
+        if (getenv("UAVM_RANSAC_EVAL_BPSM")) bpsm = atoi(getenv("UAVM_RANSAC_EVAL_BPSM"));
+        if (bpsm == 1) pad_smem = 100 * 1024; else if (bpsm == 2) pad_smem = 60 * 1024;
+        static size_t attr_smem = 0;
+        if (pad_smem > attr_smem) {
+            UAVM_CUDA(ctx, cudaFuncSetAttribute(k4_ransac_eval, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pad_smem));
+            attr_smem = pad_smem;
+        }
+        k4_ransac_eval<<<grid, kEvalThreads, pad_smem, ctx->stream>>>(pb->d_pairs, pb->d_cand_xy1, pb->d_cand_xy2, pb->d_cand_n,
                                                                thr2, groups, pb->d_tuple_res, pb->d_tuple_h);
         UAVM_CHECK_LAUNCH(ctx);
     }

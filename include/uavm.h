@@ -69,6 +69,12 @@ int uavm_ctx_create(int device, uavm_ctx** out);
 void uavm_ctx_destroy(uavm_ctx* ctx);
 int uavm_ctx_set_stream(uavm_ctx* ctx, void* cuda_stream);   /* cudaStream_t of the caller (e.g. torch's) */
 int uavm_ctx_sync(uavm_ctx* ctx);
+/* run independent stages concurrently: after fork() launches go to an internal side stream (ordered after all
+ * work queued so far); unfork() returns to the main stream without waiting; join() orders the main stream
+ * after the side work.  E.g. fork, ransac, unfork, warp, join: RANSAC (latency bound) overlaps the warp. */
+int uavm_ctx_fork(uavm_ctx* ctx);
+int uavm_ctx_unfork(uavm_ctx* ctx);
+int uavm_ctx_join(uavm_ctx* ctx);
 const char* uavm_last_error(const uavm_ctx* ctx);
 int64_t uavm_ctx_launch_count(const uavm_ctx* ctx);          /* kernels launched so far by this ctx */
 int uavm_ctx_sm_count(const uavm_ctx* ctx);

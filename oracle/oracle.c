@@ -13,6 +13,20 @@
 /* ------------------------------------------------------------------------------------------ */
 /* sample stream: MSVC rand() (the original runtime of the reference, M/mosaicimage.h:1777)    */
 /* ------------------------------------------------------------------------------------------ */
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+/* number of host threads used by the parallel loops (torchrun exports OMP_NUM_THREADS=1 by default) */
+int orc_set_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+    return omp_get_max_threads();
+#else
+    (void)n; return 1;
+#endif
+}
+
 uint32_t orc_lcg_next(uint32_t* s)
 {
     *s = *s * 214013u + 2531011u;

@@ -14,7 +14,7 @@
  *     approximate + randomised: parity for FLANN itself is UNPINNED, contract = exact 1-NN).
  *   - orc_warp_chip / orc_seam_masks / the overlap filter are pinned byte-for-byte against the
  *     reference's own loops (M/MosaicImage.cpp:2350-2448, :1761-1881, :2070-2201) compiled in place
- *     (oracle/_ref) and against golden vectors generated from them (tests/golden/*.npz).
+ *     (oracle/_ref) and against golden vectors generated from them (the .npz files under tests/golden).
  *   - orc_multiband_blend restates OpenCV's detail::MultiBandBlender (third-party, not under
  *     /root/reference; version 2.4.0 per Readme.md:7); pinned against cv2 4.13's blender.
  *
@@ -30,6 +30,7 @@ extern "C" {
 /* ---------------- sample stream (replaces srand(time(0)), M/mosaicimage.h:1777) ------------- */
 /* MSVC rand(): s = s*214013 + 2531011; return (s >> 16) & 0x7fff */
 uint32_t orc_lcg_next(uint32_t* state);
+int orc_set_threads(int n);   /* OpenMP threads for the parallel loops; returns the value in effect */
 
 /* ---------------- K2: exact brute-force L2 1-NN (replaces FLANN, M/MosaicWithoutPos.cpp:5108) */
 /* A: na x 128 u8, B: nb x 128 u8.  train_idx[i] = argmin_j |A_i - B_j|^2 (lowest j on ties),

@@ -73,6 +73,10 @@ def ref():
     return _REF
 
 
+def set_threads(n):
+    return lib().orc_set_threads(int(n))
+
+
 def _f32(a):
     return np.ascontiguousarray(a, dtype=np.float32)
 
