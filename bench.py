@@ -287,6 +287,21 @@ def run_ours(args):
     e2e_ms = e0.elapsed_time(e1)
     clocks = sampler.stop() if sampler else None
 
+    # ---- seam masks + multi-band blend of the whole strip (reported separately) ----
+    blend_info = None
+    if rank == 0 and not args.no_blend:
+        b0 = torch.cuda.Event(enable_timing=True); b1 = torch.cuda.Event(enable_timing=True); b2 = torch.cuda.Event(enable_timing=True)
+        cv.warp(); cv.seam_masks(); cv.blend(5)              # warm-up (allocates the canvas pyramid)
+        torch.cuda.synchronize()
+        cv.warp()
+        b0.record(); cv.seam_masks(); b1.record(); cv.blend(5); b2.record()
+        torch.cuda.synchronize()
+        cpx = cv.layout.canvas_w * cv.layout.canvas_h
+        fed = sum(cv.chips[k].chip_w * cv.chips[k].chip_h for k in range(NIMG) if cv.chips[k].keep)
+        blend_info = {"canvas": [cv.layout.canvas_w, cv.layout.canvas_h], "fed_chips": n_pairs, "fed_mpx": fed / 1e6,
+                      "k6_seam_masks_ms": b0.elapsed_time(b1), "k7_blend_ms": b1.elapsed_time(b2),
+                      "canvas_mpx_per_s": cpx / 1e6 / (b1.elapsed_time(b2) / 1000.0), "bands": 5}
+
     t = torch.tensor([ms_total, e2e_ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -327,6 +342,7 @@ def run_ours(args):
                     "ms_per_step": e2e_ms / e_steps},
             "gpu_launches": int(launches),
             "clocks": clocks,
+            "blend": blend_info,
         }
         # ---- CPU baseline on a bounded sample (rank 0, N=1 only) ----
         if world == 1 and not args.no_cpu:
@@ -351,6 +367,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-blend", action="store_true", help="skip the separate seam-mask + multi-band blend measurement")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
