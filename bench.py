@@ -319,6 +319,11 @@ def run_ours(args):
         match_flop = 2.0 * NKP * NKP * 128 * n_pairs
         warp_gbs = warp_bytes / (stage_ms[3] / 1000.0) / 1e9
         match_tf = match_flop / (stage_ms[0] / 1000.0) / 1e12
+        traffic = None
+        try:                                                # dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["k5_warp_chips"]["traffic"]
+        except Exception:
+            pass
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -328,7 +333,7 @@ def run_ours(args):
                        "l2": "per-step working set 5 GB (frames + chips) >> 126 MB L2; the warp pass evicts the 52 MB descriptor pool between match passes",
                        "parallelism": f"pairs sharded over {world} GPU(s), no data-path collective"},
             "roofline": {"kernel": "k5_warp_chips", "bound": "hbm", "achieved": warp_gbs, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                         "frac": warp_gbs / pk["hbm_gbs"], "traffic": None, "peak_src": pk["src"],
+                         "frac": warp_gbs / pk["hbm_gbs"], "traffic": traffic, "peak_src": pk["src"],
                          "algorithmic_bytes_per_launch": warp_bytes, "ms_per_launch": float(stage_ms[3])},
             "kernels": {"note": "k2/k3/k5: CUDA events inside the timed region (k4 runs on the side stream, overlapping k5); "
                                 "serial_ms: each stage alone on the stream, 3 extra untimed steps",
