@@ -52,7 +52,8 @@ constexpr int kWarpTileH = 8 * kWarpRows;
 template <bool AFFINE>
 __global__ void __launch_bounds__(256)
 k5_warp_chips(const ChipDesc* __restrict__ descs, int img_w, int img_h, int src_step_px, float dgx, float dgy,
-              uint32_t two23 /* = 0x4B000000, bits of 2^23: a kernel argument so PRMT takes the SELECTOR as its immediate */)
+              uint32_t two23 /* = 0x4B000000, bits of 2^23: a kernel argument so PRMT takes the SELECTOR as its immediate */,
+              float w1f, float h1f)
 {
     const ChipDesc& D = descs[blockIdx.z];
     if (!D.keep || (D.affine != 0) != AFFINE) return;
@@ -61,7 +62,7 @@ k5_warp_chips(const ChipDesc* __restrict__ descs, int img_w, int img_h, int src_
     if (x0 >= D.chip_w || blockIdx.y * kWarpTileH >= D.chip_h) return;
     const float iv0 = D.inv[0], iv1 = D.inv[1], iv2 = D.inv[2], iv3 = D.inv[3], iv4 = D.inv[4], iv5 = D.inv[5];
     const float iv6 = D.inv[6], iv7 = D.inv[7], iv8 = D.inv[8];
-    const float w1 = (float)(img_w - 1), h1 = (float)(img_h - 1);
+    const float w1 = w1f, h1 = h1f;                 // (float)(width-1), (float)(height-1): kernel arguments, not re-converted per pixel
     const uint32_t* __restrict__ src = reinterpret_cast<const uint32_t*>(D.src);
     const float fbx = (float)D.beg_x, fby = (float)D.beg_y, sx = D.sx, sy = D.sy;
     // xTemp = xDst - dGx - sx + begBoxX (:2356); (float)(x0 + i) == (float)x0 + i exactly (both < 2^24)
@@ -94,8 +95,9 @@ k5_warp_chips(const ChipDesc* __restrict__ descs, int img_w, int img_h, int src_
                 const float p = ys - (float)iy, q = xs - (float)ix;
                 const float omp = 1.0f - p, omq = 1.0f - q;
                 const float c_omp = -8388608.0f * omp, c_p = -8388608.0f * p;        // exact (power-of-two scale)
-                const uint32_t* r0 = src + iy * src_step_px + ix;
-                const uint32_t t00 = __ldg(r0), t01 = __ldg(r0 + 1), t10 = __ldg(r0 + src_step_px), t11 = __ldg(r0 + src_step_px + 1);
+                const uint32_t off = (uint32_t)(iy * src_step_px + ix);        // < 2^24 pixels per frame: 32-bit offset from the frame base
+                const uint32_t t00 = __ldg(src + off), t01 = __ldg(src + off + 1u);
+                const uint32_t t10 = __ldg(src + off + (uint32_t)src_step_px), t11 = __ldg(src + off + (uint32_t)src_step_px + 1u);
                 o[3 * i] = bilinear_channel<0>(t00, t01, t10, t11, p, q, omp, omq, c_omp, c_p, two23);
                 o[3 * i + 1] = bilinear_channel<1>(t00, t01, t10, t11, p, q, omp, omq, c_omp, c_p, two23);
                 o[3 * i + 2] = bilinear_channel<2>(t00, t01, t10, t11, p, q, omp, omq, c_omp, c_p, two23);
@@ -103,9 +105,10 @@ k5_warp_chips(const ChipDesc* __restrict__ descs, int img_w, int img_h, int src_
             }
         }
         uint32_t* crow = reinterpret_cast<uint32_t*>(chip_row + (size_t)ry * 8 * D.chip_step);
-        crow[0] = o[0] | (o[1] << 8) | (o[2] << 16) | (o[3] << 24);
-        crow[1] = o[4] | (o[5] << 8) | (o[6] << 16) | (o[7] << 24);
-        crow[2] = o[8] | (o[9] << 8) | (o[10] << 16) | (o[11] << 24);
+        // 12 bytes -> 3 words with byte permutes (3 PRMT per word instead of shift/or chains)
+        crow[0] = __byte_perm(__byte_perm(o[0], o[1], 0x0040), __byte_perm(o[2], o[3], 0x0040), 0x5410);
+        crow[1] = __byte_perm(__byte_perm(o[4], o[5], 0x0040), __byte_perm(o[6], o[7], 0x0040), 0x5410);
+        crow[2] = __byte_perm(__byte_perm(o[8], o[9], 0x0040), __byte_perm(o[10], o[11], 0x0040), 0x5410);
         *reinterpret_cast<uint32_t*>(mask_row + (size_t)ry * 8 * D.mask_step) = mbits;
     }
 }
@@ -222,11 +225,13 @@ extern "C" int uavm_canvas_warp(uavm_ctx* ctx, uavm_canvas* cv)
     for (int k = 0; k < cv->n; k++)
         if (cv->desc[k].keep) { if (cv->desc[k].affine) any_affine = true; else any_proj = true; }
     if (any_affine) {
-        k5_warp_chips<true><<<grid, block, 0, ctx->stream>>>(cv->d_desc, cv->img_w, cv->img_h, cv->src_step_px, cv->layout.dgx, cv->layout.dgy, 0x4B000000u);
+        k5_warp_chips<true><<<grid, block, 0, ctx->stream>>>(cv->d_desc, cv->img_w, cv->img_h, cv->src_step_px, cv->layout.dgx, cv->layout.dgy, 0x4B000000u,
+                                                             (float)(cv->img_w - 1), (float)(cv->img_h - 1));
         UAVM_CHECK_LAUNCH(ctx);
     }
     if (any_proj) {
-        k5_warp_chips<false><<<grid, block, 0, ctx->stream>>>(cv->d_desc, cv->img_w, cv->img_h, cv->src_step_px, cv->layout.dgx, cv->layout.dgy, 0x4B000000u);
+        k5_warp_chips<false><<<grid, block, 0, ctx->stream>>>(cv->d_desc, cv->img_w, cv->img_h, cv->src_step_px, cv->layout.dgx, cv->layout.dgy, 0x4B000000u,
+                                                             (float)(cv->img_w - 1), (float)(cv->img_h - 1));
         UAVM_CHECK_LAUNCH(ctx);
     }
     cv->warped = true;
