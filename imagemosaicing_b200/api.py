@@ -280,6 +280,13 @@ class Canvas:
         self.ctx.check(L.lib().uavm_canvas_set_image(self.ctx._h, self._h, int(image), _ptr(bgr, u8p), int(step), dev))
         self._keep = bgr
 
+    def set_band(self, y0, y1, halo=128):
+        """Multi-GPU canvas sharding: compute only canvas rows [y0, y1) (+ halo); see uavm_canvas_set_band."""
+        self.ctx.check(L.lib().uavm_canvas_set_band(self.ctx._h, self._h, int(y0), int(y1), int(halo)))
+
+    def is_active(self, image):
+        return bool(L.lib().uavm_canvas_is_active(self._h, int(image)))
+
     def warp(self):
         self.ctx.check(L.lib().uavm_canvas_warp(self.ctx._h, self._h))
 
@@ -307,6 +314,11 @@ class Canvas:
         self.ctx.check(L.lib().uavm_canvas_get_result(self.ctx._h, self._h, _ptr(out, u8p), out.strides[0],
                                                       _ptr(mask, u8p), mask.strides[0]))
         return out, mask
+
+    def copy_result_rows(self, y0, y1, dst):
+        """Rows [y0, y1) of the result into `dst` (torch CUDA uint8 tensor or numpy array, (y1-y0, W, 3))."""
+        dev = 1 if _is_torch_cuda(dst) else 0
+        self.ctx.check(L.lib().uavm_canvas_copy_result_rows(self.ctx._h, self._h, int(y0), int(y1), _ptr(dst, u8p), dev))
 
     def close(self):
         if self._h:

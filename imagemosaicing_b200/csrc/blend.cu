@@ -18,7 +18,7 @@ namespace {
 constexpr int kMaxBands = 8;
 
 struct BlendWs {
-    int nb = 0, W = 0, H = 0;
+    int nb = 0, W = 0, H = 0, Y0 = 0, Y1 = 0;   // Y0..Y1: canvas rows held by this workspace (band + halo)
     int lw[kMaxBands + 1], lh[kMaxBands + 1];
     short* dlap[kMaxBands + 1] = {nullptr};
     float* dw[kMaxBands + 1] = {nullptr};
@@ -221,21 +221,40 @@ extern "C" int uavm_canvas_blend(uavm_ctx* ctx, uavm_canvas* cv, int num_bands)
     const double max_len = (double)(cw > ch ? cw : ch);
     int nb = (int)ceil(log(max_len) / log(2.0));
     if (num_bands < nb) nb = num_bands;
+    const int W = pad_to(cw, nb), H = pad_to(ch, nb);
+    // canvas rows computed by this context: the whole padded canvas, or a band + halo (uavm_canvas_set_band).
+    // Tile equivalence: cutting the pyramids at a row that is a multiple of 2^nb perturbs at most
+    // 2^(nb+2) - 2 rows next to the cut after the collapse (pyrDown reaches 2 rows, pyrUp 1 row per level),
+    // so a halo >= 128 rows (5 bands) leaves the band interior bit-identical to the untiled blend.
+    int Y0 = 0, Y1 = H;
+    if (cv->banded) {
+        Y0 = cv->band_Y0; Y1 = cv->band_Y1 < H ? cv->band_Y1 : H;
+        if ((Y0 % (1 << nb)) || ((Y1 % (1 << nb)) && Y1 != H)) { UAVM_SET_ERR(ctx, "band rows not aligned to 2^bands"); return UAVM_EINVAL; }
+    }
+    const int BH = Y1 - Y0;
     BlendWs* ws = (BlendWs*)cv->blend_ws;
-    if (ws && ws->nb != nb) { free_ws(ws); ws = nullptr; cv->blend_ws = nullptr; }
+    if (ws && (ws->nb != nb || ws->Y0 != Y0 || ws->Y1 != Y1)) { free_ws(ws); ws = nullptr; cv->blend_ws = nullptr; }
+    auto sub_roi = [&](const ChipDesc& d, Roi& r, int& sub_t, int& sub_h) {
+        r = feed_roi(d.beg_x, d.beg_y, d.chip_w, d.chip_h, W, H, nb);
+        sub_t = r.tly > Y0 ? r.tly : Y0;
+        const int sub_b = r.tly + r.height < Y1 ? r.tly + r.height : Y1;
+        sub_h = sub_b - sub_t;
+        return sub_h > 0;
+    };
     if (!ws) {
         ws = new BlendWs();
         cv->blend_ws = ws;
-        ws->nb = nb; ws->W = pad_to(cw, nb); ws->H = pad_to(ch, nb);
+        ws->nb = nb; ws->W = W; ws->H = H; ws->Y0 = Y0; ws->Y1 = Y1;
         size_t roi_cap = 0;
         for (int k = 0; k < cv->n; k++) {
             const ChipDesc& d = cv->desc[k];
             if (!d.keep) continue;
-            Roi r = feed_roi(d.beg_x, d.beg_y, d.chip_w, d.chip_h, ws->W, ws->H, nb);
-            if ((size_t)r.width * r.height > roi_cap) roi_cap = (size_t)r.width * r.height;
+            Roi r; int st, sh;
+            if (!sub_roi(d, r, st, sh)) continue;
+            if ((size_t)r.width * sh > roi_cap) roi_cap = (size_t)r.width * sh;
         }
         ws->roi_cap = roi_cap;
-        ws->lw[0] = ws->W; ws->lh[0] = ws->H;
+        ws->lw[0] = W; ws->lh[0] = BH;
         size_t cap = roi_cap;
         for (int i = 0; i <= nb; i++) {
             if (i > 0) { ws->lw[i] = (ws->lw[i - 1] + 1) / 2; ws->lh[i] = (ws->lh[i - 1] + 1) / 2; cap = (cap + 3) / 4 + 4096; }
@@ -250,6 +269,8 @@ extern "C" int uavm_canvas_blend(uavm_ctx* ctx, uavm_canvas* cv, int num_bands)
         cudaFree(cv->d_result); cudaFree(cv->d_result_mask); cv->d_result = nullptr; cv->d_result_mask = nullptr;
         UAVM_CUDA(ctx, cudaMalloc(&cv->d_result, (size_t)cw * ch * 3));
         UAVM_CUDA(ctx, cudaMalloc(&cv->d_result_mask, (size_t)cw * ch));
+        UAVM_CUDA(ctx, cudaMemsetAsync(cv->d_result, 0, (size_t)cw * ch * 3, ctx->stream));
+        UAVM_CUDA(ctx, cudaMemsetAsync(cv->d_result_mask, 0, (size_t)cw * ch, ctx->stream));
         cv->result_w = cw; cv->result_h = ch;
     }
     for (int i = 0; i <= nb; i++) {
@@ -261,13 +282,14 @@ extern "C" int uavm_canvas_blend(uavm_ctx* ctx, uavm_canvas* cv, int num_bands)
     for (int k = 0; k < cv->n; k++) {
         const ChipDesc& d = cv->desc[k];
         if (!d.keep) continue;
-        const Roi r = feed_roi(d.beg_x, d.beg_y, d.chip_w, d.chip_h, ws->W, ws->H, nb);
+        Roi r; int sub_t, sub_h;
+        if (!sub_roi(d, r, sub_t, sub_h)) continue;
         int pw[kMaxBands + 1], ph[kMaxBands + 1];
-        pw[0] = r.width; ph[0] = r.height;
+        pw[0] = r.width; ph[0] = sub_h;
         {
-            dim3 grid((r.width + 255) / 256, r.height);
-            k7_feed_level0<<<grid, 256, 0, ctx->stream>>>(d.chip, d.chip_step, d.mask, d.mask_step, d.chip_w, d.chip_h, r.left, r.top,
-                                                           r.width, r.height, ws->pyr[0], ws->wp[0]);
+            dim3 grid((r.width + 255) / 256, sub_h);
+            k7_feed_level0<<<grid, 256, 0, ctx->stream>>>(d.chip, d.chip_step, d.mask, d.mask_step, d.chip_w, d.chip_h, r.left, d.beg_y - sub_t,
+                                                           r.width, sub_h, ws->pyr[0], ws->wp[0]);
             UAVM_CHECK_LAUNCH(ctx);
         }
         for (int i = 0; i < nb; i++) {
@@ -276,7 +298,7 @@ extern "C" int uavm_canvas_blend(uavm_ctx* ctx, uavm_canvas* cv, int num_bands)
             k7_pyrdown<<<grid, 256, 0, ctx->stream>>>(ws->pyr[i], ws->wp[i], pw[i], ph[i], ws->pyr[i + 1], ws->wp[i + 1], pw[i + 1], ph[i + 1]);
             UAVM_CHECK_LAUNCH(ctx);
         }
-        int x_tl = r.tlx, y_tl = r.tly;
+        int x_tl = r.tlx, y_tl = sub_t - Y0;
         for (int i = 0; i <= nb; i++) {
             dim3 grid((pw[i] + 255) / 256, ph[i]);
             k7_lap_accumulate<<<grid, 256, 0, ctx->stream>>>(ws->pyr[i], i < nb ? ws->pyr[i + 1] : nullptr, ws->wp[i], pw[i], ph[i],
@@ -297,8 +319,10 @@ extern "C" int uavm_canvas_blend(uavm_ctx* ctx, uavm_canvas* cv, int num_bands)
         UAVM_CHECK_LAUNCH(ctx);
     }
     {
-        dim3 grid((cw + 255) / 256, ch);
-        k7_output<<<grid, 256, 0, ctx->stream>>>(ws->dlap[0], ws->dw[0], ws->W, cw, ch, cv->d_result, cv->d_result_mask);
+        const int oy0 = cv->banded ? cv->band_y0 : 0, oy1 = cv->banded ? cv->band_y1 : ch;
+        dim3 grid((cw + 255) / 256, oy1 - oy0);
+        k7_output<<<grid, 256, 0, ctx->stream>>>(ws->dlap[0] + (size_t)(oy0 - Y0) * W * 3, ws->dw[0] + (size_t)(oy0 - Y0) * W, W, cw, oy1 - oy0,
+                                                  cv->d_result + (size_t)oy0 * cw * 3, cv->d_result_mask + (size_t)oy0 * cw);
         UAVM_CHECK_LAUNCH(ctx);
     }
     cv->blended = true;
@@ -326,5 +350,19 @@ extern "C" int uavm_canvas_result_size(uavm_canvas* cv, int* w, int* h)
 {
     if (!cv || !w || !h) return UAVM_EINVAL;
     *w = cv->result_w; *h = cv->result_h;
+    return UAVM_OK;
+}
+
+// rows [y0, y1) of the result (dense, canvas_w * 3 bytes per row) into a caller buffer; is_device != 0: device
+// memory (stream-ordered device-to-device copy, e.g. into the send buffer of an NCCL gather of canvas bands)
+extern "C" int uavm_canvas_copy_result_rows(uavm_ctx* ctx, uavm_canvas* cv, int y0, int y1, uint8_t* dst, int is_device)
+{
+    if (!ctx || !cv || !dst || y0 < 0 || y1 > cv->result_h || y0 > y1) return UAVM_EINVAL;
+    if (!cv->blended || !cv->d_result) { UAVM_SET_ERR(ctx, "copy_result_rows before blend"); return UAVM_EINVAL; }
+    const size_t row = (size_t)cv->result_w * 3;
+    if (y1 > y0)
+        UAVM_CUDA(ctx, cudaMemcpyAsync(dst, cv->d_result + (size_t)y0 * row, (size_t)(y1 - y0) * row,
+                                       is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, ctx->stream));
+    if (!is_device) UAVM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return UAVM_OK;
 }

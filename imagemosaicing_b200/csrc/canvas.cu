@@ -175,10 +175,46 @@ extern "C" int uavm_canvas_create(uavm_ctx* ctx, int n_images, int img_w, int im
         if (!d.keep) continue;
         d.chip = cv->d_chips + coff[k]; d.mask = cv->d_masks + moff[k];
     }
+    cv->band_y0 = 0; cv->band_y1 = cv->layout.canvas_h; cv->band_Y0 = 0; cv->band_Y1 = (cv->layout.canvas_h + 31) & ~31;
     rc = uavm_canvas_upload_desc(ctx, cv);
     if (rc != UAVM_OK) { uavm_canvas_destroy(ctx, cv); return rc; }
     *out = cv;
     return UAVM_OK;
+}
+
+// Multi-GPU canvas sharding: this context computes only canvas rows [y0, y1) (+ halo rows on both sides that make
+// the band interior bit-identical to the untiled blend, see blend.cu).  Chips that cannot touch the computed rows
+// are deactivated: they are neither warped nor masked nor fed.  y0, y1, halo: multiples of 32 (y1 may be the
+// canvas height).  y0 = 0, y1 = canvas_h, halo = 0 restores the whole canvas.
+extern "C" int uavm_canvas_set_band(uavm_ctx* ctx, uavm_canvas* cv, int y0, int y1, int halo)
+{
+    if (!ctx || !cv) return UAVM_EINVAL;
+    const int ch = cv->layout.canvas_h;
+    if (y0 < 0 || y1 > ch || y0 >= y1 || halo < 0 || (y0 % 32) || (halo % 32) || ((y1 % 32) && y1 != ch)) {
+        UAVM_SET_ERR(ctx, "set_band: rows must be multiples of 32 inside the canvas"); return UAVM_EINVAL;
+    }
+    const int Hpad = (ch + 31) & ~31;
+    cv->band_y0 = y0; cv->band_y1 = y1;
+    cv->band_Y0 = y0 - halo > 0 ? y0 - halo : 0;
+    cv->band_Y1 = ((y1 + 31) & ~31) + halo < Hpad ? ((y1 + 31) & ~31) + halo : Hpad;
+    cv->banded = !(y0 == 0 && y1 == ch);
+    const int gap = 3 * 32 + 32;                        // feed ROI grows a chip by 3 * 2^5 rows, then aligns to 32
+    cv->max_chip_w = 0; cv->max_chip_h = 0;
+    for (int k = 0; k < cv->n; k++) {
+        ChipDesc& d = cv->desc[k];
+        const uavm_chip_layout& c = cv->chips[k];
+        bool active = c.keep != 0;
+        if (active && cv->banded) active = (c.beg_y - gap < cv->band_Y1) && (c.beg_y + c.chip_h + gap > cv->band_Y0);
+        d.keep = active ? 1 : 0;
+        if (active) { if (c.chip_w > cv->max_chip_w) cv->max_chip_w = c.chip_w; if (c.chip_h > cv->max_chip_h) cv->max_chip_h = c.chip_h; }
+    }
+    cv->nbr_dirty = true; cv->warped = false; cv->seamed = false; cv->blended = false;
+    return uavm_canvas_upload_desc(ctx, cv);
+}
+extern "C" int uavm_canvas_is_active(uavm_canvas* cv, int image)
+{
+    if (!cv || image < 0 || image >= cv->n) return 0;
+    return cv->desc[image].keep;
 }
 
 extern "C" void uavm_canvas_destroy(uavm_ctx* ctx, uavm_canvas* cv)

@@ -38,6 +38,10 @@ struct uavm_canvas {
     // result canvas (K7 / paste)
     uint8_t* d_result = nullptr;     // canvas_h x canvas_w x 3
     uint8_t* d_result_mask = nullptr;
+    // canvas band owned by this context/rank (multi-GPU canvas sharding): output rows [band_y0, band_y1), computed
+    // rows [band_Y0, band_Y1) = band + halo, all multiples of 2^bands; default = the whole canvas
+    int band_y0 = 0, band_y1 = 0, band_Y0 = 0, band_Y1 = 0;
+    bool banded = false, nbr_dirty = true;
     int result_w = 0, result_h = 0;  // size of d_result (blend: canvas layout; paste: MosaicImagesRefined's own bbox)
     bool warped = false, seamed = false, blended = false;
     void* blend_ws = nullptr;        // opaque workspace owned by blend.cu

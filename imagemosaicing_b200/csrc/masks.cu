@@ -125,6 +125,10 @@ extern "C" int uavm_canvas_seam_masks(uavm_ctx* ctx, uavm_canvas* cv)
     if (!cv->d_dist) {
         UAVM_CUDA(ctx, cudaMalloc(&cv->d_dist, cv->masks_bytes * sizeof(float) + 1024));
         UAVM_CUDA(ctx, cudaMalloc(&cv->d_dist_max, (size_t)cv->n * sizeof(float)));
+        cv->nbr_dirty = true;
+    }
+    if (cv->nbr_dirty) {
+        cudaFree(cv->d_nbr); cv->d_nbr = nullptr;
         // edge lines, distance-map pointers and box-intersection neighbour lists
         std::vector<int32_t> nbr;
         for (int k = 0; k < cv->n; k++) {
@@ -150,6 +154,7 @@ extern "C" int uavm_canvas_seam_masks(uavm_ctx* ctx, uavm_canvas* cv)
             UAVM_CUDA(ctx, cudaMemcpyAsync(cv->d_nbr, nbr.data(), nbr.size() * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
         int rc = uavm_canvas_upload_desc(ctx, cv);
         if (rc != UAVM_OK) return rc;
+        cv->nbr_dirty = false;
     }
     UAVM_CUDA(ctx, cudaMemsetAsync(cv->d_dist_max, 0, (size_t)cv->n * sizeof(float), ctx->stream));
     dim3 grid((cv->max_chip_w + kTileW - 1) / kTileW, (cv->max_chip_h + kTileH - 1) / kTileH, cv->n);

@@ -45,3 +45,15 @@ def gather_match_pairs(local_records, local_pair_ids, n_pairs, group=None, devic
         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
         buf = t.cpu().numpy().view(MPP_DTYPE).copy()
     return buf
+
+
+def canvas_bands(canvas_h, world, align=32):
+    """Split the canvas rows into `world` horizontal bands whose edges are multiples of `align`
+    (the last band ends at canvas_h).  Returns [(y0, y1)] per rank; ranks beyond the available rows get (0, 0)."""
+    n_units = (canvas_h + align - 1) // align
+    out = []
+    for r in range(world):
+        u0 = (n_units * r) // world; u1 = (n_units * (r + 1)) // world
+        y0 = u0 * align; y1 = min(u1 * align, canvas_h)
+        out.append((y0, y1) if y1 > y0 else (0, 0))
+    return out

@@ -143,6 +143,11 @@ int uavm_resample_by_overlap(const float* H, int n, int img_w, int img_h, float 
 int uavm_canvas_create(uavm_ctx* ctx, int n_images, int img_w, int img_h, const float* H, const int32_t* keep, uavm_canvas** out);
 void uavm_canvas_destroy(uavm_ctx* ctx, uavm_canvas* cv);
 int uavm_canvas_get_layout(uavm_canvas* cv, uavm_canvas_layout* canvas, uavm_chip_layout* chips);
+/* multi-GPU canvas sharding: this ctx computes only canvas rows [y0, y1) (multiples of 32; halo >= 128 rows of
+ * redundant computation on each side make the band bit-identical to the untiled blend).  Chips that cannot touch
+ * the band are deactivated (uavm_canvas_is_active == 0: no need to set their image). */
+int uavm_canvas_set_band(uavm_ctx* ctx, uavm_canvas* cv, int y0, int y1, int halo);
+int uavm_canvas_is_active(uavm_canvas* cv, int image);
 /* source frame n (BGR u8 interleaved, `step` bytes per row); is_device != 0: device pointer */
 int uavm_canvas_set_image(uavm_ctx* ctx, uavm_canvas* cv, int image, const uint8_t* bgr, int step, int is_device);
 /* K5: bilinear warp of every kept frame into its chip + validity mask (:2350-2448) */
@@ -157,6 +162,9 @@ int uavm_canvas_paste(uavm_ctx* ctx, uavm_canvas* cv);
 int uavm_canvas_get_chip(uavm_ctx* ctx, uavm_canvas* cv, int image, uint8_t* chip_bgr, int chip_step, uint8_t* mask, int mask_step);
 int uavm_canvas_result_size(uavm_canvas* cv, int* w, int* h);   /* size of the blended / pasted result */
 int uavm_canvas_get_result(uavm_ctx* ctx, uavm_canvas* cv, uint8_t* bgr, int step, uint8_t* mask, int mask_step);
+/* rows [y0, y1) of the result, dense (canvas_w * 3 bytes per row); is_device != 0: dst is device memory (stream-ordered
+ * copy, e.g. the send buffer of the NCCL gather of canvas bands) */
+int uavm_canvas_copy_result_rows(uavm_ctx* ctx, uavm_canvas* cv, int y0, int y1, uint8_t* dst, int is_device);
 
 /* ---- top-level shim with the shape of MosaicVavImages (M/MosaicWithoutPos.h:638-645,
  *      M/MosaicWithoutPos.cpp:10148-10214).  Features are supplied by the caller (SIFT extraction is
