@@ -287,8 +287,13 @@ class Canvas:
     def is_active(self, image):
         return bool(L.lib().uavm_canvas_is_active(self._h, int(image)))
 
-    def warp(self):
-        self.ctx.check(L.lib().uavm_canvas_warp(self.ctx._h, self._h))
+    def warp(self, first=None, count=None):
+        """K5 for every kept frame, or for frames [first, first + count) (streaming callers warp each group of
+        frames as soon as it has been set, while the next frames are still crossing PCIe)."""
+        if first is None:
+            self.ctx.check(L.lib().uavm_canvas_warp(self.ctx._h, self._h))
+        else:
+            self.ctx.check(L.lib().uavm_canvas_warp_range(self.ctx._h, self._h, int(first), int(count)))
 
     def seam_masks(self):
         self.ctx.check(L.lib().uavm_canvas_seam_masks(self.ctx._h, self._h))

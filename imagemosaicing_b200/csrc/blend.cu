@@ -41,16 +41,16 @@ __device__ __forceinline__ short sat16(int v) { return (short)max(-32768, min(32
 
 // level 0 of the fed image: copyMakeBorder(REFLECT) of the chip (u8 -> s16) and mask/255 with a zero border
 __global__ void __launch_bounds__(256)
-k7_feed_level0(const uint8_t* __restrict__ chip, int chip_step, const uint8_t* __restrict__ mask, int mask_step,
+k7_feed_level0(const uint32_t* __restrict__ chip, int chip_step /* words */, const uint8_t* __restrict__ mask, int mask_step,
                int cw, int ch, int left, int top, int width, int height, short* __restrict__ pyr0, float* __restrict__ wp0)
 {
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
     if (x >= width || y >= height) return;
     const int ix = x - left, iy = y - top;
     const int sx = reflect_edge(ix, cw), sy = reflect_edge(iy, ch);
-    const uint8_t* s = chip + (size_t)sy * chip_step + 3 * sx;
+    const uint32_t s = chip[(size_t)sy * chip_step + sx];                   // BGRA
     short* d = pyr0 + ((size_t)y * width + x) * 3;
-    d[0] = s[0]; d[1] = s[1]; d[2] = s[2];
+    d[0] = (short)(s & 0xffu); d[1] = (short)((s >> 8) & 0xffu); d[2] = (short)((s >> 16) & 0xffu);
     float wv = 0.0f;
     if (ix >= 0 && ix < cw && iy >= 0 && iy < ch) wv = (float)mask[(size_t)iy * mask_step + ix] * (float)(1. / 255.);
     wp0[(size_t)y * width + x] = wv;
@@ -216,6 +216,7 @@ extern "C" int uavm_canvas_blend(uavm_ctx* ctx, uavm_canvas* cv, int num_bands)
     if (!ctx || !cv || num_bands < 0 || num_bands > kMaxBands) return UAVM_EINVAL;
     if (!cv->warped) { UAVM_SET_ERR(ctx, "blend before warp"); return UAVM_EINVAL; }
     UAVM_CUDA(ctx, cudaSetDevice(ctx->device));
+    { int rc = uavm_canvas_mask_plane(ctx, cv); if (rc != UAVM_OK) return rc; }     // feed masks: K6's, else the validity masks
     const int cw = cv->layout.canvas_w, ch = cv->layout.canvas_h;
     // prepare(): crop the band count, pad the canvas
     const double max_len = (double)(cw > ch ? cw : ch);

@@ -4,10 +4,13 @@
 //
 // HBM layout: source frames are stored as BGRA (uchar4) so that one 32-bit load returns a whole pixel
 // (a BGR triple straddles words; 12 byte loads per output pixel would make the kernel LSU-bound);
-// chips are packed BGR u8 with a row step of 3*align4(chip_w) so every thread stores whole 12-byte
-// groups; masks are u8 with a row step of align4(chip_w).
+// chips are BGRA words too (row step align4(chip_w) words): B, G, R = the warped pixel, alpha != 0 = the
+// reference's validity mask (:2443-2456) — the same 3 + 1 bytes per pixel as a BGR chip plus a mask plane,
+// written with one coalesced 32-bit store per pixel.  The u8 mask plane (row step align4(chip_w)) is K6's output.
+#include <stdlib.h>
 #include <string.h>
 #include "canvas.h"
+#include "ptx.cuh"
 
 namespace {
 
@@ -20,6 +23,28 @@ __global__ void __launch_bounds__(256) k5_bgr_to_bgra(const uint8_t* __restrict_
     if (x >= w || y >= h) return;
     const uint8_t* s = src + (size_t)y * step + 3 * x;
     dst[(size_t)y * dst_step_px + x] = make_uchar4(s[0], s[1], s[2], 0);
+}
+
+// same, 4 pixels per thread: three aligned 32-bit loads, one 16-byte store (rows and base 4-byte aligned)
+__global__ void __launch_bounds__(128) k5_bgr_to_bgra_x4(const uint8_t* __restrict__ src, int w, int step, uchar4* __restrict__ dst, int dst_step_px)
+{
+    const int x = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const int y = blockIdx.y;
+    if (x >= w) return;
+    const uint8_t* s = src + (size_t)y * step + 3 * x;
+    uchar4* d = dst + (size_t)y * dst_step_px + x;
+    if (x + 4 <= w && (dst_step_px % 4) == 0) {
+        const uint32_t* s32 = reinterpret_cast<const uint32_t*>(s);
+        const uint32_t a = __ldg(s32), b = __ldg(s32 + 1), c = __ldg(s32 + 2);        // B0G0R0B1 G1R1B2G2 R2B3G3R3
+        uint4 o;
+        o.x = a & 0x00ffffffu;
+        o.y = __byte_perm(a, b, 0x0543) & 0x00ffffffu;
+        o.z = __byte_perm(b, c, 0x0432) & 0x00ffffffu;
+        o.w = c >> 8;
+        *reinterpret_cast<uint4*>(d) = o;
+    } else {
+        for (int i = 0; i < 4 && x + i < w; i++) d[i] = make_uchar4(s[3 * i], s[3 * i + 1], s[3 * i + 2], 0);
+    }
 }
 
 // one channel of the reference's bilinear expression (:2398-2410), evaluated left to right in float:
@@ -43,12 +68,19 @@ __device__ __forceinline__ uint32_t bilinear_channel(uint32_t t00, uint32_t t01,
     return (uint32_t)__float2int_rz(v);            // truncation, value in [0, 255]
 }
 
-constexpr int kWarpTileW = 128;   // 32 threads x 4 px
+// Thread -> pixel mapping of both warp kernels: a CTA (32 x 8 threads) covers a 128 x 32 chip tile; a thread owns the
+// pixels x = tile_x + lane + 32 k (k = 0..3) of the rows y = tile_y + ty + 8 r (r = 0..3).  The 32 lanes of a warp
+// therefore sample 32 NEIGHBOURING source pixels per tap load (a 128 B line or two, + a line per source-row crossing)
+// and store 32 consecutive BGRA words: the L1 sees ~3 tags per load instead of ~11 with 4 consecutive pixels per
+// thread (ncu, profiles/r1d_*), which was what bounded the kernel.
+constexpr int kWarpTileW = 128;   // 32 lanes x 4 px
 constexpr int kWarpRows = 4;      // rows per thread
 constexpr int kWarpTileH = 8 * kWarpRows;
+constexpr int kFootprintSmem = 40 * 1024;   // dynamic shared memory per CTA for the staged source footprint (5 CTAs / SM)
 
-// AFFINE: inv[6] == inv[7] == 0 and inv[8] == 1, so the reference's denominator is exactly 1.0f for every
-// pixel and x / 1.0f == x: the two divides per coordinate (:2359-2362) are skipped without changing a bit.
+// Generic (projective) warp, scalar.  AFFINE: inv[6] == inv[7] == 0 and inv[8] == 1, so the reference's denominator is
+// exactly 1.0f for every pixel and x / 1.0f == x: the two divides per coordinate (:2359-2362) are skipped without
+// changing a bit (kept as the A/B twin of the packed affine kernel below).
 template <bool AFFINE>
 __global__ void __launch_bounds__(256)
 k5_warp_chips(const ChipDesc* __restrict__ descs, int img_w, int img_h, int src_step_px, float dgx, float dgy,
@@ -57,31 +89,28 @@ k5_warp_chips(const ChipDesc* __restrict__ descs, int img_w, int img_h, int src_
 {
     const ChipDesc& D = descs[blockIdx.z];
     if (!D.keep || (D.affine != 0) != AFFINE) return;
-    const int x0 = blockIdx.x * kWarpTileW + threadIdx.x * 4;
+    const int xl = blockIdx.x * kWarpTileW + threadIdx.x;
     const int ybase = blockIdx.y * kWarpTileH + threadIdx.y;
-    if (x0 >= D.chip_w || blockIdx.y * kWarpTileH >= D.chip_h) return;
+    if (blockIdx.x * kWarpTileW >= D.chip_w || blockIdx.y * kWarpTileH >= D.chip_h) return;
     const float iv0 = D.inv[0], iv1 = D.inv[1], iv2 = D.inv[2], iv3 = D.inv[3], iv4 = D.inv[4], iv5 = D.inv[5];
     const float iv6 = D.inv[6], iv7 = D.inv[7], iv8 = D.inv[8];
     const float w1 = w1f, h1 = h1f;                 // (float)(width-1), (float)(height-1): kernel arguments, not re-converted per pixel
     const uint32_t* __restrict__ src = reinterpret_cast<const uint32_t*>(D.src);
     const float fbx = (float)D.beg_x, fby = (float)D.beg_y, sx = D.sx, sy = D.sy;
-    // xTemp = xDst - dGx - sx + begBoxX (:2356); (float)(x0 + i) == (float)x0 + i exactly (both < 2^24)
+    // xTemp = xDst - dGx - sx + begBoxX (:2356)
     float xt[4];
-    const float fx0 = (float)x0;
 #pragma unroll
-    for (int i = 0; i < 4; i++) xt[i] = (fx0 + (float)i) - dgx - sx + fbx;
-    uint8_t* chip_row = D.chip + (size_t)ybase * D.chip_step + 3 * x0;
-    uint8_t* mask_row = D.mask + (size_t)ybase * D.mask_step + x0;
+    for (int i = 0; i < 4; i++) xt[i] = (float)(xl + 32 * i) - dgx - sx + fbx;
 #pragma unroll
     for (int ry = 0; ry < kWarpRows; ry++) {
         const int yd = ybase + ry * 8;
         if (yd >= D.chip_h) break;
         const float yt = (float)yd - dgy - sy + fby;               // yTemp (:2357)
         const float ya = yt * iv1, yb = yt * iv4;
-        uint32_t o[12];
-        uint32_t mbits = 0;
+        uint32_t* crow = D.chip + (size_t)yd * D.chip_step;
 #pragma unroll
         for (int i = 0; i < 4; i++) {
+            if (xl + 32 * i >= D.chip_w) break;
             float xs = xt[i] * iv0 + ya + iv2;
             float ys = xt[i] * iv3 + yb + iv5;
             if (!AFFINE) {
@@ -89,29 +118,285 @@ k5_warp_chips(const ChipDesc* __restrict__ descs, int img_w, int img_h, int src_
                 xs = xs / den;
                 ys = ys / den;
             }
-            o[3 * i] = 0; o[3 * i + 1] = 0; o[3 * i + 2] = 0;
+            uint32_t word = 0;                                     // outside the source: BGR = 0, alpha = 0 (mask 0, :2443-2446)
             if ((xs >= 0.0f) && (xs < w1) && (ys >= 0.0f) && (ys < h1)) {
                 const int iy = __float2int_rz(ys), ix = __float2int_rz(xs);
                 const float p = ys - (float)iy, q = xs - (float)ix;
                 const float omp = 1.0f - p, omq = 1.0f - q;
                 const float c_omp = -8388608.0f * omp, c_p = -8388608.0f * p;        // exact (power-of-two scale)
-                const uint32_t off = (uint32_t)(iy * src_step_px + ix);        // < 2^24 pixels per frame: 32-bit offset from the frame base
+                const uint32_t off = (uint32_t)(iy * src_step_px + ix);
                 const uint32_t t00 = __ldg(src + off), t01 = __ldg(src + off + 1u);
                 const uint32_t t10 = __ldg(src + off + (uint32_t)src_step_px), t11 = __ldg(src + off + (uint32_t)src_step_px + 1u);
-                o[3 * i] = bilinear_channel<0>(t00, t01, t10, t11, p, q, omp, omq, c_omp, c_p, two23);
-                o[3 * i + 1] = bilinear_channel<1>(t00, t01, t10, t11, p, q, omp, omq, c_omp, c_p, two23);
-                o[3 * i + 2] = bilinear_channel<2>(t00, t01, t10, t11, p, q, omp, omq, c_omp, c_p, two23);
-                mbits |= 0xffu << (8 * i);
+                const uint32_t b = bilinear_channel<0>(t00, t01, t10, t11, p, q, omp, omq, c_omp, c_p, two23);
+                const uint32_t g = bilinear_channel<1>(t00, t01, t10, t11, p, q, omp, omq, c_omp, c_p, two23);
+                const uint32_t r = bilinear_channel<2>(t00, t01, t10, t11, p, q, omp, omq, c_omp, c_p, two23);
+                word = __byte_perm(__byte_perm(b, g, 0x0040), r, 0x0410) | 0xff000000u;
             }
+            crow[xl + 32 * i] = word;
         }
-        uint32_t* crow = reinterpret_cast<uint32_t*>(chip_row + (size_t)ry * 8 * D.chip_step);
-        // 12 bytes -> 3 words with byte permutes (3 PRMT per word instead of shift/or chains)
-        crow[0] = __byte_perm(__byte_perm(o[0], o[1], 0x0040), __byte_perm(o[2], o[3], 0x0040), 0x5410);
-        crow[1] = __byte_perm(__byte_perm(o[4], o[5], 0x0040), __byte_perm(o[6], o[7], 0x0040), 0x5410);
-        crow[2] = __byte_perm(__byte_perm(o[8], o[9], 0x0040), __byte_perm(o[10], o[11], 0x0040), 0x5410);
-        *reinterpret_cast<uint32_t*>(mask_row + (size_t)ry * 8 * D.mask_step) = mbits;
     }
 }
+
+// ------------------------------------------------------------------------------------------------
+// Packed-f32x2 variant of the AFFINE warp.  sm_100a has two-lane FP32 instructions (FFMA2 / FMUL2 / FADD2):
+// one issue slot performs the same IEEE-754 round-to-nearest operation on two independent floats, so the
+// kernel evaluates the reference expression for two pixels per instruction.  Every lane still performs exactly
+// the reference's operation sequence:
+//   * a product that feeds a sum must not be contracted.  ptxas contracts mul.f32x2 + add.f32x2 into FFMA2
+//     even under -fmad=false, so those sums are written as fma2(t, ONE, s) with ONE = 1.0f passed as a KERNEL
+//     ARGUMENT (opaque to ptxas): fma(t, 1, s) rounds t + s once, i.e. it IS the IEEE addition;
+//   * int(v) for 0 <= v < 2^23 is add.rz(v, 2^23): the sum is rounded toward zero to a multiple of 1.0, which
+//     leaves 2^23 + floor(v) — the integer sits in the low mantissa bits, and subtracting 2^23 (exact) gives
+//     (float)int(v).  This removes F2I / I2F (XU pipe, 1/8 rate) from the kernel altogether.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void unpk2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ void unpk2u(f32x2 v, uint32_t& lo, uint32_t& hi) { asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) { f32x2 d; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f32x2 add2_rz(f32x2 a, f32x2 b) { f32x2 d; asm("add.rz.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+
+// one channel, two pixels: returns 2^23 + int(v) per lane (the output byte is the low byte of each word)
+template <int K>
+__device__ __forceinline__ f32x2 bilinear_channel2(const uint32_t (&ta)[4], const uint32_t (&tb)[4], f32x2 P, f32x2 Q, f32x2 OMP, f32x2 OMQ,
+                                                   f32x2 C_OMP, f32x2 C_P, f32x2 ONE, f32x2 T23, uint32_t two23)
+{
+    const f32x2 G1 = pk2(__int_as_float(__byte_perm(ta[0], two23, 0x7540 | K)), __int_as_float(__byte_perm(tb[0], two23, 0x7540 | K)));
+    const f32x2 G2 = pk2(__int_as_float(__byte_perm(ta[1], two23, 0x7540 | K)), __int_as_float(__byte_perm(tb[1], two23, 0x7540 | K)));
+    const f32x2 G3 = pk2(__int_as_float(__byte_perm(ta[2], two23, 0x7540 | K)), __int_as_float(__byte_perm(tb[2], two23, 0x7540 | K)));
+    const f32x2 G4 = pk2(__int_as_float(__byte_perm(ta[3], two23, 0x7540 | K)), __int_as_float(__byte_perm(tb[3], two23, 0x7540 | K)));
+    const f32x2 a1 = fma2(G1, OMP, C_OMP), a2 = fma2(G2, OMP, C_OMP);          // g1*(1-p), g2*(1-p)   (exact-FFMA trick, see bilinear_channel)
+    const f32x2 a3 = fma2(G3, P, C_P), a4 = fma2(G4, P, C_P);                  // g3*p, g4*p
+    f32x2 s = mul2(a1, OMQ);
+    s = fma2(mul2(a2, Q), ONE, s);                                             // + (g2*(1-p))*q      (ONE is opaque: no contraction)
+    s = fma2(mul2(a3, OMQ), ONE, s);
+    s = fma2(mul2(a4, Q), ONE, s);
+    return add2_rz(s, T23);                                                    // 2^23 + int(v)
+}
+
+// Source staging (SMEM = true).  The taps of a 128 x 32 chip tile fall into a small source rectangle (its footprint:
+// the image of the tile under the inverse transform, ~140 x 47 px for a UAV strip).  Fetching taps with per-thread
+// loads leaves every warp waiting on an L2/HBM round trip per pixel pair (ncu: ~90 % of resident warps stalled on the
+// long scoreboard, no unit above 60 %).  Instead warp 0 copies the footprint rows into shared memory with bulk async
+// copies (cp.async.bulk -> UBLKCP, completion on an mbarrier) while all threads do their per-thread set-up, and the
+// taps become LDS: with lane-consecutive pixels and a row pitch that is a multiple of 32 words they are bank-conflict
+// free.  Tiles whose footprint exceeds the shared-memory budget use the direct global-load path (SMEM = false).
+//
+// CHECK = false: the caller proved every pixel of this thread's 4 x 4 block lies inside the source, so the
+// per-pixel validity test, the tap clamping and the zeroing are skipped.
+__device__ __forceinline__ uint32_t lds_u32(uint32_t saddr) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr)); return v; }
+
+template <bool CHECK, bool SMEM>
+__device__ __forceinline__ void warp_affine_rows(const ChipDesc& D, const f32x2 (&MX)[2], const f32x2 (&MY)[2], int xl, int ybase, float dgy, float sy, float fby,
+                                                 float iv1, float iv4, f32x2 IV2, f32x2 IV5, uint32_t step4, unsigned long long base_adj,
+                                                 uint32_t sm_adj, uint32_t sm_pitch4, float clampx, float clampy,
+                                                 uint32_t one_u, uint32_t two23, float w1f, float h1f, f32x2 ONE)
+{
+    const f32x2 T23 = pk2(8388608.0f, 8388608.0f), N23 = pk2(-8388608.0f, -8388608.0f), ONEI = pk2(1.0f, 1.0f);
+#pragma unroll
+    for (int ry = 0; ry < kWarpRows; ry++) {
+        const int yd = ybase + ry * 8;
+        if (CHECK && yd >= D.chip_h) break;
+        const float yt = ((float)ybase + (float)(ry * 8)) - dgy - sy + fby;       // yTemp (:2357); (float)(ybase + 8 ry) is exact
+        const float ya = yt * iv1, yb = yt * iv4;
+        const f32x2 YA = pk2(ya, ya), YB = pk2(yb, yb);
+        uint32_t* crow = D.chip + (size_t)yd * D.chip_step + xl;
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            f32x2 XS = add2(fma2(MX[h], ONE, YA), IV2);            // (x*inv0 + y*inv1) + inv2
+            f32x2 YS = add2(fma2(MY[h], ONE, YB), IV5);
+            bool va = true, vb = true;
+            if (CHECK) {
+                float xsa, xsb, ysa, ysb;
+                unpk2(XS, xsa, xsb); unpk2(YS, ysa, ysb);
+                va = (xsa >= 0.0f) && (xsa < w1f) && (ysa >= 0.0f) && (ysa < h1f);
+                vb = (xsb >= 0.0f) && (xsb < w1f) && (ysb >= 0.0f) && (ysb < h1f);
+                if (!va) { xsa = clampx; ysa = clampy; }            // keep the taps in bounds; the word is zeroed below
+                if (!vb) { xsb = clampx; ysb = clampy; }
+                XS = pk2(xsa, xsb); YS = pk2(ysa, ysb);
+            }
+            const f32x2 TX = add2_rz(XS, T23), TY = add2_rz(YS, T23);      // 2^23 + int(xs), 2^23 + int(ys)
+            const f32x2 Q = sub2(XS, sub2(TX, T23)), P = sub2(YS, sub2(TY, T23));   // q = xs - ix, p = ys - iy
+            const f32x2 OMP = sub2(ONEI, P), OMQ = sub2(ONEI, Q);
+            const f32x2 C_OMP = mul2(OMP, N23), C_P = mul2(P, N23);        // -2^23 * w, exact
+            uint32_t ixa, ixb, iya, iyb;
+            unpk2u(TX, ixa, ixb); unpk2u(TY, iya, iyb);
+            uint32_t ta[4], tb[4];
+            if (SMEM) {
+                // shared address of tap (ix, iy) = sm_adj + iy_bits * pitch + ix_bits * 4 (biases and footprint origin folded into sm_adj)
+                const uint32_t sa = iya * sm_pitch4 + (ixa * 4u + sm_adj), sb = iyb * sm_pitch4 + (ixb * 4u + sm_adj);
+                ta[0] = lds_u32(sa); ta[1] = lds_u32(sa + 4u); ta[2] = lds_u32(sa + sm_pitch4); ta[3] = lds_u32(sa + sm_pitch4 + 4u);
+                tb[0] = lds_u32(sb); tb[1] = lds_u32(sb + 4u); tb[2] = lds_u32(sb + sm_pitch4); tb[3] = lds_u32(sb + sm_pitch4 + 4u);
+            } else {
+                // byte address of tap (ix, iy) = base_adj + iy_bits * 4 step + ix_bits * 4 (the 0x4B000000 biases are folded into base_adj)
+                const unsigned long long pa = base_adj + (unsigned long long)iya * step4 + (unsigned long long)ixa * 4u;
+                const unsigned long long pb = base_adj + (unsigned long long)iyb * step4 + (unsigned long long)ixb * 4u;
+                const unsigned long long pa1 = pa + (unsigned long long)step4 * one_u, pb1 = pb + (unsigned long long)step4 * one_u;   // one IMAD.WIDE each
+                ta[0] = __ldg(reinterpret_cast<const uint32_t*>(pa)); ta[1] = __ldg(reinterpret_cast<const uint32_t*>(pa + 4));
+                ta[2] = __ldg(reinterpret_cast<const uint32_t*>(pa1)); ta[3] = __ldg(reinterpret_cast<const uint32_t*>(pa1 + 4));
+                tb[0] = __ldg(reinterpret_cast<const uint32_t*>(pb)); tb[1] = __ldg(reinterpret_cast<const uint32_t*>(pb + 4));
+                tb[2] = __ldg(reinterpret_cast<const uint32_t*>(pb1)); tb[3] = __ldg(reinterpret_cast<const uint32_t*>(pb1 + 4));
+            }
+            uint32_t ba, bb, ga, gb, ra, rb;
+            unpk2u(bilinear_channel2<0>(ta, tb, P, Q, OMP, OMQ, C_OMP, C_P, ONE, T23, two23), ba, bb);
+            unpk2u(bilinear_channel2<1>(ta, tb, P, Q, OMP, OMQ, C_OMP, C_P, ONE, T23, two23), ga, gb);
+            unpk2u(bilinear_channel2<2>(ta, tb, P, Q, OMP, OMQ, C_OMP, C_P, ONE, T23, two23), ra, rb);
+            // BGRA word: B, G, R = low bytes; alpha = top byte of 2^23 + r (0x4B, non-zero = valid)
+            uint32_t wa = __byte_perm(__byte_perm(ba, ga, 0x0040), ra, 0x7410);
+            uint32_t wb = __byte_perm(__byte_perm(bb, gb, 0x0040), rb, 0x7410);
+            if (CHECK) {
+                if (!va) wa = 0u;
+                if (!vb) wb = 0u;
+                if (xl + 64 * h < D.chip_w) crow[64 * h] = wa;
+                if (xl + 64 * h + 32 < D.chip_w) crow[64 * h + 32] = wb;
+            } else {
+                crow[64 * h] = wa; crow[64 * h + 32] = wb;
+            }
+        }
+    }
+}
+
+template <int MINB>
+__global__ void __launch_bounds__(256, MINB)
+k5_warp_affine_x2(const ChipDesc* __restrict__ descs, int img_w, int img_h, int src_step_px, float dgx, float dgy, uint32_t two23, float w1f, float h1f, float one,
+                  uint32_t one_u /* = 1, opaque: row-1 tap address = row-0 address + step4 * 1 as a single 64-bit IMAD */,
+                  unsigned long long bias /* = 0x4B000000 * (4 step + 4): the add.rz biases of iy and ix in byte-address units */,
+                  int smem_budget /* bytes of dynamic shared memory for the source footprint; 0 = always load taps directly */)
+{
+    extern __shared__ __align__(128) uint8_t fp_smem[];
+    __shared__ __align__(8) uint64_t fp_bar;
+    __shared__ int fp[6];                            // footprint: x0 (multiple of 4), y0, pitch (words), rows, copy bytes per row, state
+
+    const ChipDesc& D = descs[blockIdx.z];
+    if (!D.keep || !D.affine) return;
+    const int xl = blockIdx.x * kWarpTileW + threadIdx.x;
+    const int ybase = blockIdx.y * kWarpTileH + threadIdx.y;
+    if (blockIdx.x * kWarpTileW >= D.chip_w || blockIdx.y * kWarpTileH >= D.chip_h) return;
+    const float iv0 = D.inv[0], iv1 = D.inv[1], iv2 = D.inv[2], iv3 = D.inv[3], iv4 = D.inv[4], iv5 = D.inv[5];
+    const float fbx = (float)D.beg_x, fby = (float)D.beg_y, sx = D.sx, sy = D.sy;
+    const int tid = threadIdx.y * 32 + threadIdx.x;
+
+    // ---- footprint of the tile (thread 0): xs, ys are monotone in the pixel column and in the row (every rounding
+    // step is monotone), so their extremes over the tile are attained at its corner pixels
+    if (tid == 0) {
+        int state = 0;                                // 0: direct loads, 1: staged, 2: tile entirely outside the source
+        if (smem_budget > 0) {
+            const int cx0 = blockIdx.x * kWarpTileW, cy0 = blockIdx.y * kWarpTileH;
+            const int cx1 = min(cx0 + kWarpTileW, D.chip_w) - 1, cy1 = min(cy0 + kWarpTileH, D.chip_h) - 1;
+            float xmn = 3.0e38f, xmx = -3.0e38f, ymn = 3.0e38f, ymx = -3.0e38f;
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                const float xt = (float)((c & 1) ? cx1 : cx0) - dgx - sx + fbx, yt = (float)((c & 2) ? cy1 : cy0) - dgy - sy + fby;
+                const float xs = xt * iv0 + yt * iv1 + iv2, ys = xt * iv3 + yt * iv4 + iv5;
+                xmn = fminf(xmn, xs); xmx = fmaxf(xmx, xs); ymn = fminf(ymn, ys); ymx = fmaxf(ymx, ys);
+            }
+            if (!(xmx >= 0.0f) || !(xmn < w1f) || !(ymx >= 0.0f) || !(ymn < h1f)) state = 2;
+            else {
+                // valid samples have 0 <= xs < w-1: taps in columns int(xs), int(xs)+1 <= w-1 (same for rows)
+                const int x0 = ((int)fmaxf(xmn, 0.0f)) & ~3, x1 = min((int)fminf(xmx, w1f) + 1, img_w - 1);
+                const int y0 = (int)fmaxf(ymn, 0.0f), y1 = min((int)fminf(ymx, h1f) + 1, img_h - 1);
+                const int wpx = (x1 - x0 + 1 + 3) & ~3;                                     // copied pixels per row (16-byte granules)
+                const int pitch = (wpx + 31) & ~31;                                          // row pitch in words: multiple of 32 banks
+                const int rows = y1 - y0 + 1;
+                if ((long long)pitch * 4 * rows <= (long long)smem_budget && (src_step_px & 3) == 0 && x0 + wpx <= src_step_px) {
+                    state = 1; fp[0] = x0; fp[1] = y0; fp[2] = pitch; fp[3] = rows; fp[4] = wpx * 4;
+                }
+            }
+            if (state == 1) { uavm::ptx::mbar_init(&fp_bar, 1); uavm::ptx::fence_mbar_init(); }
+        }
+        fp[5] = state;
+    }
+    __syncthreads();
+    const int state = fp[5];
+    if (state == 2) {                                 // nothing of this tile is inside the source: BGR = 0, alpha = 0
+#pragma unroll
+        for (int ry = 0; ry < kWarpRows; ry++) {
+            const int yd = ybase + ry * 8;
+            if (yd >= D.chip_h) break;
+#pragma unroll
+            for (int i = 0; i < 4; i++) if (xl + 32 * i < D.chip_w) D.chip[(size_t)yd * D.chip_step + xl + 32 * i] = 0u;
+        }
+        return;
+    }
+    uint32_t sm_adj = 0, sm_pitch4 = 0;
+    float clampx = 0.0f, clampy = 0.0f;
+    if (state == 1) {
+        const int x0 = fp[0], y0 = fp[1], pitch = fp[2], rows = fp[3], row_bytes = fp[4];
+        const uint32_t sbase = uavm::ptx::smem_u32(fp_smem);
+        if (tid < 32) {                               // warp 0: one bulk async copy per footprint row
+            if (tid == 0) uavm::ptx::mbar_arrive_expect_tx(&fp_bar, (uint32_t)(rows * row_bytes));
+            __syncwarp();
+            const uint8_t* g = reinterpret_cast<const uint8_t*>(D.src) + ((size_t)y0 * src_step_px + x0) * 4;
+            for (int r = tid; r < rows; r += 32)
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             :: "r"(sbase + (uint32_t)(r * pitch * 4)), "l"(g + (size_t)r * src_step_px * 4), "r"((uint32_t)row_bytes),
+                                "r"(uavm::ptx::smem_u32(&fp_bar)) : "memory");
+        }
+        sm_pitch4 = (uint32_t)pitch * 4u;
+        sm_adj = sbase - (0x4B000000u * sm_pitch4 + 0x4B000000u * 4u) - ((uint32_t)y0 * sm_pitch4 + (uint32_t)x0 * 4u);
+        clampx = (float)x0; clampy = (float)y0;
+    }
+    const f32x2 ONE = pk2(one, one);
+    const f32x2 IV2 = pk2(iv2, iv2), IV5 = pk2(iv5, iv5);
+    const uint32_t step4 = 4u * (uint32_t)src_step_px;
+    // the raw add.rz results are 0x4B000000 + ix / + iy: fold both biases into the frame base (64-bit, wraps are harmless)
+    const unsigned long long base_adj = reinterpret_cast<unsigned long long>(D.src) - bias;
+    f32x2 MX[2], MY[2];                              // xTemp * inv[0], xTemp * inv[3] for the pixel pairs (k = 2h, 2h + 1): row invariant
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        const float xa = (float)(xl + 64 * h) - dgx - sx + fbx, xb = (float)(xl + 64 * h + 32) - dgx - sx + fbx;   // :2356
+        MX[h] = pk2(xa * iv0, xb * iv0); MY[h] = pk2(xa * iv3, xb * iv3);
+    }
+    // Is the whole 4 x 4 block of this thread inside the source?  (same monotonicity argument, per thread)
+    bool inside = (ybase + 8 * (kWarpRows - 1) < D.chip_h) && (xl + 96 < D.chip_w);
+    {
+        float mxa, mxb, mya, myb, t;
+        unpk2(MX[0], mxa, t); unpk2(MX[1], t, mxb); unpk2(MY[0], mya, t); unpk2(MY[1], t, myb);
+#pragma unroll
+        for (int c = 0; c < 2; c++) {
+            const float yt = (float)(ybase + c * 8 * (kWarpRows - 1)) - dgy - sy + fby;
+            const float ya = yt * iv1, yb = yt * iv4;
+            const float xs0 = mxa + ya + iv2, xs1 = mxb + ya + iv2, ys0 = mya + yb + iv5, ys1 = myb + yb + iv5;
+            inside = inside && (xs0 >= 0.0f) && (xs0 < w1f) && (xs1 >= 0.0f) && (xs1 < w1f) && (ys0 >= 0.0f) && (ys0 < h1f) && (ys1 >= 0.0f) && (ys1 < h1f);
+        }
+    }
+#define K5_ROWS_ARGS D, MX, MY, xl, ybase, dgy, sy, fby, iv1, iv4, IV2, IV5, step4, base_adj, sm_adj, sm_pitch4, clampx, clampy, one_u, two23, w1f, h1f, ONE
+    if (state == 1) {
+        uavm::ptx::mbar_wait(&fp_bar, 0);             // footprint has landed in shared memory
+        if (inside) warp_affine_rows<false, true>(K5_ROWS_ARGS);
+        else        warp_affine_rows<true, true>(K5_ROWS_ARGS);
+    } else {
+        if (inside) warp_affine_rows<false, false>(K5_ROWS_ARGS);
+        else        warp_affine_rows<true, false>(K5_ROWS_ARGS);
+    }
+#undef K5_ROWS_ARGS
+}
+
+// chip (BGRA, alpha != 0 = inside the source) -> the u8 mask plane (255 / 0): the validity mask the reference keeps
+// per chip (:2443-2456), materialised only when somebody needs it before K6 overwrites it with the seam masks
+__global__ void __launch_bounds__(256) k5_alpha_to_mask(const ChipDesc* __restrict__ descs)
+{
+    const ChipDesc& D = descs[blockIdx.z];
+    if (!D.keep) return;
+    const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4, y = blockIdx.y;
+    if (x0 >= D.chip_w || y >= D.chip_h) return;
+    const uint4 v = *reinterpret_cast<const uint4*>(D.chip + (size_t)y * D.chip_step + x0);
+    const uint32_t bits = ((v.x >> 24) ? 0xffu : 0u) | ((v.y >> 24) ? 0xff00u : 0u) | ((v.z >> 24) ? 0xff0000u : 0u) | ((v.w >> 24) ? 0xff000000u : 0u);
+    *reinterpret_cast<uint32_t*>(D.mask + (size_t)y * D.mask_step + x0) = bits;
+}
+
+// BGRA chip -> packed BGR rows (for uavm_canvas_get_chip)
+__global__ void __launch_bounds__(256) k5_chip_to_bgr(const uint32_t* __restrict__ chip, int chip_step, int w, int h, uint8_t* __restrict__ out)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= w || y >= h) return;
+    const uint32_t v = chip[(size_t)y * chip_step + x];
+    uint8_t* o = out + ((size_t)y * w + x) * 3;
+    o[0] = (uint8_t)v; o[1] = (uint8_t)(v >> 8); o[2] = (uint8_t)(v >> 16);
+}
+
 
 inline int align4(int v) { return (v + 3) & ~3; }
 
@@ -151,12 +436,12 @@ extern "C" int uavm_canvas_create(uavm_ctx* ctx, int n_images, int img_w, int im
             delete cv; return UAVM_EINVAL;
         }
         d.chip_w = c.chip_w; d.chip_h = c.chip_h;
-        d.mask_step = align4(c.chip_w); d.chip_step = 3 * d.mask_step;
+        d.mask_step = align4(c.chip_w); d.chip_step = d.mask_step;
         d.beg_x = c.beg_x; d.beg_y = c.beg_y; d.sx = c.sx; d.sy = c.sy;
         memcpy(d.inv, c.inv, sizeof(d.inv)); memcpy(d.quad, c.quad, sizeof(d.quad));
         d.affine = (c.inv[6] == 0.0f && c.inv[7] == 0.0f && c.inv[8] == 1.0f) ? 1 : 0;
         coff[k] = chip_off; moff[k] = mask_off;
-        chip_off += (size_t)d.chip_step * d.chip_h; mask_off += (size_t)d.mask_step * d.chip_h;
+        chip_off += (size_t)d.chip_step * d.chip_h * 4; mask_off += (size_t)d.mask_step * d.chip_h;
         chip_off = (chip_off + 255) & ~(size_t)255; mask_off = (mask_off + 255) & ~(size_t)255;
         if (c.chip_w > cv->max_chip_w) cv->max_chip_w = c.chip_w;
         if (c.chip_h > cv->max_chip_h) cv->max_chip_h = c.chip_h;
@@ -166,14 +451,21 @@ extern "C" int uavm_canvas_create(uavm_ctx* ctx, int n_images, int img_w, int im
     UAVM_CUDA(ctx, cudaMalloc(&cv->d_src, (size_t)n_images * img_h * cv->src_step_px * sizeof(uchar4)));
     UAVM_CUDA(ctx, cudaMalloc(&cv->d_chips, chip_off + 256));
     UAVM_CUDA(ctx, cudaMalloc(&cv->d_masks, mask_off + 256));
+    UAVM_CUDA(ctx, cudaMemsetAsync(cv->d_chips, 0, chip_off + 256, ctx->stream));       // row padding stays zero
+    UAVM_CUDA(ctx, cudaMemsetAsync(cv->d_masks, 0, mask_off + 256, ctx->stream));
     UAVM_CUDA(ctx, cudaMalloc(&cv->d_desc, (size_t)n_images * sizeof(ChipDesc)));
-    cv->stage_bytes = (size_t)img_h * img_w * 3;
-    UAVM_CUDA(ctx, cudaMalloc(&cv->d_stage, cv->stage_bytes));
+    cv->stage_pitch = (img_w * 3 + 15) & ~15;
+    cv->stage_bytes = (size_t)img_h * cv->stage_pitch;
+    for (int s = 0; s < uavm_canvas::kStageSlots; s++) {
+        UAVM_CUDA(ctx, cudaMalloc(&cv->d_stage[s], cv->stage_bytes));
+        UAVM_CUDA(ctx, cudaEventCreateWithFlags(&cv->ev_copied[s], cudaEventDisableTiming));
+        UAVM_CUDA(ctx, cudaEventCreateWithFlags(&cv->ev_free[s], cudaEventDisableTiming));
+    }
     for (int k = 0; k < n_images; k++) {
         ChipDesc& d = cv->desc[k];
         d.src = cv->d_src + (size_t)k * img_h * cv->src_step_px;
         if (!d.keep) continue;
-        d.chip = cv->d_chips + coff[k]; d.mask = cv->d_masks + moff[k];
+        d.chip = cv->d_chips + coff[k] / 4; d.mask = cv->d_masks + moff[k];
     }
     cv->band_y0 = 0; cv->band_y1 = cv->layout.canvas_h; cv->band_Y0 = 0; cv->band_Y1 = (cv->layout.canvas_h + 31) & ~31;
     rc = uavm_canvas_upload_desc(ctx, cv);
@@ -208,7 +500,7 @@ extern "C" int uavm_canvas_set_band(uavm_ctx* ctx, uavm_canvas* cv, int y0, int 
         d.keep = active ? 1 : 0;
         if (active) { if (c.chip_w > cv->max_chip_w) cv->max_chip_w = c.chip_w; if (c.chip_h > cv->max_chip_h) cv->max_chip_h = c.chip_h; }
     }
-    cv->nbr_dirty = true; cv->warped = false; cv->seamed = false; cv->blended = false;
+    cv->nbr_dirty = true; cv->warped = false; cv->seamed = false; cv->blended = false; cv->mask_plane_valid = false;
     return uavm_canvas_upload_desc(ctx, cv);
 }
 extern "C" int uavm_canvas_is_active(uavm_canvas* cv, int image)
@@ -220,10 +512,15 @@ extern "C" int uavm_canvas_is_active(uavm_canvas* cv, int image)
 extern "C" void uavm_canvas_destroy(uavm_ctx* ctx, uavm_canvas* cv)
 {
     if (!cv) return;
-    if (ctx) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
+    if (ctx) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream); }
+    for (int s = 0; s < uavm_canvas::kStageSlots; s++) {
+        cudaFree(cv->d_stage[s]);
+        if (cv->ev_copied[s]) cudaEventDestroy(cv->ev_copied[s]);
+        if (cv->ev_free[s]) cudaEventDestroy(cv->ev_free[s]);
+    }
     uavm_blend_free(cv);
     cudaFree(cv->d_src); cudaFree(cv->d_chips); cudaFree(cv->d_masks); cudaFree(cv->d_dist); cudaFree(cv->d_dist_max);
-    cudaFree(cv->d_desc); cudaFree(cv->d_nbr); cudaFree(cv->d_stage); cudaFree(cv->d_result); cudaFree(cv->d_result_mask);
+    cudaFree(cv->d_desc); cudaFree(cv->d_nbr); cudaFree(cv->d_result); cudaFree(cv->d_result_mask);
     delete cv;
 }
 
@@ -239,38 +536,87 @@ extern "C" int uavm_canvas_set_image(uavm_ctx* ctx, uavm_canvas* cv, int image, 
 {
     if (!ctx || !cv || image < 0 || image >= cv->n || !bgr || step < cv->img_w * 3) return UAVM_EINVAL;
     const uint8_t* src = bgr; int sstep = step;
+    int slot = -1;
     if (!is_device) {
-        UAVM_CUDA(ctx, cudaMemcpy2DAsync(cv->d_stage, (size_t)cv->img_w * 3, bgr, (size_t)step, (size_t)cv->img_w * 3, cv->img_h,
-                                         cudaMemcpyHostToDevice, ctx->stream));
-        src = cv->d_stage; sstep = cv->img_w * 3;
+        // host frame: PCIe copy on the copy stream into a ring slot; the compute stream only waits for THIS frame
+        slot = cv->stage_next; cv->stage_next = (slot + 1) % uavm_canvas::kStageSlots;
+        UAVM_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, cv->ev_free[slot], 0));          // previous user of the slot has been converted
+        UAVM_CUDA(ctx, cudaMemcpy2DAsync(cv->d_stage[slot], (size_t)cv->stage_pitch, bgr, (size_t)step, (size_t)cv->img_w * 3, cv->img_h,
+                                         cudaMemcpyHostToDevice, ctx->copy_stream));
+        UAVM_CUDA(ctx, cudaEventRecord(cv->ev_copied[slot], ctx->copy_stream));
+        UAVM_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, cv->ev_copied[slot], 0));
+        src = cv->d_stage[slot]; sstep = cv->stage_pitch;
     }
-    dim3 grid((cv->img_w + 255) / 256, cv->img_h);
-    k5_bgr_to_bgra<<<grid, 256, 0, ctx->stream>>>(src, cv->img_w, cv->img_h, sstep,
-                                                   cv->d_src + (size_t)image * cv->img_h * cv->src_step_px, cv->src_step_px);
+    uchar4* dst = cv->d_src + (size_t)image * cv->img_h * cv->src_step_px;
+    if ((sstep % 4) == 0 && (reinterpret_cast<uintptr_t>(src) % 4) == 0) {
+        dim3 grid(((cv->img_w + 3) / 4 + 127) / 128, cv->img_h);
+        k5_bgr_to_bgra_x4<<<grid, 128, 0, ctx->stream>>>(src, cv->img_w, sstep, dst, cv->src_step_px);
+    } else {
+        dim3 grid((cv->img_w + 255) / 256, cv->img_h);
+        k5_bgr_to_bgra<<<grid, 256, 0, ctx->stream>>>(src, cv->img_w, cv->img_h, sstep, dst, cv->src_step_px);
+    }
     UAVM_CHECK_LAUNCH(ctx);
+    if (slot >= 0) UAVM_CUDA(ctx, cudaEventRecord(cv->ev_free[slot], ctx->stream));
+    return UAVM_OK;
+}
+
+// images [first, first + count): lets a caller that streams frames in warp each group as soon as it has been set
+extern "C" int uavm_canvas_warp_range(uavm_ctx* ctx, uavm_canvas* cv, int first, int count)
+{
+    if (!ctx || !cv || first < 0 || count < 0 || first + count > cv->n) return UAVM_EINVAL;
+    if (cv->max_chip_w <= 0 || count == 0) return UAVM_OK;
+    dim3 grid((cv->max_chip_w + kWarpTileW - 1) / kWarpTileW, (cv->max_chip_h + kWarpTileH - 1) / kWarpTileH, count);
+    dim3 block(32, 8);
+    bool any_affine = false, any_proj = false;
+    for (int k = first; k < first + count; k++)
+        if (cv->desc[k].keep) { if (cv->desc[k].affine) any_affine = true; else any_proj = true; }
+    if (any_affine) {
+        static const bool scalar = getenv("UAVM_K5_SCALAR") != nullptr;       // A/B switch for profiling; both are bit-exact
+        // the packed kernel derives tap offsets from 23-bit mantissas and 32-bit pixel offsets
+        static const int minb = getenv("UAVM_K5_MINB") ? atoi(getenv("UAVM_K5_MINB")) : 3;
+        if (!scalar && cv->img_w < (1 << 22) && cv->img_h < (1 << 22) && (int64_t)cv->img_h * cv->src_step_px < ((int64_t)1 << 31)) {
+#define K5X2_ARGS cv->d_desc + first, cv->img_w, cv->img_h, cv->src_step_px, cv->layout.dgx, cv->layout.dgy, 0x4B000000u, (float)(cv->img_w - 1), \
+                  (float)(cv->img_h - 1), 1.0f, 1u, 0x4B000000ull * (4ull * (unsigned long long)cv->src_step_px + 4ull), smem
+            static const int smem = getenv("UAVM_K5_SMEM") ? atoi(getenv("UAVM_K5_SMEM")) : kFootprintSmem;
+            static bool attr_done = false;
+            if (!attr_done) {
+                cudaFuncSetAttribute(k5_warp_affine_x2<3>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+                cudaFuncSetAttribute(k5_warp_affine_x2<4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+                cudaFuncSetAttribute(k5_warp_affine_x2<5>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+                attr_done = true;
+            }
+            if (minb == 5) k5_warp_affine_x2<5><<<grid, block, smem, ctx->stream>>>(K5X2_ARGS);
+            else if (minb == 4) k5_warp_affine_x2<4><<<grid, block, smem, ctx->stream>>>(K5X2_ARGS);
+            else k5_warp_affine_x2<3><<<grid, block, smem, ctx->stream>>>(K5X2_ARGS);
+        }
+        else
+            k5_warp_chips<true><<<grid, block, 0, ctx->stream>>>(cv->d_desc + first, cv->img_w, cv->img_h, cv->src_step_px, cv->layout.dgx, cv->layout.dgy, 0x4B000000u,
+                                                                 (float)(cv->img_w - 1), (float)(cv->img_h - 1));
+        UAVM_CHECK_LAUNCH(ctx);
+    }
+    if (any_proj) {
+        k5_warp_chips<false><<<grid, block, 0, ctx->stream>>>(cv->d_desc + first, cv->img_w, cv->img_h, cv->src_step_px, cv->layout.dgx, cv->layout.dgy, 0x4B000000u,
+                                                             (float)(cv->img_w - 1), (float)(cv->img_h - 1));
+        UAVM_CHECK_LAUNCH(ctx);
+    }
+    cv->warped = true; cv->seamed = false; cv->mask_plane_valid = false;
     return UAVM_OK;
 }
 
 extern "C" int uavm_canvas_warp(uavm_ctx* ctx, uavm_canvas* cv)
 {
     if (!ctx || !cv) return UAVM_EINVAL;
-    if (cv->max_chip_w <= 0) return UAVM_OK;
-    dim3 grid((cv->max_chip_w + kWarpTileW - 1) / kWarpTileW, (cv->max_chip_h + kWarpTileH - 1) / kWarpTileH, cv->n);
-    dim3 block(32, 8);
-    bool any_affine = false, any_proj = false;
-    for (int k = 0; k < cv->n; k++)
-        if (cv->desc[k].keep) { if (cv->desc[k].affine) any_affine = true; else any_proj = true; }
-    if (any_affine) {
-        k5_warp_chips<true><<<grid, block, 0, ctx->stream>>>(cv->d_desc, cv->img_w, cv->img_h, cv->src_step_px, cv->layout.dgx, cv->layout.dgy, 0x4B000000u,
-                                                             (float)(cv->img_w - 1), (float)(cv->img_h - 1));
-        UAVM_CHECK_LAUNCH(ctx);
-    }
-    if (any_proj) {
-        k5_warp_chips<false><<<grid, block, 0, ctx->stream>>>(cv->d_desc, cv->img_w, cv->img_h, cv->src_step_px, cv->layout.dgx, cv->layout.dgy, 0x4B000000u,
-                                                             (float)(cv->img_w - 1), (float)(cv->img_h - 1));
-        UAVM_CHECK_LAUNCH(ctx);
-    }
-    cv->warped = true;
+    return uavm_canvas_warp_range(ctx, cv, 0, cv->n);
+}
+
+// expands the validity masks (chip alpha) into the u8 mask plane unless the plane already holds them or K6's seam masks
+int uavm_canvas_mask_plane(uavm_ctx* ctx, uavm_canvas* cv)
+{
+    if (cv->seamed || cv->mask_plane_valid || cv->max_chip_w <= 0) return UAVM_OK;
+    dim3 grid(((cv->max_chip_w + 3) / 4 + 255) / 256, cv->max_chip_h, cv->n);
+    k5_alpha_to_mask<<<grid, 256, 0, ctx->stream>>>(cv->d_desc);
+    UAVM_CHECK_LAUNCH(ctx);
+    cv->mask_plane_valid = true;
     return UAVM_OK;
 }
 
@@ -279,14 +625,28 @@ extern "C" int uavm_canvas_get_chip(uavm_ctx* ctx, uavm_canvas* cv, int image, u
     if (!ctx || !cv || image < 0 || image >= cv->n) return UAVM_EINVAL;
     const ChipDesc& d = cv->desc[image];
     if (!d.keep) return UAVM_EINVAL;
+    uint8_t* tmp = nullptr;
     if (chip_bgr) {
         if (chip_step < d.chip_w * 3) return UAVM_EINVAL;
-        UAVM_CUDA(ctx, cudaMemcpy2DAsync(chip_bgr, (size_t)chip_step, d.chip, (size_t)d.chip_step, (size_t)d.chip_w * 3, d.chip_h, cudaMemcpyDeviceToHost, ctx->stream));
+        UAVM_CUDA(ctx, cudaMalloc(&tmp, (size_t)d.chip_w * d.chip_h * 3));
+        dim3 grid((d.chip_w + 255) / 256, d.chip_h);
+        k5_chip_to_bgr<<<grid, 256, 0, ctx->stream>>>(d.chip, d.chip_step, d.chip_w, d.chip_h, tmp);
+        if (cudaGetLastError() != cudaSuccess) { cudaFree(tmp); return UAVM_EFAIL; }
+        ctx->launches++;
+        if (cudaMemcpy2DAsync(chip_bgr, (size_t)chip_step, tmp, (size_t)d.chip_w * 3, (size_t)d.chip_w * 3, d.chip_h, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) {
+            cudaFree(tmp); return UAVM_EFAIL;
+        }
     }
     if (mask) {
-        if (mask_step < d.chip_w) return UAVM_EINVAL;
-        UAVM_CUDA(ctx, cudaMemcpy2DAsync(mask, (size_t)mask_step, d.mask, (size_t)d.mask_step, (size_t)d.chip_w, d.chip_h, cudaMemcpyDeviceToHost, ctx->stream));
+        if (mask_step < d.chip_w) { cudaFree(tmp); return UAVM_EINVAL; }
+        int rc = uavm_canvas_mask_plane(ctx, cv);
+        if (rc != UAVM_OK) { cudaFree(tmp); return rc; }
+        if (cudaMemcpy2DAsync(mask, (size_t)mask_step, d.mask, (size_t)d.mask_step, (size_t)d.chip_w, d.chip_h, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) {
+            cudaFree(tmp); return UAVM_EFAIL;
+        }
     }
-    UAVM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(tmp);
+    if (e != cudaSuccess) { UAVM_SET_ERR(ctx, "get_chip: %s", cudaGetErrorString(e)); return UAVM_EFAIL; }
     return UAVM_OK;
 }

@@ -4,8 +4,9 @@
 
 struct ChipDesc {               // one per image, device-visible
     const uchar4* src;          // BGRA source frame
-    uint8_t* chip;              // packed BGR, chip_step bytes per row (= 3 * align4(chip_w))
-    uint8_t* mask;              // u8, mask_step bytes per row (= align4(chip_w))
+    uint32_t* chip;             // BGRA words, chip_step WORDS per row (= align4(chip_w)); alpha != 0 <=> pixel inside the source
+    uint8_t* mask;              // u8 mask plane, mask_step bytes per row (= align4(chip_w)): K6 seam masks (or the validity mask,
+                                // expanded from alpha on demand: uavm_canvas_mask_plane)
     float* dist;                // K6 distance map, mask_step floats per row (nullptr until K6 runs)
     int32_t keep;
     int32_t chip_w, chip_h, chip_step, mask_step;
@@ -25,13 +26,18 @@ struct uavm_canvas {
     std::vector<uavm_chip_layout> chips;
     std::vector<ChipDesc> desc;
     uchar4* d_src = nullptr;
-    uint8_t* d_chips = nullptr;
+    uint32_t* d_chips = nullptr;     // BGRA chips
     uint8_t* d_masks = nullptr;
     float* d_dist = nullptr;
     float* d_dist_max = nullptr;     // [n] per-image maximum of the distance map (as uint bits)
     int32_t* d_nbr = nullptr;        // K6 neighbour lists
     ChipDesc* d_desc = nullptr;
-    uint8_t* d_stage = nullptr;      // staging for host BGR frames
+    // staging ring for host BGR frames: slot s is filled by the ctx's copy stream and drained by the BGR->BGRA
+    // kernel on the compute stream, so the PCIe copy of frame k+1 overlaps the conversion / warp of frame k
+    static constexpr int kStageSlots = 3;
+    uint8_t* d_stage[kStageSlots] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev_copied[kStageSlots] = {nullptr, nullptr, nullptr}, ev_free[kStageSlots] = {nullptr, nullptr, nullptr};
+    int stage_next = 0, stage_pitch = 0;
     size_t stage_bytes = 0;
     size_t chips_bytes = 0, masks_bytes = 0;
     int max_chip_w = 0, max_chip_h = 0;
@@ -44,8 +50,10 @@ struct uavm_canvas {
     bool banded = false, nbr_dirty = true;
     int result_w = 0, result_h = 0;  // size of d_result (blend: canvas layout; paste: MosaicImagesRefined's own bbox)
     bool warped = false, seamed = false, blended = false;
+    bool mask_plane_valid = false;   // d_masks currently holds the seam masks (seamed) or the validity masks (expanded from alpha)
     void* blend_ws = nullptr;        // opaque workspace owned by blend.cu
 };
 
 int uavm_canvas_upload_desc(uavm_ctx* ctx, uavm_canvas* cv);
+int uavm_canvas_mask_plane(uavm_ctx* ctx, uavm_canvas* cv);   // makes sure d_masks is populated (validity masks if K6 has not run)
 void uavm_blend_free(uavm_canvas* cv);

@@ -38,7 +38,8 @@ extern "C" int uavm_ctx_create(int device, uavm_ctx** out) {
     c->main_stream = c->stream;
     int prio_lo = 0, prio_hi = 0;
     cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);          // side stream = highest priority: its (latency-bound)
-    if (cudaStreamCreateWithPriority(&c->side_stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||   // blocks are placed first
+    if (cudaStreamCreateWithPriority(&c->side_stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||   // blocks are placed first
 
         cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&c->ev_side, cudaEventDisableTiming) != cudaSuccess) { delete c; return UAVM_EFAIL; }
@@ -50,6 +51,7 @@ extern "C" void uavm_ctx_destroy(uavm_ctx* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->own_stream && ctx->main_stream) cudaStreamDestroy(ctx->main_stream);
     if (ctx->side_stream) cudaStreamDestroy(ctx->side_stream);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_side) cudaEventDestroy(ctx->ev_side);
     delete ctx;

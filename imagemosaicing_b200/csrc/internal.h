@@ -14,6 +14,7 @@ struct uavm_ctx {
     cudaStream_t stream = nullptr;     // stream every launch of this ctx goes to (main or, between fork/unfork, side)
     bool own_stream = false;
     cudaStream_t main_stream = nullptr, side_stream = nullptr;
+    cudaStream_t copy_stream = nullptr; // host->device frame copies (overlap with compute on `stream`, ordered by events)
     cudaEvent_t ev_fork = nullptr, ev_side = nullptr;
     bool forked = false, side_pending = false;
     int64_t launches = 0;

@@ -26,13 +26,15 @@ k6_dist_map(const ChipDesc* __restrict__ descs, float* __restrict__ dist_max)
     if (blockIdx.x * kTileW >= D.chip_w || blockIdx.y * kTileH >= D.chip_h) return;
     float mx = 0.0f;
     if (x0 < D.chip_w && r < D.chip_h) {
-        const uint32_t m4 = *reinterpret_cast<const uint32_t*>(D.mask + (size_t)r * D.mask_step + x0);
+        // validity = chip alpha (K5 writes BGRA chips; the u8 mask plane is this stage's OUTPUT)
+        const uint4 c4 = *reinterpret_cast<const uint4*>(D.chip + (size_t)r * D.chip_step + x0);
+        const uint32_t valid[4] = {c4.x >> 24, c4.y >> 24, c4.z >> 24, c4.w >> 24};
         float out[4];
 #pragma unroll
         for (int i = 0; i < 4; i++) {
             const int c = x0 + i;
             float mind = 0.0f;
-            if (((m4 >> (8 * i)) & 0xffu) != 0 && c < D.chip_w) {
+            if (valid[i] != 0 && c < D.chip_w) {
                 mind = 536870912.0f;                                   // float minDist = 1<<29
 #pragma unroll
                 for (int e = 0; e < 4; e++) {
@@ -165,6 +167,6 @@ extern "C" int uavm_canvas_seam_masks(uavm_ctx* ctx, uavm_canvas* cv)
     UAVM_CHECK_LAUNCH(ctx);
     k6_owner<<<grid, block, 0, ctx->stream>>>(cv->d_desc, cv->d_nbr);
     UAVM_CHECK_LAUNCH(ctx);
-    cv->seamed = true;
+    cv->seamed = true; cv->mask_plane_valid = true;
     return UAVM_OK;
 }

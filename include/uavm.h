@@ -152,6 +152,9 @@ int uavm_canvas_is_active(uavm_canvas* cv, int image);
 int uavm_canvas_set_image(uavm_ctx* ctx, uavm_canvas* cv, int image, const uint8_t* bgr, int step, int is_device);
 /* K5: bilinear warp of every kept frame into its chip + validity mask (:2350-2448) */
 int uavm_canvas_warp(uavm_ctx* ctx, uavm_canvas* cv);
+/* same for images [first, first + count) only: a caller that streams frames in (uavm_canvas_set_image copies host
+ * frames on an internal copy stream) warps each group as soon as it is set, overlapping PCIe with compute */
+int uavm_canvas_warp_range(uavm_ctx* ctx, uavm_canvas* cv, int first, int count);
 /* K6: FindMasksByDistMap (:1761-1881) */
 int uavm_canvas_seam_masks(uavm_ctx* ctx, uavm_canvas* cv);
 /* K7: MultiBandBlender prepare/feed/blend + convertTo(CV_8U) (:2296-2299, :2476-2486) */
