@@ -76,7 +76,9 @@ __device__ __forceinline__ uint32_t bilinear_channel(uint32_t t00, uint32_t t01,
 constexpr int kWarpTileW = 128;   // 32 lanes x 4 px
 constexpr int kWarpRows = 4;      // rows per thread
 constexpr int kWarpTileH = 8 * kWarpRows;
-constexpr int kFootprintSmem = 40 * 1024;   // dynamic shared memory per CTA for the staged source footprint (5 CTAs / SM)
+constexpr int kFpBoxW = 160, kFpBoxH = 16;        // TMA box (pixels): the staged footprint is up to kFpBoxes boxes stacked vertically
+constexpr int kFpBoxBytes = kFpBoxW * kFpBoxH * 4;
+constexpr int kFpBoxes = 4;                       // 160 x 64 px = 40 KB of dynamic shared memory per CTA (5 CTAs / SM)
 
 // Generic (projective) warp, scalar.  AFFINE: inv[6] == inv[7] == 0 and inv[8] == 1, so the reference's denominator is
 // exactly 1.0f for every pixel and x / 1.0f == x: the two divides per coordinate (:2359-2362) are skipped without
@@ -186,15 +188,17 @@ __device__ __forceinline__ f32x2 bilinear_channel2(const uint32_t (&ta)[4], cons
 //
 // CHECK = false: the caller proved every pixel of this thread's 4 x 4 block lies inside the source, so the
 // per-pixel validity test, the tap clamping and the zeroing are skipped.
-__device__ __forceinline__ uint32_t lds_u32(uint32_t saddr) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr)); return v; }
+
+__device__ __forceinline__ uint32_t lds_u32(const uint8_t* base, uint32_t off) { return *reinterpret_cast<const uint32_t*>(base + off); }
 
 template <bool CHECK, bool SMEM>
-__device__ __forceinline__ void warp_affine_rows(const ChipDesc& D, const f32x2 (&MX)[2], const f32x2 (&MY)[2], int xl, int ybase, float dgy, float sy, float fby,
+__device__ __forceinline__ void warp_affine_rows(const uint8_t* fp_base, const ChipDesc& D, const f32x2 (&MX)[2], const f32x2 (&MY)[2], int xl, int ybase, float dgy, float sy, float fby,
                                                  float iv1, float iv4, f32x2 IV2, f32x2 IV5, uint32_t step4, unsigned long long base_adj,
-                                                 uint32_t sm_adj, uint32_t sm_pitch4, float clampx, float clampy,
+                                                 uint32_t sm_adj, float clampx, float clampy,
                                                  uint32_t one_u, uint32_t two23, float w1f, float h1f, f32x2 ONE)
 {
     const f32x2 T23 = pk2(8388608.0f, 8388608.0f), N23 = pk2(-8388608.0f, -8388608.0f), ONEI = pk2(1.0f, 1.0f);
+    constexpr uint32_t sm_pitch4 = kFpBoxW * 4u;
 #pragma unroll
     for (int ry = 0; ry < kWarpRows; ry++) {
         const int yd = ybase + ry * 8;
@@ -225,10 +229,10 @@ __device__ __forceinline__ void warp_affine_rows(const ChipDesc& D, const f32x2 
             unpk2u(TX, ixa, ixb); unpk2u(TY, iya, iyb);
             uint32_t ta[4], tb[4];
             if (SMEM) {
-                // shared address of tap (ix, iy) = sm_adj + iy_bits * pitch + ix_bits * 4 (biases and footprint origin folded into sm_adj)
+                // offset of tap (ix, iy) in the staged footprint = sm_adj + iy_bits * pitch + ix_bits * 4 (biases and footprint origin folded into sm_adj)
                 const uint32_t sa = iya * sm_pitch4 + (ixa * 4u + sm_adj), sb = iyb * sm_pitch4 + (ixb * 4u + sm_adj);
-                ta[0] = lds_u32(sa); ta[1] = lds_u32(sa + 4u); ta[2] = lds_u32(sa + sm_pitch4); ta[3] = lds_u32(sa + sm_pitch4 + 4u);
-                tb[0] = lds_u32(sb); tb[1] = lds_u32(sb + 4u); tb[2] = lds_u32(sb + sm_pitch4); tb[3] = lds_u32(sb + sm_pitch4 + 4u);
+                ta[0] = lds_u32(fp_base, sa); ta[1] = lds_u32(fp_base, sa + 4u); ta[2] = lds_u32(fp_base, sa + sm_pitch4); ta[3] = lds_u32(fp_base, sa + sm_pitch4 + 4u);
+                tb[0] = lds_u32(fp_base, sb); tb[1] = lds_u32(fp_base, sb + 4u); tb[2] = lds_u32(fp_base, sb + sm_pitch4); tb[3] = lds_u32(fp_base, sb + sm_pitch4 + 4u);
             } else {
                 // byte address of tap (ix, iy) = base_adj + iy_bits * 4 step + ix_bits * 4 (the 0x4B000000 biases are folded into base_adj)
                 const unsigned long long pa = base_adj + (unsigned long long)iya * step4 + (unsigned long long)ixa * 4u;
@@ -258,16 +262,43 @@ __device__ __forceinline__ void warp_affine_rows(const ChipDesc& D, const f32x2 
     }
 }
 
-template <int MINB>
-__global__ void __launch_bounds__(256, MINB)
-k5_warp_affine_x2(const ChipDesc* __restrict__ descs, int img_w, int img_h, int src_step_px, float dgx, float dgy, uint32_t two23, float w1f, float h1f, float one,
+// Footprint of chip tile (bx, by): the source rectangle its taps fall into.  xs, ys are monotone in the pixel column and
+// in the row (every rounding step is monotone), so their extremes over the tile are attained at its corner pixels.
+// Returns 0: use direct loads, 1: stage rows [y0, y0 + rows) x columns [x0, x0 + kFpBoxW), 2: tile entirely outside.
+__device__ __forceinline__ int tile_footprint(const ChipDesc& D, int bx, int by, int img_w, int img_h, float dgx, float dgy,
+                                              float w1f, float h1f, int max_boxes, int& x0, int& y0, int& rows)
+{
+    const float iv0 = D.inv[0], iv1 = D.inv[1], iv2 = D.inv[2], iv3 = D.inv[3], iv4 = D.inv[4], iv5 = D.inv[5];
+    const float fbx = (float)D.beg_x, fby = (float)D.beg_y, sx = D.sx, sy = D.sy;
+    const int cx0 = bx * kWarpTileW, cy0 = by * kWarpTileH;
+    const int cx1 = min(cx0 + kWarpTileW, D.chip_w) - 1, cy1 = min(cy0 + kWarpTileH, D.chip_h) - 1;
+    float xmn = 3.0e38f, xmx = -3.0e38f, ymn = 3.0e38f, ymx = -3.0e38f;
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+        const float xt = (float)((c & 1) ? cx1 : cx0) - dgx - sx + fbx, yt = (float)((c & 2) ? cy1 : cy0) - dgy - sy + fby;
+        const float xs = xt * iv0 + yt * iv1 + iv2, ys = xt * iv3 + yt * iv4 + iv5;
+        xmn = fminf(xmn, xs); xmx = fmaxf(xmx, xs); ymn = fminf(ymn, ys); ymx = fmaxf(ymx, ys);
+    }
+    if (!(xmx >= 0.0f) || !(xmn < w1f) || !(ymx >= 0.0f) || !(ymn < h1f)) return 2;
+    // valid samples have 0 <= xs < w-1: taps in columns int(xs), int(xs)+1 <= w-1 (same for rows)
+    x0 = ((int)fmaxf(xmn, 0.0f)) & ~3;                                         // 16-byte aligned box origin
+    const int x1 = min((int)fminf(xmx, w1f) + 1, img_w - 1);
+    y0 = (int)fmaxf(ymn, 0.0f);
+    const int y1 = min((int)fminf(ymx, h1f) + 1, img_h - 1);
+    rows = y1 - y0 + 1;
+    return (x1 - x0 + 1 <= kFpBoxW && rows <= max_boxes * kFpBoxH) ? 1 : 0;
+}
+
+__global__ void __launch_bounds__(256, 4)
+k5_warp_affine_x2(const __grid_constant__ CUtensorMap tmap_src, const ChipDesc* __restrict__ descs, int img_w, int img_h, int src_step_px, float dgx, float dgy,
+                  uint32_t two23, float w1f, float h1f, float one,
                   uint32_t one_u /* = 1, opaque: row-1 tap address = row-0 address + step4 * 1 as a single 64-bit IMAD */,
                   unsigned long long bias /* = 0x4B000000 * (4 step + 4): the add.rz biases of iy and ix in byte-address units */,
-                  int smem_budget /* bytes of dynamic shared memory for the source footprint; 0 = always load taps directly */)
+                  int max_boxes /* TMA boxes of dynamic shared memory for the source footprint; 0 = always load taps directly */)
 {
     extern __shared__ __align__(128) uint8_t fp_smem[];
     __shared__ __align__(8) uint64_t fp_bar;
-    __shared__ int fp[6];                            // footprint: x0 (multiple of 4), y0, pitch (words), rows, copy bytes per row, state
+    __shared__ int fp[4];                            // footprint: x0, y0, rows, state
 
     const ChipDesc& D = descs[blockIdx.z];
     if (!D.keep || !D.affine) return;
@@ -278,38 +309,25 @@ k5_warp_affine_x2(const ChipDesc* __restrict__ descs, int img_w, int img_h, int 
     const float fbx = (float)D.beg_x, fby = (float)D.beg_y, sx = D.sx, sy = D.sy;
     const int tid = threadIdx.y * 32 + threadIdx.x;
 
-    // ---- footprint of the tile (thread 0): xs, ys are monotone in the pixel column and in the row (every rounding
-    // step is monotone), so their extremes over the tile are attained at its corner pixels
+    // ---- thread 0: footprint of this tile, then one TMA box copy per 16 footprint rows (completion on fp_bar)
     if (tid == 0) {
         int state = 0;                                // 0: direct loads, 1: staged, 2: tile entirely outside the source
-        if (smem_budget > 0) {
-            const int cx0 = blockIdx.x * kWarpTileW, cy0 = blockIdx.y * kWarpTileH;
-            const int cx1 = min(cx0 + kWarpTileW, D.chip_w) - 1, cy1 = min(cy0 + kWarpTileH, D.chip_h) - 1;
-            float xmn = 3.0e38f, xmx = -3.0e38f, ymn = 3.0e38f, ymx = -3.0e38f;
-#pragma unroll
-            for (int c = 0; c < 4; c++) {
-                const float xt = (float)((c & 1) ? cx1 : cx0) - dgx - sx + fbx, yt = (float)((c & 2) ? cy1 : cy0) - dgy - sy + fby;
-                const float xs = xt * iv0 + yt * iv1 + iv2, ys = xt * iv3 + yt * iv4 + iv5;
-                xmn = fminf(xmn, xs); xmx = fmaxf(xmx, xs); ymn = fminf(ymn, ys); ymx = fmaxf(ymx, ys);
+        if (max_boxes > 0) {
+            int x0, y0, rows;
+            state = tile_footprint(D, blockIdx.x, blockIdx.y, img_w, img_h, dgx, dgy, w1f, h1f, max_boxes, x0, y0, rows);
+            if (state == 1) {
+                fp[0] = x0; fp[1] = y0; fp[2] = rows;
+                uavm::ptx::mbar_init(&fp_bar, 1); uavm::ptx::fence_mbar_init();
+                const int boxes = (rows + kFpBoxH - 1) / kFpBoxH;
+                uavm::ptx::mbar_arrive_expect_tx(&fp_bar, (uint32_t)(boxes * kFpBoxBytes));
+                for (int k = 0; k < boxes; k++)
+                    uavm::ptx::tma_load_2d(fp_smem + k * kFpBoxBytes, &tmap_src, &fp_bar, x0, D.src_row0 + y0 + k * kFpBoxH);
             }
-            if (!(xmx >= 0.0f) || !(xmn < w1f) || !(ymx >= 0.0f) || !(ymn < h1f)) state = 2;
-            else {
-                // valid samples have 0 <= xs < w-1: taps in columns int(xs), int(xs)+1 <= w-1 (same for rows)
-                const int x0 = ((int)fmaxf(xmn, 0.0f)) & ~3, x1 = min((int)fminf(xmx, w1f) + 1, img_w - 1);
-                const int y0 = (int)fmaxf(ymn, 0.0f), y1 = min((int)fminf(ymx, h1f) + 1, img_h - 1);
-                const int wpx = (x1 - x0 + 1 + 3) & ~3;                                     // copied pixels per row (16-byte granules)
-                const int pitch = (wpx + 31) & ~31;                                          // row pitch in words: multiple of 32 banks
-                const int rows = y1 - y0 + 1;
-                if ((long long)pitch * 4 * rows <= (long long)smem_budget && (src_step_px & 3) == 0 && x0 + wpx <= src_step_px) {
-                    state = 1; fp[0] = x0; fp[1] = y0; fp[2] = pitch; fp[3] = rows; fp[4] = wpx * 4;
-                }
-            }
-            if (state == 1) { uavm::ptx::mbar_init(&fp_bar, 1); uavm::ptx::fence_mbar_init(); }
         }
-        fp[5] = state;
+        fp[3] = state;
     }
     __syncthreads();
-    const int state = fp[5];
+    const int state = fp[3];
     if (state == 2) {                                 // nothing of this tile is inside the source: BGR = 0, alpha = 0
 #pragma unroll
         for (int ry = 0; ry < kWarpRows; ry++) {
@@ -320,22 +338,12 @@ k5_warp_affine_x2(const ChipDesc* __restrict__ descs, int img_w, int img_h, int 
         }
         return;
     }
-    uint32_t sm_adj = 0, sm_pitch4 = 0;
+    uint32_t sm_adj = 0;
+    constexpr uint32_t sm_pitch4 = kFpBoxW * 4u;      // the boxes stack into rows of kFpBoxW words: a multiple of 32 banks
     float clampx = 0.0f, clampy = 0.0f;
     if (state == 1) {
-        const int x0 = fp[0], y0 = fp[1], pitch = fp[2], rows = fp[3], row_bytes = fp[4];
-        const uint32_t sbase = uavm::ptx::smem_u32(fp_smem);
-        if (tid < 32) {                               // warp 0: one bulk async copy per footprint row
-            if (tid == 0) uavm::ptx::mbar_arrive_expect_tx(&fp_bar, (uint32_t)(rows * row_bytes));
-            __syncwarp();
-            const uint8_t* g = reinterpret_cast<const uint8_t*>(D.src) + ((size_t)y0 * src_step_px + x0) * 4;
-            for (int r = tid; r < rows; r += 32)
-                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                             :: "r"(sbase + (uint32_t)(r * pitch * 4)), "l"(g + (size_t)r * src_step_px * 4), "r"((uint32_t)row_bytes),
-                                "r"(uavm::ptx::smem_u32(&fp_bar)) : "memory");
-        }
-        sm_pitch4 = (uint32_t)pitch * 4u;
-        sm_adj = sbase - (0x4B000000u * sm_pitch4 + 0x4B000000u * 4u) - ((uint32_t)y0 * sm_pitch4 + (uint32_t)x0 * 4u);
+        const int x0 = fp[0], y0 = fp[1];
+        sm_adj = 0u - (0x4B000000u * sm_pitch4 + 0x4B000000u * 4u) - ((uint32_t)y0 * sm_pitch4 + (uint32_t)x0 * 4u);   // offset from fp_smem
         clampx = (float)x0; clampy = (float)y0;
     }
     const f32x2 ONE = pk2(one, one);
@@ -362,7 +370,7 @@ k5_warp_affine_x2(const ChipDesc* __restrict__ descs, int img_w, int img_h, int 
             inside = inside && (xs0 >= 0.0f) && (xs0 < w1f) && (xs1 >= 0.0f) && (xs1 < w1f) && (ys0 >= 0.0f) && (ys0 < h1f) && (ys1 >= 0.0f) && (ys1 < h1f);
         }
     }
-#define K5_ROWS_ARGS D, MX, MY, xl, ybase, dgy, sy, fby, iv1, iv4, IV2, IV5, step4, base_adj, sm_adj, sm_pitch4, clampx, clampy, one_u, two23, w1f, h1f, ONE
+#define K5_ROWS_ARGS fp_smem, D, MX, MY, xl, ybase, dgy, sy, fby, iv1, iv4, IV2, IV5, step4, base_adj, sm_adj, clampx, clampy, one_u, two23, w1f, h1f, ONE
     if (state == 1) {
         uavm::ptx::mbar_wait(&fp_bar, 0);             // footprint has landed in shared memory
         if (inside) warp_affine_rows<false, true>(K5_ROWS_ARGS);
@@ -464,9 +472,16 @@ extern "C" int uavm_canvas_create(uavm_ctx* ctx, int n_images, int img_w, int im
     for (int k = 0; k < n_images; k++) {
         ChipDesc& d = cv->desc[k];
         d.src = cv->d_src + (size_t)k * img_h * cv->src_step_px;
+        d.src_row0 = k * img_h;
         if (!d.keep) continue;
         d.chip = cv->d_chips + coff[k] / 4; d.mask = cv->d_masks + moff[k];
     }
+    // K5 stages the source footprint of a chip tile with TMA boxes of kFpBoxW x kFpBoxH pixels
+    cv->tmap_src_ok = false;
+    if ((cv->src_step_px & 3) == 0 && (int64_t)n_images * img_h < ((int64_t)1 << 31) &&
+        uavm_encode_tmap_2d(ctx, &cv->tmap_src, (int)CU_TENSOR_MAP_DATA_TYPE_UINT32, cv->d_src, (uint64_t)cv->src_step_px, (uint64_t)n_images * img_h,
+                            (uint64_t)cv->src_step_px * 4, kFpBoxW, kFpBoxH, 0) == UAVM_OK)
+        cv->tmap_src_ok = true;
     cv->band_y0 = 0; cv->band_y1 = cv->layout.canvas_h; cv->band_Y0 = 0; cv->band_Y1 = (cv->layout.canvas_h + 31) & ~31;
     rc = uavm_canvas_upload_desc(ctx, cv);
     if (rc != UAVM_OK) { uavm_canvas_destroy(ctx, cv); return rc; }
@@ -573,21 +588,17 @@ extern "C" int uavm_canvas_warp_range(uavm_ctx* ctx, uavm_canvas* cv, int first,
     if (any_affine) {
         static const bool scalar = getenv("UAVM_K5_SCALAR") != nullptr;       // A/B switch for profiling; both are bit-exact
         // the packed kernel derives tap offsets from 23-bit mantissas and 32-bit pixel offsets
-        static const int minb = getenv("UAVM_K5_MINB") ? atoi(getenv("UAVM_K5_MINB")) : 3;
         if (!scalar && cv->img_w < (1 << 22) && cv->img_h < (1 << 22) && (int64_t)cv->img_h * cv->src_step_px < ((int64_t)1 << 31)) {
-#define K5X2_ARGS cv->d_desc + first, cv->img_w, cv->img_h, cv->src_step_px, cv->layout.dgx, cv->layout.dgy, 0x4B000000u, (float)(cv->img_w - 1), \
-                  (float)(cv->img_h - 1), 1.0f, 1u, 0x4B000000ull * (4ull * (unsigned long long)cv->src_step_px + 4ull), smem
-            static const int smem = getenv("UAVM_K5_SMEM") ? atoi(getenv("UAVM_K5_SMEM")) : kFootprintSmem;
+            static const int env_boxes = getenv("UAVM_K5_BOXES") ? atoi(getenv("UAVM_K5_BOXES")) : kFpBoxes;   // 0: direct tap loads (A/B)
+            const int boxes = cv->tmap_src_ok ? env_boxes : 0;
             static bool attr_done = false;
             if (!attr_done) {
-                cudaFuncSetAttribute(k5_warp_affine_x2<3>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-                cudaFuncSetAttribute(k5_warp_affine_x2<4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-                cudaFuncSetAttribute(k5_warp_affine_x2<5>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+                cudaFuncSetAttribute(k5_warp_affine_x2, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
                 attr_done = true;
             }
-            if (minb == 5) k5_warp_affine_x2<5><<<grid, block, smem, ctx->stream>>>(K5X2_ARGS);
-            else if (minb == 4) k5_warp_affine_x2<4><<<grid, block, smem, ctx->stream>>>(K5X2_ARGS);
-            else k5_warp_affine_x2<3><<<grid, block, smem, ctx->stream>>>(K5X2_ARGS);
+            k5_warp_affine_x2<<<grid, block, boxes * kFpBoxBytes, ctx->stream>>>(
+                cv->tmap_src, cv->d_desc + first, cv->img_w, cv->img_h, cv->src_step_px, cv->layout.dgx, cv->layout.dgy, 0x4B000000u,
+                (float)(cv->img_w - 1), (float)(cv->img_h - 1), 1.0f, 1u, 0x4B000000ull * (4ull * (unsigned long long)cv->src_step_px + 4ull), boxes);
         }
         else
             k5_warp_chips<true><<<grid, block, 0, ctx->stream>>>(cv->d_desc + first, cv->img_w, cv->img_h, cv->src_step_px, cv->layout.dgx, cv->layout.dgy, 0x4B000000u,

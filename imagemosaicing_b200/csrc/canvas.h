@@ -14,6 +14,7 @@ struct ChipDesc {               // one per image, device-visible
     float sx, sy;
     float inv[9];
     float quad[8];
+    int32_t src_row0;           // first row of this frame in the stacked source tensor (image index * img_h)
     int32_t affine;             // inv[6] == 0 && inv[7] == 0 && inv[8] == 1: the projective divide is exact identity
     float lineA[4], lineB[4], lineC[4], lineInv[4];   // K6: quad edges as A x + B y + C = 0 and 1/sqrt(A^2+B^2)
     int32_t nbr_off, nbr_cnt;   // K6: chips whose boxes intersect this one (indices into the neighbour list)
@@ -32,6 +33,8 @@ struct uavm_canvas {
     float* d_dist_max = nullptr;     // [n] per-image maximum of the distance map (as uint bits)
     int32_t* d_nbr = nullptr;        // K6 neighbour lists
     ChipDesc* d_desc = nullptr;
+    CUtensorMap tmap_src;            // all source frames as one [n * img_h][src_step_px] tensor of BGRA words (K5 footprint staging)
+    bool tmap_src_ok = false;
     // staging ring for host BGR frames: slot s is filled by the ctx's copy stream and drained by the BGR->BGRA
     // kernel on the compute stream, so the PCIe copy of frame k+1 overlaps the conversion / warp of frame k
     static constexpr int kStageSlots = 3;

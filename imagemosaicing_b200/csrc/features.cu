@@ -142,7 +142,9 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-static int make_tmap(uavm_ctx* ctx, CUtensorMap* tm, void* base, int64_t rows, int box_rows) {
+// generic 2-D tiled tensor map (dim0 = contiguous), shared by the descriptor pool (match) and the source frames (warp)
+int uavm_encode_tmap_2d(uavm_ctx* ctx, CUtensorMap* tm, int dtype, void* base, uint64_t dim0, uint64_t dim1, uint64_t stride1_bytes,
+                        uint32_t box0, uint32_t box1, int swizzle128) {
     static PFN_encodeTiled encode = nullptr;
     if (!encode) {
         void* fn = nullptr;
@@ -151,15 +153,19 @@ static int make_tmap(uavm_ctx* ctx, CUtensorMap* tm, void* base, int64_t rows, i
         if (!fn || qres != cudaDriverEntryPointSuccess) { UAVM_SET_ERR(ctx, "cuTensorMapEncodeTiled not available"); return UAVM_EFAIL; }
         encode = (PFN_encodeTiled)fn;
     }
-    cuuint64_t gdim[2] = {128, (cuuint64_t)rows};
-    cuuint64_t gstride[1] = {128};
-    cuuint32_t box[2] = {128, (cuuint32_t)box_rows};
+    cuuint64_t gdim[2] = {(cuuint64_t)dim0, (cuuint64_t)dim1};
+    cuuint64_t gstride[1] = {(cuuint64_t)stride1_bytes};
+    cuuint32_t box[2] = {(cuuint32_t)box0, (cuuint32_t)box1};
     cuuint32_t estride[2] = {1, 1};
-    CUresult r = encode(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, base, gdim, gstride, box, estride,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r = encode(tm, (CUtensorMapDataType)dtype, 2, base, gdim, gstride, box, estride,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { UAVM_SET_ERR(ctx, "cuTensorMapEncodeTiled failed: %d", (int)r); return UAVM_EFAIL; }
     return UAVM_OK;
+}
+
+static int make_tmap(uavm_ctx* ctx, CUtensorMap* tm, void* base, int64_t rows, int box_rows) {
+    return uavm_encode_tmap_2d(ctx, tm, (int)CU_TENSOR_MAP_DATA_TYPE_UINT8, base, 128, (uint64_t)rows, 128, 128, (uint32_t)box_rows, 1);
 }
 
 extern "C" int uavm_featureset_create(uavm_ctx* ctx, int n_images, const int32_t* n_keypoints, uavm_featureset** out) {

@@ -111,6 +111,8 @@ struct uavm_pairbatch {
     bool matched = false, selected = false, ransacked = false;
 };
 
+int uavm_encode_tmap_2d(uavm_ctx* ctx, CUtensorMap* tm, int dtype, void* base, uint64_t dim0, uint64_t dim1, uint64_t stride1_bytes,
+                        uint32_t box0, uint32_t box1, int swizzle128);
 int uavm_launch_match(uavm_ctx* ctx, uavm_pairbatch* pb);
 int uavm_launch_select(uavm_ctx* ctx, uavm_pairbatch* pb, int width, int height, int gx, int gy, int max_num, double frac);
 int uavm_launch_ransac(uavm_ctx* ctx, uavm_pairbatch* pb, float dist, int sample_times);

@@ -82,6 +82,53 @@ def test_warp_skip_flags_and_full_frame(ctx, oracle):
         assert np.array_equal(mask, o_mask) and np.array_equal(px, o_px)
 
 
+def _affine(angle_deg, scale, tx, ty):
+    a = np.deg2rad(angle_deg)
+    return np.array([[scale * np.cos(a), -scale * np.sin(a), tx], [scale * np.sin(a), scale * np.cos(a), ty], [0, 0, 1.0]])
+
+
+@pytest.mark.parametrize("w,h,angle,scale", [(640, 480, 33.0, 1.0), (640, 480, -80.0, 1.3), (512, 384, 3.0, 0.45), (640, 480, 2.0, 2.6),
+                                              (514, 390, 5.0, 1.0), (40, 30, 10.0, 1.0), (700, 500, 180.0, 1.0)])
+def test_warp_affine_staging_edges(ctx, oracle, w, h, angle, scale):
+    """The packed affine kernel stages the source footprint of every 128 x 32 chip tile in shared memory (TMA boxes of
+    160 x 64 px at most).  Strong rotations / reductions make footprints that do not fit (direct-load path), enlargements
+    make tiny ones, an image width that is not a multiple of 4 disables the tensor map, and the rotated chips have tiles
+    entirely outside the source (zero fill).  All paths must stay byte-identical to the reference loop."""
+    rng = np.random.default_rng(int(abs(angle) * 10) + w)
+    H = np.stack([np.eye(3), _affine(angle, scale, 0.31 * w, -0.22 * h)]).astype(np.float32).reshape(2, 9)
+    imgs = [synth.texture_image(rng, w, h, 8) for _ in range(2)]
+    cv = api.Canvas(ctx, H, w, h)
+    o_canvas, o_chips = oracle.canvas_layout(H, None, w, h)
+    _compare_layout(cv.layout, cv.chips, o_canvas, o_chips, 2)
+    for k in range(2):
+        cv.set_image(k, imgs[k])
+    cv.warp()
+    for k in range(2):
+        px, mask = cv.chip(k)
+        o_px, o_mask = oracle.warp_chip(imgs[k], o_canvas, o_chips[k])
+        assert np.array_equal(mask, o_mask), f"chip {k}: {(mask != o_mask).sum()} differing mask bytes"
+        assert np.array_equal(px, o_px), f"chip {k}: {(px != o_px).sum()} differing bytes"
+
+
+def test_warp_range_equals_warp(ctx):
+    """uavm_canvas_warp_range over consecutive groups == one uavm_canvas_warp (streaming callers warp group by group)."""
+    rng = np.random.default_rng(11)
+    w, h, n = 640, 480, 5
+    H = _transforms(rng, n, w, h)
+    imgs = [synth.texture_image(rng, w, h, 6) for _ in range(n)]
+    a = api.Canvas(ctx, H, w, h); b = api.Canvas(ctx, H, w, h)
+    for k in range(n):
+        a.set_image(k, imgs[k])
+    a.warp()
+    for g0 in range(0, n, 2):
+        for k in range(g0, min(g0 + 2, n)):
+            b.set_image(k, imgs[k])
+        b.warp(g0, min(2, n - g0))
+    for k in range(n):
+        pa, ma = a.chip(k); pb_, mb = b.chip(k)
+        assert np.array_equal(pa, pb_) and np.array_equal(ma, mb)
+
+
 @pytest.mark.parametrize("w,h,n,bands", [(320, 240, 3, 5), (500, 375, 4, 5), (257, 190, 2, 3), (640, 480, 5, 5)])
 def test_multiband_blend_parity(ctx, oracle, w, h, n, bands):
     """K7 against the oracle's restatement of MultiBandBlender (bit-exact) and against the cv2 4.13 blender
