@@ -556,8 +556,11 @@ extern "C" int uavm_canvas_set_image(uavm_ctx* ctx, uavm_canvas* cv, int image, 
         // host frame: PCIe copy on the copy stream into a ring slot; the compute stream only waits for THIS frame
         slot = cv->stage_next; cv->stage_next = (slot + 1) % uavm_canvas::kStageSlots;
         UAVM_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, cv->ev_free[slot], 0));          // previous user of the slot has been converted
-        UAVM_CUDA(ctx, cudaMemcpy2DAsync(cv->d_stage[slot], (size_t)cv->stage_pitch, bgr, (size_t)step, (size_t)cv->img_w * 3, cv->img_h,
-                                         cudaMemcpyHostToDevice, ctx->copy_stream));
+        if (step == cv->stage_pitch)                     // contiguous frame: one linear DMA (the 2-D path is slower over PCIe)
+            UAVM_CUDA(ctx, cudaMemcpyAsync(cv->d_stage[slot], bgr, (size_t)step * cv->img_h, cudaMemcpyHostToDevice, ctx->copy_stream));
+        else
+            UAVM_CUDA(ctx, cudaMemcpy2DAsync(cv->d_stage[slot], (size_t)cv->stage_pitch, bgr, (size_t)step, (size_t)cv->img_w * 3, cv->img_h,
+                                             cudaMemcpyHostToDevice, ctx->copy_stream));
         UAVM_CUDA(ctx, cudaEventRecord(cv->ev_copied[slot], ctx->copy_stream));
         UAVM_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, cv->ev_copied[slot], 0));
         src = cv->d_stage[slot]; sstep = cv->stage_pitch;

@@ -218,9 +218,16 @@ static int upload_impl(uavm_ctx* ctx, uavm_featureset* fs, int image, const T* d
     size_t r0 = (size_t)fs->row0[image];
     const T* src = desc;
     if (!is_device) {
-        // stream-ordered: the staging buffer is reused only after the previous pack kernel (same stream)
-        UAVM_CUDA(ctx, cudaMemcpyAsync(fs->d_stage, desc, (size_t)n * 128 * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
-        src = (const T*)fs->d_stage;
+        if (sizeof(T) == 1) {
+            // u8 host descriptors land directly in their pool rows and are "packed" in place (each warp reads its row before
+            // writing it back): no staging buffer, so the copies of consecutive images queue back to back on the DMA engine
+            UAVM_CUDA(ctx, cudaMemcpyAsync(fs->d_desc + r0 * 128, desc, (size_t)n * 128, cudaMemcpyHostToDevice, ctx->stream));
+            src = (const T*)(fs->d_desc + r0 * 128);
+        } else {
+            // stream-ordered: the staging buffer is reused only after the previous pack kernel (same stream)
+            UAVM_CUDA(ctx, cudaMemcpyAsync(fs->d_stage, desc, (size_t)n * 128 * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+            src = (const T*)fs->d_stage;
+        }
     }
     k1_pack_rows<T><<<(n * 32 + 255) / 256, 256, 0, ctx->stream>>>(src, n, fs->d_desc + r0 * 128, fs->d_norm + r0, fs->d_ckey + r0);
     UAVM_CHECK_LAUNCH(ctx);
