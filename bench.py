@@ -68,21 +68,42 @@ def make_workload(rank, n_img=NIMG):
 # CPU leg (oracle port) — used for cpu_baseline and for --impl reference
 # ------------------------------------------------------------------------------------------------
 def cpu_pairs(descs, kps, T, frames, pairs, seeds):
-    """Runs the CPU path on the given pairs; returns seconds."""
+    """Runs the CPU path on the given pairs with every host core; returns seconds.  Like the reference
+    (M/MosaicWithoutPos.cpp:5244-5295: worker threads striding over image pairs) the pairs are spread over host
+    threads; the cores left over when there are fewer pairs than cores go to OpenMP inside match and warp."""
+    from concurrent.futures import ThreadPoolExecutor
     from oracle import oracle as O
-    O.set_threads(host_threads())          # torchrun exports OMP_NUM_THREADS=1; the CPU arm uses every host core
+    cores = host_threads()
+    workers = max(1, min(len(pairs), cores))
+    inner = max(1, cores // workers)
     canvas, chips = O.canvas_layout(T, None, W, H)
     use_ref = O.ref() is not None
-    t0 = time.perf_counter()
-    for (i, j), seed in zip(pairs, seeds):
-        idx, d2 = O.match_l2(descs[i], descs[j])
+
+    def unit(arg):
+        (i, j), seed = arg
+        O.set_threads(inner)               # per-thread OpenMP team size (torchrun exports OMP_NUM_THREADS=1)
+        idx, d2 = O.match_l2_fast(descs[i], descs[j])
         x1, i1, x2, i2 = O.select(idx, d2, kps[i], kps[j], W, H)
         if use_ref:
             O.ref_ransac2d(x1, x2, RANSAC_DIST, SAMPLE_TIMES, seed)
         else:
             O.ransac2d(x1, x2, RANSAC_DIST, SAMPLE_TIMES, seed)
         O.warp_chip(frames[j], canvas, chips[j])
+
+    t0 = time.perf_counter()
+    if workers == 1:
+        for a in zip(pairs, seeds):
+            unit(a)
+    else:
+        with ThreadPoolExecutor(workers) as ex:
+            list(ex.map(unit, zip(pairs, seeds)))
     return time.perf_counter() - t0
+
+
+def cpu_sample_note(n_sample, O):
+    cores = host_threads(); workers = max(1, min(n_sample, cores))
+    return (f"{n_sample} of 49 pairs per step on {workers} host threads x {max(1, cores // workers)} OpenMP threads (exact brute-force match with AVX2 integer dot products, "
+            f"select, {'reference Ransac2D compiled from /root/reference' if O.ref() is not None else 'oracle Ransac2D restatement'}, warp)")
 
 
 def host_threads():
@@ -96,7 +117,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n_sample = 4                       # pairs per step (bounded sample of the 49-pair workload)
+    n_sample = max(4, min(48, host_threads()))      # pairs per step (bounded sample of the 49-pair workload): one per host thread
     descs, kps, Hs, T, base = make_workload(0, n_img=n_sample + 1)
     frames = [base] * (n_sample + 1)
     pairs = [(i, i + 1) for i in range(n_sample)]
@@ -117,8 +138,7 @@ def run_reference(args):
         "config": {"workload": "configs[1]: 50-image strip 4000x3000, 8192 kp/image, sequential pairs",
                    "pairs_per_step": n_sample},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores,
-                         "kind": "port", "sample": f"{n_sample} of 49 pairs per step; brute-force match + warp on {cores} OpenMP threads, "
-                                                   f"RANSAC 1 thread ({'reference Ransac2D compiled from /root/reference' if O.ref() is not None else 'oracle restatement'})"},
+                         "kind": "port", "sample": cpu_sample_note(n_sample, O)},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -378,15 +398,14 @@ def run_ours(args):
         }
         # ---- CPU baseline on a bounded sample (rank 0, N=1 only) ----
         if world == 1 and not args.no_cpu:
-            n_sample = 6
+            n_sample = max(4, min(48, host_threads()))
             frames = [h_frames[k].numpy() for k in range(n_sample + 1)]
             sp = [(i, i + 1) for i in range(n_sample)]
             cpu_pairs(descs, kps, T[:n_sample + 1], frames, sp[:1], [1000])       # warm
             t_cpu = cpu_pairs(descs, kps, T[:n_sample + 1], frames, sp, [1000 + p for p in range(n_sample)])
             from oracle import oracle as O
             line["cpu_baseline"] = {"value": n_sample / t_cpu, "unit": UNIT, "cores": host_threads(), "kind": "port",
-                                    "sample": f"{n_sample} of 49 pairs; brute-force match + warp on {host_threads()} OpenMP threads, RANSAC 1 thread "
-                                              f"({'reference Ransac2D compiled from /root/reference' if O.ref() is not None else 'oracle restatement'})"}
+                                    "sample": cpu_sample_note(n_sample, O)}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

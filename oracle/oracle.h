@@ -35,6 +35,8 @@ int orc_set_threads(int n);   /* OpenMP threads for the parallel loops; returns 
 /* ---------------- K2: exact brute-force L2 1-NN (replaces FLANN, M/MosaicWithoutPos.cpp:5108) */
 /* A: na x 128 u8, B: nb x 128 u8.  train_idx[i] = argmin_j |A_i - B_j|^2 (lowest j on ties),
  * d2[i] = that squared distance (exact integer).  DMatch.distance == sqrtf((float)d2). */
+/* same results, AVX2 integer dot products (oracle_fast.c): the matcher of bench.py's CPU arm */
+void orc_match_l2_fast(const uint8_t* A, int na, const uint8_t* B, int nb, int dim, int32_t* train_idx, int32_t* d2);
 void orc_match_l2(const uint8_t* A, int na, const uint8_t* B, int nb, int dim,
                   int32_t* train_idx, int32_t* d2);
 

@@ -39,7 +39,7 @@ class CanvasLayout(C.Structure):
 def build(force=False):
     """Compile liboracle.so (and _ref/libref_ransac.so when /root/reference is present)."""
     so = os.path.join(_HERE, "liboracle.so")
-    srcs = [os.path.join(_HERE, f) for f in ("oracle.c", "oracle_blend.c", "oracle.h") if os.path.exists(os.path.join(_HERE, f))]
+    srcs = [os.path.join(_HERE, f) for f in ("oracle.c", "oracle_blend.c", "oracle_fast.c", "oracle.h") if os.path.exists(os.path.join(_HERE, f))]
     if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["make", "-C", _HERE, "-s"], stdout=subprocess.DEVNULL)
     ref_so = os.path.join(_HERE, "_ref", "libref_ransac.so")
@@ -91,6 +91,15 @@ def match_l2(A, B):
     na, dim = A.shape; nb = B.shape[0]
     idx = np.empty(na, np.int32); d2 = np.empty(na, np.int32)
     lib().orc_match_l2(_p(A, u8p), na, _p(B, u8p), nb, dim, _p(idx, i32p), _p(d2, i32p))
+    return idx, d2
+
+
+def match_l2_fast(A, B):
+    """Same result as match_l2 (exact, lowest index on ties), tuned (AVX2 integer dot products): bench.py's CPU arm."""
+    A = np.ascontiguousarray(A, dtype=np.uint8); B = np.ascontiguousarray(B, dtype=np.uint8)
+    na, dim = A.shape; nb = B.shape[0]
+    idx = np.empty(na, np.int32); d2 = np.empty(na, np.int32)
+    lib().orc_match_l2_fast(_p(A, u8p), na, _p(B, u8p), nb, dim, _p(idx, i32p), _p(d2, i32p))
     return idx, d2
 
 

@@ -26,11 +26,10 @@ using namespace std;
 #define _declspec(x)
 #define veTemp vtTemp   /* typo in a never-instantiated template, M/Bitmap.h:229 */
 
-extern "C" {
-extern uint32_t g_ref_seed;       /* seed to install at the next srand() */
-extern uint32_t g_ref_state;
-extern uint64_t g_ref_rand_calls; /* number of rand() calls since last srand() */
-}
+/* thread_local: bench.py's CPU arm runs one Ransac2D per host thread, like the reference's worker threads */
+extern thread_local uint32_t g_ref_seed;       /* seed to install at the next srand() */
+extern thread_local uint32_t g_ref_state;
+extern thread_local uint64_t g_ref_rand_calls; /* number of rand() calls since last srand() */
 static inline void ref_srand_hook(unsigned) { g_ref_state = g_ref_seed; g_ref_rand_calls = 0; }
 static inline int ref_rand_hook() {
     g_ref_state = g_ref_state * 214013u + 2531011u;

@@ -21,10 +21,11 @@
 #undef rand
 #undef time
 
+thread_local uint32_t g_ref_seed = 1;
+thread_local uint32_t g_ref_state = 1;
+thread_local uint64_t g_ref_rand_calls = 0;
+
 extern "C" {
-uint32_t g_ref_seed = 1;
-uint32_t g_ref_state = 1;
-uint64_t g_ref_rand_calls = 0;
 
 /* Ransac2D (M/mosaicimage.h:1729).  xy1/xy2: n x 2 floats.  Returns the function's bool.
  * inlier_mask[n] is derived from the ids of the returned inlier lists. */

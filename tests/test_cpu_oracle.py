@@ -201,6 +201,21 @@ def test_oracle_match_vs_numpy_and_cv2(oracle):
     assert np.array_equal(cv_d.view(np.uint32), np.sqrt(d2.astype(np.float32)).view(np.uint32))
 
 
+def test_fast_cpu_matcher_equals_oracle(oracle):
+    """bench.py's CPU arm uses a tuned (AVX2) matcher; it must return exactly what the plain restatement returns."""
+    from imagemosaicing_b200 import synth
+    rng = np.random.default_rng(5)
+    for na, nb in [(1, 1), (3, 5), (257, 1031), (1024, 777)]:
+        A = synth.sift_like_descriptors(rng, na); B = synth.sift_like_descriptors(rng, nb)
+        if nb > 4:
+            B[4] = B[1]; A[0] = B[1]
+        a = oracle.match_l2(A, B); b = oracle.match_l2_fast(A, B)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    A = np.full((4, 128), 255, np.uint8); B = np.zeros((6, 128), np.uint8)      # largest distance 128 * 255^2
+    a = oracle.match_l2(A, B); b = oracle.match_l2_fast(A, B)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and a[1][0] == 128 * 255 * 255
+
+
 def _select_py(train, d2, kp1, kp2, w, h, gx=3, gy=3, max_num=400, frac=0.3):
     """Literal Python restatement of std::sort + SelectMatchPairs with the (d2, queryIdx) order."""
     order = sorted(range(len(train)), key=lambda q: (int(d2[q]), q))
