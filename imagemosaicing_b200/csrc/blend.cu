@@ -6,7 +6,7 @@
 // (sum+128)>>8, pyrUp with (sum+32)>>6, reflect-101 / replicate borders), f32 Gaussian weight pyramids,
 // dst += short(src * w), wsum += w, dst = short(dst / (wsum + 1e-5)), collapse with saturating adds.
 //
-// HBM layout: the canvas pyramid (int16 x3 interleaved + f32 weights per level, canvas padded to a multiple
+// HBM layout: the canvas pyramid (int16 x4 pixels = B, G, R, pad + f32 weights per level, canvas padded to a multiple
 // of 2^bands) stays resident; every fed chip gets a scratch pyramid of its padded ROI that is reused for the
 // next chip.  Images are fed in index order (the f32 weight sums are order dependent), pixels in parallel.
 #include <math.h>
@@ -39,6 +39,19 @@ __device__ __forceinline__ int reflect_edge(int p, int n) {     // BORDER_REFLEC
 }
 __device__ __forceinline__ short sat16(int v) { return (short)max(-32768, min(32767, v)); }
 
+// Pyramid pixels are 4 x int16 (B, G, R, 0): one aligned 8-byte load / store per pixel instead of three 2-byte ones
+// (a 6-byte interleaved pixel straddles words; the kernels were LSU-instruction bound with it).
+__device__ __forceinline__ void ld3(const short* base, size_t px, int& a, int& b, int& c)
+{
+    const int2 v = *reinterpret_cast<const int2*>(base + px * 4);
+    a = (short)(v.x & 0xffff); b = v.x >> 16; c = (short)(v.y & 0xffff);
+}
+__device__ __forceinline__ void st3(short* base, size_t px, int a, int b, int c)
+{
+    int2 v; v.x = (a & 0xffff) | (b << 16); v.y = c & 0xffff;
+    *reinterpret_cast<int2*>(base + px * 4) = v;
+}
+
 // level 0 of the fed image: copyMakeBorder(REFLECT) of the chip (u8 -> s16) and mask/255 with a zero border
 __global__ void __launch_bounds__(256)
 k7_feed_level0(const uint32_t* __restrict__ chip, int chip_step /* words */, const uint8_t* __restrict__ mask, int mask_step,
@@ -49,8 +62,7 @@ k7_feed_level0(const uint32_t* __restrict__ chip, int chip_step /* words */, con
     const int ix = x - left, iy = y - top;
     const int sx = reflect_edge(ix, cw), sy = reflect_edge(iy, ch);
     const uint32_t s = chip[(size_t)sy * chip_step + sx];                   // BGRA
-    short* d = pyr0 + ((size_t)y * width + x) * 3;
-    d[0] = (short)(s & 0xffu); d[1] = (short)((s >> 8) & 0xffu); d[2] = (short)((s >> 16) & 0xffu);
+    st3(pyr0, (size_t)y * width + x, (int)(s & 0xffu), (int)((s >> 8) & 0xffu), (int)((s >> 16) & 0xffu));
     float wv = 0.0f;
     if (ix >= 0 && ix < cw && iy >= 0 && iy < ch) wv = (float)mask[(size_t)iy * mask_step + ix] * (float)(1. / 255.);
     wp0[(size_t)y * width + x] = wv;
@@ -71,22 +83,22 @@ k7_pyrdown(const short* __restrict__ src, const float* __restrict__ wsrc, int w,
     const int kw[5] = {1, 4, 6, 4, 1};
 #pragma unroll
     for (int r = 0; r < 5; r++) {
-        const short* srow = src + (size_t)ys[r] * w * 3;
+        const size_t rbase = (size_t)ys[r] * w;
         int ra[3] = {0, 0, 0};
 #pragma unroll
         for (int k = 0; k < 5; k++) {
-            const short* px = srow + xs[k] * 3;
-            ra[0] += kw[k] * px[0]; ra[1] += kw[k] * px[1]; ra[2] += kw[k] * px[2];
+            int p0, p1, p2;
+            ld3(src, rbase + xs[k], p0, p1, p2);
+            ra[0] += kw[k] * p0; ra[1] += kw[k] * p1; ra[2] += kw[k] * p2;
         }
         acc[0] += kw[r] * ra[0]; acc[1] += kw[r] * ra[1]; acc[2] += kw[r] * ra[2];
         if (wsrc) {
-            const float* wr = wsrc + (size_t)ys[r] * w;
+            const float* wr = wsrc + rbase;
             const float s0 = wr[xs[0]], s1 = wr[xs[1]], s2 = wr[xs[2]], s3 = wr[xs[3]], s4 = wr[xs[4]];
             frow[r] = s2 * 6.0f + (s1 + s3) * 4.0f + s0 + s4;           // row pass, oracle order
         }
     }
-    short* d = dst + ((size_t)y * dw + x) * 3;
-    d[0] = sat16((acc[0] + 128) >> 8); d[1] = sat16((acc[1] + 128) >> 8); d[2] = sat16((acc[2] + 128) >> 8);
+    st3(dst, (size_t)y * dw + x, sat16((acc[0] + 128) >> 8), sat16((acc[1] + 128) >> 8), sat16((acc[2] + 128) >> 8));
     if (wsrc) {
         const float v = frow[2] * 6.0f + (frow[1] + frow[3]) * 4.0f + frow[0] + frow[4];   // column pass
         wdst[(size_t)y * dw + x] = v * (1.0f / 256.0f);
@@ -107,8 +119,11 @@ __device__ __forceinline__ void pyrup_at(const short* __restrict__ lo, int lw, i
 #pragma unroll
     for (int r = 0; r < 3; r++) {
         if (wy[r] == 0) continue;
-        const short* row = lo + (size_t)rows[r] * lw * 3;
-        const short* a = row + xm * 3; const short* b = row + cx * 3; const short* c = row + xp * 3;
+        const size_t rbase = (size_t)rows[r] * lw;
+        int a[3], b[3], c[3];
+        if (wx0) ld3(lo, rbase + xm, a[0], a[1], a[2]); else { a[0] = a[1] = a[2] = 0; }
+        ld3(lo, rbase + cx, b[0], b[1], b[2]);
+        ld3(lo, rbase + xp, c[0], c[1], c[2]);
 #pragma unroll
         for (int k = 0; k < 3; k++) acc[k] += wy[r] * (wx0 * a[k] + wx1 * b[k] + wx2 * c[k]);
     }
@@ -124,8 +139,11 @@ k7_lap_accumulate(const short* __restrict__ cur, const short* __restrict__ next,
 {
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
     if (x >= w || y >= h) return;
-    const short* c = cur + ((size_t)y * w + x) * 3;
-    int lap[3] = {c[0], c[1], c[2]};
+    // Seam masks give every canvas pixel one owner, so most of a fed chip has weight exactly 0 (about 2/3 of level 0
+    // for a 3x-covered strip): dst + short(lap * 0) == dst and wsum + 0 == wsum, the read-modify-write is skipped.
+    if (wcur[(size_t)y * w + x] == 0.0f) return;
+    int lap[3];
+    ld3(cur, (size_t)y * w + x, lap[0], lap[1], lap[2]);
     if (next) {
         int up[3];
         pyrup_at(next, nw, nh, x, y, up);
@@ -134,37 +152,69 @@ k7_lap_accumulate(const short* __restrict__ cur, const short* __restrict__ next,
     }
     const float wv = wcur[(size_t)y * w + x];
     const size_t di = (size_t)(y + y_tl) * dst_w + (x + x_tl);
-    short* d = dlap + di * 3;
+    int d[3];
+    ld3(dlap, di, d[0], d[1], d[2]);
 #pragma unroll
     for (int k = 0; k < 3; k++) d[k] = (short)(d[k] + (short)__float2int_rz((float)lap[k] * wv));
+    st3(dlap, di, d[0], d[1], d[2]);
     dwsum[di] += wv;
 }
 
-__global__ void __launch_bounds__(256)
-k7_normalize(short* __restrict__ dlap, const float* __restrict__ dwsum, size_t n)
+// blend(): dst = short(dst / (wsum + 1e-5)) per level, then restoreImageFromLaplacePyr: hi = sat(pyrUp(lo) + hi) from the
+// top down.  The normalisation of level i is fused into the collapse step that consumes it (lo is already final), and
+// at level 0 the step writes the u8 mosaic directly: crop, zero where wsum <= 1e-5, convertTo(CV_8U) (saturate).
+__device__ __forceinline__ void normalized3(const short* lap, const float* wsum, size_t i, int d[3])
 {
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const float wv = dwsum[i] + 1e-5f;
-    short* d = dlap + i * 3;
+    const float wv = wsum[i] + 1e-5f;
+    ld3(lap, i, d[0], d[1], d[2]);
 #pragma unroll
     for (int k = 0; k < 3; k++) d[k] = (short)__float2int_rz((float)d[k] / wv);
 }
 
-// restoreImageFromLaplacePyr step: hi = sat(pyrUp(lo) + hi)
 __global__ void __launch_bounds__(256)
-k7_collapse(const short* __restrict__ lo, int lw, int lh, short* __restrict__ hi, int w, int h)
+k7_normalize(short* __restrict__ dlap, const float* __restrict__ dwsum, size_t n)        // top level only
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int d[3];
+    normalized3(dlap, dwsum, i, d);
+    st3(dlap, i, d[0], d[1], d[2]);
+}
+
+__global__ void __launch_bounds__(256)
+k7_collapse(const short* __restrict__ lo, int lw, int lh, short* __restrict__ hi, const float* __restrict__ hi_wsum, int w, int h)
 {
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
     if (x >= w || y >= h) return;
-    int up[3];
+    int up[3], d[3];
     pyrup_at(lo, lw, lh, x, y, up);
-    short* d = hi + ((size_t)y * w + x) * 3;
-#pragma unroll
-    for (int k = 0; k < 3; k++) d[k] = sat16(up[k] + d[k]);
+    normalized3(hi, hi_wsum, (size_t)y * w + x, d);
+    st3(hi, (size_t)y * w + x, sat16(up[0] + d[0]), sat16(up[1] + d[1]), sat16(up[2] + d[2]));
 }
 
-// crop, zero where wsum <= 1e-5, convertTo(CV_8U) (saturate)
+// last step (level 0) fused with the output: rows [oy0, oy1) x columns [0, cw) of the padded level go to the mosaic
+__global__ void __launch_bounds__(256)
+k7_collapse_output(const short* __restrict__ lo, int lw, int lh, const short* __restrict__ hi, const float* __restrict__ hi_wsum, int w, int h,
+                   int oy0, int oy1, int cw, uint8_t* __restrict__ out, uint8_t* __restrict__ out_mask)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = oy0 + blockIdx.y;
+    if (x >= cw || y >= oy1) return;
+    const size_t i = (size_t)y * w + x;
+    const bool m = hi_wsum[i] > 1e-5f;
+    int v[3] = {0, 0, 0};
+    if (m) {
+        int up[3], d[3];
+        pyrup_at(lo, lw, lh, x, y, up);
+        normalized3(hi, hi_wsum, i, d);
+#pragma unroll
+        for (int k = 0; k < 3; k++) v[k] = max(0, min(255, (int)sat16(up[k] + d[k])));
+    }
+    const size_t o = (size_t)blockIdx.y * cw + x;
+    out[o * 3] = (uint8_t)v[0]; out[o * 3 + 1] = (uint8_t)v[1]; out[o * 3 + 2] = (uint8_t)v[2];
+    out_mask[o] = m ? 255 : 0;
+}
+
+// no bands: the canvas level 0 is the (normalised) image itself
 __global__ void __launch_bounds__(256)
 k7_output(const short* __restrict__ lap0, const float* __restrict__ w0, int W, int cw, int ch,
           uint8_t* __restrict__ out, uint8_t* __restrict__ out_mask)
@@ -172,10 +222,11 @@ k7_output(const short* __restrict__ lap0, const float* __restrict__ w0, int W, i
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
     if (x >= cw || y >= ch) return;
     const bool m = w0[(size_t)y * W + x] > 1e-5f;
-    const short* s = lap0 + ((size_t)y * W + x) * 3;
+    int s[3];
+    ld3(lap0, (size_t)y * W + x, s[0], s[1], s[2]);
     uint8_t* d = out + ((size_t)y * cw + x) * 3;
 #pragma unroll
-    for (int k = 0; k < 3; k++) d[k] = m ? (uint8_t)max(0, min(255, (int)s[k])) : 0;
+    for (int k = 0; k < 3; k++) d[k] = m ? (uint8_t)max(0, min(255, s[k])) : 0;
     out_mask[(size_t)y * cw + x] = m ? 255 : 0;
 }
 
@@ -260,9 +311,9 @@ extern "C" int uavm_canvas_blend(uavm_ctx* ctx, uavm_canvas* cv, int num_bands)
         for (int i = 0; i <= nb; i++) {
             if (i > 0) { ws->lw[i] = (ws->lw[i - 1] + 1) / 2; ws->lh[i] = (ws->lh[i - 1] + 1) / 2; cap = (cap + 3) / 4 + 4096; }
             const size_t px = (size_t)ws->lw[i] * ws->lh[i];
-            UAVM_CUDA(ctx, cudaMalloc(&ws->dlap[i], px * 3 * sizeof(short)));
+            UAVM_CUDA(ctx, cudaMalloc(&ws->dlap[i], px * 4 * sizeof(short)));
             UAVM_CUDA(ctx, cudaMalloc(&ws->dw[i], px * sizeof(float)));
-            UAVM_CUDA(ctx, cudaMalloc(&ws->pyr[i], (cap + 16) * 3 * sizeof(short)));
+            UAVM_CUDA(ctx, cudaMalloc(&ws->pyr[i], (cap + 16) * 4 * sizeof(short)));
             UAVM_CUDA(ctx, cudaMalloc(&ws->wp[i], (cap + 16) * sizeof(float)));
         }
     }
@@ -276,7 +327,7 @@ extern "C" int uavm_canvas_blend(uavm_ctx* ctx, uavm_canvas* cv, int num_bands)
     }
     for (int i = 0; i <= nb; i++) {
         const size_t px = (size_t)ws->lw[i] * ws->lh[i];
-        UAVM_CUDA(ctx, cudaMemsetAsync(ws->dlap[i], 0, px * 3 * sizeof(short), ctx->stream));
+        UAVM_CUDA(ctx, cudaMemsetAsync(ws->dlap[i], 0, px * 4 * sizeof(short), ctx->stream));
         UAVM_CUDA(ctx, cudaMemsetAsync(ws->dw[i], 0, px * sizeof(float), ctx->stream));
     }
     // feed(), image by image in index order
@@ -308,22 +359,27 @@ extern "C" int uavm_canvas_blend(uavm_ctx* ctx, uavm_canvas* cv, int num_bands)
             x_tl /= 2; y_tl /= 2;
         }
     }
-    // blend(): normalise every level, collapse from the top, crop + mask + convertTo(CV_8U)
-    for (int i = 0; i <= nb; i++) {
-        const size_t px = (size_t)ws->lw[i] * ws->lh[i];
-        k7_normalize<<<(unsigned)((px + 255) / 256), 256, 0, ctx->stream>>>(ws->dlap[i], ws->dw[i], px);
+    // blend(): normalise the top level, collapse from the top (normalising each level as it is consumed); the level-0 step
+    // writes the cropped u8 mosaic and its mask directly
+    {
+        const size_t px = (size_t)ws->lw[nb] * ws->lh[nb];
+        k7_normalize<<<(unsigned)((px + 255) / 256), 256, 0, ctx->stream>>>(ws->dlap[nb], ws->dw[nb], px);
         UAVM_CHECK_LAUNCH(ctx);
     }
-    for (int i = nb; i > 0; i--) {
+    for (int i = nb; i > 1; i--) {
         dim3 grid((ws->lw[i - 1] + 255) / 256, ws->lh[i - 1]);
-        k7_collapse<<<grid, 256, 0, ctx->stream>>>(ws->dlap[i], ws->lw[i], ws->lh[i], ws->dlap[i - 1], ws->lw[i - 1], ws->lh[i - 1]);
+        k7_collapse<<<grid, 256, 0, ctx->stream>>>(ws->dlap[i], ws->lw[i], ws->lh[i], ws->dlap[i - 1], ws->dw[i - 1], ws->lw[i - 1], ws->lh[i - 1]);
         UAVM_CHECK_LAUNCH(ctx);
     }
     {
         const int oy0 = cv->banded ? cv->band_y0 : 0, oy1 = cv->banded ? cv->band_y1 : ch;
         dim3 grid((cw + 255) / 256, oy1 - oy0);
-        k7_output<<<grid, 256, 0, ctx->stream>>>(ws->dlap[0] + (size_t)(oy0 - Y0) * W * 3, ws->dw[0] + (size_t)(oy0 - Y0) * W, W, cw, oy1 - oy0,
-                                                  cv->d_result + (size_t)oy0 * cw * 3, cv->d_result_mask + (size_t)oy0 * cw);
+        if (nb >= 1)
+            k7_collapse_output<<<grid, 256, 0, ctx->stream>>>(ws->dlap[1], ws->lw[1], ws->lh[1], ws->dlap[0], ws->dw[0], W, BH, oy0 - Y0, oy1 - Y0, cw,
+                                                               cv->d_result + (size_t)oy0 * cw * 3, cv->d_result_mask + (size_t)oy0 * cw);
+        else
+            k7_output<<<grid, 256, 0, ctx->stream>>>(ws->dlap[0] + (size_t)(oy0 - Y0) * W * 4, ws->dw[0] + (size_t)(oy0 - Y0) * W, W, cw, oy1 - oy0,
+                                                      cv->d_result + (size_t)oy0 * cw * 3, cv->d_result_mask + (size_t)oy0 * cw);
         UAVM_CHECK_LAUNCH(ctx);
     }
     cv->blended = true;
