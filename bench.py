@@ -13,7 +13,8 @@ processes its own strip (weak scaling, no data-path collective: pairs are indepe
 `value`  = pairs/s with inputs resident in HBM, timed with CUDA events on the launching stream.
 `e2e`    = pairs/s through the host-buffer API: every step copies the strip's descriptors, keypoints and
            frames from pinned host memory, runs the path and reads the inlier match list back.
-`roofline` = the dominant kernel of the step (K5 warp: HBM bound; algorithmic 7 B per source pixel).
+`roofline` = the dominant kernel of the step (K5 warp, k5_warp_affine_x2: reported against HBM; algorithmic 7 B per
+             source pixel = frame read once + chip and mask written).
 `cpu_baseline` = the CPU oracle port timed on this box's host cores on a bounded sample of the same pairs.
 --impl reference times the CPU path only (oracle port; RANSAC through the reference's own compiled
 Ransac2D when oracle/_ref is present).
@@ -367,7 +368,7 @@ def run_ours(args):
         match_tf = match_flop / (serial_ms[0] / 1000.0) / 1e12
         traffic = None
         try:                                                # dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["k5_warp_chips"]["traffic"]
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["k5_warp_affine_x2"]["traffic"]
         except Exception:
             pass
         line = {
@@ -378,7 +379,7 @@ def run_ours(args):
                        "pairs_per_step_per_gpu": n_pairs, "ransac": "396 candidates, 1000 counted hypotheses, ~50% inliers",
                        "l2": "per-step working set 5 GB (frames + chips) >> 126 MB L2; the warp pass evicts the 52 MB descriptor pool between match passes",
                        "parallelism": f"pairs sharded over {world} GPU(s), no data-path collective"},
-            "roofline": {"kernel": "k5_warp_chips", "bound": "hbm", "achieved": warp_gbs, "peak": pk["hbm_gbs"], "unit": "GB/s",
+            "roofline": {"kernel": "k5_warp_affine_x2", "bound": "hbm", "achieved": warp_gbs, "peak": pk["hbm_gbs"], "unit": "GB/s",
                          "frac": warp_gbs / pk["hbm_gbs"], "traffic": traffic, "peak_src": pk["src"],
                          "algorithmic_bytes_per_launch": warp_bytes, "ms_per_launch": float(stage_ms[3])},
             "kernels": {"note": "timed region: k4 runs on the high-priority side stream concurrently with k5 on the main stream "
@@ -387,7 +388,7 @@ def run_ours(args):
                                              "peak_bf16_tflops": pk["bf16_tflops"], "frac_of_bf16_peak": match_tf / pk["bf16_tflops"]},
                         "k3_select": {"ms": float(stage_ms[1]), "serial_ms": float(serial_ms[1])},
                         "k4_ransac_eval+finalize": {"serial_ms": float(serial_ms[2]), "draw_groups_per_s": n_pairs * 2304 / (serial_ms[2] / 1000.0)},
-                        "k5_warp_chips": {"ms": float(stage_ms[3]), "serial_ms": float(serial_ms[3]), "achieved_gbs": warp_gbs,
+                        "k5_warp_affine_x2": {"ms": float(stage_ms[3]), "serial_ms": float(serial_ms[3]), "achieved_gbs": warp_gbs,
                                           "serial_gbs": warp_bytes / (serial_ms[3] / 1000.0) / 1e9}},
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": e_steps,
                     "ms_per_step": e2e_ms / e_steps, "pcie_h2d_probe_gbs": pcie_gbs,

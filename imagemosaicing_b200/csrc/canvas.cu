@@ -326,26 +326,7 @@ k5_warp_affine_x2(const __grid_constant__ CUtensorMap tmap_src, const ChipDesc* 
         }
         fp[3] = state;
     }
-    __syncthreads();
-    const int state = fp[3];
-    if (state == 2) {                                 // nothing of this tile is inside the source: BGR = 0, alpha = 0
-#pragma unroll
-        for (int ry = 0; ry < kWarpRows; ry++) {
-            const int yd = ybase + ry * 8;
-            if (yd >= D.chip_h) break;
-#pragma unroll
-            for (int i = 0; i < 4; i++) if (xl + 32 * i < D.chip_w) D.chip[(size_t)yd * D.chip_step + xl + 32 * i] = 0u;
-        }
-        return;
-    }
-    uint32_t sm_adj = 0;
-    constexpr uint32_t sm_pitch4 = kFpBoxW * 4u;      // the boxes stack into rows of kFpBoxW words: a multiple of 32 banks
-    float clampx = 0.0f, clampy = 0.0f;
-    if (state == 1) {
-        const int x0 = fp[0], y0 = fp[1];
-        sm_adj = 0u - (0x4B000000u * sm_pitch4 + 0x4B000000u * 4u) - ((uint32_t)y0 * sm_pitch4 + (uint32_t)x0 * 4u);   // offset from fp_smem
-        clampx = (float)x0; clampy = (float)y0;
-    }
+    // per-thread set-up first: it overlaps thread 0's footprint plan and the flight of the TMA copies
     const f32x2 ONE = pk2(one, one);
     const f32x2 IV2 = pk2(iv2, iv2), IV5 = pk2(iv5, iv5);
     const uint32_t step4 = 4u * (uint32_t)src_step_px;
@@ -369,6 +350,26 @@ k5_warp_affine_x2(const __grid_constant__ CUtensorMap tmap_src, const ChipDesc* 
             const float xs0 = mxa + ya + iv2, xs1 = mxb + ya + iv2, ys0 = mya + yb + iv5, ys1 = myb + yb + iv5;
             inside = inside && (xs0 >= 0.0f) && (xs0 < w1f) && (xs1 >= 0.0f) && (xs1 < w1f) && (ys0 >= 0.0f) && (ys0 < h1f) && (ys1 >= 0.0f) && (ys1 < h1f);
         }
+    }
+    __syncthreads();
+    const int state = fp[3];
+    if (state == 2) {                                 // nothing of this tile is inside the source: BGR = 0, alpha = 0
+#pragma unroll
+        for (int ry = 0; ry < kWarpRows; ry++) {
+            const int yd = ybase + ry * 8;
+            if (yd >= D.chip_h) break;
+#pragma unroll
+            for (int i = 0; i < 4; i++) if (xl + 32 * i < D.chip_w) D.chip[(size_t)yd * D.chip_step + xl + 32 * i] = 0u;
+        }
+        return;
+    }
+    uint32_t sm_adj = 0;
+    constexpr uint32_t sm_pitch4 = kFpBoxW * 4u;      // the boxes stack into rows of kFpBoxW words: a multiple of 32 banks
+    float clampx = 0.0f, clampy = 0.0f;
+    if (state == 1) {
+        const int x0 = fp[0], y0 = fp[1];
+        sm_adj = 0u - (0x4B000000u * sm_pitch4 + 0x4B000000u * 4u) - ((uint32_t)y0 * sm_pitch4 + (uint32_t)x0 * 4u);   // offset from fp_smem
+        clampx = (float)x0; clampy = (float)y0;
     }
 #define K5_ROWS_ARGS fp_smem, D, MX, MY, xl, ybase, dgy, sy, fby, iv1, iv4, IV2, IV5, step4, base_adj, sm_adj, clampx, clampy, one_u, two23, w1f, h1f, ONE
     if (state == 1) {
