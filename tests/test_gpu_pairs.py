@@ -65,6 +65,30 @@ def test_match_batched_pairs_full_size(ctx, oracle):
             assert np.array_equal(d2, od2.astype(np.int64))
 
 
+def test_match_32k_microbench_size(ctx, oracle):
+    """BASELINE configs[3]: 32768 x 32768 SIFT-128 distance matrix (274.9 GFLOP, never materialised).  Checked by
+    size-independent properties (distances recomputed from the returned indices; A against itself returns the
+    identity) and against the oracle on a sample of query rows (full train set, so the arg-min is the global one)."""
+    rng = np.random.default_rng(32768)
+    n = 32768
+    A = synth.sift_like_descriptors(rng, n); B = synth.sift_like_descriptors(rng, n)
+    B[12345] = A[777]; B[23456] = A[777]                       # tie across far-apart tiles: lowest index wins
+    fs = api.FeatureSet(ctx, [n, n])
+    fs.upload(0, A, None); fs.upload(1, B, None)
+    pb = api.PairBatch(ctx, fs, [[0, 1], [0, 0]])
+    pb.match()
+    m = pb.matches(0)
+    d2 = ((A.astype(np.int64) - B[m["trainIdx"]].astype(np.int64)) ** 2).sum(1)
+    assert np.array_equal(np.rint(m["distance"].astype(np.float64) ** 2).astype(np.int64), d2)
+    assert m["trainIdx"][777] == 12345 and d2[777] == 0
+    rows = rng.choice(n, 96, replace=False); rows[0] = 777
+    idx, od2 = oracle.match_l2_fast(A[rows], B)
+    assert np.array_equal(m["trainIdx"][rows], idx) and np.array_equal(d2[rows], od2.astype(np.int64))
+    ms = pb.matches(1)                                          # A against itself
+    ds = ((A.astype(np.int64) - A[ms["trainIdx"]].astype(np.int64)) ** 2).sum(1)
+    assert (ds == 0).all() and (ms["trainIdx"] <= np.arange(n)).all()
+
+
 @pytest.mark.parametrize("n,w,h", [(2048, 512, 512), (8192, 4000, 3000), (2000, 1000, 750), (30, 512, 512), (1335, 4000, 3000)])
 def test_select_parity(ctx, oracle, n, w, h):
     rng = np.random.default_rng(n + w)
