@@ -38,6 +38,11 @@ class MatchPointPairs(C.Structure):  # M/MosaicWithoutPos.h:135-153 (40 bytes)
                 ("ptB", SfPoint), ("ptB_i", C.c_int32), ("ptB_Fixed", C.c_int32)]
 
 
+class KeyPoint(C.Structure):          # cv::KeyPoint of OpenCV 2.4 (28 bytes), record of keypoint_%d.key
+    _fields_ = [("x", C.c_float), ("y", C.c_float), ("size", C.c_float), ("angle", C.c_float), ("response", C.c_float),
+                ("octave", C.c_int32), ("class_id", C.c_int32)]
+
+
 class Image(C.Structure):
     _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("nChannels", C.c_int32), ("widthStep", C.c_int32),
                 ("imageData", C.c_void_p)]

@@ -337,29 +337,142 @@ class Canvas:
             pass
 
 
-def mosaic_images(ctx, images, descs, kps, param=None, scale=1.0):
-    """MosaicVavImages-shaped entry (uavm_mosaic_images): images = list of (h,w,3) u8 BGR frames, descs = list of
-    (n_i,128) f32/u8 descriptors, kps = list of (n_i,2) f32.  Returns (mosaic u8 (H,W,3), transforms (n,9) f32, fixed (n,))."""
+def _image_array(images):
     n = len(images)
     ims = [np.ascontiguousarray(i, np.uint8) for i in images]
-    ds = [np.ascontiguousarray(d, np.float32) for d in descs]
-    ks = [np.ascontiguousarray(k, np.float32) for k in kps]
     arr = (L.Image * n)()
     for i, im in enumerate(ims):
         arr[i].width, arr[i].height, arr[i].nChannels, arr[i].widthStep = im.shape[1], im.shape[0], 3, im.strides[0]
         arr[i].imageData = im.ctypes.data
-    dp = (f32p * n)(*[_ptr(d, f32p) for d in ds]); kp = (f32p * n)(*[_ptr(k, f32p) for k in ks])
-    nk = np.array([len(d) for d in ds], np.int32)
+    return ims, arr
+
+
+def _param(param):
     P = L.Param()
     L.lib().uavm_param_default(C.byref(P))
     for k, v in (param or {}).items():
         setattr(P, k, v)
-    res = L.Image(); nm = C.c_int(0); tr = (ImageTransform * n)()
-    rc = L.lib().uavm_mosaic_images(ctx._h, arr, n, dp, kp, _ptr(nk, i32p), C.byref(P), C.c_float(scale), C.byref(res), C.byref(nm), tr)
-    ctx.check(rc)
+    return P
+
+
+def _take_result(res, tr, n):
     buf = (C.c_uint8 * (res.widthStep * res.height)).from_address(res.imageData)
     out = np.frombuffer(buf, np.uint8).reshape(res.height, res.widthStep)[:, :res.width * 3].reshape(res.height, res.width, 3).copy()
     L.lib().uavm_free(C.c_void_p(res.imageData))
     T = np.array([[tr[i].h.m[t] for t in range(9)] for i in range(n)], np.float32)
     fixed = np.array([tr[i].fixed for i in range(n)], np.int32)
     return out, T, fixed
+
+
+def mosaic_images(ctx, images, descs, kps, param=None, scale=1.0, return_matches=False):
+    """MosaicVavImages-shaped entry (uavm_mosaic_images): images = list of (h,w,3) u8 BGR frames, descs = list of
+    (n_i,128) f32/u8 descriptors, kps = list of (n_i,2) f32.  Returns (mosaic u8 (H,W,3), transforms (n,9) f32, fixed (n,))
+    and, with return_matches, the accepted inlier matches (MatchPointPairs array: what the reference writes to
+    feature_temp/matchPairs.match)."""
+    n = len(images)
+    ims, arr = _image_array(images)
+    ds = [np.ascontiguousarray(d, np.float32) for d in descs]
+    ks = [np.ascontiguousarray(k, np.float32) for k in kps]
+    dp = (f32p * n)(*[_ptr(d, f32p) for d in ds]); kp = (f32p * n)(*[_ptr(k, f32p) for k in ks])
+    nk = np.array([len(d) for d in ds], np.int32)
+    P = _param(param)
+    res = L.Image(); nm = C.c_int(0); tr = (ImageTransform * n)()
+    pp = C.POINTER(MatchPointPairs)(); npairs = C.c_int(0)
+    rc = L.lib().uavm_mosaic_images_ex(ctx._h, arr, n, dp, kp, _ptr(nk, i32p), C.byref(P), C.c_float(scale), C.byref(res), C.byref(nm), tr,
+                                       C.byref(pp), C.byref(npairs))
+    matches = None
+    if npairs.value > 0:
+        matches = (MatchPointPairs * npairs.value)()
+        C.memmove(matches, pp, C.sizeof(MatchPointPairs) * npairs.value)
+        L.lib().uavm_free(C.cast(pp, C.c_void_p))
+    ctx.check(rc)
+    out = _take_result(res, tr, n)
+    return out + (matches,) if return_matches else out
+
+
+def mosaic_from_matches(ctx, images, matches, param=None, scale=1.0):
+    """The loadMatchPairs = 1 path (M/MosaicWithoutPos.cpp:4465-4477) without the stdin prompt: `matches` (a ctypes array of
+    MatchPointPairs, e.g. from read_match_file) replaces feature matching."""
+    n = len(images)
+    ims, arr = _image_array(images)
+    P = _param(param)
+    res = L.Image(); nm = C.c_int(0); tr = (ImageTransform * n)()
+    ctx.check(L.lib().uavm_mosaic_from_matches(ctx._h, arr, n, matches, len(matches), C.byref(P), C.c_float(scale), C.byref(res), C.byref(nm), tr))
+    return _take_result(res, tr, n)
+
+
+# ---- the reference's on-disk artefacts (host only; csrc/formats_host.cpp) --------------------------------------------------
+def _io_check(rc, what, path):
+    if rc != 0:
+        raise UavmError(f"{what}({path!r}) failed with {rc}")
+
+
+def read_match_file(path):
+    """matchPairs.match (LoadMatchPairs, M/MosaicWithoutPos.cpp:4774-4797) -> ctypes array of MatchPointPairs."""
+    n = C.c_int(0)
+    _io_check(L.lib().uavm_match_file_count(path.encode(), C.byref(n)), "uavm_match_file_count", path)
+    arr = (MatchPointPairs * max(n.value, 1))()
+    _io_check(L.lib().uavm_match_file_read(path.encode(), arr, n.value, C.byref(n)), "uavm_match_file_read", path)
+    return (MatchPointPairs * n.value).from_buffer(arr) if n.value else (MatchPointPairs * 0)()
+
+
+def write_match_file(path, matches):
+    _io_check(L.lib().uavm_match_file_write(path.encode(), matches, len(matches)), "uavm_match_file_write", path)
+
+
+def write_match_text(path, matches):
+    """matchPairs.txt (WriteMatchPairs_ASC2, :4751-4772)."""
+    _io_check(L.lib().uavm_match_text_write(path.encode(), matches, len(matches)), "uavm_match_text_write", path)
+
+
+def read_match_text(path, cap=1 << 22):
+    arr = (MatchPointPairs * cap)(); n = C.c_int(0)
+    _io_check(L.lib().uavm_match_text_read(path.encode(), arr, cap, C.byref(n)), "uavm_match_text_read", path)
+    out = (MatchPointPairs * n.value)()
+    C.memmove(out, arr, C.sizeof(MatchPointPairs) * n.value)
+    return out
+
+
+def _transforms_to_ctypes(T, fixed):
+    T = np.ascontiguousarray(T, np.float32).reshape(-1, 9); n = len(T)
+    arr = (ImageTransform * n)()
+    for i in range(n):
+        for j in range(9):
+            arr[i].h.m[j] = float(T[i, j])
+        arr[i].fixed = int(fixed[i])
+    return arr
+
+
+def write_transform_file(path, T, fixed):
+    """tran0.txt (OutTransform, :2798-2818): rows for images 1..N-1."""
+    arr = _transforms_to_ctypes(T, fixed)
+    _io_check(L.lib().uavm_transform_file_write(path.encode(), arr, len(arr)), "uavm_transform_file_write", path)
+
+
+def read_transform_file(path, cap=10000, imported=False):
+    """tran0.txt -> (T (n,9) f32, fixed (n,)); imported=True reads ImportTransform's count-prefixed format (:2820-2843)."""
+    arr = (ImageTransform * cap)(); n = C.c_int(0)
+    fn = L.lib().uavm_transform_import if imported else L.lib().uavm_transform_file_read
+    _io_check(fn(path.encode(), arr, cap, C.byref(n)), "uavm_transform_file_read", path)
+    T = np.array([[arr[i].h.m[t] for t in range(9)] for i in range(n.value)], np.float32).reshape(-1, 9)
+    return T, np.array([arr[i].fixed for i in range(n.value)], np.int32)
+
+
+def write_feature_files(key_path, xml_path, keypoints, desc):
+    """keypoint_%d.key + discriptor_%d.xml (WriteSurfKeyPoints, :4682-4704).  keypoints: ctypes array of _lib.KeyPoint."""
+    desc = np.ascontiguousarray(desc, np.float32)
+    _io_check(L.lib().uavm_key_file_write(key_path.encode(), keypoints, len(keypoints)), "uavm_key_file_write", key_path)
+    _io_check(L.lib().uavm_descriptor_xml_write(xml_path.encode(), _ptr(desc, f32p), desc.shape[0], desc.shape[1]), "uavm_descriptor_xml_write", xml_path)
+
+
+def read_feature_files(key_path, xml_path, cap=1 << 20):
+    """LoadSurfKeyPoints (:4706-4734) -> (ctypes array of KeyPoint, (rows, cols) f32 descriptors)."""
+    kp = (L.KeyPoint * cap)(); n = C.c_int(0)
+    _io_check(L.lib().uavm_key_file_read(key_path.encode(), kp, cap, C.byref(n)), "uavm_key_file_read", key_path)
+    out = (L.KeyPoint * n.value)()
+    C.memmove(out, kp, C.sizeof(L.KeyPoint) * n.value)
+    r = C.c_int(0); c = C.c_int(0)
+    _io_check(L.lib().uavm_descriptor_xml_size(xml_path.encode(), C.byref(r), C.byref(c)), "uavm_descriptor_xml_size", xml_path)
+    d = np.zeros((r.value, c.value), np.float32)
+    _io_check(L.lib().uavm_descriptor_xml_read(xml_path.encode(), _ptr(d, f32p), d.size, C.byref(r), C.byref(c)), "uavm_descriptor_xml_read", xml_path)
+    return out, d

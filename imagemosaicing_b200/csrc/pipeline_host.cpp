@@ -7,25 +7,38 @@
 #include <vector>
 #include "internal.h"
 
-extern "C" int uavm_mosaic_images(uavm_ctx* ctx, const uavm_image* images, int n_images,
-                                  const float* const* desc, const float* const* kp_xy, const int32_t* n_kp,
-                                  const uavm_param* param_in, float scale,
-                                  uavm_image* result, int* num_mosaiced, uavm_imagetransform* transforms_out)
+static int check_images(const uavm_image* images, int n_images)
+{
+    const int w = images[0].width, h = images[0].height;              // size taken from image 0 (:10185-10186)
+    for (int i = 0; i < n_images; i++)
+        if (!images[i].imageData || images[i].nChannels != 3 || images[i].width != w || images[i].height != h || images[i].widthStep < 3 * w) return UAVM_EINVAL;
+    return UAVM_OK;
+}
+
+static int mosaic_tail(uavm_ctx* ctx, const uavm_image* images, int n_images, std::vector<uavm_matchpointpairs>& matches, const uavm_param& P,
+                       float scale, uavm_image* result, int* num_mosaiced, uavm_imagetransform* transforms_out);
+
+extern "C" int uavm_mosaic_images_ex(uavm_ctx* ctx, const uavm_image* images, int n_images,
+                                     const float* const* desc, const float* const* kp_xy, const int32_t* n_kp,
+                                     const uavm_param* param_in, float scale,
+                                     uavm_image* result, int* num_mosaiced, uavm_imagetransform* transforms_out,
+                                     uavm_matchpointpairs** pairs_out, int* n_pairs_out)
 {
     // argument checks of MosaicVavImages (:10157-10165): -1 on invalid input
     if (!ctx || !images || n_images < 2 || !desc || !kp_xy || !n_kp || !result) return UAVM_EINVAL;
     memset(result, 0, sizeof(*result));
+    if (pairs_out) *pairs_out = nullptr;
+    if (n_pairs_out) *n_pairs_out = 0;
     uavm_param P;
     if (param_in) P = *param_in; else uavm_param_default(&P);
-    const int w = images[0].width, h = images[0].height;              // size taken from image 0 (:10185-10186)
-    for (int i = 0; i < n_images; i++) {
-        if (!images[i].imageData || images[i].nChannels != 3 || images[i].width != w || images[i].height != h ||
-            images[i].widthStep < 3 * w || n_kp[i] < 0 || (n_kp[i] > 0 && (!desc[i] || !kp_xy[i]))) return UAVM_EINVAL;
-    }
+    if (check_images(images, n_images) != UAVM_OK) return UAVM_EINVAL;
+    const int w = images[0].width, h = images[0].height;
+    for (int i = 0; i < n_images; i++)
+        if (n_kp[i] < 0 || (n_kp[i] > 0 && (!desc[i] || !kp_xy[i]))) return UAVM_EINVAL;
     if (num_mosaiced) *num_mosaiced = 0;
 
     // ---- [A] feature matching: GetMatchedPairsOneToAllSIFT_MultiThread (:5244) ----
-    uavm_featureset* fs = nullptr; uavm_pairbatch* pb = nullptr; uavm_canvas* cv = nullptr;
+    uavm_featureset* fs = nullptr; uavm_pairbatch* pb = nullptr;
     int rc = uavm_featureset_create(ctx, n_images, n_kp, &fs);
     for (int i = 0; rc == UAVM_OK && i < n_images; i++) rc = uavm_featureset_upload_f32(ctx, fs, i, desc[i], kp_xy[i], 0);
     std::vector<int32_t> pair_ij;
@@ -48,6 +61,46 @@ extern "C" int uavm_mosaic_images(uavm_ctx* ctx, const uavm_image* images, int n
     uavm_pairbatch_destroy(ctx, pb);
     uavm_featureset_destroy(ctx, fs);
     if (rc != UAVM_OK) return UAVM_EFAIL;
+    if (pairs_out && !matches.empty()) {                               // what the reference writes to matchPairs.match (:4492)
+        *pairs_out = (uavm_matchpointpairs*)malloc(matches.size() * sizeof(uavm_matchpointpairs));
+        if (!*pairs_out) return UAVM_EFAIL;
+        memcpy(*pairs_out, matches.data(), matches.size() * sizeof(uavm_matchpointpairs));
+        if (n_pairs_out) *n_pairs_out = (int)matches.size();
+    }
+    return mosaic_tail(ctx, images, n_images, matches, P, scale, result, num_mosaiced, transforms_out);
+}
+
+extern "C" int uavm_mosaic_images(uavm_ctx* ctx, const uavm_image* images, int n_images,
+                                  const float* const* desc, const float* const* kp_xy, const int32_t* n_kp,
+                                  const uavm_param* param_in, float scale,
+                                  uavm_image* result, int* num_mosaiced, uavm_imagetransform* transforms_out)
+{
+    return uavm_mosaic_images_ex(ctx, images, n_images, desc, kp_xy, n_kp, param_in, scale, result, num_mosaiced, transforms_out, nullptr, nullptr);
+}
+
+extern "C" int uavm_mosaic_from_matches(uavm_ctx* ctx, const uavm_image* images, int n_images,
+                                        const uavm_matchpointpairs* pairs, int n_pairs, const uavm_param* param_in, float scale,
+                                        uavm_image* result, int* num_mosaiced, uavm_imagetransform* transforms_out)
+{
+    if (!ctx || !images || n_images < 2 || !pairs || n_pairs < 0 || !result) return UAVM_EINVAL;
+    memset(result, 0, sizeof(*result));
+    uavm_param P;
+    if (param_in) P = *param_in; else uavm_param_default(&P);
+    if (check_images(images, n_images) != UAVM_OK) return UAVM_EINVAL;
+    for (int m = 0; m < n_pairs; m++)
+        if (pairs[m].ptA_i < 0 || pairs[m].ptA_i >= n_images || pairs[m].ptB_i < 0 || pairs[m].ptB_i >= n_images) return UAVM_EINVAL;
+    if (num_mosaiced) *num_mosaiced = 0;
+    std::vector<uavm_matchpointpairs> matches(pairs, pairs + n_pairs);
+    return mosaic_tail(ctx, images, n_images, matches, P, scale, result, num_mosaiced, transforms_out);
+}
+
+// stages [B]-[D] of MosaicWithoutPose, shared by the matching path and the loadMatchPairs path
+static int mosaic_tail(uavm_ctx* ctx, const uavm_image* images, int n_images, std::vector<uavm_matchpointpairs>& matches, const uavm_param& P,
+                       float scale, uavm_image* result, int* num_mosaiced, uavm_imagetransform* transforms_out)
+{
+    const int w = images[0].width, h = images[0].height;
+    uavm_canvas* cv = nullptr;
+    int rc = UAVM_OK;
 
     // ---- [B] largest connected component, reference image 0 fixed (:4501-4571) ----
     std::vector<int32_t> label(n_images, 0);

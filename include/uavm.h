@@ -33,6 +33,9 @@ typedef struct {                                                         /* Matc
     uavm_sfpoint ptA; int32_t ptA_i; int32_t ptA_Fixed;
     uavm_sfpoint ptB; int32_t ptB_i; int32_t ptB_Fixed;
 } uavm_matchpointpairs;
+typedef struct {                                                         /* cv::KeyPoint of OpenCV 2.4 (28 B): record of keypoint_%d.key */
+    float x, y, size, angle, response; int32_t octave, class_id;
+} uavm_keypoint;
 typedef struct {                                                         /* fields of IplImage the path reads (CV/core/types_c.h:460-493) */
     int32_t width, height, nChannels, widthStep;
     uint8_t* imageData;
@@ -177,7 +180,40 @@ int uavm_mosaic_images(uavm_ctx* ctx, const uavm_image* images, int n_images,
                        const float* const* desc, const float* const* kp_xy, const int32_t* n_kp,
                        const uavm_param* param, float scale,
                        uavm_image* result, int* num_mosaiced, uavm_imagetransform* transforms_out);
+/* the loadMatchPairs = 1 path of MosaicWithoutPose (M/MosaicWithoutPos.cpp:4465-4477), without the stdin prompt: the match
+ * list (e.g. uavm_match_file_read of a matchPairs.match written by the original tool or by uavm_match_file_write) replaces
+ * feature matching; connectivity -> global alignment -> warp / blend run as in uavm_mosaic_images. */
+int uavm_mosaic_from_matches(uavm_ctx* ctx, const uavm_image* images, int n_images,
+                             const uavm_matchpointpairs* pairs, int n_pairs, const uavm_param* param, float scale,
+                             uavm_image* result, int* num_mosaiced, uavm_imagetransform* transforms_out);
+/* same as uavm_mosaic_images, and also returns the accepted inlier matches (what the reference writes to
+ * feature_temp/matchPairs.match, :4492): *pairs_out is allocated by the library (uavm_free) */
+int uavm_mosaic_images_ex(uavm_ctx* ctx, const uavm_image* images, int n_images,
+                          const float* const* desc, const float* const* kp_xy, const int32_t* n_kp,
+                          const uavm_param* param, float scale,
+                          uavm_image* result, int* num_mosaiced, uavm_imagetransform* transforms_out,
+                          uavm_matchpointpairs** pairs_out, int* n_pairs_out);
 void uavm_free(void* p);
+
+/* ---- the reference's on-disk artefacts (host only, csrc/formats_host.cpp) -------------------------------------------------
+ * matchPairs.match: int32 n + n x 40 B MatchPointPairs (WriteMatchPairs / LoadMatchPairs, M/MosaicWithoutPos.cpp:4736-4797) */
+int uavm_match_file_count(const char* path, int* n_out);
+int uavm_match_file_read(const char* path, uavm_matchpointpairs* out, int cap, int* n_out);
+int uavm_match_file_write(const char* path, const uavm_matchpointpairs* pairs, int n);
+/* matchPairs.txt: "imgA xA yA fixedA imgB xB yB fixedB" per line (WriteMatchPairs_ASC2, :4751-4772); ids are not stored */
+int uavm_match_text_write(const char* path, const uavm_matchpointpairs* pairs, int n);
+int uavm_match_text_read(const char* path, uavm_matchpointpairs* out, int cap, int* n_out);
+/* tran0.txt: rows for images 1..N-1, "m0 .. m7 fixed" (OutTransform, :2798-2818); read returns image 0 = identity, fixed */
+int uavm_transform_file_write(const char* path, const uavm_imagetransform* t, int n_images);
+int uavm_transform_file_read(const char* path, uavm_imagetransform* out, int cap, int* n_images_out);
+/* ImportTransform's format (:2820-2843): count, then 9 floats per image */
+int uavm_transform_import(const char* path, uavm_imagetransform* out, int cap, int* n_images_out);
+/* keypoint_%d.key: int32 n + n x 28 B cv::KeyPoint; discriptor_%d.xml: FileStorage node "descriptor", CV_32F (:4682-4734) */
+int uavm_key_file_read(const char* path, uavm_keypoint* out, int cap, int* n_out);
+int uavm_key_file_write(const char* path, const uavm_keypoint* kp, int n);
+int uavm_descriptor_xml_size(const char* path, int* rows, int* cols);
+int uavm_descriptor_xml_read(const char* path, float* out, int cap_floats, int* rows, int* cols);
+int uavm_descriptor_xml_write(const char* path, const float* desc, int rows, int cols);
 
 #ifdef __cplusplus
 }

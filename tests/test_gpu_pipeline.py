@@ -48,3 +48,27 @@ def test_mosaic_images_argument_errors(ctx):
         rng = np.random.default_rng(0)
         bad = [synth.sift_like_descriptors(rng, nk).astype(np.float32) for _ in range(n)]
         api.mosaic_images(ctx, images, bad, kps)
+
+
+def test_load_match_pairs_resume_path(ctx, tmp_path):
+    """loadMatchPairs = 1 (M/MosaicWithoutPos.cpp:4465-4477): the matches of a first run, written to and read back from a
+    matchPairs.match file, reproduce the same transforms and the same mosaic without the matching stage."""
+    n, w, h, nk = 5, 640, 480, 2048
+    images, descs, kps, _ = _scene(n, w, h, nk, 78)
+    prm = {"blending": 2, "pairWindow": 3, "seed": 9}
+    out, T, fixed, matches = api.mosaic_images(ctx, images, [d.astype(np.float32) for d in descs], kps, prm, 1.0, return_matches=True)
+    assert matches is not None and len(matches) > 100
+    path = str(tmp_path / "matchPairs.match")
+    api.write_match_file(path, matches)
+    loaded = api.read_match_file(path)
+    assert bytes(loaded) == bytes(matches)
+    out2, T2, fixed2 = api.mosaic_from_matches(ctx, images, loaded, prm, 1.0)
+    assert np.array_equal(T, T2) and np.array_equal(fixed, fixed2) and np.array_equal(out, out2)
+    # transforms survive tran0.txt to its 6 printed digits
+    tpath = str(tmp_path / "tran0.txt")
+    api.write_transform_file(tpath, T, fixed)
+    T3, _ = api.read_transform_file(tpath)
+    assert np.allclose(T3[:, :6], T[:, :6], rtol=2e-5, atol=1e-6)
+    with pytest.raises(api.UavmError):                      # image index out of range in the loaded list: -1
+        bad = type(loaded).from_buffer_copy(loaded); bad[0].ptA_i = 99
+        api.mosaic_from_matches(ctx, images, bad, prm, 1.0)
