@@ -52,20 +52,48 @@ __device__ __forceinline__ void st3(short* base, size_t px, int a, int b, int c)
     *reinterpret_cast<int2*>(base + px * 4) = v;
 }
 
-// level 0 of the fed image: copyMakeBorder(REFLECT) of the chip (u8 -> s16) and mask/255 with a zero border
+// level 0 of the fed image: copyMakeBorder(REFLECT) of the chip (u8 -> s16) and mask/255 with a zero border.
+// Four pixels per thread; groups that lie inside the chip with 4-pixel alignment on both sides move as vectors.
 __global__ void __launch_bounds__(256)
 k7_feed_level0(const uint32_t* __restrict__ chip, int chip_step /* words */, const uint8_t* __restrict__ mask, int mask_step,
                int cw, int ch, int left, int top, int width, int height, short* __restrict__ pyr0, float* __restrict__ wp0)
 {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
-    if (x >= width || y >= height) return;
-    const int ix = x - left, iy = y - top;
-    const int sx = reflect_edge(ix, cw), sy = reflect_edge(iy, ch);
-    const uint32_t s = chip[(size_t)sy * chip_step + sx];                   // BGRA
-    st3(pyr0, (size_t)y * width + x, (int)(s & 0xffu), (int)((s >> 8) & 0xffu), (int)((s >> 16) & 0xffu));
-    float wv = 0.0f;
-    if (ix >= 0 && ix < cw && iy >= 0 && iy < ch) wv = (float)mask[(size_t)iy * mask_step + ix] * (float)(1. / 255.);
-    wp0[(size_t)y * width + x] = wv;
+    const int x0 = 4 * (blockIdx.x * blockDim.x + threadIdx.x), y = blockIdx.y;
+    if (x0 >= width || y >= height) return;
+    const int iy = y - top, sy = reflect_edge(iy, ch);
+    const int ix0 = x0 - left;
+    const size_t o = (size_t)y * width + x0;
+    if (ix0 >= 0 && ix0 + 4 <= cw && x0 + 4 <= width && (width & 3) == 0) {
+        const uint32_t* crow = chip + (size_t)sy * chip_step + ix0;                                    // 4 BGRA pixels
+        uint32_t sv[4];
+        if ((ix0 & 3) == 0) { const uint4 s = *reinterpret_cast<const uint4*>(crow); sv[0] = s.x; sv[1] = s.y; sv[2] = s.z; sv[3] = s.w; }
+        else { sv[0] = crow[0]; sv[1] = crow[1]; sv[2] = crow[2]; sv[3] = crow[3]; }
+        int4 a, b;
+        a.x = (int)((sv[0] & 0xffu) | ((sv[0] & 0xff00u) << 8)); a.y = (int)((sv[0] >> 16) & 0xffu);
+        a.z = (int)((sv[1] & 0xffu) | ((sv[1] & 0xff00u) << 8)); a.w = (int)((sv[1] >> 16) & 0xffu);
+        b.x = (int)((sv[2] & 0xffu) | ((sv[2] & 0xff00u) << 8)); b.y = (int)((sv[2] >> 16) & 0xffu);
+        b.z = (int)((sv[3] & 0xffu) | ((sv[3] & 0xff00u) << 8)); b.w = (int)((sv[3] >> 16) & 0xffu);
+        *reinterpret_cast<int4*>(pyr0 + o * 4) = a; *reinterpret_cast<int4*>(pyr0 + (o + 2) * 4) = b;
+        float4 wv = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        if (iy >= 0 && iy < ch) {
+            // 4 mask bytes at an arbitrary byte offset: two aligned words (rows are padded to align4, + 256 B slack) and a funnel shift
+            const uint32_t* mrow = reinterpret_cast<const uint32_t*>(mask + (size_t)iy * mask_step + (ix0 & ~3));
+            const uint32_t m = (ix0 & 3) ? __funnelshift_r(mrow[0], mrow[1], 8 * (ix0 & 3)) : mrow[0];
+            wv.x = (float)(m & 0xffu) * (float)(1. / 255.); wv.y = (float)((m >> 8) & 0xffu) * (float)(1. / 255.);
+            wv.z = (float)((m >> 16) & 0xffu) * (float)(1. / 255.); wv.w = (float)(m >> 24) * (float)(1. / 255.);
+        }
+        *reinterpret_cast<float4*>(wp0 + o) = wv;
+        return;
+    }
+    for (int i = 0; i < 4 && x0 + i < width; i++) {
+        const int ix = ix0 + i;
+        const int sx = reflect_edge(ix, cw);
+        const uint32_t s = chip[(size_t)sy * chip_step + sx];                   // BGRA
+        st3(pyr0, o + i, (int)(s & 0xffu), (int)((s >> 8) & 0xffu), (int)((s >> 16) & 0xffu));
+        float wv = 0.0f;
+        if (ix >= 0 && ix < cw && iy >= 0 && iy < ch) wv = (float)mask[(size_t)iy * mask_step + ix] * (float)(1. / 255.);
+        wp0[o + i] = wv;
+    }
 }
 
 // pyrDown of the int16 x3 image and of the f32 weight map, one output pixel per thread
@@ -171,6 +199,62 @@ __device__ __forceinline__ void normalized3(const short* lap, const float* wsum,
     for (int k = 0; k < 3; k++) d[k] = (short)__float2int_rz((float)d[k] / wv);
 }
 
+// Same for the levels that have a coarser level below them, one 2 x 2 quad of pixels per thread: the four pixels share
+// the 3 x 3 neighbourhood of the coarser level (9 loads instead of 9 + 6 + 6 + 4) and pyrUp separates into three horizontal
+// sums per parity and a vertical combination; cur / dst / weights move as aligned 16- and 8-byte vectors.  Level sizes and
+// the paste offsets (x_tl, y_tl) are even below the top level (ROIs are aligned to 2^bands), so quads tile exactly.
+__global__ void __launch_bounds__(256)
+k7_lap_accumulate_quad(const short* __restrict__ cur, const short* __restrict__ next, const float* __restrict__ wcur,
+                       int w, int h, int nw, int nh, short* __restrict__ dlap, float* __restrict__ dwsum, int dst_w, int x_tl, int y_tl)
+{
+    const int cx = blockIdx.x * blockDim.x + threadIdx.x, cy = blockIdx.y;          // quad index = coordinates in the coarser level
+    const int x = 2 * cx, y = 2 * cy;
+    if (x >= w || y >= h) return;
+    const float2 w0 = *reinterpret_cast<const float2*>(wcur + (size_t)y * w + x);
+    const float2 w1 = *reinterpret_cast<const float2*>(wcur + (size_t)(y + 1) * w + x);
+    if (w0.x == 0.0f && w0.y == 0.0f && w1.x == 0.0f && w1.y == 0.0f) return;       // dst + short(lap * 0) == dst, wsum + 0 == wsum
+    // pyrUp border rules (see pyrup_at): reflect-101 at the near edge, replicate at the far edge
+    const int xm = (cx == 0) ? (nw > 1 ? 1 : 0) : cx - 1, xp = (cx == nw - 1) ? nw - 1 : cx + 1;
+    const int ym = (cy == 0) ? (nh > 1 ? 1 : 0) : cy - 1, yp = (cy == nh - 1) ? nh - 1 : cy + 1;
+    const int rows[3] = {ym, cy, yp};
+    int he[3][3], ho[3][3];                        // [row][channel]: even-x sum a + 6 b + c, odd-x sum 4 (b + c)
+#pragma unroll
+    for (int r = 0; r < 3; r++) {
+        const size_t rb = (size_t)rows[r] * nw;
+        int a[3], b[3], c[3];
+        ld3(next, rb + xm, a[0], a[1], a[2]); ld3(next, rb + cx, b[0], b[1], b[2]); ld3(next, rb + xp, c[0], c[1], c[2]);
+#pragma unroll
+        for (int k = 0; k < 3; k++) { he[r][k] = a[k] + 6 * b[k] + c[k]; ho[r][k] = 4 * (b[k] + c[k]); }
+    }
+    const float wq[2][2] = {{w0.x, w0.y}, {w1.x, w1.y}};
+#pragma unroll
+    for (int dy = 0; dy < 2; dy++) {
+        const int4 c4 = *reinterpret_cast<const int4*>(cur + ((size_t)(y + dy) * w + x) * 4);
+        const size_t di = (size_t)(y + dy + y_tl) * dst_w + (x + x_tl);
+        int4 d4 = *reinterpret_cast<const int4*>(dlap + di * 4);
+        float2 ws = *reinterpret_cast<const float2*>(dwsum + di);
+        const int cw2[2][2] = {{c4.x, c4.y}, {c4.z, c4.w}};
+        int dw2[2][2] = {{d4.x, d4.y}, {d4.z, d4.w}};
+#pragma unroll
+        for (int dx = 0; dx < 2; dx++) {
+            const int cc[3] = {(short)(cw2[dx][0] & 0xffff), cw2[dx][0] >> 16, (short)(cw2[dx][1] & 0xffff)};
+            int dd[3] = {(short)(dw2[dx][0] & 0xffff), dw2[dx][0] >> 16, (short)(dw2[dx][1] & 0xffff)};
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                const int h0 = dx ? ho[0][k] : he[0][k], h1 = dx ? ho[1][k] : he[1][k], h2 = dx ? ho[2][k] : he[2][k];
+                const int acc = dy ? 4 * (h1 + h2) : h0 + 6 * h1 + h2;
+                const int lap = sat16(cc[k] - sat16((acc + 32) >> 6));
+                dd[k] = (short)(dd[k] + (short)__float2int_rz((float)lap * wq[dy][dx]));
+            }
+            dw2[dx][0] = (dd[0] & 0xffff) | (dd[1] << 16); dw2[dx][1] = dd[2] & 0xffff;
+        }
+        d4.x = dw2[0][0]; d4.y = dw2[0][1]; d4.z = dw2[1][0]; d4.w = dw2[1][1];
+        ws.x += wq[dy][0]; ws.y += wq[dy][1];
+        *reinterpret_cast<int4*>(dlap + di * 4) = d4;
+        *reinterpret_cast<float2*>(dwsum + di) = ws;
+    }
+}
+
 __global__ void __launch_bounds__(256)
 k7_normalize(short* __restrict__ dlap, const float* __restrict__ dwsum, size_t n)        // top level only
 {
@@ -192,26 +276,42 @@ k7_collapse(const short* __restrict__ lo, int lw, int lh, short* __restrict__ hi
     st3(hi, (size_t)y * w + x, sat16(up[0] + d[0]), sat16(up[1] + d[1]), sat16(up[2] + d[2]));
 }
 
-// last step (level 0) fused with the output: rows [oy0, oy1) x columns [0, cw) of the padded level go to the mosaic
+// last step (level 0) fused with the output: rows [oy0, oy1) x columns [0, cw) of the padded level go to the mosaic.
+// Four pixels per thread: the 12 output bytes are three aligned words when the mosaic row pitch allows it.
 __global__ void __launch_bounds__(256)
 k7_collapse_output(const short* __restrict__ lo, int lw, int lh, const short* __restrict__ hi, const float* __restrict__ hi_wsum, int w, int h,
                    int oy0, int oy1, int cw, uint8_t* __restrict__ out, uint8_t* __restrict__ out_mask)
 {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = oy0 + blockIdx.y;
-    if (x >= cw || y >= oy1) return;
-    const size_t i = (size_t)y * w + x;
-    const bool m = hi_wsum[i] > 1e-5f;
-    int v[3] = {0, 0, 0};
-    if (m) {
-        int up[3], d[3];
-        pyrup_at(lo, lw, lh, x, y, up);
-        normalized3(hi, hi_wsum, i, d);
+    const int x0 = 4 * (blockIdx.x * blockDim.x + threadIdx.x), y = oy0 + blockIdx.y;
+    if (x0 >= cw || y >= oy1) return;
+    uint32_t px[4] = {0, 0, 0, 0};                    // B | G << 8 | R << 16
+    uint32_t mk = 0;
 #pragma unroll
-        for (int k = 0; k < 3; k++) v[k] = max(0, min(255, (int)sat16(up[k] + d[k])));
+    for (int i = 0; i < 4; i++) {
+        const int x = x0 + i;
+        if (x >= cw) break;
+        const size_t idx = (size_t)y * w + x;
+        if (hi_wsum[idx] > 1e-5f) {
+            int up[3], d[3];
+            pyrup_at(lo, lw, lh, x, y, up);
+            normalized3(hi, hi_wsum, idx, d);
+            const int b = max(0, min(255, (int)sat16(up[0] + d[0]))), g = max(0, min(255, (int)sat16(up[1] + d[1]))),
+                      r = max(0, min(255, (int)sat16(up[2] + d[2])));
+            px[i] = (uint32_t)b | ((uint32_t)g << 8) | ((uint32_t)r << 16);
+            mk |= 0xffu << (8 * i);
+        }
     }
-    const size_t o = (size_t)blockIdx.y * cw + x;
-    out[o * 3] = (uint8_t)v[0]; out[o * 3 + 1] = (uint8_t)v[1]; out[o * 3 + 2] = (uint8_t)v[2];
-    out_mask[o] = m ? 255 : 0;
+    const size_t o = (size_t)blockIdx.y * cw + x0;
+    if (x0 + 4 <= cw && (cw & 3) == 0) {              // 12 bytes = 3 words, rows are 4-byte aligned
+        uint32_t* o32 = reinterpret_cast<uint32_t*>(out + o * 3);
+        o32[0] = px[0] | (px[1] << 24); o32[1] = (px[1] >> 8) | (px[2] << 16); o32[2] = (px[2] >> 16) | (px[3] << 8);
+        *reinterpret_cast<uint32_t*>(out_mask + o) = mk;
+    } else {
+        for (int i = 0; i < 4 && x0 + i < cw; i++) {
+            out[(o + i) * 3] = (uint8_t)px[i]; out[(o + i) * 3 + 1] = (uint8_t)(px[i] >> 8); out[(o + i) * 3 + 2] = (uint8_t)(px[i] >> 16);
+            out_mask[o + i] = (uint8_t)(mk >> (8 * i));
+        }
+    }
 }
 
 // no bands: the canvas level 0 is the (normalised) image itself
@@ -339,7 +439,7 @@ extern "C" int uavm_canvas_blend(uavm_ctx* ctx, uavm_canvas* cv, int num_bands)
         int pw[kMaxBands + 1], ph[kMaxBands + 1];
         pw[0] = r.width; ph[0] = sub_h;
         {
-            dim3 grid((r.width + 255) / 256, sub_h);
+            dim3 grid(((r.width + 3) / 4 + 255) / 256, sub_h);
             k7_feed_level0<<<grid, 256, 0, ctx->stream>>>(d.chip, d.chip_step, d.mask, d.mask_step, d.chip_w, d.chip_h, r.left, d.beg_y - sub_t,
                                                            r.width, sub_h, ws->pyr[0], ws->wp[0]);
             UAVM_CHECK_LAUNCH(ctx);
@@ -352,9 +452,16 @@ extern "C" int uavm_canvas_blend(uavm_ctx* ctx, uavm_canvas* cv, int num_bands)
         }
         int x_tl = r.tlx, y_tl = sub_t - Y0;
         for (int i = 0; i <= nb; i++) {
-            dim3 grid((pw[i] + 255) / 256, ph[i]);
-            k7_lap_accumulate<<<grid, 256, 0, ctx->stream>>>(ws->pyr[i], i < nb ? ws->pyr[i + 1] : nullptr, ws->wp[i], pw[i], ph[i],
-                                                              i < nb ? pw[i + 1] : 0, i < nb ? ph[i + 1] : 0, ws->dlap[i], ws->dw[i], ws->lw[i], x_tl, y_tl);
+            const bool quad = i < nb && !(pw[i] & 1) && !(ph[i] & 1) && !(x_tl & 1) && !(y_tl & 1) && !(ws->lw[i] & 1);
+            if (quad) {
+                dim3 grid((pw[i] / 2 + 255) / 256, ph[i] / 2);
+                k7_lap_accumulate_quad<<<grid, 256, 0, ctx->stream>>>(ws->pyr[i], ws->pyr[i + 1], ws->wp[i], pw[i], ph[i], pw[i + 1], ph[i + 1],
+                                                                       ws->dlap[i], ws->dw[i], ws->lw[i], x_tl, y_tl);
+            } else {
+                dim3 grid((pw[i] + 255) / 256, ph[i]);
+                k7_lap_accumulate<<<grid, 256, 0, ctx->stream>>>(ws->pyr[i], i < nb ? ws->pyr[i + 1] : nullptr, ws->wp[i], pw[i], ph[i],
+                                                                  i < nb ? pw[i + 1] : 0, i < nb ? ph[i + 1] : 0, ws->dlap[i], ws->dw[i], ws->lw[i], x_tl, y_tl);
+            }
             UAVM_CHECK_LAUNCH(ctx);
             x_tl /= 2; y_tl /= 2;
         }
@@ -373,9 +480,9 @@ extern "C" int uavm_canvas_blend(uavm_ctx* ctx, uavm_canvas* cv, int num_bands)
     }
     {
         const int oy0 = cv->banded ? cv->band_y0 : 0, oy1 = cv->banded ? cv->band_y1 : ch;
-        dim3 grid((cw + 255) / 256, oy1 - oy0);
+        dim3 grid((cw + 255) / 256, oy1 - oy0), grid4(((cw + 3) / 4 + 255) / 256, oy1 - oy0);
         if (nb >= 1)
-            k7_collapse_output<<<grid, 256, 0, ctx->stream>>>(ws->dlap[1], ws->lw[1], ws->lh[1], ws->dlap[0], ws->dw[0], W, BH, oy0 - Y0, oy1 - Y0, cw,
+            k7_collapse_output<<<grid4, 256, 0, ctx->stream>>>(ws->dlap[1], ws->lw[1], ws->lh[1], ws->dlap[0], ws->dw[0], W, BH, oy0 - Y0, oy1 - Y0, cw,
                                                                cv->d_result + (size_t)oy0 * cw * 3, cv->d_result_mask + (size_t)oy0 * cw);
         else
             k7_output<<<grid, 256, 0, ctx->stream>>>(ws->dlap[0] + (size_t)(oy0 - Y0) * W * 4, ws->dw[0] + (size_t)(oy0 - Y0) * W, W, cw, oy1 - oy0,
