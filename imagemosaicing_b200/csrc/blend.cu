@@ -265,6 +265,51 @@ k7_normalize(short* __restrict__ dlap, const float* __restrict__ dwsum, size_t n
     st3(dlap, i, d[0], d[1], d[2]);
 }
 
+// pyrUp of the coarser level for the 2 x 2 quad (cx, cy): up[dy][dx][channel]  (same separation as k7_lap_accumulate_quad)
+__device__ __forceinline__ void pyrup_quad(const short* __restrict__ lo, int lw, int lh, int cx, int cy, int up[2][2][3])
+{
+    const int xm = (cx == 0) ? (lw > 1 ? 1 : 0) : cx - 1, xp = (cx == lw - 1) ? lw - 1 : cx + 1;
+    const int ym = (cy == 0) ? (lh > 1 ? 1 : 0) : cy - 1, yp = (cy == lh - 1) ? lh - 1 : cy + 1;
+    const int rows[3] = {ym, cy, yp};
+    int he[3][3], ho[3][3];
+#pragma unroll
+    for (int r = 0; r < 3; r++) {
+        const size_t rb = (size_t)rows[r] * lw;
+        int a[3], b[3], c[3];
+        ld3(lo, rb + xm, a[0], a[1], a[2]); ld3(lo, rb + cx, b[0], b[1], b[2]); ld3(lo, rb + xp, c[0], c[1], c[2]);
+#pragma unroll
+        for (int k = 0; k < 3; k++) { he[r][k] = a[k] + 6 * b[k] + c[k]; ho[r][k] = 4 * (b[k] + c[k]); }
+    }
+#pragma unroll
+    for (int dx = 0; dx < 2; dx++)
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            const int h0 = dx ? ho[0][k] : he[0][k], h1 = dx ? ho[1][k] : he[1][k], h2 = dx ? ho[2][k] : he[2][k];
+            up[0][dx][k] = sat16((h0 + 6 * h1 + h2 + 32) >> 6);
+            up[1][dx][k] = sat16((4 * (h1 + h2) + 32) >> 6);
+        }
+}
+
+// collapse step for even level sizes: one 2 x 2 quad per thread
+__global__ void __launch_bounds__(256)
+k7_collapse_quad(const short* __restrict__ lo, int lw, int lh, short* __restrict__ hi, const float* __restrict__ hi_wsum, int w, int h)
+{
+    const int cx = blockIdx.x * blockDim.x + threadIdx.x, cy = blockIdx.y;
+    const int x = 2 * cx, y = 2 * cy;
+    if (x >= w || y >= h) return;
+    int up[2][2][3];
+    pyrup_quad(lo, lw, lh, cx, cy, up);
+#pragma unroll
+    for (int dy = 0; dy < 2; dy++)
+#pragma unroll
+        for (int dx = 0; dx < 2; dx++) {
+            int d[3];
+            const size_t i = (size_t)(y + dy) * w + x + dx;
+            normalized3(hi, hi_wsum, i, d);
+            st3(hi, i, sat16(up[dy][dx][0] + d[0]), sat16(up[dy][dx][1] + d[1]), sat16(up[dy][dx][2] + d[2]));
+        }
+}
+
 __global__ void __launch_bounds__(256)
 k7_collapse(const short* __restrict__ lo, int lw, int lh, short* __restrict__ hi, const float* __restrict__ hi_wsum, int w, int h)
 {
@@ -277,39 +322,56 @@ k7_collapse(const short* __restrict__ lo, int lw, int lh, short* __restrict__ hi
 }
 
 // last step (level 0) fused with the output: rows [oy0, oy1) x columns [0, cw) of the padded level go to the mosaic.
-// Four pixels per thread: the 12 output bytes are three aligned words when the mosaic row pitch allows it.
+// A thread owns a 4 x 2 block (two quads): per row the 12 output bytes are three aligned words when the mosaic row pitch
+// allows it.  oy0 is even (band edges are multiples of 32).
 __global__ void __launch_bounds__(256)
 k7_collapse_output(const short* __restrict__ lo, int lw, int lh, const short* __restrict__ hi, const float* __restrict__ hi_wsum, int w, int h,
                    int oy0, int oy1, int cw, uint8_t* __restrict__ out, uint8_t* __restrict__ out_mask)
 {
-    const int x0 = 4 * (blockIdx.x * blockDim.x + threadIdx.x), y = oy0 + blockIdx.y;
-    if (x0 >= cw || y >= oy1) return;
-    uint32_t px[4] = {0, 0, 0, 0};                    // B | G << 8 | R << 16
-    uint32_t mk = 0;
+    const int x0 = 4 * (blockIdx.x * blockDim.x + threadIdx.x), y0 = oy0 + 2 * blockIdx.y;
+    if (x0 >= cw || y0 >= oy1) return;
+    uint32_t px[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};   // B | G << 8 | R << 16
+    uint32_t mk[2] = {0, 0};
 #pragma unroll
-    for (int i = 0; i < 4; i++) {
-        const int x = x0 + i;
-        if (x >= cw) break;
-        const size_t idx = (size_t)y * w + x;
-        if (hi_wsum[idx] > 1e-5f) {
-            int up[3], d[3];
-            pyrup_at(lo, lw, lh, x, y, up);
-            normalized3(hi, hi_wsum, idx, d);
-            const int b = max(0, min(255, (int)sat16(up[0] + d[0]))), g = max(0, min(255, (int)sat16(up[1] + d[1]))),
-                      r = max(0, min(255, (int)sat16(up[2] + d[2])));
-            px[i] = (uint32_t)b | ((uint32_t)g << 8) | ((uint32_t)r << 16);
-            mk |= 0xffu << (8 * i);
+    for (int q = 0; q < 2; q++) {
+        const int x = x0 + 2 * q;
+        if (x >= w) break;                              // w is even and >= cw
+        float ws[2][2];
+        bool any = false;
+#pragma unroll
+        for (int dy = 0; dy < 2; dy++) {
+            const float2 f = *reinterpret_cast<const float2*>(hi_wsum + (size_t)(y0 + dy) * w + x);
+            ws[dy][0] = f.x; ws[dy][1] = f.y; any = any || f.x > 1e-5f || f.y > 1e-5f;
         }
+        if (!any) continue;
+        int up[2][2][3];
+        pyrup_quad(lo, lw, lh, x >> 1, y0 >> 1, up);
+#pragma unroll
+        for (int dy = 0; dy < 2; dy++)
+#pragma unroll
+            for (int dx = 0; dx < 2; dx++) {
+                if (!(ws[dy][dx] > 1e-5f)) continue;
+                int d[3];
+                normalized3(hi, hi_wsum, (size_t)(y0 + dy) * w + x + dx, d);
+                const int b = max(0, min(255, (int)sat16(up[dy][dx][0] + d[0]))), g = max(0, min(255, (int)sat16(up[dy][dx][1] + d[1]))),
+                          r = max(0, min(255, (int)sat16(up[dy][dx][2] + d[2])));
+                px[dy][2 * q + dx] = (uint32_t)b | ((uint32_t)g << 8) | ((uint32_t)r << 16);
+                mk[dy] |= 0xffu << (8 * (2 * q + dx));
+            }
     }
-    const size_t o = (size_t)blockIdx.y * cw + x0;
-    if (x0 + 4 <= cw && (cw & 3) == 0) {              // 12 bytes = 3 words, rows are 4-byte aligned
-        uint32_t* o32 = reinterpret_cast<uint32_t*>(out + o * 3);
-        o32[0] = px[0] | (px[1] << 24); o32[1] = (px[1] >> 8) | (px[2] << 16); o32[2] = (px[2] >> 16) | (px[3] << 8);
-        *reinterpret_cast<uint32_t*>(out_mask + o) = mk;
-    } else {
-        for (int i = 0; i < 4 && x0 + i < cw; i++) {
-            out[(o + i) * 3] = (uint8_t)px[i]; out[(o + i) * 3 + 1] = (uint8_t)(px[i] >> 8); out[(o + i) * 3 + 2] = (uint8_t)(px[i] >> 16);
-            out_mask[o + i] = (uint8_t)(mk >> (8 * i));
+#pragma unroll
+    for (int dy = 0; dy < 2; dy++) {
+        if (y0 + dy >= oy1) break;
+        const size_t o = (size_t)(2 * blockIdx.y + dy) * cw + x0;
+        if (x0 + 4 <= cw && (cw & 3) == 0) {          // 12 bytes = 3 words, rows are 4-byte aligned
+            uint32_t* o32 = reinterpret_cast<uint32_t*>(out + o * 3);
+            o32[0] = px[dy][0] | (px[dy][1] << 24); o32[1] = (px[dy][1] >> 8) | (px[dy][2] << 16); o32[2] = (px[dy][2] >> 16) | (px[dy][3] << 8);
+            *reinterpret_cast<uint32_t*>(out_mask + o) = mk[dy];
+        } else {
+            for (int i = 0; i < 4 && x0 + i < cw; i++) {
+                out[(o + i) * 3] = (uint8_t)px[dy][i]; out[(o + i) * 3 + 1] = (uint8_t)(px[dy][i] >> 8); out[(o + i) * 3 + 2] = (uint8_t)(px[dy][i] >> 16);
+                out_mask[o + i] = (uint8_t)(mk[dy] >> (8 * i));
+            }
         }
     }
 }
@@ -474,13 +536,18 @@ extern "C" int uavm_canvas_blend(uavm_ctx* ctx, uavm_canvas* cv, int num_bands)
         UAVM_CHECK_LAUNCH(ctx);
     }
     for (int i = nb; i > 1; i--) {
-        dim3 grid((ws->lw[i - 1] + 255) / 256, ws->lh[i - 1]);
-        k7_collapse<<<grid, 256, 0, ctx->stream>>>(ws->dlap[i], ws->lw[i], ws->lh[i], ws->dlap[i - 1], ws->dw[i - 1], ws->lw[i - 1], ws->lh[i - 1]);
+        if (!(ws->lw[i - 1] & 1) && !(ws->lh[i - 1] & 1)) {
+            dim3 grid((ws->lw[i - 1] / 2 + 255) / 256, ws->lh[i - 1] / 2);
+            k7_collapse_quad<<<grid, 256, 0, ctx->stream>>>(ws->dlap[i], ws->lw[i], ws->lh[i], ws->dlap[i - 1], ws->dw[i - 1], ws->lw[i - 1], ws->lh[i - 1]);
+        } else {
+            dim3 grid((ws->lw[i - 1] + 255) / 256, ws->lh[i - 1]);
+            k7_collapse<<<grid, 256, 0, ctx->stream>>>(ws->dlap[i], ws->lw[i], ws->lh[i], ws->dlap[i - 1], ws->dw[i - 1], ws->lw[i - 1], ws->lh[i - 1]);
+        }
         UAVM_CHECK_LAUNCH(ctx);
     }
     {
         const int oy0 = cv->banded ? cv->band_y0 : 0, oy1 = cv->banded ? cv->band_y1 : ch;
-        dim3 grid((cw + 255) / 256, oy1 - oy0), grid4(((cw + 3) / 4 + 255) / 256, oy1 - oy0);
+        dim3 grid((cw + 255) / 256, oy1 - oy0), grid4(((cw + 3) / 4 + 255) / 256, (oy1 - oy0 + 1) / 2);
         if (nb >= 1)
             k7_collapse_output<<<grid4, 256, 0, ctx->stream>>>(ws->dlap[1], ws->lw[1], ws->lh[1], ws->dlap[0], ws->dw[0], W, BH, oy0 - Y0, oy1 - Y0, cw,
                                                                cv->d_result + (size_t)oy0 * cw * 3, cv->d_result_mask + (size_t)oy0 * cw);
