@@ -133,6 +133,71 @@ k7_pyrdown(const short* __restrict__ src, const float* __restrict__ wsrc, int w,
     }
 }
 
+// Tiled pyrDown: a CTA produces a 64 x 8 output tile from a 131 x 19 source window staged in shared memory with coalesced
+// loads (every source line is requested once instead of ~5 times through L1), split into even / odd columns so that the
+// stride-2 taps become unit-stride, conflict-free LDS.  A thread computes two vertically adjacent outputs: 7 window rows,
+// each filtered horizontally once (integer sums are order free; the f32 passes keep the oracle's expression order).
+constexpr int kPdW = 64, kPdH = 8, kPdCols = 2 * kPdW + 4 /* 131 used, even/odd halves of 66 */, kPdRows = 2 * kPdH + 3;
+__global__ void __launch_bounds__(256)
+k7_pyrdown_tiled(const short* __restrict__ src, const float* __restrict__ wsrc, int w, int h,
+                 short* __restrict__ dst, float* __restrict__ wdst, int dw, int dh)
+{
+    __shared__ int2 sE[kPdRows][kPdCols / 2], sO[kPdRows][kPdCols / 2];      // pixel = 4 x int16 = int2
+    __shared__ float wE[kPdRows][kPdCols / 2], wO[kPdRows][kPdCols / 2];
+    const int tid = threadIdx.y * kPdW + threadIdx.x;
+    const int ox0 = blockIdx.x * kPdW, oy0 = blockIdx.y * kPdH;
+    const int sx0 = 2 * ox0 - 2, sy0 = 2 * oy0 - 2;                           // window origin (even column)
+    const bool even_w = (w & 1) == 0;
+    for (int e = tid; e < kPdRows * (kPdCols / 2); e += 256) {               // one (even, odd) column pair per step
+        const int r = e / (kPdCols / 2), j = e - r * (kPdCols / 2);
+        const size_t rb = (size_t)reflect101(sy0 + r, h) * w;
+        const int gx = sx0 + 2 * j;
+        if (even_w && gx >= 0 && gx + 1 < w) {                                // aligned 16-byte pixel pair + 8-byte weight pair
+            const int4 v = *reinterpret_cast<const int4*>(src + (rb + gx) * 4);
+            sE[r][j] = make_int2(v.x, v.y); sO[r][j] = make_int2(v.z, v.w);
+            float2 f = make_float2(0.0f, 0.0f);
+            if (wsrc) f = *reinterpret_cast<const float2*>(wsrc + rb + gx);
+            wE[r][j] = f.x; wO[r][j] = f.y;
+        } else {                                                              // border columns: reflect-101 per pixel
+            const size_t g0 = rb + reflect101(gx, w), g1 = rb + reflect101(gx + 1, w);
+            sE[r][j] = *reinterpret_cast<const int2*>(src + g0 * 4); sO[r][j] = *reinterpret_cast<const int2*>(src + g1 * 4);
+            wE[r][j] = wsrc ? wsrc[g0] : 0.0f; wO[r][j] = wsrc ? wsrc[g1] : 0.0f;
+        }
+    }
+    __syncthreads();
+    const int x = ox0 + threadIdx.x, ty = threadIdx.y;                        // outputs (x, oy0 + 2 ty) and (x, oy0 + 2 ty + 1)
+    if (x >= dw) return;
+    const int i = threadIdx.x;                                                // window column 2 i .. 2 i + 4 = E[i], O[i], E[i+1], O[i+1], E[i+2]
+    int acc[2][3] = {{0, 0, 0}, {0, 0, 0}};
+    float F[7];
+    const int kw[5] = {1, 4, 6, 4, 1};
+#pragma unroll
+    for (int r = 0; r < 7; r++) {
+        const int wr = 4 * ty + r;                                            // window row
+        const int2 p0 = sE[wr][i], p1 = sO[wr][i], p2 = sE[wr][i + 1], p3 = sO[wr][i + 1], p4 = sE[wr][i + 2];
+        int hs[3];
+        hs[0] = (short)(p0.x & 0xffff) + (short)(p4.x & 0xffff) + 4 * ((short)(p1.x & 0xffff) + (short)(p3.x & 0xffff)) + 6 * (short)(p2.x & 0xffff);
+        hs[1] = (p0.x >> 16) + (p4.x >> 16) + 4 * ((p1.x >> 16) + (p3.x >> 16)) + 6 * (p2.x >> 16);
+        hs[2] = (short)(p0.y & 0xffff) + (short)(p4.y & 0xffff) + 4 * ((short)(p1.y & 0xffff) + (short)(p3.y & 0xffff)) + 6 * (short)(p2.y & 0xffff);
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            if (r < 5) acc[0][c] += kw[r] * hs[c];
+            if (r >= 2) acc[1][c] += kw[r - 2] * hs[c];
+        }
+        if (wsrc) F[r] = wE[wr][i + 1] * 6.0f + (wO[wr][i] + wO[wr][i + 1]) * 4.0f + wE[wr][i] + wE[wr][i + 2];     // row pass, oracle order
+    }
+#pragma unroll
+    for (int o = 0; o < 2; o++) {
+        const int y = oy0 + 2 * ty + o;
+        if (y >= dh) break;
+        st3(dst, (size_t)y * dw + x, sat16((acc[o][0] + 128) >> 8), sat16((acc[o][1] + 128) >> 8), sat16((acc[o][2] + 128) >> 8));
+        if (wsrc) {
+            const float v = F[2 + 2 * o] * 6.0f + (F[1 + 2 * o] + F[3 + 2 * o]) * 4.0f + F[0 + 2 * o] + F[4 + 2 * o];  // column pass
+            wdst[(size_t)y * dw + x] = v * (1.0f / 256.0f);
+        }
+    }
+}
+
 // value of pyrUp(lo) at (x, y) of the 2x larger level; lo is lw x lh, 3 channels
 __device__ __forceinline__ void pyrup_at(const short* __restrict__ lo, int lw, int lh, int x, int y, int out[3])
 {
@@ -508,8 +573,13 @@ extern "C" int uavm_canvas_blend(uavm_ctx* ctx, uavm_canvas* cv, int num_bands)
         }
         for (int i = 0; i < nb; i++) {
             pw[i + 1] = (pw[i] + 1) / 2; ph[i + 1] = (ph[i] + 1) / 2;
-            dim3 grid((pw[i + 1] + 255) / 256, ph[i + 1]);
-            k7_pyrdown<<<grid, 256, 0, ctx->stream>>>(ws->pyr[i], ws->wp[i], pw[i], ph[i], ws->pyr[i + 1], ws->wp[i + 1], pw[i + 1], ph[i + 1]);
+            if (pw[i + 1] >= 2 * kPdW && ph[i + 1] >= kPdH && pw[i] >= 8 && ph[i] >= 8) {
+                dim3 grid((pw[i + 1] + kPdW - 1) / kPdW, (ph[i + 1] + kPdH - 1) / kPdH);
+                k7_pyrdown_tiled<<<grid, dim3(kPdW, 4), 0, ctx->stream>>>(ws->pyr[i], ws->wp[i], pw[i], ph[i], ws->pyr[i + 1], ws->wp[i + 1], pw[i + 1], ph[i + 1]);
+            } else {
+                dim3 grid((pw[i + 1] + 255) / 256, ph[i + 1]);
+                k7_pyrdown<<<grid, 256, 0, ctx->stream>>>(ws->pyr[i], ws->wp[i], pw[i], ph[i], ws->pyr[i + 1], ws->wp[i + 1], pw[i + 1], ph[i + 1]);
+            }
             UAVM_CHECK_LAUNCH(ctx);
         }
         int x_tl = r.tlx, y_tl = sub_t - Y0;
