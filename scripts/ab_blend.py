@@ -24,7 +24,7 @@ h = hashlib.sha256(); h.update(out[::7].tobytes()); h.update(m[::7].tobytes())
 print(f"k6_ms={e[0].elapsed_time(e[1]):.3f} k7_ms={e[1].elapsed_time(e[2]):.3f} canvas={out.shape} sha={h.hexdigest()[:16]}")
 if os.environ.get("AB_TRACE"):
     from torch.profiler import profile, ProfilerActivity
-    cv.warp(); cv.seam_masks(); torch.cuda.synchronize()
+    cv.warp(); torch.cuda.synchronize()
     with profile(activities=[ProfilerActivity.CUDA]) as prof:
-        cv.blend(5); torch.cuda.synchronize()
+        cv.seam_masks(); cv.blend(5); torch.cuda.synchronize()
     print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=12, max_name_column_width=60))
