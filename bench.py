@@ -89,7 +89,10 @@ def cpu_pairs(descs, kps, T, frames, pairs, seeds):
             O.ref_ransac2d(x1, x2, RANSAC_DIST, SAMPLE_TIMES, seed)
         else:
             O.ransac2d(x1, x2, RANSAC_DIST, SAMPLE_TIMES, seed)
-        O.warp_chip(frames[j], canvas, chips[j])
+        if use_ref:
+            O.ref_warp_chip(frames[j], canvas, chips[j])        # the reference's own chip loop (M/MosaicImage.cpp:2350-2448), compiled in place
+        else:
+            O.warp_chip(frames[j], canvas, chips[j])
 
     t0 = time.perf_counter()
     if workers == 1:
@@ -104,7 +107,7 @@ def cpu_pairs(descs, kps, T, frames, pairs, seeds):
 def cpu_sample_note(n_sample, O):
     cores = host_threads(); workers = max(1, min(n_sample, cores))
     return (f"{n_sample} of 49 pairs per step on {workers} host threads x {max(1, cores // workers)} OpenMP threads (exact brute-force match with AVX2 integer dot products, "
-            f"select, {'reference Ransac2D compiled from /root/reference' if O.ref() is not None else 'oracle Ransac2D restatement'}, warp)")
+            f"select, {'Ransac2D and the chip-warp loop compiled from the reference sources (oracle/_ref)' if O.ref() is not None else 'oracle restatements of Ransac2D and the warp loop'})")
 
 
 def host_threads():
