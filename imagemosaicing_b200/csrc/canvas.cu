@@ -75,7 +75,11 @@ __device__ __forceinline__ uint32_t bilinear_channel(uint32_t t00, uint32_t t01,
 // thread (ncu, profiles/r1d_*), which was what bounded the kernel.
 constexpr int kWarpTileW = 128;   // 32 lanes x 4 px
 constexpr int kWarpRows = 4;      // rows per thread
-constexpr int kWarpTileH = 8 * kWarpRows;
+#ifndef UAVM_K5_WARPS
+#define UAVM_K5_WARPS 8
+#endif
+constexpr int kWarpsY = UAVM_K5_WARPS;   // warps (= thread rows) per CTA; a thread's rows are kWarpsY apart
+constexpr int kWarpTileH = kWarpsY * kWarpRows;
 constexpr int kFpBoxW = 160, kFpBoxH = 16;        // TMA box (pixels): the staged footprint is up to kFpBoxes boxes stacked vertically
 constexpr int kFpBoxBytes = kFpBoxW * kFpBoxH * 4;
 constexpr int kFpBoxes = 4;                       // 160 x 64 px = 40 KB of dynamic shared memory per CTA (5 CTAs / SM)
@@ -84,7 +88,7 @@ constexpr int kFpBoxes = 4;                       // 160 x 64 px = 40 KB of dyna
 // exactly 1.0f for every pixel and x / 1.0f == x: the two divides per coordinate (:2359-2362) are skipped without
 // changing a bit (kept as the A/B twin of the packed affine kernel below).
 template <bool AFFINE>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(32 * kWarpsY)
 k5_warp_chips(const ChipDesc* __restrict__ descs, int img_w, int img_h, int src_step_px, float dgx, float dgy,
               uint32_t two23 /* = 0x4B000000, bits of 2^23: a kernel argument so PRMT takes the SELECTOR as its immediate */,
               float w1f, float h1f)
@@ -105,7 +109,7 @@ k5_warp_chips(const ChipDesc* __restrict__ descs, int img_w, int img_h, int src_
     for (int i = 0; i < 4; i++) xt[i] = (float)(xl + 32 * i) - dgx - sx + fbx;
 #pragma unroll
     for (int ry = 0; ry < kWarpRows; ry++) {
-        const int yd = ybase + ry * 8;
+        const int yd = ybase + ry * kWarpsY;
         if (yd >= D.chip_h) break;
         const float yt = (float)yd - dgy - sy + fby;               // yTemp (:2357)
         const float ya = yt * iv1, yb = yt * iv4;
@@ -201,9 +205,9 @@ __device__ __forceinline__ void warp_affine_rows(const uint8_t* fp_base, const C
     constexpr uint32_t sm_pitch4 = kFpBoxW * 4u;
 #pragma unroll
     for (int ry = 0; ry < kWarpRows; ry++) {
-        const int yd = ybase + ry * 8;
+        const int yd = ybase + ry * kWarpsY;
         if (CHECK && yd >= D.chip_h) break;
-        const float yt = ((float)ybase + (float)(ry * 8)) - dgy - sy + fby;       // yTemp (:2357); (float)(ybase + 8 ry) is exact
+        const float yt = ((float)ybase + (float)(ry * kWarpsY)) - dgy - sy + fby;       // yTemp (:2357); (float)(ybase + kWarpsY ry) is exact
         const float ya = yt * iv1, yb = yt * iv4;
         const f32x2 YA = pk2(ya, ya), YB = pk2(yb, yb);
         uint32_t* crow = D.chip + (size_t)yd * D.chip_step + xl;
@@ -289,7 +293,7 @@ __device__ __forceinline__ int tile_footprint(const ChipDesc& D, int bx, int by,
     return (x1 - x0 + 1 <= kFpBoxW && rows <= max_boxes * kFpBoxH) ? 1 : 0;
 }
 
-__global__ void __launch_bounds__(256, 4)
+__global__ void __launch_bounds__(32 * kWarpsY, 1024 / (32 * kWarpsY))
 k5_warp_affine_x2(const __grid_constant__ CUtensorMap tmap_src, const ChipDesc* __restrict__ descs, int img_w, int img_h, int src_step_px, float dgx, float dgy,
                   uint32_t two23, float w1f, float h1f, float one,
                   uint32_t one_u /* = 1, opaque: row-1 tap address = row-0 address + step4 * 1 as a single 64-bit IMAD */,
@@ -339,13 +343,13 @@ k5_warp_affine_x2(const __grid_constant__ CUtensorMap tmap_src, const ChipDesc* 
         MX[h] = pk2(xa * iv0, xb * iv0); MY[h] = pk2(xa * iv3, xb * iv3);
     }
     // Is the whole 4 x 4 block of this thread inside the source?  (same monotonicity argument, per thread)
-    bool inside = (ybase + 8 * (kWarpRows - 1) < D.chip_h) && (xl + 96 < D.chip_w);
+    bool inside = (ybase + kWarpsY * (kWarpRows - 1) < D.chip_h) && (xl + 96 < D.chip_w);
     {
         float mxa, mxb, mya, myb, t;
         unpk2(MX[0], mxa, t); unpk2(MX[1], t, mxb); unpk2(MY[0], mya, t); unpk2(MY[1], t, myb);
 #pragma unroll
         for (int c = 0; c < 2; c++) {
-            const float yt = (float)(ybase + c * 8 * (kWarpRows - 1)) - dgy - sy + fby;
+            const float yt = (float)(ybase + c * kWarpsY * (kWarpRows - 1)) - dgy - sy + fby;
             const float ya = yt * iv1, yb = yt * iv4;
             const float xs0 = mxa + ya + iv2, xs1 = mxb + ya + iv2, ys0 = mya + yb + iv5, ys1 = myb + yb + iv5;
             inside = inside && (xs0 >= 0.0f) && (xs0 < w1f) && (xs1 >= 0.0f) && (xs1 < w1f) && (ys0 >= 0.0f) && (ys0 < h1f) && (ys1 >= 0.0f) && (ys1 < h1f);
@@ -356,7 +360,7 @@ k5_warp_affine_x2(const __grid_constant__ CUtensorMap tmap_src, const ChipDesc* 
     if (state == 2) {                                 // nothing of this tile is inside the source: BGR = 0, alpha = 0
 #pragma unroll
         for (int ry = 0; ry < kWarpRows; ry++) {
-            const int yd = ybase + ry * 8;
+            const int yd = ybase + ry * kWarpsY;
             if (yd >= D.chip_h) break;
 #pragma unroll
             for (int i = 0; i < 4; i++) if (xl + 32 * i < D.chip_w) D.chip[(size_t)yd * D.chip_step + xl + 32 * i] = 0u;
@@ -585,7 +589,7 @@ extern "C" int uavm_canvas_warp_range(uavm_ctx* ctx, uavm_canvas* cv, int first,
     if (!ctx || !cv || first < 0 || count < 0 || first + count > cv->n) return UAVM_EINVAL;
     if (cv->max_chip_w <= 0 || count == 0) return UAVM_OK;
     dim3 grid((cv->max_chip_w + kWarpTileW - 1) / kWarpTileW, (cv->max_chip_h + kWarpTileH - 1) / kWarpTileH, count);
-    dim3 block(32, 8);
+    dim3 block(32, kWarpsY);
     bool any_affine = false, any_proj = false;
     for (int k = first; k < first + count; k++)
         if (cv->desc[k].keep) { if (cv->desc[k].affine) any_affine = true; else any_proj = true; }
