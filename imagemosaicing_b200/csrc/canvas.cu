@@ -91,10 +91,11 @@ template <bool AFFINE>
 __global__ void __launch_bounds__(32 * kWarpsY)
 k5_warp_chips(const ChipDesc* __restrict__ descs, int img_w, int img_h, int src_step_px, float dgx, float dgy,
               uint32_t two23 /* = 0x4B000000, bits of 2^23: a kernel argument so PRMT takes the SELECTOR as its immediate */,
-              float w1f, float h1f)
+              float w1f, float h1f, int row0, int row1 /* canvas rows to produce (band-sharded canvases skip the other tiles) */)
 {
     const ChipDesc& D = descs[blockIdx.z];
     if (!D.keep || (D.affine != 0) != AFFINE) return;
+    if ((int)(blockIdx.y * kWarpTileH) + D.beg_y >= row1 || (int)(blockIdx.y * kWarpTileH) + kWarpTileH + D.beg_y <= row0) return;
     const int xl = blockIdx.x * kWarpTileW + threadIdx.x;
     const int ybase = blockIdx.y * kWarpTileH + threadIdx.y;
     if (blockIdx.x * kWarpTileW >= D.chip_w || blockIdx.y * kWarpTileH >= D.chip_h) return;
@@ -298,7 +299,8 @@ k5_warp_affine_x2(const __grid_constant__ CUtensorMap tmap_src, const ChipDesc* 
                   uint32_t two23, float w1f, float h1f, float one,
                   uint32_t one_u /* = 1, opaque: row-1 tap address = row-0 address + step4 * 1 as a single 64-bit IMAD */,
                   unsigned long long bias /* = 0x4B000000 * (4 step + 4): the add.rz biases of iy and ix in byte-address units */,
-                  int max_boxes /* TMA boxes of dynamic shared memory for the source footprint; 0 = always load taps directly */)
+                  int max_boxes /* TMA boxes of dynamic shared memory for the source footprint; 0 = always load taps directly */,
+                  int row0, int row1 /* canvas rows to produce (band-sharded canvases skip the other tiles) */)
 {
     extern __shared__ __align__(128) uint8_t fp_smem[];
     __shared__ __align__(8) uint64_t fp_bar;
@@ -306,6 +308,7 @@ k5_warp_affine_x2(const __grid_constant__ CUtensorMap tmap_src, const ChipDesc* 
 
     const ChipDesc& D = descs[blockIdx.z];
     if (!D.keep || !D.affine) return;
+    if ((int)(blockIdx.y * kWarpTileH) + D.beg_y >= row1 || (int)(blockIdx.y * kWarpTileH) + kWarpTileH + D.beg_y <= row0) return;
     const int xl = blockIdx.x * kWarpTileW + threadIdx.x;
     const int ybase = blockIdx.y * kWarpTileH + threadIdx.y;
     if (blockIdx.x * kWarpTileW >= D.chip_w || blockIdx.y * kWarpTileH >= D.chip_h) return;
@@ -590,6 +593,9 @@ extern "C" int uavm_canvas_warp_range(uavm_ctx* ctx, uavm_canvas* cv, int first,
     if (cv->max_chip_w <= 0 || count == 0) return UAVM_OK;
     dim3 grid((cv->max_chip_w + kWarpTileW - 1) / kWarpTileW, (cv->max_chip_h + kWarpTileH - 1) / kWarpTileH, count);
     dim3 block(32, kWarpsY);
+    // a band-sharded canvas needs its rows + halo, and 128 more on each side: K7's feed reflects up to 3 * 2^5 + 31 chip rows
+    // at a chip edge that lies inside the band (everything else is never read)
+    const int row0 = cv->banded ? cv->band_Y0 - 128 : -(1 << 30), row1 = cv->banded ? cv->band_Y1 + 128 : (1 << 30);
     bool any_affine = false, any_proj = false;
     for (int k = first; k < first + count; k++)
         if (cv->desc[k].keep) { if (cv->desc[k].affine) any_affine = true; else any_proj = true; }
@@ -606,16 +612,16 @@ extern "C" int uavm_canvas_warp_range(uavm_ctx* ctx, uavm_canvas* cv, int first,
             }
             k5_warp_affine_x2<<<grid, block, boxes * kFpBoxBytes, ctx->stream>>>(
                 cv->tmap_src, cv->d_desc + first, cv->img_w, cv->img_h, cv->src_step_px, cv->layout.dgx, cv->layout.dgy, 0x4B000000u,
-                (float)(cv->img_w - 1), (float)(cv->img_h - 1), 1.0f, 1u, 0x4B000000ull * (4ull * (unsigned long long)cv->src_step_px + 4ull), boxes);
+                (float)(cv->img_w - 1), (float)(cv->img_h - 1), 1.0f, 1u, 0x4B000000ull * (4ull * (unsigned long long)cv->src_step_px + 4ull), boxes, row0, row1);
         }
         else
             k5_warp_chips<true><<<grid, block, 0, ctx->stream>>>(cv->d_desc + first, cv->img_w, cv->img_h, cv->src_step_px, cv->layout.dgx, cv->layout.dgy, 0x4B000000u,
-                                                                 (float)(cv->img_w - 1), (float)(cv->img_h - 1));
+                                                                 (float)(cv->img_w - 1), (float)(cv->img_h - 1), row0, row1);
         UAVM_CHECK_LAUNCH(ctx);
     }
     if (any_proj) {
         k5_warp_chips<false><<<grid, block, 0, ctx->stream>>>(cv->d_desc + first, cv->img_w, cv->img_h, cv->src_step_px, cv->layout.dgx, cv->layout.dgy, 0x4B000000u,
-                                                             (float)(cv->img_w - 1), (float)(cv->img_h - 1));
+                                                             (float)(cv->img_w - 1), (float)(cv->img_h - 1), row0, row1);
         UAVM_CHECK_LAUNCH(ctx);
     }
     cv->warped = true; cv->seamed = false; cv->mask_plane_valid = false;

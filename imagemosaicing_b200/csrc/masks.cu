@@ -16,8 +16,12 @@ namespace {
 
 constexpr int kTileW = 128, kTileH = 8;
 
+// Validity is recomputed from the pixel coordinates with exactly K5's expression chain (M/MosaicImage.cpp:2356-2362, :2370)
+// instead of being read back from the chip: the pass is compute-only for rows this context does not hold (a band-sharded
+// canvas warps and masks only its rows, yet the per-image maximum needs every pixel of the chip), and it saves the read.
+// Rows outside canvas rows [row0, row1) are not stored.
 __global__ void __launch_bounds__(256)
-k6_dist_map(const ChipDesc* __restrict__ descs, float* __restrict__ dist_max)
+k6_dist_map(const ChipDesc* __restrict__ descs, float* __restrict__ dist_max, float dgx, float dgy, float w1f, float h1f, int row0, int row1)
 {
     const ChipDesc& D = descs[blockIdx.z];
     if (!D.keep) return;
@@ -26,15 +30,22 @@ k6_dist_map(const ChipDesc* __restrict__ descs, float* __restrict__ dist_max)
     if (blockIdx.x * kTileW >= D.chip_w || blockIdx.y * kTileH >= D.chip_h) return;
     float mx = 0.0f;
     if (x0 < D.chip_w && r < D.chip_h) {
-        // validity = chip alpha (K5 writes BGRA chips; the u8 mask plane is this stage's OUTPUT)
-        const uint4 c4 = *reinterpret_cast<const uint4*>(D.chip + (size_t)r * D.chip_step + x0);
-        const uint32_t valid[4] = {c4.x >> 24, c4.y >> 24, c4.z >> 24, c4.w >> 24};
+        const float yt = (float)r - dgy - D.sy + (float)D.beg_y;          // yTemp (:2357)
+        const float ya = yt * D.inv[1], yb = yt * D.inv[4];
         float out[4];
 #pragma unroll
         for (int i = 0; i < 4; i++) {
             const int c = x0 + i;
+            const float xt = (float)c - dgx - D.sx + (float)D.beg_x;      // xTemp (:2356)
+            float xs = xt * D.inv[0] + ya + D.inv[2];
+            float ys = xt * D.inv[3] + yb + D.inv[5];
+            if (!D.affine) {
+                const float den = xt * D.inv[6] + yt * D.inv[7] + D.inv[8];
+                xs = xs / den; ys = ys / den;
+            }
+            const bool valid = (xs >= 0.0f) && (xs < w1f) && (ys >= 0.0f) && (ys < h1f);
             float mind = 0.0f;
-            if (valid[i] != 0 && c < D.chip_w) {
+            if (valid && c < D.chip_w) {
                 mind = 536870912.0f;                                   // float minDist = 1<<29
 #pragma unroll
                 for (int e = 0; e < 4; e++) {
@@ -45,7 +56,9 @@ k6_dist_map(const ChipDesc* __restrict__ descs, float* __restrict__ dist_max)
             }
             out[i] = mind;
         }
-        *reinterpret_cast<float4*>(D.dist + (size_t)r * D.mask_step + x0) = make_float4(out[0], out[1], out[2], out[3]);
+        const int gy = r + D.beg_y;
+        if (gy >= row0 && gy < row1)
+            *reinterpret_cast<float4*>(D.dist + (size_t)r * D.mask_step + x0) = make_float4(out[0], out[1], out[2], out[3]);
     }
     // block max -> one atomic per block (distances are >= 0, so the uint order of the bits is the float order)
     __shared__ float smax[8];
@@ -61,13 +74,13 @@ k6_dist_map(const ChipDesc* __restrict__ descs, float* __restrict__ dist_max)
 }
 
 __global__ void __launch_bounds__(256)
-k6_normalize(const ChipDesc* __restrict__ descs, const float* __restrict__ dist_max)
+k6_normalize(const ChipDesc* __restrict__ descs, const float* __restrict__ dist_max, int row0, int row1)
 {
     const ChipDesc& D = descs[blockIdx.z];
     if (!D.keep) return;
     const int x0 = blockIdx.x * kTileW + threadIdx.x * 4;
     const int r = blockIdx.y * kTileH + threadIdx.y;
-    if (x0 >= D.chip_w || r >= D.chip_h) return;
+    if (x0 >= D.chip_w || r >= D.chip_h || r + D.beg_y < row0 || r + D.beg_y >= row1) return;
     const float mx = dist_max[blockIdx.z];
     float4* p = reinterpret_cast<float4*>(D.dist + (size_t)r * D.mask_step + x0);
     float4 v = *p;
@@ -76,14 +89,14 @@ k6_normalize(const ChipDesc* __restrict__ descs, const float* __restrict__ dist_
 }
 
 __global__ void __launch_bounds__(256)
-k6_owner(const ChipDesc* __restrict__ descs, const int32_t* __restrict__ nbr)
+k6_owner(const ChipDesc* __restrict__ descs, const int32_t* __restrict__ nbr, int row0, int row1)
 {
     const int n = blockIdx.z;
     const ChipDesc& D = descs[n];
     if (!D.keep) return;
     const int x0 = blockIdx.x * kTileW + threadIdx.x * 4;
     const int r = blockIdx.y * kTileH + threadIdx.y;
-    if (x0 >= D.chip_w || r >= D.chip_h) return;
+    if (x0 >= D.chip_w || r >= D.chip_h || r + D.beg_y < row0 || r + D.beg_y >= row1) return;
     const float4 own4 = *reinterpret_cast<const float4*>(D.dist + (size_t)r * D.mask_step + x0);
     const float own[4] = {own4.x, own4.y, own4.z, own4.w};
     bool win[4];
@@ -161,11 +174,13 @@ extern "C" int uavm_canvas_seam_masks(uavm_ctx* ctx, uavm_canvas* cv)
     UAVM_CUDA(ctx, cudaMemsetAsync(cv->d_dist_max, 0, (size_t)cv->n * sizeof(float), ctx->stream));
     dim3 grid((cv->max_chip_w + kTileW - 1) / kTileW, (cv->max_chip_h + kTileH - 1) / kTileH, cv->n);
     dim3 block(32, 8);
-    k6_dist_map<<<grid, block, 0, ctx->stream>>>(cv->d_desc, cv->d_dist_max);
+    // canvas rows this context holds (band + halo; the whole canvas when it is not sharded): the only rows K7 feeds from
+    const int row0 = cv->banded ? cv->band_Y0 : 0, row1 = cv->banded ? cv->band_Y1 : cv->layout.canvas_h + 64;
+    k6_dist_map<<<grid, block, 0, ctx->stream>>>(cv->d_desc, cv->d_dist_max, cv->layout.dgx, cv->layout.dgy, (float)(cv->img_w - 1), (float)(cv->img_h - 1), row0, row1);
     UAVM_CHECK_LAUNCH(ctx);
-    k6_normalize<<<grid, block, 0, ctx->stream>>>(cv->d_desc, cv->d_dist_max);
+    k6_normalize<<<grid, block, 0, ctx->stream>>>(cv->d_desc, cv->d_dist_max, row0, row1);
     UAVM_CHECK_LAUNCH(ctx);
-    k6_owner<<<grid, block, 0, ctx->stream>>>(cv->d_desc, cv->d_nbr);
+    k6_owner<<<grid, block, 0, ctx->stream>>>(cv->d_desc, cv->d_nbr, row0, row1);
     UAVM_CHECK_LAUNCH(ctx);
     cv->seamed = true; cv->mask_plane_valid = true;
     return UAVM_OK;
