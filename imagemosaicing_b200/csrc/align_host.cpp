@@ -60,28 +60,39 @@ extern "C" int uavm_connected_images(const uavm_matchpointpairs* pairs, int n_pa
     return UAVM_OK;
 }
 
+// Dense double Cholesky restricted to the ENVELOPE of the normal matrix (first non-zero column of every row): the pair graph
+// of a strip or block couples an image only with nearby images, so rows are short (a 200-image block: 1194 unknowns, rows of
+// <= ~150 entries) and the factorisation costs n * row^2 instead of n^3 / 3.  Fill-in stays inside the envelope and every
+// skipped term is an exact zero, so the result is bit-identical to the full dense factorisation.
 static int cholesky_solve(std::vector<double>& N, std::vector<double>& b, int n)
 {
+    std::vector<int> first(n);
+    for (int i = 0; i < n; i++) {
+        int f = 0;
+        while (f < i && N[(size_t)i * n + f] == 0.0) f++;
+        first[i] = f;
+    }
     for (int j = 0; j < n; j++) {
         double s = N[(size_t)j * n + j];
-        for (int k = 0; k < j; k++) s -= N[(size_t)j * n + k] * N[(size_t)j * n + k];
+        for (int k = first[j]; k < j; k++) s -= N[(size_t)j * n + k] * N[(size_t)j * n + k];
         if (!(s > 0)) return -1;
         const double l = sqrt(s);
         N[(size_t)j * n + j] = l;
         for (int i = j + 1; i < n; i++) {
+            if (first[i] > j) continue;                                   // N[i][j] is and stays 0
             double t = N[(size_t)i * n + j];
-            for (int k = 0; k < j; k++) t -= N[(size_t)i * n + k] * N[(size_t)j * n + k];
+            for (int k = first[i] > first[j] ? first[i] : first[j]; k < j; k++) t -= N[(size_t)i * n + k] * N[(size_t)j * n + k];
             N[(size_t)i * n + j] = t / l;
         }
     }
     for (int i = 0; i < n; i++) {
         double t = b[i];
-        for (int k = 0; k < i; k++) t -= N[(size_t)i * n + k] * b[k];
+        for (int k = first[i]; k < i; k++) t -= N[(size_t)i * n + k] * b[k];
         b[i] = t / N[(size_t)i * n + i];
     }
     for (int i = n - 1; i >= 0; i--) {
         double t = b[i];
-        for (int k = i + 1; k < n; k++) t -= N[(size_t)k * n + i] * b[k];
+        for (int k = i + 1; k < n; k++) if (first[k] <= i) t -= N[(size_t)k * n + i] * b[k];
         b[i] = t / N[(size_t)i * n + i];
     }
     return 0;

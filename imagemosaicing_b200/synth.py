@@ -110,3 +110,57 @@ def texture_image(rng, w, h, n_waves=24):
         acc = (acc - acc.min()) / max(float(acc.max() - acc.min()), 1e-6)
         img[..., c] = acc * 255.0
     return img.astype(np.uint8)
+
+
+def block_poses(rng, rows, cols, w, h, along=0.30, cross=0.70, max_rot_deg=5.0, scale=(0.95, 1.05)):
+    """Absolute poses T_k (image k -> mosaic frame) of a UAV block of `rows` strips x `cols` frames (BASELINE configs[2]):
+    along-track step `along`*w (70 % overlap), cross-track step `cross`*h (30 % overlap), rotation / scale jitter about the
+    image centre, a few px of position jitter.  T_0 = identity."""
+    cx, cy = (w - 1) / 2.0, (h - 1) / 2.0
+    T = []
+    for r in range(rows):
+        for c in range(cols):
+            if r == 0 and c == 0:
+                T.append(np.eye(3)); continue
+            th = np.deg2rad(rng.uniform(-max_rot_deg, max_rot_deg)); s = rng.uniform(*scale)
+            tx = c * along * w + rng.uniform(-0.02, 0.02) * w; ty = r * cross * h + rng.uniform(-0.02, 0.02) * h
+            co, si = np.cos(th) * s, np.sin(th) * s
+            T.append(np.array([[co, -si, cx - co * cx + si * cy + tx], [si, co, cy - si * cx - co * cy + ty], [0, 0, 1.0]]))
+    return T
+
+
+def make_block(rows, cols, w, h, n_kp, seed=SEED_BASE, true_frac=0.5, desc_noise=4.0, pos_noise=0.5):
+    """2-D block with a shared WORLD point model: world points (each with one SIFT-like descriptor) are scattered over the
+    block so that an image sees ~true_frac * n_kp of them; every image observes the world points inside its footprint
+    (position noise, descriptor noise) and fills the rest of its n_kp keypoints with clutter.  Any two overlapping images
+    therefore share true correspondences, along and across strips, and the pair graph has loops.
+    Returns (descs, kps, poses, pairs): poses = absolute ground-truth T_k, pairs = every (i, j), i < j, whose footprints'
+    bounding boxes intersect (the 'all pairs in overlap' list of configs[2])."""
+    rng = np.random.default_rng(seed)
+    poses = block_poses(np.random.default_rng(seed + 424243), rows, cols, w, h)
+    n = rows * cols
+    corners = np.array([[0, 0], [w - 1, 0], [w - 1, h - 1], [0, h - 1]], np.float64)
+    boxes = []
+    for T in poses:
+        q = apply_h(T, corners); boxes.append((q[:, 0].min(), q[:, 1].min(), q[:, 0].max(), q[:, 1].max()))
+    x0 = min(b[0] for b in boxes); y0 = min(b[1] for b in boxes); x1 = max(b[2] for b in boxes); y1 = max(b[3] for b in boxes)
+    n_world = int(true_frac * n_kp * (x1 - x0) * (y1 - y0) / (w * h))
+    wp = np.stack([rng.uniform(x0, x1, n_world), rng.uniform(y0, y1, n_world)], 1)
+    wd = sift_like_descriptors(rng, n_world)
+    descs, kps = [], []
+    for k, T in enumerate(poses):
+        r = np.random.default_rng(seed + 7919 * (k + 1))
+        b = boxes[k]
+        cand = np.nonzero((wp[:, 0] >= b[0]) & (wp[:, 0] <= b[2]) & (wp[:, 1] >= b[1]) & (wp[:, 1] <= b[3]))[0]
+        p = apply_h(np.linalg.inv(T), wp[cand]) + r.normal(0, pos_noise, size=(len(cand), 2))
+        ok = (p[:, 0] >= 0) & (p[:, 0] <= w - 1) & (p[:, 1] >= 0) & (p[:, 1] <= h - 1)
+        cand = cand[ok][:n_kp]; p = p[ok][:n_kp]
+        d_true = np.clip(np.rint(wd[cand].astype(np.float32) + r.normal(0, desc_noise, size=(len(cand), 128))), 0, 255).astype(np.uint8)
+        n_rand = n_kp - len(cand)
+        d = np.concatenate([d_true, sift_like_descriptors(r, n_rand)], 0)
+        q = np.concatenate([p.astype(np.float32), random_keypoints(r, n_rand, w, h)], 0)
+        perm = r.permutation(n_kp)
+        descs.append(np.ascontiguousarray(d[perm])); kps.append(np.ascontiguousarray(q[perm]))
+    pairs = [(i, j) for i in range(n) for j in range(i + 1, n)
+             if boxes[i][0] < boxes[j][2] and boxes[j][0] < boxes[i][2] and boxes[i][1] < boxes[j][3] and boxes[j][1] < boxes[i][3]]
+    return descs, kps, poses, np.array(pairs, np.int32).reshape(-1, 2)

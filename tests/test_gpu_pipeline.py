@@ -72,3 +72,52 @@ def test_load_match_pairs_resume_path(ctx, tmp_path):
     with pytest.raises(api.UavmError):                      # image index out of range in the loaded list: -1
         bad = type(loaded).from_buffer_copy(loaded); bad[0].ptA_i = 99
         api.mosaic_from_matches(ctx, images, bad, prm, 1.0)
+
+
+def test_block_alignment_recovers_ground_truth(ctx, oracle):
+    """configs[2] in small: a 3 x 4 UAV block with a shared world-point model (pairs along and across strips, loops in the
+    pair graph).  All overlapping pairs go through the GPU pair path, the accepted matches through connectivity and the
+    global affine alignment; the recovered transforms must reproduce the ground-truth poses to about a pixel, and the
+    match list must be the one the CPU oracle produces (same pairs, same inliers, same order)."""
+    import ctypes as C
+    from imagemosaicing_b200 import _lib as L
+    rows, cols, w, h, nk = 3, 4, 640, 480, 2048
+    descs, kps, poses, pairs = synth.make_block(rows, cols, w, h, nk, seed=11)
+    n = rows * cols
+    fs = api.FeatureSet(ctx, [nk] * n)
+    for i in range(n):
+        fs.upload(i, descs[i], kps[i])
+    pb = api.PairBatch(ctx, fs, pairs)
+    pb.match(); pb.select(w, h); pb.ransac(2.5, 1000, seeds=(1000 + np.arange(len(pairs))).astype(np.uint32))
+    out, n_m, n_acc = pb.collect(30)
+    mp = (L.MatchPointPairs * n_m).from_buffer_copy(bytes(out)[:n_m * 40])
+    # oracle composition of the same pair path
+    o_rows = []
+    for p, (i, j) in enumerate(pairs):
+        idx, d2 = oracle.match_l2_fast(descs[i], descs[j])
+        x1, i1, x2, i2 = oracle.select(idx, d2, kps[i], kps[j], w, h)
+        ok, mask, Hm, ni, st = oracle.ransac2d(x1, x2, 2.5, 1000, 1000 + p)
+        if ni > 30:
+            for k in np.nonzero(mask)[0]:
+                o_rows.append((i, x1[k, 0], x1[k, 1], j, x2[k, 0], x2[k, 1]))
+    assert n_m == len(o_rows)
+    for r, o in zip(mp, o_rows):
+        assert (r.ptA_i, r.ptA.x, r.ptA.y, r.ptB_i, r.ptB.x, r.ptB.y) == o
+    label = (C.c_int32 * n)()
+    assert L.lib().uavm_connected_images(mp, n_m, n, label) == 0 and list(label) == [1] * n
+    for r in mp:
+        if r.ptA_i == 0: r.ptA_Fixed = 1
+        if r.ptB_i == 0: r.ptB_Fixed = 1
+    init = (L.ImageTransform * n)(); res = (L.ImageTransform * n)()
+    for i in range(n):
+        for t in range(9):
+            init[i].h.m[t] = 1.0 if t in (0, 4, 8) else 0.0
+        init[i].fixed = 1 if i == 0 else 0
+    assert L.lib().uavm_align_affine(mp, n_m, init, n, 1, res) == 0
+    corners = np.array([[0, 0], [w - 1, 0], [w - 1, h - 1], [0, h - 1]], np.float64)
+    err = []
+    for k in range(n):
+        G = np.linalg.inv(poses[0]) @ poses[k]
+        T = np.array([res[k].h.m[t] for t in range(9)], np.float64).reshape(3, 3)
+        err.append(np.abs(synth.apply_h(G, corners) - synth.apply_h(T, corners)).max())
+    assert max(err) < 2.0 and np.median(err) < 1.0, (max(err), np.median(err))
