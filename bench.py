@@ -149,6 +149,29 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def prefer_gpu_numa_node(local):
+    """Host side of the e2e path: pinned frame buffers should live on the NUMA node the GPU hangs off, otherwise every
+    PCIe read crosses the socket interconnect (8 ranks copying at once).  Sets the calling thread's memory policy to
+    MPOL_PREFERRED(node of the GPU) before the pinned buffers are allocated; silently does nothing when the node cannot be
+    determined or the container's cpuset forbids it.  UAVM_BENCH_NO_NUMA=1 disables it."""
+    import ctypes
+    if os.environ.get("UAVM_BENCH_NO_NUMA"):
+        return None
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(local)
+        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read().strip())
+        if node < 0:
+            return None
+        mask = ctypes.c_ulong(1 << node)
+        libc = ctypes.CDLL(None, use_errno=True)
+        rc = libc.syscall(238, 1, ctypes.byref(mask), ctypes.c_ulong(64))      # set_mempolicy(MPOL_PREFERRED, &mask, maxnode)
+        return node if rc == 0 else None
+    except Exception:
+        return None
+
+
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
     Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
@@ -216,6 +239,7 @@ def run_ours(args):
     keep = np.ones(NIMG, np.int32); keep[0] = 0            # pair (i, i+1) warps frame i+1: 49 frames per step
 
     # ---- pinned host copies (e2e inputs) ----
+    numa_node = prefer_gpu_numa_node(local)
     h_desc = [torch.from_numpy(d).pin_memory() for d in descs]
     h_kp = [torch.from_numpy(k).pin_memory() for k in kps]
     h_frames = []
@@ -394,7 +418,7 @@ def run_ours(args):
                         "k5_warp_affine_x2": {"ms": float(stage_ms[3]), "serial_ms": float(serial_ms[3]), "achieved_gbs": warp_gbs,
                                           "serial_gbs": warp_bytes / (serial_ms[3] / 1000.0) / 1e9}},
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": e_steps,
-                    "ms_per_step": e2e_ms / e_steps, "pcie_h2d_probe_gbs": pcie_gbs,
+                    "ms_per_step": e2e_ms / e_steps, "pcie_h2d_probe_gbs": pcie_gbs, "host_numa_node_rank0": numa_node,
                     "note": "PCIe bound: frames are copied on the library's copy stream while match/RANSAC/warp run"},
             "gpu_launches": int(launches),
             "clocks": clocks,
