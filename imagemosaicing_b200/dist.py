@@ -47,6 +47,23 @@ def gather_match_pairs(local_records, local_pair_ids, n_pairs, group=None, devic
     return buf
 
 
+def split_collected(records, local_pairs):
+    """uavm_pairbatch_collect returns the accepted pairs' inlier records concatenated in local pair order; this splits them
+    back into one array per local pair (empty for rejected pairs), the form gather_match_pairs takes.
+    records: MPP_DTYPE array; local_pairs: (n, 2) image indices of this rank's pairs, in the PairBatch's order."""
+    out = []
+    k = 0
+    n = len(records)
+    for i, j in local_pairs:
+        k0 = k
+        while k < n and records["ia"][k] == i and records["ib"][k] == j:
+            k += 1
+        out.append(records[k0:k])
+    if k != n:
+        raise ValueError("records are not grouped in local pair order")
+    return out
+
+
 def canvas_bands(canvas_h, world, align=32):
     """Split the canvas rows into `world` horizontal bands whose edges are multiples of `align`
     (the last band ends at canvas_h).  Returns [(y0, y1)] per rank; ranks beyond the available rows get (0, 0)."""

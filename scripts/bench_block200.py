@@ -46,30 +46,11 @@ e0.record()
 for _ in range(args.steps): pair_path()
 e1.record(); torch.cuda.synchronize()
 pair_ms = e0.elapsed_time(e1) / args.steps
-# accepted matches of this rank, tagged with the global pair id so that the merged list is in global pair order
+# accepted matches of this rank, merged over the ranks in global pair order (two all-reduces of disjoint slots)
 out, n_m, n_acc = pb.collect(30)
 rec = np.frombuffer(bytes(out)[:n_m * 40], dtype=D.MPP_DTYPE).copy()
-pid_of = {(int(a), int(b)): int(g) for g, (a, b) in zip(mine, pairs[mine])}
-gid = np.array([pid_of[(int(r["ia"]), int(r["ib"]))] for r in rec], np.int64)
 t1 = time.perf_counter()
-if world > 1:
-    sizes = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
-    dist.all_gather(sizes, torch.tensor([len(rec)], dtype=torch.int64, device=dev))
-    mx = int(max(int(s) for s in sizes))
-    buf = torch.zeros((mx, 12), dtype=torch.int32, device=dev)            # 40-byte record (10 words) + 64-bit pair id (2 words)
-    if len(rec):
-        packed = np.zeros((len(rec), 12), np.int32)
-        packed[:, :10] = rec.view(np.int32).reshape(-1, 10); packed[:, 10:] = gid.view(np.int32).reshape(-1, 2)
-        buf[:len(rec)] = torch.from_numpy(packed).to(dev)
-    allb = [torch.zeros_like(buf) for _ in range(world)]
-    dist.all_gather(allb, buf)
-    parts = [b[:int(s)].cpu().numpy() for b, s in zip(allb, sizes)]
-    allp = np.concatenate(parts, 0)
-    gid_all = np.ascontiguousarray(allp[:, 10:]).view(np.int64).ravel()
-    order = np.argsort(gid_all, kind="stable")
-    rec_all = np.ascontiguousarray(allp[order, :10]).view(D.MPP_DTYPE).ravel()
-else:
-    rec_all = rec
+rec_all = D.gather_match_pairs(D.split_collected(rec, pairs[mine]), mine, len(pairs), device=dev)     # global pair order, identical on every rank
 gather_ms = (time.perf_counter() - t1) * 1e3
 tt = torch.tensor([pair_ms], device=dev, dtype=torch.float64)
 if world > 1: dist.all_reduce(tt, op=dist.ReduceOp.MAX)

@@ -44,6 +44,24 @@ def test_pair_sharding_and_gather_world2(tmp_path):
         assert np.array_equal(got.view(np.uint8), serial.view(np.uint8))
 
 
+def test_split_collected_roundtrip():
+    """collect() concatenates the accepted pairs' records in local pair order; split_collected undoes it (rejected pairs
+    become empty arrays), including consecutive pairs that share an image."""
+    pairs = np.array([(0, 1), (0, 2), (1, 2), (2, 5), (5, 6)], np.int32)
+    per_pair = [_fake_pair_records(p, *pairs[p]) for p in range(len(pairs))]
+    per_pair[1] = per_pair[1][:0]                                     # a rejected pair
+    cat = np.concatenate(per_pair)
+    back = D.split_collected(cat, pairs)
+    assert len(back) == len(pairs)
+    for a, b in zip(back, per_pair):
+        assert np.array_equal(a.view(np.uint8), b.view(np.uint8))
+    try:
+        D.split_collected(cat[::-1].copy(), pairs)
+        assert False, "out-of-order records must be rejected"
+    except ValueError:
+        pass
+
+
 def test_reference_pair_window():
     p = D.reference_pair_list(200, 182)
     assert len(p) == 19729                       # SURVEY §8 a3: the reference rule on a 200-image block
