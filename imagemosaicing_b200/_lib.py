@@ -8,7 +8,7 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libuavmosaic.so")
+LIB_PATH = os.environ.get("UAVM_LIB_PATH") or os.path.join(_HERE, "libuavmosaic.so")   # UAVM_LIB_PATH: sanitizer / debug builds
 _lib = None
 
 f32p = C.POINTER(C.c_float)
@@ -88,7 +88,11 @@ def lib():
             raise RuntimeError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
                                "(there is no CPU fallback)")
         L = C.CDLL(LIB_PATH)
-        L.uavm_last_error.restype = C.c_char_p
-        L.uavm_ctx_launch_count.restype = C.c_int64
+        try:                                   # absent only in a host-only sanitizer build (UAVM_LIB_PATH)
+            L.uavm_last_error.restype = C.c_char_p
+            L.uavm_ctx_launch_count.restype = C.c_int64
+        except AttributeError:
+            if not os.environ.get("UAVM_LIB_PATH"):
+                raise
         _lib = L
     return _lib
