@@ -605,10 +605,9 @@ extern "C" int uavm_canvas_warp_range(uavm_ctx* ctx, uavm_canvas* cv, int first,
         if (!scalar && cv->img_w < (1 << 22) && cv->img_h < (1 << 22) && (int64_t)cv->img_h * cv->src_step_px < ((int64_t)1 << 31)) {
             static const int env_boxes = getenv("UAVM_K5_BOXES") ? atoi(getenv("UAVM_K5_BOXES")) : kFpBoxes;   // 0: direct tap loads (A/B)
             const int boxes = cv->tmap_src_ok ? env_boxes : 0;
-            static bool attr_done = false;
-            if (!attr_done) {
+            if (!ctx->k5_attr_set) {                      // function attributes are per device: once per context
                 cudaFuncSetAttribute(k5_warp_affine_x2, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-                attr_done = true;
+                ctx->k5_attr_set = true;
             }
             k5_warp_affine_x2<<<grid, block, boxes * kFpBoxBytes, ctx->stream>>>(
                 cv->tmap_src, cv->d_desc + first, cv->img_w, cv->img_h, cv->src_step_px, cv->layout.dgx, cv->layout.dgy, 0x4B000000u,

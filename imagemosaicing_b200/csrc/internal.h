@@ -18,6 +18,7 @@ struct uavm_ctx {
     cudaEvent_t ev_fork = nullptr, ev_side = nullptr;
     bool forked = false, side_pending = false;
     int64_t launches = 0;
+    bool k5_attr_set = false;          // per-device function attributes of the K5 kernel applied
     char err[512] = {0};
 };
 
