@@ -539,7 +539,7 @@ int orc_canvas_layout_compute(const float* H, const int32_t* keep_in, int n, int
         if (keep_in && keep_in[k] == 0) continue;
         if (m[8] == 0) continue;
         chips[k].keep = 1;
-        float bmaxx = (float)(-1 << 29), bmaxy = (float)(-1 << 29), bminx = (float)(1 << 29), bminy = (float)(1 << 29);
+        float bmaxx = (float)(-(1 << 29)), bmaxy = (float)(-(1 << 29)), bminx = (float)(1 << 29), bminy = (float)(1 << 29);
         for (int i = 0; i < 4; i++) {
             float xs = cx[i], ys = cy[i];
             float xd = (xs * m[0] + ys * m[1] + m[2]) / (xs * m[6] + ys * m[7] + m[8]);
@@ -692,7 +692,7 @@ static void apply_project9(const float* h, float x, float y, float* xd, float* y
 int orc_paste(const float* H, int n, int img_w, int img_h, const uint8_t** srcs, int src_step,
               int* out_w, int* out_h, uint8_t* out, int out_step)
 {
-    float minX = (float)(1 << 29), minY = (float)(1 << 29), maxX = (float)(-1 << 29), maxY = (float)(-1 << 29);
+    float minX = (float)(1 << 29), minY = (float)(1 << 29), maxX = (float)(-(1 << 29)), maxY = (float)(-(1 << 29));
     float cx[4] = {0, (float)(img_w - 1), (float)(img_w - 1), 0}, cy[4] = {0, 0, (float)(img_h - 1), (float)(img_h - 1)};
     for (int k = 0; k < n; k++) {
         const float* m = H + (size_t)k * 9;
@@ -717,7 +717,7 @@ int orc_paste(const float* H, int n, int img_w, int img_h, const uint8_t** srcs,
         if (m[8] == 0) continue;
         float inv[9]; memset(inv, 0, sizeof(inv));
         orc_inverse_matrix(m, 3, inv, 1e-12f);
-        float bminx = (float)(1 << 29), bminy = (float)(1 << 29), bmaxx = (float)(-1 << 29), bmaxy = (float)(-1 << 29);
+        float bminx = (float)(1 << 29), bminy = (float)(1 << 29), bmaxx = (float)(-(1 << 29)), bmaxy = (float)(-(1 << 29));
         for (int i = 0; i < 4; i++) {
             float bx, by;
             apply_project9(m, cx[i], cy[i], &bx, &by);

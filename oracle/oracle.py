@@ -51,7 +51,7 @@ def lib():
     global _LIB
     if _LIB is None:
         build()
-        _LIB = C.CDLL(os.path.join(_HERE, "liboracle.so"))
+        _LIB = C.CDLL(os.environ.get("ORACLE_LIB_PATH") or os.path.join(_HERE, "liboracle.so"))   # ORACLE_LIB_PATH: sanitizer build
         _LIB.orc_ransac2d.restype = C.c_int
         _LIB.orc_select.restype = C.c_int
     return _LIB
