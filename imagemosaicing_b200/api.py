@@ -401,6 +401,32 @@ def mosaic_from_matches(ctx, images, matches, param=None, scale=1.0):
     return _take_result(res, tr, n)
 
 
+def mosaic_sequence(ctx, images, descs, kps, max_once, param=None, scale=1.0):
+    """The chunk loop of MosaicUavVideo (M/MosaicWithoutPos.cpp:10252-10300) over decoded frames (uavm_mosaic_sequence).
+    Returns a list of (first_frame, mosaic or None)."""
+    n = len(images)
+    ims, arr = _image_array(images)
+    ds = [np.ascontiguousarray(d, np.float32) for d in descs]
+    ks = [np.ascontiguousarray(k, np.float32) for k in kps]
+    dp = (f32p * n)(*[_ptr(d, f32p) for d in ds]); kp = (f32p * n)(*[_ptr(k, f32p) for k in ks])
+    nk = np.array([len(d) for d in ds], np.int32)
+    P = _param(param)
+    res = C.POINTER(L.Image)(); first = i32p(); nres = C.c_int(0)
+    ctx.check(L.lib().uavm_mosaic_sequence(ctx._h, arr, n, dp, kp, _ptr(nk, i32p), C.byref(P), C.c_float(scale), int(max_once),
+                                           C.byref(res), C.byref(first), C.byref(nres)))
+    out = []
+    for k in range(nres.value):
+        r = res[k]
+        img = None
+        if r.imageData:
+            buf = (C.c_uint8 * (r.widthStep * r.height)).from_address(r.imageData)
+            img = np.frombuffer(buf, np.uint8).reshape(r.height, r.widthStep)[:, :r.width * 3].reshape(r.height, r.width, 3).copy()
+            L.lib().uavm_free(C.c_void_p(r.imageData))
+        out.append((int(first[k]), img))
+    L.lib().uavm_free(C.cast(res, C.c_void_p)); L.lib().uavm_free(C.cast(first, C.c_void_p))
+    return out
+
+
 # ---- the reference's on-disk artefacts (host only; csrc/formats_host.cpp) --------------------------------------------------
 def _io_check(rc, what, path):
     if rc != 0:

@@ -163,3 +163,38 @@ static int mosaic_tail(uavm_ctx* ctx, const uavm_image* images, int n_images, st
     uavm_canvas_destroy(ctx, cv);
     return rc == UAVM_OK ? UAVM_OK : UAVM_EFAIL;                        // -2: mosaic failed (:4675-4676)
 }
+
+
+// Chunked mosaicking of a frame sequence: the loop of MosaicUavVideo (M/MosaicWithoutPos.cpp:10252-10300) without the video
+// decoding (ConvertVideo2Bmp / cvLoadImage are upstream of this library): frames [n, min(n + max_once, total))
+// are mosaicked independently, the next chunk starts at n + numMosaiced.  A chunk that fails yields an empty result
+// (width = height = 0, imageData = NULL) and the loop goes on, as the reference does (it ignores nRet); unlike the reference,
+// a chunk that reports numMosaiced = 0 advances by the chunk length instead of looping forever.
+extern "C" int uavm_mosaic_sequence(uavm_ctx* ctx, const uavm_image* images, int n_images,
+                                    const float* const* desc, const float* const* kp_xy, const int32_t* n_kp,
+                                    const uavm_param* param, float scale, int max_once_mosaic_num,
+                                    uavm_image** results_out, int32_t** first_frame_out, int* n_results_out)
+{
+    if (!ctx || !images || n_images <= 1 || !desc || !kp_xy || !n_kp || !results_out || !n_results_out || max_once_mosaic_num < 2) return UAVM_EINVAL;
+    *results_out = nullptr; *n_results_out = 0;
+    if (first_frame_out) *first_frame_out = nullptr;
+    std::vector<uavm_image> res; std::vector<int32_t> first;
+    for (int n = 0; n < n_images;) {
+        const int beg = n, end = (n + max_once_mosaic_num - 1 < n_images - 1) ? n + max_once_mosaic_num - 1 : n_images - 1;
+        const int cnt = end - beg + 1;
+        uavm_image r; memset(&r, 0, sizeof(r));
+        int num = 0;
+        if (cnt >= 2) uavm_mosaic_images(ctx, images + beg, cnt, desc + beg, kp_xy + beg, n_kp + beg, param, scale, &r, &num, nullptr);
+        res.push_back(r); first.push_back(beg);
+        n = beg + (num > 0 ? num : cnt);
+    }
+    *results_out = (uavm_image*)malloc(res.size() * sizeof(uavm_image));
+    if (!*results_out) { for (auto& r : res) free(r.imageData); return UAVM_EFAIL; }
+    memcpy(*results_out, res.data(), res.size() * sizeof(uavm_image));
+    if (first_frame_out) {
+        *first_frame_out = (int32_t*)malloc(first.size() * sizeof(int32_t));
+        if (*first_frame_out) memcpy(*first_frame_out, first.data(), first.size() * sizeof(int32_t));
+    }
+    *n_results_out = (int)res.size();
+    return UAVM_OK;
+}

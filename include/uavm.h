@@ -193,6 +193,13 @@ int uavm_mosaic_images_ex(uavm_ctx* ctx, const uavm_image* images, int n_images,
                           const uavm_param* param, float scale,
                           uavm_image* result, int* num_mosaiced, uavm_imagetransform* transforms_out,
                           uavm_matchpointpairs** pairs_out, int* n_pairs_out);
+/* the chunk loop of MosaicUavVideo (M/MosaicWithoutPos.cpp:10252-10300) over an already decoded frame sequence: frames
+ * [n, n + max_once_mosaic_num) are mosaicked independently, the next chunk starts at n + numMosaiced.  *results_out (and every
+ * results_out[k].imageData) and *first_frame_out are allocated by the library (uavm_free); a failed chunk has imageData = NULL. */
+int uavm_mosaic_sequence(uavm_ctx* ctx, const uavm_image* images, int n_images,
+                         const float* const* desc, const float* const* kp_xy, const int32_t* n_kp,
+                         const uavm_param* param, float scale, int max_once_mosaic_num,
+                         uavm_image** results_out, int32_t** first_frame_out, int* n_results_out);
 void uavm_free(void* p);
 
 /* ---- the reference's on-disk artefacts (host only, csrc/formats_host.cpp) -------------------------------------------------

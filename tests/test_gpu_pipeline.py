@@ -121,3 +121,21 @@ def test_block_alignment_recovers_ground_truth(ctx, oracle):
         T = np.array([res[k].h.m[t] for t in range(9)], np.float64).reshape(3, 3)
         err.append(np.abs(synth.apply_h(G, corners) - synth.apply_h(T, corners)).max())
     assert max(err) < 2.0 and np.median(err) < 1.0, (max(err), np.median(err))
+
+
+def test_mosaic_sequence_chunks_like_mosaic_uav_video(ctx):
+    """uavm_mosaic_sequence = the chunk loop of MosaicUavVideo (M/MosaicWithoutPos.cpp:10252-10300): every chunk of
+    max_once frames equals uavm_mosaic_images on that slice; chunks start at n + numMosaiced."""
+    n, w, h, nk = 7, 480, 360, 1536
+    images, descs, kps, _ = _scene(n, w, h, nk, 31)
+    d32 = [d.astype(np.float32) for d in descs]
+    prm = {"blending": 2, "pairWindow": 3, "seed": 5}
+    chunks = api.mosaic_sequence(ctx, images, d32, kps, 3, prm, 1.0)
+    assert [c[0] for c in chunks] == [0, 3, 6] or [c[0] for c in chunks] == [0, 3]      # the last chunk holds one frame: no mosaic
+    for first, img in chunks:
+        cnt = min(3, n - first)
+        if cnt < 2:
+            assert img is None
+            continue
+        ref, _, _ = api.mosaic_images(ctx, images[first:first + cnt], d32[first:first + cnt], kps[first:first + cnt], prm, 1.0)
+        assert img is not None and np.array_equal(img, ref)
