@@ -14,8 +14,8 @@
  * int16 kernels: pyrDown = separable [1 4 6 4 1], BORDER_REFLECT_101, (sum + 128) >> 8;
  *                pyrUp (dst = 2 x src) = even: s[i-1] + 6 s[i] + s[i+1], odd: 4 (s[i] + s[i+1]), reflect-101 at the
  *                near edge, replicate at the far edge, (sum + 32) >> 6.
- * Parity: pinned against cv2 4.13 detail_MultiBandBlender (tests/test_cpu_blend.py); parity with the exact
- * 2.4.0 binary is UNPINNED (no mosaic image ships with the reference).
+ * Parity: pinned BIT FOR BIT against cv2 4.13 detail_MultiBandBlender, including the operation order of the f32 weight
+ * pyrDown (tests/test_cpu_blend.py); parity with the exact 2.4.0 binary is UNPINNED (no mosaic image ships with the reference).
  */
 #include "oracle.h"
 #include <math.h>
@@ -89,10 +89,22 @@ void orc_pyr_up_s16(const int16_t* src, int w, int h, int ch, int16_t* dst, int 
     free(rows);
 }
 
-/* f32 pyrDown of the weight maps: row pass s2*6 + (s1+s3)*4 + s0 + s4, column pass the same, times 1/256 */
+/* f32 pyrDown of the weight maps, in the EXACT operation order of OpenCV 4.13's imgproc/pyramids.cpp as shipped in the
+ * opencv-python wheels (pyramids.cpp is not a CPU-dispatched file, so it runs the SSE baseline: 4 float lanes, v_muladd = mul
+ * then add, no FMA).  Float addition is not associative, so which form produced an output column is part of the result:
+ *   row pass    column x = 0 (left border) and columns past the vector loop:  ((s2*6 + (s1+s3)*4) + s0) + s4      (scalar loop)
+ *               columns 1 <= x < 1 + 4*floor((width0-1)/4):                   s2*6 + ((s1+s3)*4 + (s0+s4))        (PyrDownVecH)
+ *               with width0 = min((w-3)/2 + 1, dw)  (the columns that need no border lookup)
+ *   column pass columns x < 4*floor(dw/4):   (((r1+r3)+r2)*4 + ((r0+r4)+(r2+r2))) * (1/256)                       (PyrDownVecV)
+ *               the tail:                    (((r2*6 + (r1+r3)*4) + r0) + r4) * (1/256)                           (scalar loop)
+ * Pinned bit for bit against cv2.pyrDown on random f32 images of 1..60 columns (tests/test_cpu_blend.py).  OpenCV 2.4.0 (the
+ * reference's binary, unpinned) used the scalar row form everywhere and the same column forms with 8-column groups. */
 void orc_pyr_down_f32(const float* src, int w, int h, float* dst)
 {
     int dw = (w + 1) / 2, dh = (h + 1) / 2;
+    int width0 = (w - 3) / 2 + 1; if (w < 3) width0 = 0; if (width0 > dw) width0 = dw;
+    const int hvec_end = 1 + 4 * ((width0 - 1 > 0 ? width0 - 1 : 0) / 4);      /* columns [1, hvec_end) take the vector row form */
+    const int vvec_end = 4 * (dw / 4);
     float* row = (float*)malloc(sizeof(float) * (size_t)dw * 5);
     for (int y = 0; y < dh; y++) {
         for (int k = 0; k < 5; k++) {
@@ -102,11 +114,18 @@ void orc_pyr_down_f32(const float* src, int w, int h, float* dst)
             for (int x = 0; x < dw; x++) {
                 int x0 = reflect101(2 * x - 2, w), x1 = reflect101(2 * x - 1, w), x2 = reflect101(2 * x, w);
                 int x3 = reflect101(2 * x + 1, w), x4 = reflect101(2 * x + 2, w);
-                r[x] = s[x2] * 6 + (s[x1] + s[x3]) * 4 + s[x0] + s[x4];
+                if (x >= 1 && x < hvec_end) {
+                    float t = (s[x1] + s[x3]) * 4.f; float u = s[x0] + s[x4]; t = t + u;
+                    r[x] = s[x2] * 6.f + t;
+                } else
+                    r[x] = s[x2] * 6.f + (s[x1] + s[x3]) * 4.f + s[x0] + s[x4];
             }
         }
         for (int x = 0; x < dw; x++) {
-            float v = row[2 * dw + x] * 6 + (row[dw + x] + row[3 * dw + x]) * 4 + row[x] + row[4 * dw + x];
+            const float r0 = row[x], r1 = row[dw + x], r2 = row[2 * dw + x], r3 = row[3 * dw + x], r4 = row[4 * dw + x];
+            float v;
+            if (x < vvec_end) { float a = (r1 + r3) + r2; float b = (r0 + r4) + (r2 + r2); v = a * 4.f + b; }
+            else v = r2 * 6.f + (r1 + r3) * 4.f + r0 + r4;
             dst[(size_t)y * dw + x] = v * (1.f / 256.f);
         }
     }
