@@ -280,9 +280,13 @@ class Canvas:
         self.ctx.check(L.lib().uavm_canvas_set_image(self.ctx._h, self._h, int(image), _ptr(bgr, u8p), int(step), dev))
         self._keep = bgr
 
-    def set_band(self, y0, y1, halo=128):
-        """Multi-GPU canvas sharding: compute only canvas rows [y0, y1) (+ halo); see uavm_canvas_set_band."""
+    def set_band(self, y0, y1, halo=0):
+        """Multi-GPU canvas sharding: produce only canvas rows [y0, y1); see uavm_canvas_set_band (`halo` is ignored)."""
         self.ctx.check(L.lib().uavm_canvas_set_band(self.ctx._h, self._h, int(y0), int(y1), int(halo)))
+
+    def set_rect(self, x0, y0, x1, y1):
+        """Multi-GPU canvas sharding: produce only the canvas rectangle [x0, x1) x [y0, y1) (even edges); uavm_canvas_set_rect."""
+        self.ctx.check(L.lib().uavm_canvas_set_rect(self.ctx._h, self._h, int(x0), int(y0), int(x1), int(y1)))
 
     def is_active(self, image):
         return bool(L.lib().uavm_canvas_is_active(self._h, int(image)))
@@ -324,6 +328,11 @@ class Canvas:
         """Rows [y0, y1) of the result into `dst` (torch CUDA uint8 tensor or numpy array, (y1-y0, W, 3))."""
         dev = 1 if _is_torch_cuda(dst) else 0
         self.ctx.check(L.lib().uavm_canvas_copy_result_rows(self.ctx._h, self._h, int(y0), int(y1), _ptr(dst, u8p), dev))
+
+    def copy_result_rect(self, x0, y0, x1, y1, dst):
+        """Rectangle [x0, x1) x [y0, y1) of the result, dense, into `dst` (torch CUDA uint8 tensor or numpy array)."""
+        dev = 1 if _is_torch_cuda(dst) else 0
+        self.ctx.check(L.lib().uavm_canvas_copy_result_rect(self.ctx._h, self._h, int(x0), int(y0), int(x1), int(y1), _ptr(dst, u8p), dev))
 
     def close(self):
         if self._h:

@@ -3,28 +3,54 @@
 //
 // The blender itself is OpenCV code (third party, not under /root/reference); the arithmetic restated here is
 // the one documented in oracle/oracle_blend.c: int16 Laplacian pyramids ([1 4 6 4 1] pyrDown with
-// (sum+128)>>8, pyrUp with (sum+32)>>6, reflect-101 / replicate borders), f32 Gaussian weight pyramids,
-// dst += short(src * w), wsum += w, dst = short(dst / (wsum + 1e-5)), collapse with saturating adds.
+// (sum+128)>>8, pyrUp with (sum+32)>>6, reflect-101 / replicate borders), f32 Gaussian weight pyramids in OpenCV's
+// operation order, dst += short(src * w), wsum += w, dst = short(dst / (wsum + 1e-5)), collapse with saturating adds.
 //
-// HBM layout: the canvas pyramid (int16 x4 pixels = B, G, R, pad + f32 weights per level, canvas padded to a multiple
-// of 2^bands) stays resident; every fed chip gets a scratch pyramid of its padded ROI that is reused for the
-// next chip.  Images are fed in index order (the f32 weight sums are order dependent), pixels in parallel.
+// Organisation (B200-first; OpenCV feeds image after image and keeps a full canvas pyramid of int16 x3 + f32):
+//   1. per chip, all chips in one launch per level (blockIdx.z = chip): Gaussian pyramids of the chip's ROI, restricted to
+//      the rectangles C_i the planner derives from the chip's seam-mask bounding box (blend_plan.h).  Level 0 is never
+//      materialised: the first pyrDown reads the BGRA chip and its mask directly (copyMakeBorder(REFLECT) / zero border).
+//   2. per canvas level, top down, ONE kernel over canvas tiles: gather the weighted Laplacian contributions of the chips
+//      that touch the tile IN IMAGE INDEX ORDER (the f32 weight sums are order dependent; the int16 sums wrap and are
+//      not), normalise, add pyrUp of the already final coarser level, store the final level (int16 x4) — or, at level 0,
+//      the cropped u8 mosaic and its mask.  The canvas Laplacian / weight pyramids are never stored.
+// A context that owns only a rectangle of the canvas (uavm_canvas_set_rect) runs the same kernels on the level rectangles
+// S_i its output depends on; chip pyramids are computed in ROI coordinates exactly as in the unsharded case, so sharded
+// results are bit-identical by construction (no halo heuristics).
 #include <math.h>
 #include <string.h>
 #include "canvas.h"
+#include "blend_plan.h"
 
 namespace {
 
-constexpr int kMaxBands = 8;
+using namespace uavm_plan;
+
+struct BlendChip {                          // device-visible plan of one active chip
+    const uint32_t* chip; const uint8_t* mask;
+    int32_t chip_step, mask_step, cw, ch, left, top;
+    int32_t tlx, tly;                       // ROI origin in padded canvas coordinates (multiples of 2^bands)
+    int32_t pw[kMaxBands + 1], ph[kMaxBands + 1];
+    int32_t ux0[kMaxBands + 1], uy0[kMaxBands + 1], ux1[kMaxBands + 1], uy1[kMaxBands + 1];
+    int32_t cx0[kMaxBands + 1], cy0[kMaxBands + 1], cw_[kMaxBands + 1], ch_[kMaxBands + 1];
+    short* pyr[kMaxBands + 1];              // levels >= 1: int16 x4 pixels of C_i, pitch cw_[i]
+    float* wp[kMaxBands + 1];
+};
+
+struct LevelArgs {
+    int32_t level, n_chips;
+    int32_t sx0, sy0, sx1, sy1;             // S_i: canvas level-i rectangle to produce
+    short* fin; int32_t fin_x0, fin_y0, fin_pitch;                               // final level i (int16 x4), storage origin = S_i origin
+    const short* nxt; int32_t nxt_x0, nxt_y0, nxt_pitch, nxt_w, nxt_h;           // final level i+1 storage; nxt_w/h = full level size (border rules)
+    uint8_t* out; uint8_t* out_mask; int32_t cw, ch;                             // level 0: mosaic (pitch cw pixels) and its mask
+    int32_t ox0, oy0, ox1, oy1;                                                  // level 0: output rectangle
+};
 
 struct BlendWs {
-    int nb = 0, W = 0, H = 0, Y0 = 0, Y1 = 0;   // Y0..Y1: canvas rows held by this workspace (band + halo)
-    int lw[kMaxBands + 1], lh[kMaxBands + 1];
-    short* dlap[kMaxBands + 1] = {nullptr};
-    float* dw[kMaxBands + 1] = {nullptr};
-    short* pyr[kMaxBands + 1] = {nullptr};     // scratch pyramid of the chip being fed (capacity of the largest ROI)
-    float* wp[kMaxBands + 1] = {nullptr};
-    size_t roi_cap = 0;
+    int nb = -1;
+    BlendChip* d_chips = nullptr; size_t chips_cap = 0;
+    uint8_t* d_scratch = nullptr; size_t scratch_cap = 0;      // chip pyramids
+    short* d_fin[kMaxBands + 1] = {nullptr}; size_t fin_cap[kMaxBands + 1] = {0};
 };
 
 __device__ __forceinline__ int reflect101(int p, int n) {
@@ -37,143 +63,93 @@ __device__ __forceinline__ int reflect_edge(int p, int n) {     // BORDER_REFLEC
     while (p < 0 || p >= n) p = (p < 0) ? -p - 1 : 2 * n - 1 - p;
     return p;
 }
-__device__ __forceinline__ short sat16(int v) { return (short)max(-32768, min(32767, v)); }
+__device__ __forceinline__ int sat16(int v) { return max(-32768, min(32767, v)); }
 
-// Pyramid pixels are 4 x int16 (B, G, R, 0): one aligned 8-byte load / store per pixel instead of three 2-byte ones
-// (a 6-byte interleaved pixel straddles words; the kernels were LSU-instruction bound with it).
-__device__ __forceinline__ void ld3(const short* base, size_t px, int& a, int& b, int& c)
-{
-    const int2 v = *reinterpret_cast<const int2*>(base + px * 4);
-    a = (short)(v.x & 0xffff); b = v.x >> 16; c = (short)(v.y & 0xffff);
-}
-__device__ __forceinline__ void st3(short* base, size_t px, int a, int b, int c)
-{
-    int2 v; v.x = (a & 0xffff) | (b << 16); v.y = c & 0xffff;
-    *reinterpret_cast<int2*>(base + px * 4) = v;
-}
+// Pyramid pixels are 4 x int16 (B, G, R, 0): one aligned 8-byte load / store per pixel
+__device__ __forceinline__ void unpack3(int2 v, int& a, int& b, int& c) { a = (short)(v.x & 0xffff); b = v.x >> 16; c = (short)(v.y & 0xffff); }
+__device__ __forceinline__ int2 pack3(int a, int b, int c) { return make_int2((a & 0xffff) | (b << 16), c & 0xffff); }
+__device__ __forceinline__ int2 bgra_to_px(uint32_t s) { return make_int2((int)((s & 0xffu) | ((s & 0xff00u) << 8)), (int)((s >> 16) & 0xffu)); }
 
-// level 0 of the fed image: copyMakeBorder(REFLECT) of the chip (u8 -> s16) and mask/255 with a zero border.
-// Four pixels per thread; groups that lie inside the chip with 4-pixel alignment on both sides move as vectors.
+// ---------------------------------------------------------------------------------------------------------------------
+// Tiled pyrDown of one pyramid level for every active chip (blockIdx.z).  A CTA produces a 64 x 8 tile of C_{l+1} from a
+// 131 x 19 source window staged in shared memory, split into even / odd columns so the stride-2 taps are unit-stride,
+// conflict-free LDS; a thread filters 7 window rows horizontally once for two vertically adjacent outputs.
+// L0: the source level is the chip itself — copyMakeBorder(REFLECT) of the BGRA chip (u8 -> s16) and mask / 255 with a
+// zero border, evaluated on the fly (MultiBandBlender::feed).
+// f32 weights follow OpenCV's operation order (oracle_blend.c: vector form for columns [1, hvec_end) of the row pass and
+// [0, vvec_end) of the column pass, scalar form elsewhere), in ROI-level coordinates.
+constexpr int kPdW = 64, kPdH = 8, kPdCols = 2 * kPdW + 4, kPdRows = 2 * kPdH + 3;
+
+template <bool L0>
 __global__ void __launch_bounds__(256)
-k7_feed_level0(const uint32_t* __restrict__ chip, int chip_step /* words */, const uint8_t* __restrict__ mask, int mask_step,
-               int cw, int ch, int left, int top, int width, int height, short* __restrict__ pyr0, float* __restrict__ wp0)
+k7_pyrdown(const BlendChip* __restrict__ chips, int sl)
 {
-    const int x0 = 4 * (blockIdx.x * blockDim.x + threadIdx.x), y = blockIdx.y;
-    if (x0 >= width || y >= height) return;
-    const int iy = y - top, sy = reflect_edge(iy, ch);
-    const int ix0 = x0 - left;
-    const size_t o = (size_t)y * width + x0;
-    if (ix0 >= 0 && ix0 + 4 <= cw && x0 + 4 <= width && (width & 3) == 0) {
-        const uint32_t* crow = chip + (size_t)sy * chip_step + ix0;                                    // 4 BGRA pixels
-        uint32_t sv[4];
-        if ((ix0 & 3) == 0) { const uint4 s = *reinterpret_cast<const uint4*>(crow); sv[0] = s.x; sv[1] = s.y; sv[2] = s.z; sv[3] = s.w; }
-        else { sv[0] = crow[0]; sv[1] = crow[1]; sv[2] = crow[2]; sv[3] = crow[3]; }
-        int4 a, b;
-        a.x = (int)((sv[0] & 0xffu) | ((sv[0] & 0xff00u) << 8)); a.y = (int)((sv[0] >> 16) & 0xffu);
-        a.z = (int)((sv[1] & 0xffu) | ((sv[1] & 0xff00u) << 8)); a.w = (int)((sv[1] >> 16) & 0xffu);
-        b.x = (int)((sv[2] & 0xffu) | ((sv[2] & 0xff00u) << 8)); b.y = (int)((sv[2] >> 16) & 0xffu);
-        b.z = (int)((sv[3] & 0xffu) | ((sv[3] & 0xff00u) << 8)); b.w = (int)((sv[3] >> 16) & 0xffu);
-        *reinterpret_cast<int4*>(pyr0 + o * 4) = a; *reinterpret_cast<int4*>(pyr0 + (o + 2) * 4) = b;
-        float4 wv = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-        if (iy >= 0 && iy < ch) {
-            // 4 mask bytes at an arbitrary byte offset: two aligned words (rows are padded to align4, + 256 B slack) and a funnel shift
-            const uint32_t* mrow = reinterpret_cast<const uint32_t*>(mask + (size_t)iy * mask_step + (ix0 & ~3));
-            const uint32_t m = (ix0 & 3) ? __funnelshift_r(mrow[0], mrow[1], 8 * (ix0 & 3)) : mrow[0];
-            wv.x = (float)(m & 0xffu) * (float)(1. / 255.); wv.y = (float)((m >> 8) & 0xffu) * (float)(1. / 255.);
-            wv.z = (float)((m >> 16) & 0xffu) * (float)(1. / 255.); wv.w = (float)(m >> 24) * (float)(1. / 255.);
-        }
-        *reinterpret_cast<float4*>(wp0 + o) = wv;
-        return;
-    }
-    for (int i = 0; i < 4 && x0 + i < width; i++) {
-        const int ix = ix0 + i;
-        const int sx = reflect_edge(ix, cw);
-        const uint32_t s = chip[(size_t)sy * chip_step + sx];                   // BGRA
-        st3(pyr0, o + i, (int)(s & 0xffu), (int)((s >> 8) & 0xffu), (int)((s >> 16) & 0xffu));
-        float wv = 0.0f;
-        if (ix >= 0 && ix < cw && iy >= 0 && iy < ch) wv = (float)mask[(size_t)iy * mask_step + ix] * (float)(1. / 255.);
-        wp0[o + i] = wv;
-    }
-}
-
-// pyrDown of the int16 x3 image and of the f32 weight map, one output pixel per thread
-__global__ void __launch_bounds__(256)
-k7_pyrdown(const short* __restrict__ src, const float* __restrict__ wsrc, int w, int h,
-           short* __restrict__ dst, float* __restrict__ wdst, int dw, int dh)
-{
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
-    if (x >= dw || y >= dh) return;
-    int xs[5], ys[5];
-#pragma unroll
-    for (int k = 0; k < 5; k++) { xs[k] = reflect101(2 * x - 2 + k, w); ys[k] = reflect101(2 * y - 2 + k, h); }
-    int acc[3] = {0, 0, 0};
-    float frow[5];
-    const int kw[5] = {1, 4, 6, 4, 1};
-#pragma unroll
-    for (int r = 0; r < 5; r++) {
-        const size_t rbase = (size_t)ys[r] * w;
-        int ra[3] = {0, 0, 0};
-#pragma unroll
-        for (int k = 0; k < 5; k++) {
-            int p0, p1, p2;
-            ld3(src, rbase + xs[k], p0, p1, p2);
-            ra[0] += kw[k] * p0; ra[1] += kw[k] * p1; ra[2] += kw[k] * p2;
-        }
-        acc[0] += kw[r] * ra[0]; acc[1] += kw[r] * ra[1]; acc[2] += kw[r] * ra[2];
-        if (wsrc) {
-            const float* wr = wsrc + rbase;
-            const float s0 = wr[xs[0]], s1 = wr[xs[1]], s2 = wr[xs[2]], s3 = wr[xs[3]], s4 = wr[xs[4]];
-            frow[r] = s2 * 6.0f + (s1 + s3) * 4.0f + s0 + s4;           // row pass, oracle order
-        }
-    }
-    st3(dst, (size_t)y * dw + x, sat16((acc[0] + 128) >> 8), sat16((acc[1] + 128) >> 8), sat16((acc[2] + 128) >> 8));
-    if (wsrc) {
-        const float v = frow[2] * 6.0f + (frow[1] + frow[3]) * 4.0f + frow[0] + frow[4];   // column pass
-        wdst[(size_t)y * dw + x] = v * (1.0f / 256.0f);
-    }
-}
-
-// Tiled pyrDown: a CTA produces a 64 x 8 output tile from a 131 x 19 source window staged in shared memory with coalesced
-// loads (every source line is requested once instead of ~5 times through L1), split into even / odd columns so that the
-// stride-2 taps become unit-stride, conflict-free LDS.  A thread computes two vertically adjacent outputs: 7 window rows,
-// each filtered horizontally once (integer sums are order free; the f32 passes keep the oracle's expression order).
-constexpr int kPdW = 64, kPdH = 8, kPdCols = 2 * kPdW + 4 /* 131 used, even/odd halves of 66 */, kPdRows = 2 * kPdH + 3;
-__global__ void __launch_bounds__(256)
-k7_pyrdown_tiled(const short* __restrict__ src, const float* __restrict__ wsrc, int w, int h,
-                 short* __restrict__ dst, float* __restrict__ wdst, int dw, int dh)
-{
-    __shared__ int2 sE[kPdRows][kPdCols / 2], sO[kPdRows][kPdCols / 2];      // pixel = 4 x int16 = int2
+    __shared__ int2 sE[kPdRows][kPdCols / 2], sO[kPdRows][kPdCols / 2];
     __shared__ float wE[kPdRows][kPdCols / 2], wO[kPdRows][kPdCols / 2];
+    const BlendChip& B = chips[blockIdx.z];
+    const int dl = sl + 1;
+    const int dcw = B.cw_[dl], dch = B.ch_[dl];
+    const int tx0 = blockIdx.x * kPdW, ty0 = blockIdx.y * kPdH;                 // tile origin inside C_dl
+    if (tx0 >= dcw || ty0 >= dch) return;
+    const int ox0 = B.cx0[dl] + tx0, oy0 = B.cy0[dl] + ty0;                      // ROI level-dl coordinates
+    const int w = B.pw[sl], h = B.ph[sl];
+    const int sx0 = 2 * ox0 - 2, sy0 = 2 * oy0 - 2;                              // window origin (even column)
     const int tid = threadIdx.y * kPdW + threadIdx.x;
-    const int ox0 = blockIdx.x * kPdW, oy0 = blockIdx.y * kPdH;
-    const int sx0 = 2 * ox0 - 2, sy0 = 2 * oy0 - 2;                           // window origin (even column)
-    const bool even_w = (w & 1) == 0;
-    for (int e = tid; e < kPdRows * (kPdCols / 2); e += 256) {               // one (even, odd) column pair per step
+    // source storage (levels >= 1): C_sl, origin (scx0, scy0), pitch scw; coordinates are clamped into it (window positions
+    // that only feed outputs outside C_dl may fall outside C_sl)
+    const int scx0 = L0 ? 0 : B.cx0[sl], scy0 = L0 ? 0 : B.cy0[sl], scw = L0 ? 0 : B.cw_[sl], sch = L0 ? 0 : B.ch_[sl];
+    const short* __restrict__ src = L0 ? nullptr : B.pyr[sl];
+    const float* __restrict__ wsrc = L0 ? nullptr : B.wp[sl];
+    for (int e = tid; e < kPdRows * (kPdCols / 2); e += 256) {
         const int r = e / (kPdCols / 2), j = e - r * (kPdCols / 2);
-        const size_t rb = (size_t)reflect101(sy0 + r, h) * w;
+        const int Y = reflect101(sy0 + r, h);
         const int gx = sx0 + 2 * j;
-        if (even_w && gx >= 0 && gx + 1 < w) {                                // aligned 16-byte pixel pair + 8-byte weight pair
-            const int4 v = *reinterpret_cast<const int4*>(src + (rb + gx) * 4);
-            sE[r][j] = make_int2(v.x, v.y); sO[r][j] = make_int2(v.z, v.w);
-            float2 f = make_float2(0.0f, 0.0f);
-            if (wsrc) f = *reinterpret_cast<const float2*>(wsrc + rb + gx);
-            wE[r][j] = f.x; wO[r][j] = f.y;
-        } else {                                                              // border columns: reflect-101 per pixel
-            const size_t g0 = rb + reflect101(gx, w), g1 = rb + reflect101(gx + 1, w);
-            sE[r][j] = *reinterpret_cast<const int2*>(src + g0 * 4); sO[r][j] = *reinterpret_cast<const int2*>(src + g1 * 4);
-            wE[r][j] = wsrc ? wsrc[g0] : 0.0f; wO[r][j] = wsrc ? wsrc[g1] : 0.0f;
+        if (L0) {
+            const int iy = Y - B.top, sy = reflect_edge(iy, B.ch);
+            const bool yin = iy >= 0 && iy < B.ch;
+            const uint32_t* crow = B.chip + (size_t)sy * B.chip_step;
+            const uint8_t* mrow = B.mask + (size_t)sy * B.mask_step;
+#pragma unroll
+            for (int o = 0; o < 2; o++) {
+                const int X = reflect101(gx + o, w);
+                const int ix = X - B.left, sx = reflect_edge(ix, B.cw);
+                const int2 px = bgra_to_px(__ldg(crow + sx));
+                float wv = 0.0f;
+                if (yin && ix >= 0 && ix < B.cw) wv = (float)__ldg(mrow + ix) * (float)(1. / 255.);
+                if (o == 0) { sE[r][j] = px; wE[r][j] = wv; } else { sO[r][j] = px; wO[r][j] = wv; }
+            }
+        } else {
+            const int yy = min(max(Y - scy0, 0), sch - 1);
+            const int lx = gx - scx0;                                            // even (C origins below the top level are even)
+            if (gx >= 0 && gx + 1 < w && lx >= 0 && lx + 1 < scw) {
+                const size_t o = (size_t)yy * scw + lx;
+                const int4 v = *reinterpret_cast<const int4*>(src + o * 4);
+                sE[r][j] = make_int2(v.x, v.y); sO[r][j] = make_int2(v.z, v.w);
+                const float2 f = *reinterpret_cast<const float2*>(wsrc + o);
+                wE[r][j] = f.x; wO[r][j] = f.y;
+            } else {
+                const int x0c = min(max(reflect101(gx, w) - scx0, 0), scw - 1), x1c = min(max(reflect101(gx + 1, w) - scx0, 0), scw - 1);
+                const size_t g0 = (size_t)yy * scw + x0c, g1 = (size_t)yy * scw + x1c;
+                sE[r][j] = *reinterpret_cast<const int2*>(src + g0 * 4); sO[r][j] = *reinterpret_cast<const int2*>(src + g1 * 4);
+                wE[r][j] = wsrc[g0]; wO[r][j] = wsrc[g1];
+            }
         }
     }
     __syncthreads();
-    const int x = ox0 + threadIdx.x, ty = threadIdx.y;                        // outputs (x, oy0 + 2 ty) and (x, oy0 + 2 ty + 1)
-    if (x >= dw) return;
-    const int i = threadIdx.x;                                                // window column 2 i .. 2 i + 4 = E[i], O[i], E[i+1], O[i+1], E[i+2]
+    const int lx = tx0 + threadIdx.x;                                           // column inside C_dl
+    if (lx >= dcw) return;
+    const int x = ox0 + threadIdx.x, ty = threadIdx.y;                           // outputs (x, oy0 + 2 ty) and (x, oy0 + 2 ty + 1)
+    const int i = threadIdx.x;                                                   // window columns 2 i .. 2 i + 4 = E[i], O[i], E[i+1], O[i+1], E[i+2]
+    const int dw = B.pw[dl];
+    int width0 = (w - 3) / 2 + 1; if (w < 3) width0 = 0; if (width0 > dw) width0 = dw;
+    const bool hvec = x >= 1 && x < 1 + 4 * ((width0 - 1 > 0 ? width0 - 1 : 0) / 4);
+    const bool vvec = x < 4 * (dw / 4);
     int acc[2][3] = {{0, 0, 0}, {0, 0, 0}};
     float F[7];
     const int kw[5] = {1, 4, 6, 4, 1};
 #pragma unroll
     for (int r = 0; r < 7; r++) {
-        const int wr = 4 * ty + r;                                            // window row
+        const int wr = 4 * ty + r;
         const int2 p0 = sE[wr][i], p1 = sO[wr][i], p2 = sE[wr][i + 1], p3 = sO[wr][i + 1], p4 = sE[wr][i + 2];
         int hs[3];
         hs[0] = (short)(p0.x & 0xffff) + (short)(p4.x & 0xffff) + 4 * ((short)(p1.x & 0xffff) + (short)(p3.x & 0xffff)) + 6 * (short)(p2.x & 0xffff);
@@ -184,302 +160,287 @@ k7_pyrdown_tiled(const short* __restrict__ src, const float* __restrict__ wsrc, 
             if (r < 5) acc[0][c] += kw[r] * hs[c];
             if (r >= 2) acc[1][c] += kw[r - 2] * hs[c];
         }
-        if (wsrc) F[r] = wE[wr][i + 1] * 6.0f + (wO[wr][i] + wO[wr][i + 1]) * 4.0f + wE[wr][i] + wE[wr][i + 2];     // row pass, oracle order
+        const float s0 = wE[wr][i], s1 = wO[wr][i], s2 = wE[wr][i + 1], s3 = wO[wr][i + 1], s4 = wE[wr][i + 2];
+        F[r] = hvec ? s2 * 6.0f + ((s1 + s3) * 4.0f + (s0 + s4)) : s2 * 6.0f + (s1 + s3) * 4.0f + s0 + s4;
     }
+    short* __restrict__ dst = B.pyr[dl];
+    float* __restrict__ wdst = B.wp[dl];
 #pragma unroll
     for (int o = 0; o < 2; o++) {
-        const int y = oy0 + 2 * ty + o;
-        if (y >= dh) break;
-        st3(dst, (size_t)y * dw + x, sat16((acc[o][0] + 128) >> 8), sat16((acc[o][1] + 128) >> 8), sat16((acc[o][2] + 128) >> 8));
-        if (wsrc) {
-            const float v = F[2 + 2 * o] * 6.0f + (F[1 + 2 * o] + F[3 + 2 * o]) * 4.0f + F[0 + 2 * o] + F[4 + 2 * o];  // column pass
-            wdst[(size_t)y * dw + x] = v * (1.0f / 256.0f);
-        }
+        const int ly = ty0 + 2 * ty + o;
+        if (ly >= dch) break;
+        const size_t di = (size_t)ly * dcw + lx;
+        *reinterpret_cast<int2*>(dst + di * 4) = pack3(sat16((acc[o][0] + 128) >> 8), sat16((acc[o][1] + 128) >> 8), sat16((acc[o][2] + 128) >> 8));
+        const float r0 = F[2 * o], r1 = F[1 + 2 * o], r2 = F[2 + 2 * o], r3 = F[3 + 2 * o], r4 = F[4 + 2 * o];
+        const float v = vvec ? ((r1 + r3) + r2) * 4.0f + ((r0 + r4) + (r2 + r2)) : r2 * 6.0f + (r1 + r3) * 4.0f + r0 + r4;
+        wdst[di] = v * (1.0f / 256.0f);
     }
 }
 
-// value of pyrUp(lo) at (x, y) of the 2x larger level; lo is lw x lh, 3 channels
-__device__ __forceinline__ void pyrup_at(const short* __restrict__ lo, int lw, int lh, int x, int y, int out[3])
+// pyrUp of a coarser level for the 4 x 2 pixel block made of the quads (c0, cy) and (c0 + 1, cy): up[dy][px][channel].
+// Per axis: even sample s[i-1] + 6 s[i] + s[i+1], odd sample 4 (s[i] + s[i+1]); reflect-101 at the near edge, replicate at
+// the far edge; (sum + 32) >> 6, saturated.  lo: storage with origin (ox, oy) and `pitch` pixels per row; lw x lh = full level.
+__device__ __forceinline__ void pyrup_2quads(const short* __restrict__ lo, int pitch, int ox, int oy, int lw, int lh, int c0, int cy, int up[2][4][3])
 {
-    const int cx = x >> 1, cy = y >> 1;
-    const int xm = (cx == 0) ? (lw > 1 ? 1 : 0) : cx - 1, xp = (cx == lw - 1) ? lw - 1 : cx + 1;
-    const int ym = (cy == 0) ? (lh > 1 ? 1 : 0) : cy - 1, yp = (cy == lh - 1) ? lh - 1 : cy + 1;
-    // per axis: even sample s[i-1] + 6 s[i] + s[i+1], odd sample 4 (s[i] + s[i+1])
-    const int wx0 = (x & 1) ? 0 : 1, wx1 = (x & 1) ? 4 : 6, wx2 = (x & 1) ? 4 : 1;
-    const int wy0 = (y & 1) ? 0 : 1, wy1 = (y & 1) ? 4 : 6, wy2 = (y & 1) ? 4 : 1;
-    const int rows[3] = {ym, cy, yp}, wy[3] = {wy0, wy1, wy2};
-    int acc[3] = {0, 0, 0};
+    const int c1 = min(c0 + 1, lw - 1);
+    const int cols[4] = {c0 == 0 ? (lw > 1 ? 1 : 0) : c0 - 1, c0, c1, c1 == lw - 1 ? lw - 1 : c1 + 1};
+    const int rows[3] = {cy == 0 ? (lh > 1 ? 1 : 0) : cy - 1, cy, cy == lh - 1 ? lh - 1 : cy + 1};
+    int he[2][3][3], ho[2][3][3];                  // [quad][row][channel]: even-x sum a + 6 b + c, odd-x sum 4 (b + c)
 #pragma unroll
     for (int r = 0; r < 3; r++) {
-        if (wy[r] == 0) continue;
-        const size_t rbase = (size_t)rows[r] * lw;
-        int a[3], b[3], c[3];
-        if (wx0) ld3(lo, rbase + xm, a[0], a[1], a[2]); else { a[0] = a[1] = a[2] = 0; }
-        ld3(lo, rbase + cx, b[0], b[1], b[2]);
-        ld3(lo, rbase + xp, c[0], c[1], c[2]);
+        const short* rowp = lo + ((ptrdiff_t)(rows[r] - oy) * pitch - ox) * 4;
+        int v[4][3];
 #pragma unroll
-        for (int k = 0; k < 3; k++) acc[k] += wy[r] * (wx0 * a[k] + wx1 * b[k] + wx2 * c[k]);
-    }
-#pragma unroll
-    for (int k = 0; k < 3; k++) out[k] = sat16((acc[k] + 32) >> 6);
-}
-
-// Laplacian level (pyr[i] - pyrUp(pyr[i+1]), saturating; the top level is the Gaussian itself) times the
-// weight, accumulated into the canvas pyramid: dst += short(lap * w), wsum += w
-__global__ void __launch_bounds__(256)
-k7_lap_accumulate(const short* __restrict__ cur, const short* __restrict__ next, const float* __restrict__ wcur,
-                  int w, int h, int nw, int nh, short* __restrict__ dlap, float* __restrict__ dwsum, int dst_w, int x_tl, int y_tl)
-{
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
-    if (x >= w || y >= h) return;
-    // Seam masks give every canvas pixel one owner, so most of a fed chip has weight exactly 0 (about 2/3 of level 0
-    // for a 3x-covered strip): dst + short(lap * 0) == dst and wsum + 0 == wsum, the read-modify-write is skipped.
-    if (wcur[(size_t)y * w + x] == 0.0f) return;
-    int lap[3];
-    ld3(cur, (size_t)y * w + x, lap[0], lap[1], lap[2]);
-    if (next) {
-        int up[3];
-        pyrup_at(next, nw, nh, x, y, up);
-#pragma unroll
-        for (int k = 0; k < 3; k++) lap[k] = sat16(lap[k] - up[k]);
-    }
-    const float wv = wcur[(size_t)y * w + x];
-    const size_t di = (size_t)(y + y_tl) * dst_w + (x + x_tl);
-    int d[3];
-    ld3(dlap, di, d[0], d[1], d[2]);
-#pragma unroll
-    for (int k = 0; k < 3; k++) d[k] = (short)(d[k] + (short)__float2int_rz((float)lap[k] * wv));
-    st3(dlap, di, d[0], d[1], d[2]);
-    dwsum[di] += wv;
-}
-
-// blend(): dst = short(dst / (wsum + 1e-5)) per level, then restoreImageFromLaplacePyr: hi = sat(pyrUp(lo) + hi) from the
-// top down.  The normalisation of level i is fused into the collapse step that consumes it (lo is already final), and
-// at level 0 the step writes the u8 mosaic directly: crop, zero where wsum <= 1e-5, convertTo(CV_8U) (saturate).
-__device__ __forceinline__ void normalized3(const short* lap, const float* wsum, size_t i, int d[3])
-{
-    const float wv = wsum[i] + 1e-5f;
-    ld3(lap, i, d[0], d[1], d[2]);
-#pragma unroll
-    for (int k = 0; k < 3; k++) d[k] = (short)__float2int_rz((float)d[k] / wv);
-}
-
-// Same for the levels that have a coarser level below them, one 2 x 2 quad of pixels per thread: the four pixels share
-// the 3 x 3 neighbourhood of the coarser level (9 loads instead of 9 + 6 + 6 + 4) and pyrUp separates into three horizontal
-// sums per parity and a vertical combination; cur / dst / weights move as aligned 16- and 8-byte vectors.  Level sizes and
-// the paste offsets (x_tl, y_tl) are even below the top level (ROIs are aligned to 2^bands), so quads tile exactly.
-__global__ void __launch_bounds__(256)
-k7_lap_accumulate_quad(const short* __restrict__ cur, const short* __restrict__ next, const float* __restrict__ wcur,
-                       int w, int h, int nw, int nh, short* __restrict__ dlap, float* __restrict__ dwsum, int dst_w, int x_tl, int y_tl)
-{
-    const int cx = blockIdx.x * blockDim.x + threadIdx.x, cy = blockIdx.y;          // quad index = coordinates in the coarser level
-    const int x = 2 * cx, y = 2 * cy;
-    if (x >= w || y >= h) return;
-    const float2 w0 = *reinterpret_cast<const float2*>(wcur + (size_t)y * w + x);
-    const float2 w1 = *reinterpret_cast<const float2*>(wcur + (size_t)(y + 1) * w + x);
-    if (w0.x == 0.0f && w0.y == 0.0f && w1.x == 0.0f && w1.y == 0.0f) return;       // dst + short(lap * 0) == dst, wsum + 0 == wsum
-    // pyrUp border rules (see pyrup_at): reflect-101 at the near edge, replicate at the far edge
-    const int xm = (cx == 0) ? (nw > 1 ? 1 : 0) : cx - 1, xp = (cx == nw - 1) ? nw - 1 : cx + 1;
-    const int ym = (cy == 0) ? (nh > 1 ? 1 : 0) : cy - 1, yp = (cy == nh - 1) ? nh - 1 : cy + 1;
-    const int rows[3] = {ym, cy, yp};
-    int he[3][3], ho[3][3];                        // [row][channel]: even-x sum a + 6 b + c, odd-x sum 4 (b + c)
-#pragma unroll
-    for (int r = 0; r < 3; r++) {
-        const size_t rb = (size_t)rows[r] * nw;
-        int a[3], b[3], c[3];
-        ld3(next, rb + xm, a[0], a[1], a[2]); ld3(next, rb + cx, b[0], b[1], b[2]); ld3(next, rb + xp, c[0], c[1], c[2]);
-#pragma unroll
-        for (int k = 0; k < 3; k++) { he[r][k] = a[k] + 6 * b[k] + c[k]; ho[r][k] = 4 * (b[k] + c[k]); }
-    }
-    const float wq[2][2] = {{w0.x, w0.y}, {w1.x, w1.y}};
-#pragma unroll
-    for (int dy = 0; dy < 2; dy++) {
-        const int4 c4 = *reinterpret_cast<const int4*>(cur + ((size_t)(y + dy) * w + x) * 4);
-        const size_t di = (size_t)(y + dy + y_tl) * dst_w + (x + x_tl);
-        int4 d4 = *reinterpret_cast<const int4*>(dlap + di * 4);
-        float2 ws = *reinterpret_cast<const float2*>(dwsum + di);
-        const int cw2[2][2] = {{c4.x, c4.y}, {c4.z, c4.w}};
-        int dw2[2][2] = {{d4.x, d4.y}, {d4.z, d4.w}};
-#pragma unroll
-        for (int dx = 0; dx < 2; dx++) {
-            const int cc[3] = {(short)(cw2[dx][0] & 0xffff), cw2[dx][0] >> 16, (short)(cw2[dx][1] & 0xffff)};
-            int dd[3] = {(short)(dw2[dx][0] & 0xffff), dw2[dx][0] >> 16, (short)(dw2[dx][1] & 0xffff)};
-#pragma unroll
-            for (int k = 0; k < 3; k++) {
-                const int h0 = dx ? ho[0][k] : he[0][k], h1 = dx ? ho[1][k] : he[1][k], h2 = dx ? ho[2][k] : he[2][k];
-                const int acc = dy ? 4 * (h1 + h2) : h0 + 6 * h1 + h2;
-                const int lap = sat16(cc[k] - sat16((acc + 32) >> 6));
-                dd[k] = (short)(dd[k] + (short)__float2int_rz((float)lap * wq[dy][dx]));
-            }
-            dw2[dx][0] = (dd[0] & 0xffff) | (dd[1] << 16); dw2[dx][1] = dd[2] & 0xffff;
-        }
-        d4.x = dw2[0][0]; d4.y = dw2[0][1]; d4.z = dw2[1][0]; d4.w = dw2[1][1];
-        ws.x += wq[dy][0]; ws.y += wq[dy][1];
-        *reinterpret_cast<int4*>(dlap + di * 4) = d4;
-        *reinterpret_cast<float2*>(dwsum + di) = ws;
-    }
-}
-
-__global__ void __launch_bounds__(256)
-k7_normalize(short* __restrict__ dlap, const float* __restrict__ dwsum, size_t n)        // top level only
-{
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    int d[3];
-    normalized3(dlap, dwsum, i, d);
-    st3(dlap, i, d[0], d[1], d[2]);
-}
-
-// pyrUp of the coarser level for the 2 x 2 quad (cx, cy): up[dy][dx][channel]  (same separation as k7_lap_accumulate_quad)
-__device__ __forceinline__ void pyrup_quad(const short* __restrict__ lo, int lw, int lh, int cx, int cy, int up[2][2][3])
-{
-    const int xm = (cx == 0) ? (lw > 1 ? 1 : 0) : cx - 1, xp = (cx == lw - 1) ? lw - 1 : cx + 1;
-    const int ym = (cy == 0) ? (lh > 1 ? 1 : 0) : cy - 1, yp = (cy == lh - 1) ? lh - 1 : cy + 1;
-    const int rows[3] = {ym, cy, yp};
-    int he[3][3], ho[3][3];
-#pragma unroll
-    for (int r = 0; r < 3; r++) {
-        const size_t rb = (size_t)rows[r] * lw;
-        int a[3], b[3], c[3];
-        ld3(lo, rb + xm, a[0], a[1], a[2]); ld3(lo, rb + cx, b[0], b[1], b[2]); ld3(lo, rb + xp, c[0], c[1], c[2]);
-#pragma unroll
-        for (int k = 0; k < 3; k++) { he[r][k] = a[k] + 6 * b[k] + c[k]; ho[r][k] = 4 * (b[k] + c[k]); }
-    }
-#pragma unroll
-    for (int dx = 0; dx < 2; dx++)
+        for (int j = 0; j < 4; j++) unpack3(*reinterpret_cast<const int2*>(rowp + (ptrdiff_t)cols[j] * 4), v[j][0], v[j][1], v[j][2]);
 #pragma unroll
         for (int k = 0; k < 3; k++) {
-            const int h0 = dx ? ho[0][k] : he[0][k], h1 = dx ? ho[1][k] : he[1][k], h2 = dx ? ho[2][k] : he[2][k];
-            up[0][dx][k] = sat16((h0 + 6 * h1 + h2 + 32) >> 6);
-            up[1][dx][k] = sat16((4 * (h1 + h2) + 32) >> 6);
+            he[0][r][k] = v[0][k] + 6 * v[1][k] + v[2][k]; ho[0][r][k] = 4 * (v[1][k] + v[2][k]);
+            he[1][r][k] = v[1][k] + 6 * v[2][k] + v[3][k]; ho[1][r][k] = 4 * (v[2][k] + v[3][k]);
         }
+    }
+#pragma unroll
+    for (int q = 0; q < 2; q++)
+#pragma unroll
+        for (int dx = 0; dx < 2; dx++)
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                const int h0 = dx ? ho[q][0][k] : he[q][0][k], h1 = dx ? ho[q][1][k] : he[q][1][k], h2 = dx ? ho[q][2][k] : he[q][2][k];
+                up[0][2 * q + dx][k] = sat16((h0 + 6 * h1 + h2 + 32) >> 6);
+                up[1][2 * q + dx][k] = sat16((4 * (h1 + h2) + 32) >> 6);
+            }
 }
 
-// collapse step for even level sizes: one 2 x 2 quad per thread
-__global__ void __launch_bounds__(256)
-k7_collapse_quad(const short* __restrict__ lo, int lw, int lh, short* __restrict__ hi, const float* __restrict__ hi_wsum, int w, int h)
+// Sorted list of the chips whose contribution rectangle U_level intersects the CTA's tile, for chips [base, base + 256):
+// one candidate per thread, compacted in index order through warp ballots.  All 256 threads must call it.
+__device__ __forceinline__ int tile_chip_list(const BlendChip* __restrict__ chips, int n, int base, int level, int tx0, int ty0, int tx1, int ty1,
+                                              int* list, int* wcount)
 {
-    const int cx = blockIdx.x * blockDim.x + threadIdx.x, cy = blockIdx.y;
-    const int x = 2 * cx, y = 2 * cy;
-    if (x >= w || y >= h) return;
-    int up[2][2][3];
-    pyrup_quad(lo, lw, lh, cx, cy, up);
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int c = base + tid;
+    bool hit = false;
+    if (c < n) {
+        const BlendChip& B = chips[c];
+        const int ofx = B.tlx >> level, ofy = B.tly >> level;
+        hit = B.ux0[level] + ofx < tx1 && B.ux1[level] + ofx > tx0 && B.uy0[level] + ofy < ty1 && B.uy1[level] + ofy > ty0;
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, hit);
+    if (lane == 0) wcount[warp] = __popc(m);
+    __syncthreads();
+    int off = 0, total = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) { const int v = wcount[k]; if (k < warp) off += v; total += v; }
+    if (hit) list[off + __popc(m & ((1u << lane) - 1u))] = c;
+    __syncthreads();
+    return total;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// One canvas level below the top (it has a coarser level): a thread owns a 4 x 2 pixel block (two quads).
+//   for every chip touching the tile, in index order:  lap = pyr_i - pyrUp(pyr_{i+1});  d += short(lap * w);  wsum += w
+//   v = short(d / (wsum + 1e-5));  final = sat(pyrUp(final_{i+1}) + v)
+// L0: pyr_0 is the chip itself (a non-zero weight implies the pixel lies inside the chip), w = mask / 255, and the result is
+// written as the cropped u8 mosaic + mask (zero where wsum <= 1e-5; convertTo(CV_8U) saturates).
+template <bool L0>
+__global__ void __launch_bounds__(256)
+k7_level(const BlendChip* __restrict__ chips, const LevelArgs A)
+{
+    __shared__ int list[256];
+    __shared__ int wcount[8];
+    const int level = A.level;
+    const int tx0 = (A.sx0 & ~3) + blockIdx.x * 128, ty0 = A.sy0 + blockIdx.y * 16;
+    const int X = tx0 + 4 * threadIdx.x, Y = ty0 + 2 * threadIdx.y;               // this thread's block (canvas level coordinates)
+    const bool live = X + 4 > A.sx0 && X < A.sx1 && Y < A.sy1;
+    int d[2][4][3];
+    float ws[2][4];
 #pragma unroll
     for (int dy = 0; dy < 2; dy++)
 #pragma unroll
-        for (int dx = 0; dx < 2; dx++) {
-            int d[3];
-            const size_t i = (size_t)(y + dy) * w + x + dx;
-            normalized3(hi, hi_wsum, i, d);
-            st3(hi, i, sat16(up[dy][dx][0] + d[0]), sat16(up[dy][dx][1] + d[1]), sat16(up[dy][dx][2] + d[2]));
-        }
-}
+        for (int p = 0; p < 4; p++) { ws[dy][p] = 0.0f; d[dy][p][0] = d[dy][p][1] = d[dy][p][2] = 0; }
 
-__global__ void __launch_bounds__(256)
-k7_collapse(const short* __restrict__ lo, int lw, int lh, short* __restrict__ hi, const float* __restrict__ hi_wsum, int w, int h)
-{
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
-    if (x >= w || y >= h) return;
-    int up[3], d[3];
-    pyrup_at(lo, lw, lh, x, y, up);
-    normalized3(hi, hi_wsum, (size_t)y * w + x, d);
-    st3(hi, (size_t)y * w + x, sat16(up[0] + d[0]), sat16(up[1] + d[1]), sat16(up[2] + d[2]));
-}
-
-// last step (level 0) fused with the output: rows [oy0, oy1) x columns [0, cw) of the padded level go to the mosaic.
-// A thread owns a 4 x 2 block (two quads): per row the 12 output bytes are three aligned words when the mosaic row pitch
-// allows it.  oy0 is even (band edges are multiples of 32).
-__global__ void __launch_bounds__(256)
-k7_collapse_output(const short* __restrict__ lo, int lw, int lh, const short* __restrict__ hi, const float* __restrict__ hi_wsum, int w, int h,
-                   int oy0, int oy1, int cw, uint8_t* __restrict__ out, uint8_t* __restrict__ out_mask)
-{
-    const int x0 = 4 * (blockIdx.x * blockDim.x + threadIdx.x), y0 = oy0 + 2 * blockIdx.y;
-    if (x0 >= cw || y0 >= oy1) return;
-    uint32_t px[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};   // B | G << 8 | R << 16
-    uint32_t mk[2] = {0, 0};
+    for (int base = 0; base < A.n_chips; base += 256) {
+        const int total = tile_chip_list(chips, A.n_chips, base, level, tx0, ty0, tx0 + 128, ty0 + 16, list, wcount);
+        for (int e = 0; e < total; e++) {
+            const BlendChip& B = chips[list[e]];
+            const int x = X - (B.tlx >> level), y = Y - (B.tly >> level);         // ROI level coordinates of the block (even)
+            const int ux0 = B.ux0[level], uy0 = B.uy0[level], ux1 = B.ux1[level], uy1 = B.uy1[level];
+            if (!live || x + 4 <= ux0 || x >= ux1 || y + 2 <= uy0 || y >= uy1) continue;
+            float w[2][4];
+            bool any = false;
+            if (L0) {
+                const int ix = x - B.left, iy = y - B.top;                        // chip coordinates
 #pragma unroll
-    for (int q = 0; q < 2; q++) {
-        const int x = x0 + 2 * q;
-        if (x >= w) break;                              // w is even and >= cw
-        float ws[2][2];
-        bool any = false;
+                for (int dy = 0; dy < 2; dy++) {
+                    const bool yin = y + dy >= uy0 && y + dy < uy1;
+                    const uint8_t* mrow = B.mask + (ptrdiff_t)(iy + dy) * B.mask_step;
+                    uint32_t m = 0;
+                    if (yin) {
+                        if (x >= ux0 && x + 4 <= ux1) {
+                            // 4 mask bytes at an arbitrary byte offset: two aligned words (rows are padded to align4, + 256 B slack) and a funnel shift
+                            const uint32_t* mw = reinterpret_cast<const uint32_t*>(mrow + (ix & ~3));
+                            m = (ix & 3) ? __funnelshift_r(__ldg(mw), __ldg(mw + 1), 8 * (ix & 3)) : __ldg(mw);
+                        } else {
 #pragma unroll
-        for (int dy = 0; dy < 2; dy++) {
-            const float2 f = *reinterpret_cast<const float2*>(hi_wsum + (size_t)(y0 + dy) * w + x);
-            ws[dy][0] = f.x; ws[dy][1] = f.y; any = any || f.x > 1e-5f || f.y > 1e-5f;
-        }
-        if (!any) continue;
-        int up[2][2][3];
-        pyrup_quad(lo, lw, lh, x >> 1, y0 >> 1, up);
+                            for (int p = 0; p < 4; p++) if (x + p >= ux0 && x + p < ux1) m |= (uint32_t)__ldg(mrow + ix + p) << (8 * p);
+                        }
+                    }
 #pragma unroll
-        for (int dy = 0; dy < 2; dy++)
+                    for (int p = 0; p < 4; p++) { w[dy][p] = (float)((m >> (8 * p)) & 0xffu) * (float)(1. / 255.); any = any || ((m >> (8 * p)) & 0xffu); }
+                }
+            } else {
+                const float* __restrict__ wp = B.wp[level];
+                const int lx = x - B.cx0[level], ly = y - B.cy0[level], pitch = B.cw_[level];
 #pragma unroll
-            for (int dx = 0; dx < 2; dx++) {
-                if (!(ws[dy][dx] > 1e-5f)) continue;
-                int d[3];
-                normalized3(hi, hi_wsum, (size_t)(y0 + dy) * w + x + dx, d);
-                const int b = max(0, min(255, (int)sat16(up[dy][dx][0] + d[0]))), g = max(0, min(255, (int)sat16(up[dy][dx][1] + d[1]))),
-                          r = max(0, min(255, (int)sat16(up[dy][dx][2] + d[2])));
-                px[dy][2 * q + dx] = (uint32_t)b | ((uint32_t)g << 8) | ((uint32_t)r << 16);
-                mk[dy] |= 0xffu << (8 * (2 * q + dx));
+                for (int dy = 0; dy < 2; dy++) {
+                    const bool yin = y + dy >= uy0 && y + dy < uy1;
+#pragma unroll
+                    for (int p = 0; p < 4; p++) {
+                        float v = 0.0f;
+                        if (yin && x + p >= ux0 && x + p < ux1) v = wp[(ptrdiff_t)(ly + dy) * pitch + lx + p];
+                        w[dy][p] = v; any = any || v != 0.0f;
+                    }
+                }
             }
+            if (!any) continue;                                                   // dst + short(lap * 0) == dst, wsum + 0 == wsum
+            int up[2][4][3];
+            pyrup_2quads(B.pyr[level + 1], B.cw_[level + 1], B.cx0[level + 1], B.cy0[level + 1], B.pw[level + 1], B.ph[level + 1], x >> 1, y >> 1, up);
+#pragma unroll
+            for (int dy = 0; dy < 2; dy++)
+#pragma unroll
+                for (int p = 0; p < 4; p++) {
+                    const float wv = w[dy][p];
+                    if (wv == 0.0f) continue;
+                    int c3[3];
+                    if (L0) {
+                        const uint32_t s = __ldg(B.chip + (ptrdiff_t)(y + dy - B.top) * B.chip_step + (x + p - B.left));
+                        c3[0] = (int)(s & 0xffu); c3[1] = (int)((s >> 8) & 0xffu); c3[2] = (int)((s >> 16) & 0xffu);
+                    } else {
+                        unpack3(*reinterpret_cast<const int2*>(B.pyr[level] + ((ptrdiff_t)(y + dy - B.cy0[level]) * B.cw_[level] + (x + p - B.cx0[level])) * 4),
+                                c3[0], c3[1], c3[2]);
+                    }
+#pragma unroll
+                    for (int k = 0; k < 3; k++) {
+                        const int lap = sat16(c3[k] - up[dy][p][k]);
+                        d[dy][p][k] = (short)(d[dy][p][k] + (short)__float2int_rz((float)lap * wv));
+                    }
+                    ws[dy][p] += wv;
+                }
+        }
+        __syncthreads();
     }
+    if (!live) return;
+    int up[2][4][3];
+    pyrup_2quads(A.nxt, A.nxt_pitch, A.nxt_x0, A.nxt_y0, A.nxt_w, A.nxt_h, X >> 1, Y >> 1, up);
 #pragma unroll
     for (int dy = 0; dy < 2; dy++) {
-        if (y0 + dy >= oy1) break;
-        const size_t o = (size_t)(2 * blockIdx.y + dy) * cw + x0;
-        if (x0 + 4 <= cw && (cw & 3) == 0) {          // 12 bytes = 3 words, rows are 4-byte aligned
-            uint32_t* o32 = reinterpret_cast<uint32_t*>(out + o * 3);
-            o32[0] = px[dy][0] | (px[dy][1] << 24); o32[1] = (px[dy][1] >> 8) | (px[dy][2] << 16); o32[2] = (px[dy][2] >> 16) | (px[dy][3] << 8);
-            *reinterpret_cast<uint32_t*>(out_mask + o) = mk[dy];
+        const int yy = Y + dy;
+        int v[4][3];
+#pragma unroll
+        for (int p = 0; p < 4; p++) {
+            const float wv = ws[dy][p] + 1e-5f;
+#pragma unroll
+            for (int k = 0; k < 3; k++) v[p][k] = sat16(up[dy][p][k] + (short)__float2int_rz((float)d[dy][p][k] / wv));
+        }
+        if (!L0) {
+            if (yy >= A.sy1) break;
+            short* frow = A.fin + ((ptrdiff_t)(yy - A.fin_y0) * A.fin_pitch - A.fin_x0) * 4;
+            if (X >= A.sx0 && X + 4 <= A.sx1) {
+                const int2 a = pack3(v[0][0], v[0][1], v[0][2]), b = pack3(v[1][0], v[1][1], v[1][2]);
+                const int2 c = pack3(v[2][0], v[2][1], v[2][2]), e = pack3(v[3][0], v[3][1], v[3][2]);
+                *reinterpret_cast<int4*>(frow + (ptrdiff_t)X * 4) = make_int4(a.x, a.y, b.x, b.y);
+                *reinterpret_cast<int4*>(frow + (ptrdiff_t)(X + 2) * 4) = make_int4(c.x, c.y, e.x, e.y);
+            } else {
+#pragma unroll
+                for (int p = 0; p < 4; p++)
+                    if (X + p >= A.sx0 && X + p < A.sx1) *reinterpret_cast<int2*>(frow + (ptrdiff_t)(X + p) * 4) = pack3(v[p][0], v[p][1], v[p][2]);
+            }
         } else {
-            for (int i = 0; i < 4 && x0 + i < cw; i++) {
-                out[(o + i) * 3] = (uint8_t)px[dy][i]; out[(o + i) * 3 + 1] = (uint8_t)(px[dy][i] >> 8); out[(o + i) * 3 + 2] = (uint8_t)(px[dy][i] >> 16);
-                out_mask[o + i] = (uint8_t)(mk[dy] >> (8 * i));
+            if (yy < A.oy0 || yy >= A.oy1) continue;
+            uint32_t px[4], mk = 0;
+#pragma unroll
+            for (int p = 0; p < 4; p++) {
+                px[p] = 0;
+                if (ws[dy][p] > 1e-5f) {
+                    px[p] = (uint32_t)max(0, min(255, v[p][0])) | ((uint32_t)max(0, min(255, v[p][1])) << 8) | ((uint32_t)max(0, min(255, v[p][2])) << 16);
+                    mk |= 0xffu << (8 * p);
+                }
+            }
+            const size_t o = (size_t)yy * A.cw + X;
+            if (X >= A.ox0 && X + 4 <= A.ox1 && (A.cw & 3) == 0) {                // 12 bytes = 3 aligned words (X and the row pitch are multiples of 4)
+                uint32_t* o32 = reinterpret_cast<uint32_t*>(A.out + o * 3);
+                o32[0] = px[0] | (px[1] << 24); o32[1] = (px[1] >> 8) | (px[2] << 16); o32[2] = (px[2] >> 16) | (px[3] << 8);
+                *reinterpret_cast<uint32_t*>(A.out_mask + o) = mk;
+            } else {
+#pragma unroll
+                for (int p = 0; p < 4; p++) {
+                    if (X + p < A.ox0 || X + p >= A.ox1) continue;
+                    A.out[(o + p) * 3] = (uint8_t)px[p]; A.out[(o + p) * 3 + 1] = (uint8_t)(px[p] >> 8); A.out[(o + p) * 3 + 2] = (uint8_t)(px[p] >> 16);
+                    A.out_mask[o + p] = (uint8_t)(mk >> (8 * p));
+                }
             }
         }
     }
 }
 
-// no bands: the canvas level 0 is the (normalised) image itself
+// The top level (its Laplacian is the Gaussian itself, no coarser level), one pixel per thread; tile 32 x 8.
+// L0 (no bands at all): the level is the image, the result is the mosaic.
+template <bool L0>
 __global__ void __launch_bounds__(256)
-k7_output(const short* __restrict__ lap0, const float* __restrict__ w0, int W, int cw, int ch,
-          uint8_t* __restrict__ out, uint8_t* __restrict__ out_mask)
+k7_level_top(const BlendChip* __restrict__ chips, const LevelArgs A)
 {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
-    if (x >= cw || y >= ch) return;
-    const bool m = w0[(size_t)y * W + x] > 1e-5f;
-    int s[3];
-    ld3(lap0, (size_t)y * W + x, s[0], s[1], s[2]);
-    uint8_t* d = out + ((size_t)y * cw + x) * 3;
+    __shared__ int list[256];
+    __shared__ int wcount[8];
+    const int level = A.level;
+    const int tx0 = A.sx0 + blockIdx.x * 32, ty0 = A.sy0 + blockIdx.y * 8;
+    const int X = tx0 + threadIdx.x, Y = ty0 + threadIdx.y;
+    const bool live = X < A.sx1 && Y < A.sy1;
+    int d[3] = {0, 0, 0};
+    float ws = 0.0f;
+    for (int base = 0; base < A.n_chips; base += 256) {
+        const int total = tile_chip_list(chips, A.n_chips, base, level, tx0, ty0, tx0 + 32, ty0 + 8, list, wcount);
+        for (int e = 0; e < total; e++) {
+            const BlendChip& B = chips[list[e]];
+            const int x = X - (B.tlx >> level), y = Y - (B.tly >> level);
+            if (!live || x < B.ux0[level] || x >= B.ux1[level] || y < B.uy0[level] || y >= B.uy1[level]) continue;
+            float wv; int c3[3];
+            if (L0) {
+                const int ix = x - B.left, iy = y - B.top;
+                wv = (float)B.mask[(ptrdiff_t)iy * B.mask_step + ix] * (float)(1. / 255.);
+                if (wv == 0.0f) continue;
+                const uint32_t s = B.chip[(ptrdiff_t)iy * B.chip_step + ix];
+                c3[0] = (int)(s & 0xffu); c3[1] = (int)((s >> 8) & 0xffu); c3[2] = (int)((s >> 16) & 0xffu);
+            } else {
+                const ptrdiff_t o = (ptrdiff_t)(y - B.cy0[level]) * B.cw_[level] + (x - B.cx0[level]);
+                wv = B.wp[level][o];
+                if (wv == 0.0f) continue;
+                unpack3(*reinterpret_cast<const int2*>(B.pyr[level] + o * 4), c3[0], c3[1], c3[2]);
+            }
 #pragma unroll
-    for (int k = 0; k < 3; k++) d[k] = m ? (uint8_t)max(0, min(255, s[k])) : 0;
-    out_mask[(size_t)y * cw + x] = m ? 255 : 0;
+            for (int k = 0; k < 3; k++) d[k] = (short)(d[k] + (short)__float2int_rz((float)c3[k] * wv));
+            ws += wv;
+        }
+        __syncthreads();
+    }
+    if (!live) return;
+    int v[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) v[k] = (short)__float2int_rz((float)d[k] / (ws + 1e-5f));
+    if (!L0) {
+        *reinterpret_cast<int2*>(A.fin + ((ptrdiff_t)(Y - A.fin_y0) * A.fin_pitch + (X - A.fin_x0)) * 4) = pack3(v[0], v[1], v[2]);
+    } else if (X >= A.ox0 && X < A.ox1 && Y >= A.oy0 && Y < A.oy1) {
+        const bool m = ws > 1e-5f;
+        uint8_t* o = A.out + ((size_t)Y * A.cw + X) * 3;
+#pragma unroll
+        for (int k = 0; k < 3; k++) o[k] = m ? (uint8_t)max(0, min(255, v[k])) : 0;
+        A.out_mask[(size_t)Y * A.cw + X] = m ? 255 : 0;
+    }
 }
 
 void free_ws(BlendWs* ws)
 {
     if (!ws) return;
-    for (int i = 0; i <= kMaxBands; i++) { cudaFree(ws->dlap[i]); cudaFree(ws->dw[i]); cudaFree(ws->pyr[i]); cudaFree(ws->wp[i]); }
+    cudaFree(ws->d_chips); cudaFree(ws->d_scratch);
+    for (int i = 0; i <= kMaxBands; i++) cudaFree(ws->d_fin[i]);
     delete ws;
-}
-
-inline int pad_to(int v, int nb) { return v + ((1 << nb) - v % (1 << nb)) % (1 << nb); }
-
-struct Roi { int tlx, tly, width, height, top, left; };
-Roi feed_roi(int tl_x, int tl_y, int cw, int ch, int W, int H, int nb)
-{
-    // MultiBandBlender::feed: gap = 3 * 2^bands, corners aligned to 2^bands, shifted back inside the canvas
-    const int gap = 3 * (1 << nb);
-    int tlx = tl_x - gap > 0 ? tl_x - gap : 0, tly = tl_y - gap > 0 ? tl_y - gap : 0;
-    int brx = tl_x + cw + gap < W ? tl_x + cw + gap : W, bry = tl_y + ch + gap < H ? tl_y + ch + gap : H;
-    tlx = (tlx >> nb) << nb; tly = (tly >> nb) << nb;
-    int width = pad_to(brx - tlx, nb), height = pad_to(bry - tly, nb);
-    brx = tlx + width; bry = tly + height;
-    const int dy = bry - H > 0 ? bry - H : 0, dx = brx - W > 0 ? brx - W : 0;
-    tlx -= dx; tly -= dy;
-    Roi r; r.tlx = tlx; r.tly = tly; r.width = width; r.height = height; r.top = tl_y - tly; r.left = tl_x - tlx;
-    return r;
 }
 
 }  // namespace
@@ -487,6 +448,16 @@ Roi feed_roi(int tl_x, int tl_y, int cw, int ch, int W, int H, int nb)
 void uavm_blend_free(uavm_canvas* cv)
 {
     if (cv && cv->blend_ws) { free_ws((BlendWs*)cv->blend_ws); cv->blend_ws = nullptr; }
+}
+
+// grows a device buffer (contents are scratch)
+static int ensure_cap(uavm_ctx* ctx, void** p, size_t* cap, size_t need)
+{
+    if (need <= *cap && *p) return UAVM_OK;
+    cudaFree(*p); *p = nullptr; *cap = 0;
+    UAVM_CUDA(ctx, cudaMalloc(p, need));
+    *cap = need;
+    return UAVM_OK;
 }
 
 extern "C" int uavm_canvas_blend(uavm_ctx* ctx, uavm_canvas* cv, int num_bands)
@@ -500,50 +471,60 @@ extern "C" int uavm_canvas_blend(uavm_ctx* ctx, uavm_canvas* cv, int num_bands)
     const double max_len = (double)(cw > ch ? cw : ch);
     int nb = (int)ceil(log(max_len) / log(2.0));
     if (num_bands < nb) nb = num_bands;
-    const int W = pad_to(cw, nb), H = pad_to(ch, nb);
-    // canvas rows computed by this context: the whole padded canvas, or a band + halo (uavm_canvas_set_band).
-    // Tile equivalence: cutting the pyramids at a row that is a multiple of 2^nb perturbs at most
-    // 2^(nb+2) - 2 rows next to the cut after the collapse (pyrDown reaches 2 rows, pyrUp 1 row per level),
-    // so a halo >= 128 rows (5 bands) leaves the band interior bit-identical to the untiled blend.
-    int Y0 = 0, Y1 = H;
-    if (cv->banded) {
-        Y0 = cv->band_Y0; Y1 = cv->band_Y1 < H ? cv->band_Y1 : H;
-        if ((Y0 % (1 << nb)) || ((Y1 % (1 << nb)) && Y1 != H)) { UAVM_SET_ERR(ctx, "band rows not aligned to 2^bands"); return UAVM_EINVAL; }
+    if (cv->sharded && nb > 5) { UAVM_SET_ERR(ctx, "a sharded canvas supports at most 5 bands (uavm_canvas_set_rect sizes the chip regions for 5)"); return UAVM_EINVAL; }
+    const IRect out = cv->sharded ? IRect{cv->rect_x0, cv->rect_y0, cv->rect_x1, cv->rect_y1} : IRect{0, 0, cw, ch};
+    const CanvasPlan P = plan_canvas(cw, ch, nb, out);
+    // the pixels each chip owns (K6 bounding boxes): one small read-back, the planner needs them on the host
+    if (cv->seamed && !cv->own_bbox_valid) {
+        cv->own_bbox.resize((size_t)cv->n * 4);
+        UAVM_CUDA(ctx, cudaMemcpyAsync(cv->own_bbox.data(), cv->d_own_bbox, (size_t)cv->n * 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        UAVM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        cv->own_bbox_valid = true;
     }
-    const int BH = Y1 - Y0;
-    BlendWs* ws = (BlendWs*)cv->blend_ws;
-    if (ws && (ws->nb != nb || ws->Y0 != Y0 || ws->Y1 != Y1)) { free_ws(ws); ws = nullptr; cv->blend_ws = nullptr; }
-    auto sub_roi = [&](const ChipDesc& d, Roi& r, int& sub_t, int& sub_h) {
-        r = feed_roi(d.beg_x, d.beg_y, d.chip_w, d.chip_h, W, H, nb);
-        sub_t = r.tly > Y0 ? r.tly : Y0;
-        const int sub_b = r.tly + r.height < Y1 ? r.tly + r.height : Y1;
-        sub_h = sub_b - sub_t;
-        return sub_h > 0;
-    };
-    if (!ws) {
-        ws = new BlendWs();
-        cv->blend_ws = ws;
-        ws->nb = nb; ws->W = W; ws->H = H; ws->Y0 = Y0; ws->Y1 = Y1;
-        size_t roi_cap = 0;
-        for (int k = 0; k < cv->n; k++) {
-            const ChipDesc& d = cv->desc[k];
-            if (!d.keep) continue;
-            Roi r; int st, sh;
-            if (!sub_roi(d, r, st, sh)) continue;
-            if ((size_t)r.width * sh > roi_cap) roi_cap = (size_t)r.width * sh;
+    std::vector<BlendChip> bc;
+    std::vector<ChipPlan> plans;
+    size_t scratch = 0;
+    int max_cw[kMaxBands + 1] = {0}, max_ch[kMaxBands + 1] = {0};
+    for (int k = 0; k < cv->n; k++) {
+        const ChipDesc& dsc = cv->desc[k];
+        if (!dsc.keep) continue;
+        IRect A0{0, 0, dsc.chip_w, dsc.chip_h};
+        if (cv->seamed) {
+            const int32_t* b = &cv->own_bbox[(size_t)k * 4];
+            A0 = (b[2] < b[0] || b[3] < b[1]) ? make_empty() : IRect{b[0], b[1], b[2] + 1, b[3] + 1};
         }
-        ws->roi_cap = roi_cap;
-        ws->lw[0] = W; ws->lh[0] = BH;
-        size_t cap = roi_cap;
+        const ChipPlan c = plan_chip(dsc.beg_x, dsc.beg_y, dsc.chip_w, dsc.chip_h, A0, P);
+        if (!c.active) continue;
+        BlendChip B; memset(&B, 0, sizeof(B));
+        B.chip = dsc.chip; B.mask = dsc.mask; B.chip_step = dsc.chip_step; B.mask_step = dsc.mask_step; B.cw = dsc.chip_w; B.ch = dsc.chip_h;
+        B.left = c.roi.left; B.top = c.roi.top; B.tlx = c.roi.tlx; B.tly = c.roi.tly;
         for (int i = 0; i <= nb; i++) {
-            if (i > 0) { ws->lw[i] = (ws->lw[i - 1] + 1) / 2; ws->lh[i] = (ws->lh[i - 1] + 1) / 2; cap = (cap + 3) / 4 + 4096; }
-            const size_t px = (size_t)ws->lw[i] * ws->lh[i];
-            UAVM_CUDA(ctx, cudaMalloc(&ws->dlap[i], px * 4 * sizeof(short)));
-            UAVM_CUDA(ctx, cudaMalloc(&ws->dw[i], px * sizeof(float)));
-            UAVM_CUDA(ctx, cudaMalloc(&ws->pyr[i], (cap + 16) * 4 * sizeof(short)));
-            UAVM_CUDA(ctx, cudaMalloc(&ws->wp[i], (cap + 16) * sizeof(float)));
+            B.pw[i] = c.pw[i]; B.ph[i] = c.ph[i];
+            B.ux0[i] = c.U[i].x0; B.uy0[i] = c.U[i].y0; B.ux1[i] = c.U[i].x1; B.uy1[i] = c.U[i].y1;
+            B.cx0[i] = c.C[i].x0; B.cy0[i] = c.C[i].y0; B.cw_[i] = c.C[i].x1 - c.C[i].x0; B.ch_[i] = c.C[i].y1 - c.C[i].y0;
+            if (i >= 1) {
+                const size_t px = (size_t)B.cw_[i] * B.ch_[i];
+                B.pyr[i] = (short*)scratch; scratch += (px * 8 + 255) & ~(size_t)255;             // offsets for now, rebased below
+                B.wp[i] = (float*)scratch; scratch += (px * 4 + 255) & ~(size_t)255;
+                if (B.cw_[i] > max_cw[i]) max_cw[i] = B.cw_[i];
+                if (B.ch_[i] > max_ch[i]) max_ch[i] = B.ch_[i];
+            }
         }
+        bc.push_back(B); plans.push_back(c);
     }
+    BlendWs* ws = (BlendWs*)cv->blend_ws;
+    if (!ws) { ws = new BlendWs(); cv->blend_ws = ws; }
+    ws->nb = nb;
+    const int n_act = (int)bc.size();
+    { int rc = ensure_cap(ctx, (void**)&ws->d_chips, &ws->chips_cap, (size_t)(n_act > 0 ? n_act : 1) * sizeof(BlendChip)); if (rc != UAVM_OK) return rc; }
+    { int rc = ensure_cap(ctx, (void**)&ws->d_scratch, &ws->scratch_cap, scratch + 256); if (rc != UAVM_OK) return rc; }
+    for (int i = 1; i <= nb; i++) {
+        const size_t px = (size_t)(P.S[i].x1 - P.S[i].x0) * (P.S[i].y1 - P.S[i].y0);
+        int rc = ensure_cap(ctx, (void**)&ws->d_fin[i], &ws->fin_cap[i], px * 8 + 256); if (rc != UAVM_OK) return rc;
+    }
+    for (auto& B : bc)
+        for (int i = 1; i <= nb; i++) { B.pyr[i] = (short*)(ws->d_scratch + (size_t)B.pyr[i]); B.wp[i] = (float*)(ws->d_scratch + (size_t)B.wp[i]); }
+    if (n_act > 0) UAVM_CUDA(ctx, cudaMemcpyAsync(ws->d_chips, bc.data(), (size_t)n_act * sizeof(BlendChip), cudaMemcpyHostToDevice, ctx->stream));
     if (cv->result_w != cw || cv->result_h != ch) {
         cudaFree(cv->d_result); cudaFree(cv->d_result_mask); cv->d_result = nullptr; cv->d_result_mask = nullptr;
         UAVM_CUDA(ctx, cudaMalloc(&cv->d_result, (size_t)cw * ch * 3));
@@ -552,78 +533,38 @@ extern "C" int uavm_canvas_blend(uavm_ctx* ctx, uavm_canvas* cv, int num_bands)
         UAVM_CUDA(ctx, cudaMemsetAsync(cv->d_result_mask, 0, (size_t)cw * ch, ctx->stream));
         cv->result_w = cw; cv->result_h = ch;
     }
-    for (int i = 0; i <= nb; i++) {
-        const size_t px = (size_t)ws->lw[i] * ws->lh[i];
-        UAVM_CUDA(ctx, cudaMemsetAsync(ws->dlap[i], 0, px * 4 * sizeof(short), ctx->stream));
-        UAVM_CUDA(ctx, cudaMemsetAsync(ws->dw[i], 0, px * sizeof(float), ctx->stream));
-    }
-    // feed(), image by image in index order
-    for (int k = 0; k < cv->n; k++) {
-        const ChipDesc& d = cv->desc[k];
-        if (!d.keep) continue;
-        Roi r; int sub_t, sub_h;
-        if (!sub_roi(d, r, sub_t, sub_h)) continue;
-        int pw[kMaxBands + 1], ph[kMaxBands + 1];
-        pw[0] = r.width; ph[0] = sub_h;
-        {
-            dim3 grid(((r.width + 3) / 4 + 255) / 256, sub_h);
-            k7_feed_level0<<<grid, 256, 0, ctx->stream>>>(d.chip, d.chip_step, d.mask, d.mask_step, d.chip_w, d.chip_h, r.left, d.beg_y - sub_t,
-                                                           r.width, sub_h, ws->pyr[0], ws->wp[0]);
-            UAVM_CHECK_LAUNCH(ctx);
-        }
-        for (int i = 0; i < nb; i++) {
-            pw[i + 1] = (pw[i] + 1) / 2; ph[i + 1] = (ph[i] + 1) / 2;
-            if (pw[i + 1] >= 2 * kPdW && ph[i + 1] >= kPdH && pw[i] >= 8 && ph[i] >= 8) {
-                dim3 grid((pw[i + 1] + kPdW - 1) / kPdW, (ph[i + 1] + kPdH - 1) / kPdH);
-                k7_pyrdown_tiled<<<grid, dim3(kPdW, 4), 0, ctx->stream>>>(ws->pyr[i], ws->wp[i], pw[i], ph[i], ws->pyr[i + 1], ws->wp[i + 1], pw[i + 1], ph[i + 1]);
-            } else {
-                dim3 grid((pw[i + 1] + 255) / 256, ph[i + 1]);
-                k7_pyrdown<<<grid, 256, 0, ctx->stream>>>(ws->pyr[i], ws->wp[i], pw[i], ph[i], ws->pyr[i + 1], ws->wp[i + 1], pw[i + 1], ph[i + 1]);
-            }
-            UAVM_CHECK_LAUNCH(ctx);
-        }
-        int x_tl = r.tlx, y_tl = sub_t - Y0;
-        for (int i = 0; i <= nb; i++) {
-            const bool quad = i < nb && !(pw[i] & 1) && !(ph[i] & 1) && !(x_tl & 1) && !(y_tl & 1) && !(ws->lw[i] & 1);
-            if (quad) {
-                dim3 grid((pw[i] / 2 + 255) / 256, ph[i] / 2);
-                k7_lap_accumulate_quad<<<grid, 256, 0, ctx->stream>>>(ws->pyr[i], ws->pyr[i + 1], ws->wp[i], pw[i], ph[i], pw[i + 1], ph[i + 1],
-                                                                       ws->dlap[i], ws->dw[i], ws->lw[i], x_tl, y_tl);
-            } else {
-                dim3 grid((pw[i] + 255) / 256, ph[i]);
-                k7_lap_accumulate<<<grid, 256, 0, ctx->stream>>>(ws->pyr[i], i < nb ? ws->pyr[i + 1] : nullptr, ws->wp[i], pw[i], ph[i],
-                                                                  i < nb ? pw[i + 1] : 0, i < nb ? ph[i + 1] : 0, ws->dlap[i], ws->dw[i], ws->lw[i], x_tl, y_tl);
-            }
-            UAVM_CHECK_LAUNCH(ctx);
-            x_tl /= 2; y_tl /= 2;
-        }
-    }
-    // blend(): normalise the top level, collapse from the top (normalising each level as it is consumed); the level-0 step
-    // writes the cropped u8 mosaic and its mask directly
-    {
-        const size_t px = (size_t)ws->lw[nb] * ws->lh[nb];
-        k7_normalize<<<(unsigned)((px + 255) / 256), 256, 0, ctx->stream>>>(ws->dlap[nb], ws->dw[nb], px);
+    // 1. chip pyramids, all chips per launch
+    for (int i = 0; i < nb && n_act > 0; i++) {
+        if (max_cw[i + 1] <= 0 || max_ch[i + 1] <= 0) continue;
+        dim3 grid((max_cw[i + 1] + kPdW - 1) / kPdW, (max_ch[i + 1] + kPdH - 1) / kPdH, n_act);
+        if (grid.y > 65535) { UAVM_SET_ERR(ctx, "blend: chip pyramid level %d too tall", i + 1); return UAVM_EINVAL; }
+        if (i == 0) k7_pyrdown<true><<<grid, dim3(kPdW, 4), 0, ctx->stream>>>(ws->d_chips, 0);
+        else k7_pyrdown<false><<<grid, dim3(kPdW, 4), 0, ctx->stream>>>(ws->d_chips, i);
         UAVM_CHECK_LAUNCH(ctx);
     }
-    for (int i = nb; i > 1; i--) {
-        if (!(ws->lw[i - 1] & 1) && !(ws->lh[i - 1] & 1)) {
-            dim3 grid((ws->lw[i - 1] / 2 + 255) / 256, ws->lh[i - 1] / 2);
-            k7_collapse_quad<<<grid, 256, 0, ctx->stream>>>(ws->dlap[i], ws->lw[i], ws->lh[i], ws->dlap[i - 1], ws->dw[i - 1], ws->lw[i - 1], ws->lh[i - 1]);
+    // 2. canvas levels, top down
+    for (int i = nb; i >= 0; i--) {
+        LevelArgs A; memset(&A, 0, sizeof(A));
+        A.level = i; A.n_chips = n_act;
+        A.sx0 = P.S[i].x0; A.sy0 = P.S[i].y0; A.sx1 = P.S[i].x1; A.sy1 = P.S[i].y1;
+        if (A.sx1 <= A.sx0 || A.sy1 <= A.sy0) continue;
+        if (i >= 1) { A.fin = ws->d_fin[i]; A.fin_x0 = P.S[i].x0; A.fin_y0 = P.S[i].y0; A.fin_pitch = P.S[i].x1 - P.S[i].x0; }
+        if (i < nb) { A.nxt = ws->d_fin[i + 1]; A.nxt_x0 = P.S[i + 1].x0; A.nxt_y0 = P.S[i + 1].y0; A.nxt_pitch = P.S[i + 1].x1 - P.S[i + 1].x0; A.nxt_w = P.lw[i + 1]; A.nxt_h = P.lh[i + 1]; }
+        if (i == 0) {
+            A.out = cv->d_result; A.out_mask = cv->d_result_mask; A.cw = cw; A.ch = ch;
+            A.ox0 = out.x0; A.oy0 = out.y0; A.ox1 = out.x1 < cw ? out.x1 : cw; A.oy1 = out.y1 < ch ? out.y1 : ch;
+        }
+        if (i == nb) {
+            dim3 grid((A.sx1 - A.sx0 + 31) / 32, (A.sy1 - A.sy0 + 7) / 8);
+            if (grid.y > 65535) { UAVM_SET_ERR(ctx, "blend: canvas level %d too tall", i); return UAVM_EINVAL; }
+            if (i == 0) k7_level_top<true><<<grid, dim3(32, 8), 0, ctx->stream>>>(ws->d_chips, A);
+            else k7_level_top<false><<<grid, dim3(32, 8), 0, ctx->stream>>>(ws->d_chips, A);
         } else {
-            dim3 grid((ws->lw[i - 1] + 255) / 256, ws->lh[i - 1]);
-            k7_collapse<<<grid, 256, 0, ctx->stream>>>(ws->dlap[i], ws->lw[i], ws->lh[i], ws->dlap[i - 1], ws->dw[i - 1], ws->lw[i - 1], ws->lh[i - 1]);
+            dim3 grid((A.sx1 - (A.sx0 & ~3) + 127) / 128, (A.sy1 - A.sy0 + 15) / 16);
+            if (grid.y > 65535) { UAVM_SET_ERR(ctx, "blend: canvas level %d too tall", i); return UAVM_EINVAL; }
+            if (i == 0) k7_level<true><<<grid, dim3(32, 8), 0, ctx->stream>>>(ws->d_chips, A);
+            else k7_level<false><<<grid, dim3(32, 8), 0, ctx->stream>>>(ws->d_chips, A);
         }
-        UAVM_CHECK_LAUNCH(ctx);
-    }
-    {
-        const int oy0 = cv->banded ? cv->band_y0 : 0, oy1 = cv->banded ? cv->band_y1 : ch;
-        dim3 grid((cw + 255) / 256, oy1 - oy0), grid4(((cw + 3) / 4 + 255) / 256, (oy1 - oy0 + 1) / 2);
-        if (nb >= 1)
-            k7_collapse_output<<<grid4, 256, 0, ctx->stream>>>(ws->dlap[1], ws->lw[1], ws->lh[1], ws->dlap[0], ws->dw[0], W, BH, oy0 - Y0, oy1 - Y0, cw,
-                                                               cv->d_result + (size_t)oy0 * cw * 3, cv->d_result_mask + (size_t)oy0 * cw);
-        else
-            k7_output<<<grid, 256, 0, ctx->stream>>>(ws->dlap[0] + (size_t)(oy0 - Y0) * W * 4, ws->dw[0] + (size_t)(oy0 - Y0) * W, W, cw, oy1 - oy0,
-                                                      cv->d_result + (size_t)oy0 * cw * 3, cv->d_result_mask + (size_t)oy0 * cw);
         UAVM_CHECK_LAUNCH(ctx);
     }
     cv->blended = true;
@@ -664,6 +605,19 @@ extern "C" int uavm_canvas_copy_result_rows(uavm_ctx* ctx, uavm_canvas* cv, int 
     if (y1 > y0)
         UAVM_CUDA(ctx, cudaMemcpyAsync(dst, cv->d_result + (size_t)y0 * row, (size_t)(y1 - y0) * row,
                                        is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, ctx->stream));
+    if (!is_device) UAVM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return UAVM_OK;
+}
+
+// rectangle [x0, x1) x [y0, y1) of the result, dense ((x1 - x0) * 3 bytes per row): the piece a rank of a 2-D sharded canvas
+// contributes to the gather
+extern "C" int uavm_canvas_copy_result_rect(uavm_ctx* ctx, uavm_canvas* cv, int x0, int y0, int x1, int y1, uint8_t* dst, int is_device)
+{
+    if (!ctx || !cv || !dst || x0 < 0 || y0 < 0 || x1 > cv->result_w || y1 > cv->result_h || x0 > x1 || y0 > y1) return UAVM_EINVAL;
+    if (!cv->blended || !cv->d_result) { UAVM_SET_ERR(ctx, "copy_result_rect before blend"); return UAVM_EINVAL; }
+    if (x1 > x0 && y1 > y0)
+        UAVM_CUDA(ctx, cudaMemcpy2DAsync(dst, (size_t)(x1 - x0) * 3, cv->d_result + ((size_t)y0 * cv->result_w + x0) * 3, (size_t)cv->result_w * 3,
+                                         (size_t)(x1 - x0) * 3, (size_t)(y1 - y0), is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, ctx->stream));
     if (!is_device) UAVM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return UAVM_OK;
 }

@@ -9,7 +9,9 @@
 // written with one coalesced 32-bit store per pixel.  The u8 mask plane (row step align4(chip_w)) is K6's output.
 #include <stdlib.h>
 #include <string.h>
+#include <math.h>
 #include "canvas.h"
+#include "blend_plan.h"
 #include "ptx.cuh"
 
 namespace {
@@ -91,11 +93,13 @@ template <bool AFFINE>
 __global__ void __launch_bounds__(32 * kWarpsY)
 k5_warp_chips(const ChipDesc* __restrict__ descs, int img_w, int img_h, int src_step_px, float dgx, float dgy,
               uint32_t two23 /* = 0x4B000000, bits of 2^23: a kernel argument so PRMT takes the SELECTOR as its immediate */,
-              float w1f, float h1f, int row0, int row1 /* canvas rows to produce (band-sharded canvases skip the other tiles) */)
+              float w1f, float h1f)
 {
     const ChipDesc& D = descs[blockIdx.z];
     if (!D.keep || (D.affine != 0) != AFFINE) return;
-    if ((int)(blockIdx.y * kWarpTileH) + D.beg_y >= row1 || (int)(blockIdx.y * kWarpTileH) + kWarpTileH + D.beg_y <= row0) return;
+    // chip pixels this context needs (a sharded canvas skips the tiles nothing can read)
+    if ((int)(blockIdx.y * kWarpTileH) >= D.need_y1 || (int)(blockIdx.y * kWarpTileH) + kWarpTileH <= D.need_y0 ||
+        (int)(blockIdx.x * kWarpTileW) >= D.need_x1 || (int)(blockIdx.x * kWarpTileW) + kWarpTileW <= D.need_x0) return;
     const int xl = blockIdx.x * kWarpTileW + threadIdx.x;
     const int ybase = blockIdx.y * kWarpTileH + threadIdx.y;
     if (blockIdx.x * kWarpTileW >= D.chip_w || blockIdx.y * kWarpTileH >= D.chip_h) return;
@@ -299,8 +303,7 @@ k5_warp_affine_x2(const __grid_constant__ CUtensorMap tmap_src, const ChipDesc* 
                   uint32_t two23, float w1f, float h1f, float one,
                   uint32_t one_u /* = 1, opaque: row-1 tap address = row-0 address + step4 * 1 as a single 64-bit IMAD */,
                   unsigned long long bias /* = 0x4B000000 * (4 step + 4): the add.rz biases of iy and ix in byte-address units */,
-                  int max_boxes /* TMA boxes of dynamic shared memory for the source footprint; 0 = always load taps directly */,
-                  int row0, int row1 /* canvas rows to produce (band-sharded canvases skip the other tiles) */)
+                  int max_boxes /* TMA boxes of dynamic shared memory for the source footprint; 0 = always load taps directly */)
 {
     extern __shared__ __align__(128) uint8_t fp_smem[];
     __shared__ __align__(8) uint64_t fp_bar;
@@ -308,7 +311,8 @@ k5_warp_affine_x2(const __grid_constant__ CUtensorMap tmap_src, const ChipDesc* 
 
     const ChipDesc& D = descs[blockIdx.z];
     if (!D.keep || !D.affine) return;
-    if ((int)(blockIdx.y * kWarpTileH) + D.beg_y >= row1 || (int)(blockIdx.y * kWarpTileH) + kWarpTileH + D.beg_y <= row0) return;
+    if ((int)(blockIdx.y * kWarpTileH) >= D.need_y1 || (int)(blockIdx.y * kWarpTileH) + kWarpTileH <= D.need_y0 ||
+        (int)(blockIdx.x * kWarpTileW) >= D.need_x1 || (int)(blockIdx.x * kWarpTileW) + kWarpTileW <= D.need_x0) return;
     const int xl = blockIdx.x * kWarpTileW + threadIdx.x;
     const int ybase = blockIdx.y * kWarpTileH + threadIdx.y;
     if (blockIdx.x * kWarpTileW >= D.chip_w || blockIdx.y * kWarpTileH >= D.chip_h) return;
@@ -456,6 +460,7 @@ extern "C" int uavm_canvas_create(uavm_ctx* ctx, int n_images, int img_w, int im
         d.beg_x = c.beg_x; d.beg_y = c.beg_y; d.sx = c.sx; d.sy = c.sy;
         memcpy(d.inv, c.inv, sizeof(d.inv)); memcpy(d.quad, c.quad, sizeof(d.quad));
         d.affine = (c.inv[6] == 0.0f && c.inv[7] == 0.0f && c.inv[8] == 1.0f) ? 1 : 0;
+        d.need_x0 = 0; d.need_y0 = 0; d.need_x1 = c.chip_w; d.need_y1 = c.chip_h;
         coff[k] = chip_off; moff[k] = mask_off;
         chip_off += (size_t)d.chip_step * d.chip_h * 4; mask_off += (size_t)d.mask_step * d.chip_h;
         chip_off = (chip_off + 255) & ~(size_t)255; mask_off = (mask_off + 255) & ~(size_t)255;
@@ -490,41 +495,67 @@ extern "C" int uavm_canvas_create(uavm_ctx* ctx, int n_images, int img_w, int im
         uavm_encode_tmap_2d(ctx, &cv->tmap_src, (int)CU_TENSOR_MAP_DATA_TYPE_UINT32, cv->d_src, (uint64_t)cv->src_step_px, (uint64_t)n_images * img_h,
                             (uint64_t)cv->src_step_px * 4, kFpBoxW, kFpBoxH, 0) == UAVM_OK)
         cv->tmap_src_ok = true;
-    cv->band_y0 = 0; cv->band_y1 = cv->layout.canvas_h; cv->band_Y0 = 0; cv->band_Y1 = (cv->layout.canvas_h + 31) & ~31;
+    cv->rect_x0 = 0; cv->rect_y0 = 0; cv->rect_x1 = cv->layout.canvas_w; cv->rect_y1 = cv->layout.canvas_h;
     rc = uavm_canvas_upload_desc(ctx, cv);
     if (rc != UAVM_OK) { uavm_canvas_destroy(ctx, cv); return rc; }
     *out = cv;
     return UAVM_OK;
 }
 
-// Multi-GPU canvas sharding: this context computes only canvas rows [y0, y1) (+ halo rows on both sides that make
-// the band interior bit-identical to the untiled blend, see blend.cu).  Chips that cannot touch the computed rows
-// are deactivated: they are neither warped nor masked nor fed.  y0, y1, halo: multiples of 32 (y1 may be the
-// canvas height).  y0 = 0, y1 = canvas_h, halo = 0 restores the whole canvas.
-extern "C" int uavm_canvas_set_band(uavm_ctx* ctx, uavm_canvas* cv, int y0, int y1, int halo)
+// Multi-GPU canvas sharding: this context produces only the canvas rectangle [x0, x1) x [y0, y1) (even edges; x1 / y1 may be
+// the canvas size).  K7 computes the pyramid rectangles the output depends on (blend_plan.h), so the result is bit-identical to
+// the unsharded blend without any halo parameter.  Chips that cannot contribute are deactivated: they are neither warped nor
+// masked nor fed; active chips are warped only where K7 can read them.  The full canvas rectangle restores the default.
+extern "C" int uavm_canvas_set_rect(uavm_ctx* ctx, uavm_canvas* cv, int x0, int y0, int x1, int y1)
 {
     if (!ctx || !cv) return UAVM_EINVAL;
-    const int ch = cv->layout.canvas_h;
-    if (y0 < 0 || y1 > ch || y0 >= y1 || halo < 0 || (y0 % 32) || (halo % 32) || ((y1 % 32) && y1 != ch)) {
-        UAVM_SET_ERR(ctx, "set_band: rows must be multiples of 32 inside the canvas"); return UAVM_EINVAL;
+    const int cw = cv->layout.canvas_w, ch = cv->layout.canvas_h;
+    if (x0 < 0 || y0 < 0 || x1 > cw || y1 > ch || x0 >= x1 || y0 >= y1 || (x0 & 1) || (y0 & 1) || ((x1 & 1) && x1 != cw) || ((y1 & 1) && y1 != ch)) {
+        UAVM_SET_ERR(ctx, "set_rect: edges must be even and inside the canvas"); return UAVM_EINVAL;
     }
-    const int Hpad = (ch + 31) & ~31;
-    cv->band_y0 = y0; cv->band_y1 = y1;
-    cv->band_Y0 = y0 - halo > 0 ? y0 - halo : 0;
-    cv->band_Y1 = ((y1 + 31) & ~31) + halo < Hpad ? ((y1 + 31) & ~31) + halo : Hpad;
-    cv->banded = !(y0 == 0 && y1 == ch);
-    const int gap = 3 * 32 + 32;                        // feed ROI grows a chip by 3 * 2^5 rows, then aligns to 32
+    cv->rect_x0 = x0; cv->rect_y0 = y0; cv->rect_x1 = x1; cv->rect_y1 = y1;
+    cv->sharded = !(x0 == 0 && y0 == 0 && x1 == cw && y1 == ch);
+    // What can K7 read of a chip?  Plan the chip with its whole box as the mask box, for the deepest pyramid the blender
+    // supports at this canvas size: pyramid dependencies grow with the band count, so this covers every num_bands <= 5
+    // (the reference's constant, M/MosaicWithoutPos.cpp:2179) — uavm_canvas_blend rejects a sharded blend with more bands.
+    using namespace uavm_plan;
+    const double max_len = (double)(cw > ch ? cw : ch);
+    int nb = (int)ceil(log(max_len) / log(2.0)); if (nb > 5) nb = 5;
+    const int M = uavm_canvas::kShardMargin;
+    const IRect seam{x0 - M > 0 ? x0 - M : 0, y0 - M > 0 ? y0 - M : 0, x1 + M < cw ? x1 + M : cw, y1 + M < ch ? y1 + M : ch};   // where K6 writes masks
     cv->max_chip_w = 0; cv->max_chip_h = 0;
     for (int k = 0; k < cv->n; k++) {
         ChipDesc& d = cv->desc[k];
         const uavm_chip_layout& c = cv->chips[k];
-        bool active = c.keep != 0;
-        if (active && cv->banded) active = (c.beg_y - gap < cv->band_Y1) && (c.beg_y + c.chip_h + gap > cv->band_Y0);
-        d.keep = active ? 1 : 0;
-        if (active) { if (c.chip_w > cv->max_chip_w) cv->max_chip_w = c.chip_w; if (c.chip_h > cv->max_chip_h) cv->max_chip_h = c.chip_h; }
+        d.keep = c.keep ? 1 : 0;
+        d.need_x0 = 0; d.need_y0 = 0; d.need_x1 = c.chip_w; d.need_y1 = c.chip_h;
+        if (c.keep && cv->sharded) {
+            IRect need = make_empty();
+            for (int b = 0; b <= nb; b++) {
+                const CanvasPlan P = plan_canvas(cw, ch, b, IRect{x0, y0, x1, y1});
+                const IRect a0 = shifted(isect(IRect{c.beg_x, c.beg_y, c.beg_x + c.chip_w, c.beg_y + c.chip_h}, seam), -c.beg_x, -c.beg_y);
+                const ChipPlan cp = plan_chip(c.beg_x, c.beg_y, c.chip_w, c.chip_h, a0, P);
+                if (!cp.active) continue;
+                int lx, hx, ly, hy;
+                reflect_range(cp.C[0].x0 - cp.roi.left, cp.C[0].x1 - cp.roi.left, c.chip_w, lx, hx);
+                reflect_range(cp.C[0].y0 - cp.roi.top, cp.C[0].y1 - cp.roi.top, c.chip_h, ly, hy);
+                if (hx > lx && hy > ly) need = hull(need, IRect{lx, ly, hx, hy});
+            }
+            if (is_empty(need)) d.keep = 0;
+            else { d.need_x0 = need.x0; d.need_y0 = need.y0; d.need_x1 = need.x1; d.need_y1 = need.y1; }
+        }
+        if (d.keep) { if (c.chip_w > cv->max_chip_w) cv->max_chip_w = c.chip_w; if (c.chip_h > cv->max_chip_h) cv->max_chip_h = c.chip_h; }
     }
-    cv->nbr_dirty = true; cv->warped = false; cv->seamed = false; cv->blended = false; cv->mask_plane_valid = false;
+    cv->lines_dirty = true; cv->warped = false; cv->seamed = false; cv->blended = false; cv->mask_plane_valid = false; cv->own_bbox_valid = false;
     return uavm_canvas_upload_desc(ctx, cv);
+}
+// horizontal band [y0, y1) of the canvas.  `halo` is accepted for source compatibility and ignored: K7 derives what a
+// rectangle depends on from the band count instead of trusting a caller-supplied halo.
+extern "C" int uavm_canvas_set_band(uavm_ctx* ctx, uavm_canvas* cv, int y0, int y1, int halo)
+{
+    (void)halo;
+    if (!ctx || !cv) return UAVM_EINVAL;
+    return uavm_canvas_set_rect(ctx, cv, 0, y0, cv->layout.canvas_w, y1);
 }
 extern "C" int uavm_canvas_is_active(uavm_canvas* cv, int image)
 {
@@ -542,8 +573,8 @@ extern "C" void uavm_canvas_destroy(uavm_ctx* ctx, uavm_canvas* cv)
         if (cv->ev_free[s]) cudaEventDestroy(cv->ev_free[s]);
     }
     uavm_blend_free(cv);
-    cudaFree(cv->d_src); cudaFree(cv->d_chips); cudaFree(cv->d_masks); cudaFree(cv->d_dist); cudaFree(cv->d_dist_max);
-    cudaFree(cv->d_desc); cudaFree(cv->d_nbr); cudaFree(cv->d_result); cudaFree(cv->d_result_mask);
+    cudaFree(cv->d_src); cudaFree(cv->d_chips); cudaFree(cv->d_masks); cudaFree(cv->d_dist_max); cudaFree(cv->d_box); cudaFree(cv->d_own_bbox);
+    cudaFree(cv->d_desc); cudaFree(cv->d_result); cudaFree(cv->d_result_mask);
     delete cv;
 }
 
@@ -593,9 +624,6 @@ extern "C" int uavm_canvas_warp_range(uavm_ctx* ctx, uavm_canvas* cv, int first,
     if (cv->max_chip_w <= 0 || count == 0) return UAVM_OK;
     dim3 grid((cv->max_chip_w + kWarpTileW - 1) / kWarpTileW, (cv->max_chip_h + kWarpTileH - 1) / kWarpTileH, count);
     dim3 block(32, kWarpsY);
-    // a band-sharded canvas needs its rows + halo, and 128 more on each side: K7's feed reflects up to 3 * 2^5 + 31 chip rows
-    // at a chip edge that lies inside the band (everything else is never read)
-    const int row0 = cv->banded ? cv->band_Y0 - 128 : -(1 << 30), row1 = cv->banded ? cv->band_Y1 + 128 : (1 << 30);
     bool any_affine = false, any_proj = false;
     for (int k = first; k < first + count; k++)
         if (cv->desc[k].keep) { if (cv->desc[k].affine) any_affine = true; else any_proj = true; }
@@ -611,16 +639,16 @@ extern "C" int uavm_canvas_warp_range(uavm_ctx* ctx, uavm_canvas* cv, int first,
             }
             k5_warp_affine_x2<<<grid, block, boxes * kFpBoxBytes, ctx->stream>>>(
                 cv->tmap_src, cv->d_desc + first, cv->img_w, cv->img_h, cv->src_step_px, cv->layout.dgx, cv->layout.dgy, 0x4B000000u,
-                (float)(cv->img_w - 1), (float)(cv->img_h - 1), 1.0f, 1u, 0x4B000000ull * (4ull * (unsigned long long)cv->src_step_px + 4ull), boxes, row0, row1);
+                (float)(cv->img_w - 1), (float)(cv->img_h - 1), 1.0f, 1u, 0x4B000000ull * (4ull * (unsigned long long)cv->src_step_px + 4ull), boxes);
         }
         else
             k5_warp_chips<true><<<grid, block, 0, ctx->stream>>>(cv->d_desc + first, cv->img_w, cv->img_h, cv->src_step_px, cv->layout.dgx, cv->layout.dgy, 0x4B000000u,
-                                                                 (float)(cv->img_w - 1), (float)(cv->img_h - 1), row0, row1);
+                                                                 (float)(cv->img_w - 1), (float)(cv->img_h - 1));
         UAVM_CHECK_LAUNCH(ctx);
     }
     if (any_proj) {
         k5_warp_chips<false><<<grid, block, 0, ctx->stream>>>(cv->d_desc + first, cv->img_w, cv->img_h, cv->src_step_px, cv->layout.dgx, cv->layout.dgy, 0x4B000000u,
-                                                             (float)(cv->img_w - 1), (float)(cv->img_h - 1), row0, row1);
+                                                             (float)(cv->img_w - 1), (float)(cv->img_h - 1));
         UAVM_CHECK_LAUNCH(ctx);
     }
     cv->warped = true; cv->seamed = false; cv->mask_plane_valid = false;

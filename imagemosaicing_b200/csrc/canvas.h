@@ -17,8 +17,11 @@ struct ChipDesc {               // one per image, device-visible
     int32_t src_row0;           // first row of this frame in the stacked source tensor (image index * img_h)
     int32_t affine;             // inv[6] == 0 && inv[7] == 0 && inv[8] == 1: the projective divide is exact identity
     float lineA[4], lineB[4], lineC[4], lineInv[4];   // K6: quad edges as A x + B y + C = 0 and 1/sqrt(A^2+B^2)
-    int32_t nbr_off, nbr_cnt;   // K6: chips whose boxes intersect this one (indices into the neighbour list)
+    int32_t need_x0, need_y0, need_x1, need_y1;       // chip pixels this context has to produce (K5): the whole chip, or what a sharded
+                                                      // canvas (uavm_canvas_set_rect) can read from it
 };
+
+struct ChipBox { int32_t beg_x, beg_y, w, h; };       // compact per-image box for tile / chip intersection scans (w = 0: inactive)
 
 struct uavm_canvas {
     int n = 0, img_w = 0, img_h = 0, src_step_px = 0;
@@ -29,9 +32,11 @@ struct uavm_canvas {
     uchar4* d_src = nullptr;
     uint32_t* d_chips = nullptr;     // BGRA chips
     uint8_t* d_masks = nullptr;
-    float* d_dist = nullptr;
     float* d_dist_max = nullptr;     // [n] per-image maximum of the distance map (as uint bits)
-    int32_t* d_nbr = nullptr;        // K6 neighbour lists
+    ChipBox* d_box = nullptr;        // [n]
+    int32_t* d_own_bbox = nullptr;   // [n][4] K6: bounding box (min x, min y, max x, max y; chip coordinates) of the pixels a chip owns
+    std::vector<int32_t> own_bbox;   // host copy, fetched by K7 (valid when own_bbox_valid)
+    bool own_bbox_valid = false;
     ChipDesc* d_desc = nullptr;
     CUtensorMap tmap_src;            // all source frames as one [n * img_h][src_step_px] tensor of BGRA words (K5 footprint staging)
     bool tmap_src_ok = false;
@@ -47,10 +52,12 @@ struct uavm_canvas {
     // result canvas (K7 / paste)
     uint8_t* d_result = nullptr;     // canvas_h x canvas_w x 3
     uint8_t* d_result_mask = nullptr;
-    // canvas band owned by this context/rank (multi-GPU canvas sharding): output rows [band_y0, band_y1), computed
-    // rows [band_Y0, band_Y1) = band + halo, all multiples of 2^bands; default = the whole canvas
-    int band_y0 = 0, band_y1 = 0, band_Y0 = 0, band_Y1 = 0;
-    bool banded = false, nbr_dirty = true;
+    // canvas rectangle owned by this context/rank (multi-GPU canvas sharding): output pixels [rect_x0, rect_x1) x
+    // [rect_y0, rect_y1) (even edges); default = the whole canvas.  K6 produces seam masks on the rectangle grown by
+    // kShardMargin (what K7's pyramids of the rectangle can depend on), K5 the chip pixels K7 can read.
+    static constexpr int kShardMargin = 192;
+    int rect_x0 = 0, rect_y0 = 0, rect_x1 = 0, rect_y1 = 0;
+    bool sharded = false, lines_dirty = true;
     int result_w = 0, result_h = 0;  // size of d_result (blend: canvas layout; paste: MosaicImagesRefined's own bbox)
     bool warped = false, seamed = false, blended = false;
     bool mask_plane_valid = false;   // d_masks currently holds the seam masks (seamed) or the validity masks (expanded from alpha)

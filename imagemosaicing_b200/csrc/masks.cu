@@ -4,10 +4,13 @@
 // chip pixels, divided by the image's maximum; then every canvas pixel is owned by the image with the
 // largest normalised distance (strict >, so the lowest image index wins ties and 0 never wins) and only
 // the owner's mask is 255.
-// Here: k6_dist_map (per chip pixel, + per-image max by atomicMax on the float bits), k6_normalize
-// (true division by the max, in place), k6_owner (per chip pixel: am I the first arg-max among the chips
-// whose boxes intersect mine?).  The O(N) scan over all images per canvas pixel becomes a scan over the
-// chip's box-intersection neighbours, with the same first-wins rule.
+// Here no distance map is ever stored (the reference keeps an f32 map per chip):
+//   k6_dist_max   per chip pixel, compute only: validity from the warp's own coordinate chain (M/MosaicImage.cpp:2356-2362,
+//                 :2370), distance to the nearest edge, per-image maximum (atomicMax on the float bits);
+//   k6_owner      per CANVAS pixel: the normalised distance of every chip whose box covers the pixel is evaluated once, in
+//                 image index order with the reference's strict >; then each of those chips gets its mask byte (255 for the
+//                 owner, 0 for the others) and the bounding box of the pixels it owns (K7 only builds pyramids there).
+// The arithmetic per (chip, pixel) is exactly the reference's: same expressions, same order, IEEE division by the maximum.
 #include <math.h>
 #include <string.h>
 #include "canvas.h"
@@ -16,49 +19,42 @@ namespace {
 
 constexpr int kTileW = 128, kTileH = 8;
 
-// Validity is recomputed from the pixel coordinates with exactly K5's expression chain (M/MosaicImage.cpp:2356-2362, :2370)
-// instead of being read back from the chip: the pass is compute-only for rows this context does not hold (a band-sharded
-// canvas warps and masks only its rows, yet the per-image maximum needs every pixel of the chip), and it saves the read.
-// Rows outside canvas rows [row0, row1) are not stored.
+// distance of chip pixel (c, r) to the nearest quad edge; 0 when the pixel is outside the source frame (mask == 0)
+__device__ __forceinline__ float chip_min_dist(const ChipDesc& D, int c, int r, float dgx, float dgy, float w1f, float h1f)
+{
+    const float yt = (float)r - dgy - D.sy + (float)D.beg_y;          // yTemp (:2357)
+    const float ya = yt * D.inv[1], yb = yt * D.inv[4];
+    const float xt = (float)c - dgx - D.sx + (float)D.beg_x;          // xTemp (:2356)
+    float xs = xt * D.inv[0] + ya + D.inv[2];
+    float ys = xt * D.inv[3] + yb + D.inv[5];
+    if (!D.affine) {
+        const float den = xt * D.inv[6] + yt * D.inv[7] + D.inv[8];
+        xs = xs / den; ys = ys / den;
+    }
+    if (!((xs >= 0.0f) && (xs < w1f) && (ys >= 0.0f) && (ys < h1f))) return 0.0f;
+    float mind = 536870912.0f;                                         // float minDist = 1<<29
+#pragma unroll
+    for (int e = 0; e < 4; e++) {
+        const float d = fabsf(D.lineA[e] * (float)c + D.lineB[e] * (float)r + D.lineC[e]) * D.lineInv[e];
+        if (d < mind) mind = d;
+    }
+    return mind;
+}
+
 __global__ void __launch_bounds__(256)
-k6_dist_map(const ChipDesc* __restrict__ descs, float* __restrict__ dist_max, float dgx, float dgy, float w1f, float h1f, int row0, int row1)
+k6_dist_max(const ChipDesc* __restrict__ descs, float* __restrict__ dist_max, float dgx, float dgy, float w1f, float h1f)
 {
     const ChipDesc& D = descs[blockIdx.z];
     if (!D.keep) return;
-    const int x0 = blockIdx.x * kTileW + threadIdx.x * 4;
-    const int r = blockIdx.y * kTileH + threadIdx.y;
     if (blockIdx.x * kTileW >= D.chip_w || blockIdx.y * kTileH >= D.chip_h) return;
+    const int r = blockIdx.y * kTileH + threadIdx.y;
     float mx = 0.0f;
-    if (x0 < D.chip_w && r < D.chip_h) {
-        const float yt = (float)r - dgy - D.sy + (float)D.beg_y;          // yTemp (:2357)
-        const float ya = yt * D.inv[1], yb = yt * D.inv[4];
-        float out[4];
+    if (r < D.chip_h) {
 #pragma unroll
         for (int i = 0; i < 4; i++) {
-            const int c = x0 + i;
-            const float xt = (float)c - dgx - D.sx + (float)D.beg_x;      // xTemp (:2356)
-            float xs = xt * D.inv[0] + ya + D.inv[2];
-            float ys = xt * D.inv[3] + yb + D.inv[5];
-            if (!D.affine) {
-                const float den = xt * D.inv[6] + yt * D.inv[7] + D.inv[8];
-                xs = xs / den; ys = ys / den;
-            }
-            const bool valid = (xs >= 0.0f) && (xs < w1f) && (ys >= 0.0f) && (ys < h1f);
-            float mind = 0.0f;
-            if (valid && c < D.chip_w) {
-                mind = 536870912.0f;                                   // float minDist = 1<<29
-#pragma unroll
-                for (int e = 0; e < 4; e++) {
-                    const float d = fabsf(D.lineA[e] * (float)c + D.lineB[e] * (float)r + D.lineC[e]) * D.lineInv[e];
-                    if (d < mind) mind = d;
-                }
-                if (mind > mx) mx = mind;
-            }
-            out[i] = mind;
+            const int c = blockIdx.x * kTileW + threadIdx.x + 32 * i;
+            if (c < D.chip_w) mx = fmaxf(mx, chip_min_dist(D, c, r, dgx, dgy, w1f, h1f));
         }
-        const int gy = r + D.beg_y;
-        if (gy >= row0 && gy < row1)
-            *reinterpret_cast<float4*>(D.dist + (size_t)r * D.mask_step + x0) = make_float4(out[0], out[1], out[2], out[3]);
     }
     // block max -> one atomic per block (distances are >= 0, so the uint order of the bits is the float order)
     __shared__ float smax[8];
@@ -69,57 +65,103 @@ k6_dist_map(const ChipDesc* __restrict__ descs, float* __restrict__ dist_max, fl
         float m = smax[0];
 #pragma unroll
         for (int i = 1; i < 8; i++) m = fmaxf(m, smax[i]);
-        if (m > 0.0f) atomicMax(reinterpret_cast<unsigned int*>(dist_max + blockIdx.z), __float_as_uint(m));
+        if (m > 0.0f && m > dist_max[blockIdx.z]) atomicMax(reinterpret_cast<unsigned int*>(dist_max + blockIdx.z), __float_as_uint(m));
     }
 }
 
-__global__ void __launch_bounds__(256)
-k6_normalize(const ChipDesc* __restrict__ descs, const float* __restrict__ dist_max, int row0, int row1)
+// chips [base, base + 256) whose boxes intersect the tile, compacted in index order (one candidate per thread)
+__device__ __forceinline__ int tile_box_list(const ChipBox* __restrict__ box, int n, int base, int tx0, int ty0, int tx1, int ty1, int* list, int* wcount)
 {
-    const ChipDesc& D = descs[blockIdx.z];
-    if (!D.keep) return;
-    const int x0 = blockIdx.x * kTileW + threadIdx.x * 4;
-    const int r = blockIdx.y * kTileH + threadIdx.y;
-    if (x0 >= D.chip_w || r >= D.chip_h || r + D.beg_y < row0 || r + D.beg_y >= row1) return;
-    const float mx = dist_max[blockIdx.z];
-    float4* p = reinterpret_cast<float4*>(D.dist + (size_t)r * D.mask_step + x0);
-    float4 v = *p;
-    v.x = v.x / mx; v.y = v.y / mx; v.z = v.z / mx; v.w = v.w / mx;     // pMapRow[c] /= maxDist (:1830)
-    *p = v;
+    const int tid = threadIdx.y * 32 + threadIdx.x, lane = threadIdx.x, warp = threadIdx.y;
+    const int c = base + tid;
+    bool hit = false;
+    if (c < n) {
+        const ChipBox b = box[c];
+        hit = b.w > 0 && b.beg_x < tx1 && b.beg_x + b.w > tx0 && b.beg_y < ty1 && b.beg_y + b.h > ty0;
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, hit);
+    if (lane == 0) wcount[warp] = __popc(m);
+    __syncthreads();
+    int off = 0, total = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) { const int v = wcount[k]; if (k < warp) off += v; total += v; }
+    if (hit) list[off + __popc(m & ((1u << lane) - 1u))] = c;
+    __syncthreads();
+    return total;
 }
 
+// canvas rectangle [rx0, rx1) x [ry0, ry1); a CTA covers 128 x 8 canvas pixels, a thread the pixels x + 32 k of one row
 __global__ void __launch_bounds__(256)
-k6_owner(const ChipDesc* __restrict__ descs, const int32_t* __restrict__ nbr, int row0, int row1)
+k6_owner(const ChipDesc* __restrict__ descs, const ChipBox* __restrict__ box, const float* __restrict__ dist_max, int n,
+         float dgx, float dgy, float w1f, float h1f, int rx0, int ry0, int rx1, int ry1, int32_t* __restrict__ own_bbox)
 {
-    const int n = blockIdx.z;
-    const ChipDesc& D = descs[n];
-    if (!D.keep) return;
-    const int x0 = blockIdx.x * kTileW + threadIdx.x * 4;
-    const int r = blockIdx.y * kTileH + threadIdx.y;
-    if (x0 >= D.chip_w || r >= D.chip_h || r + D.beg_y < row0 || r + D.beg_y >= row1) return;
-    const float4 own4 = *reinterpret_cast<const float4*>(D.dist + (size_t)r * D.mask_step + x0);
-    const float own[4] = {own4.x, own4.y, own4.z, own4.w};
-    bool win[4];
+    __shared__ int list[256];
+    __shared__ int wcount[8];
+    __shared__ int sbb[256][4];
+    const int tx0 = rx0 + blockIdx.x * kTileW, ty0 = ry0 + blockIdx.y * kTileH;
+    const int gy = ty0 + threadIdx.y;
+    const int tid = threadIdx.y * 32 + threadIdx.x;
+    float best[4] = {0.0f, 0.0f, 0.0f, 0.0f};                         // float maxDist = 0 (:1850)
+    int owner[4] = {-1, -1, -1, -1};
+    // pass 0: arg-max in image index order; pass 1: mask bytes + owned bounding boxes
+    for (int pass = 0; pass < 2; pass++) {
+        for (int base = 0; base < n; base += 256) {
+            const int total = tile_box_list(box, n, base, tx0, ty0, min(tx0 + kTileW, rx1), min(ty0 + kTileH, ry1), list, wcount);
+            if (pass == 1) {
+                if (tid < total) { sbb[tid][0] = 1 << 30; sbb[tid][1] = 1 << 30; sbb[tid][2] = -1; sbb[tid][3] = -1; }
+                __syncthreads();
+            }
+            for (int e = 0; e < total; e++) {
+                const int m = list[e];
+                const ChipDesc& D = descs[m];
+                const int r = gy - D.beg_y;
+                if (gy >= ry1 || r < 0 || r >= D.chip_h) continue;
+                if (pass == 0) {
+                    const float mx = dist_max[m];
 #pragma unroll
-    for (int i = 0; i < 4; i++) win[i] = (own[i] > 0.0f) && (x0 + i < D.chip_w);
-    const int gy = r + D.beg_y;
-    for (int k = 0; k < D.nbr_cnt; k++) {
-        const int m = nbr[D.nbr_off + k];
-        const ChipDesc& E = descs[m];
-        const int yc = gy - E.beg_y;
-        if (yc < 0 || yc >= E.chip_h) continue;
-        const float* erow = E.dist + (size_t)yc * E.mask_step;
+                    for (int k = 0; k < 4; k++) {
+                        const int gx = tx0 + threadIdx.x + 32 * k, c = gx - D.beg_x;
+                        if (gx >= rx1 || c < 0 || c >= D.chip_w) continue;
+                        const float md = chip_min_dist(D, c, r, dgx, dgy, w1f, h1f);
+                        if (md == 0.0f) continue;                         // invalid pixel: the map holds 0 there
+                        const float dn = md / mx;                         // pMapRow[c] /= maxDist (:1830)
+                        if (dn > best[k]) { best[k] = dn; owner[k] = m; }
+                    }
+                } else {
+                    uint8_t* mrow = D.mask + (size_t)r * D.mask_step;
+                    int bx0 = 1 << 30, bx1 = -1;
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
-            const int xc = x0 + i + D.beg_x - E.beg_x;
-            if (!win[i] || xc < 0 || xc >= E.chip_w) continue;
-            const float cur = erow[xc];
-            if (m < n) { if (cur >= own[i]) win[i] = false; }        // an earlier image already holds the maximum
-            else       { if (cur > own[i]) win[i] = false; }         // a later image strictly exceeds it
+                    for (int k = 0; k < 4; k++) {
+                        const int gx = tx0 + threadIdx.x + 32 * k, c = gx - D.beg_x;
+                        if (gx >= rx1 || c < 0 || c >= D.chip_w) continue;
+                        const bool mine = owner[k] == m;
+                        mrow[c] = mine ? 255 : 0;
+                        if (mine) { bx0 = min(bx0, c); bx1 = max(bx1, c); }
+                    }
+                    const int wx0 = __reduce_min_sync(0xffffffffu, bx0), wx1 = __reduce_max_sync(0xffffffffu, bx1);
+                    if (threadIdx.x == 0 && wx1 >= 0) {
+                        atomicMin(&sbb[e][0], wx0); atomicMax(&sbb[e][2], wx1);
+                        atomicMin(&sbb[e][1], r); atomicMax(&sbb[e][3], r);
+                    }
+                }
+            }
+            __syncthreads();
+            if (pass == 1 && tid < total && sbb[tid][2] >= 0) {
+                int32_t* g = own_bbox + (size_t)list[tid] * 4;
+                if (sbb[tid][0] < g[0]) atomicMin(g + 0, sbb[tid][0]);
+                if (sbb[tid][1] < g[1]) atomicMin(g + 1, sbb[tid][1]);
+                if (sbb[tid][2] > g[2]) atomicMax(g + 2, sbb[tid][2]);
+                if (sbb[tid][3] > g[3]) atomicMax(g + 3, sbb[tid][3]);
+            }
+            __syncthreads();
         }
     }
-    const uint32_t bits = (win[0] ? 0xffu : 0u) | (win[1] ? 0xff00u : 0u) | (win[2] ? 0xff0000u : 0u) | (win[3] ? 0xff000000u : 0u);
-    *reinterpret_cast<uint32_t*>(D.mask + (size_t)r * D.mask_step + x0) = bits;
+}
+
+__global__ void k6_init_bbox(int32_t* __restrict__ bb, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { bb[4 * i] = 1 << 30; bb[4 * i + 1] = 1 << 30; bb[4 * i + 2] = -1; bb[4 * i + 3] = -1; }
 }
 
 // LineOf2Points1 (M/ImageMath.cpp:88-103)
@@ -137,51 +179,54 @@ extern "C" int uavm_canvas_seam_masks(uavm_ctx* ctx, uavm_canvas* cv)
     if (!cv->warped) { UAVM_SET_ERR(ctx, "seam_masks before warp"); return UAVM_EINVAL; }
     if (cv->max_chip_w <= 0) return UAVM_OK;
     UAVM_CUDA(ctx, cudaSetDevice(ctx->device));
-    if (!cv->d_dist) {
-        UAVM_CUDA(ctx, cudaMalloc(&cv->d_dist, cv->masks_bytes * sizeof(float) + 1024));
+    if (!cv->d_dist_max) {
         UAVM_CUDA(ctx, cudaMalloc(&cv->d_dist_max, (size_t)cv->n * sizeof(float)));
-        cv->nbr_dirty = true;
+        UAVM_CUDA(ctx, cudaMalloc(&cv->d_box, (size_t)cv->n * sizeof(ChipBox)));
+        UAVM_CUDA(ctx, cudaMalloc(&cv->d_own_bbox, (size_t)cv->n * 4 * sizeof(int32_t)));
+        cv->lines_dirty = true;
     }
-    if (cv->nbr_dirty) {
-        cudaFree(cv->d_nbr); cv->d_nbr = nullptr;
-        // edge lines, distance-map pointers and box-intersection neighbour lists
-        std::vector<int32_t> nbr;
+    if (cv->lines_dirty) {
+        // edge lines of every active chip (:1783-1787) and the compact boxes of the tile scans
+        std::vector<ChipBox> boxes(cv->n);
         for (int k = 0; k < cv->n; k++) {
             ChipDesc& d = cv->desc[k];
+            boxes[k] = ChipBox{d.beg_x, d.beg_y, d.keep ? d.chip_w : 0, d.keep ? d.chip_h : 0};
             if (!d.keep) continue;
-            d.dist = cv->d_dist + (size_t)(d.mask - cv->d_masks);
             for (int e = 0; e < 4; e++) {
                 const int f = (e + 1) & 3;
                 line_of_2_points(d.lineA[e], d.lineB[e], d.lineC[e], d.quad[2 * e], d.quad[2 * e + 1], d.quad[2 * f], d.quad[2 * f + 1]);
                 d.lineInv[e] = 1 / sqrtf(d.lineA[e] * d.lineA[e] + d.lineB[e] * d.lineB[e]);
             }
-            d.nbr_off = (int32_t)nbr.size();
-            for (int m = 0; m < cv->n; m++) {
-                const ChipDesc& e = cv->desc[m];
-                if (m == k || !e.keep) continue;
-                if (e.beg_x < d.beg_x + d.chip_w && d.beg_x < e.beg_x + e.chip_w &&
-                    e.beg_y < d.beg_y + d.chip_h && d.beg_y < e.beg_y + e.chip_h) nbr.push_back(m);
-            }
-            d.nbr_cnt = (int32_t)nbr.size() - d.nbr_off;
         }
-        UAVM_CUDA(ctx, cudaMalloc(&cv->d_nbr, (nbr.size() + 1) * sizeof(int32_t)));
-        if (!nbr.empty())
-            UAVM_CUDA(ctx, cudaMemcpyAsync(cv->d_nbr, nbr.data(), nbr.size() * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
-        int rc = uavm_canvas_upload_desc(ctx, cv);
+        UAVM_CUDA(ctx, cudaMemcpyAsync(cv->d_box, boxes.data(), boxes.size() * sizeof(ChipBox), cudaMemcpyHostToDevice, ctx->stream));
+        int rc = uavm_canvas_upload_desc(ctx, cv);          // synchronises: `boxes` may go out of scope
         if (rc != UAVM_OK) return rc;
-        cv->nbr_dirty = false;
+        cv->lines_dirty = false;
     }
     UAVM_CUDA(ctx, cudaMemsetAsync(cv->d_dist_max, 0, (size_t)cv->n * sizeof(float), ctx->stream));
-    dim3 grid((cv->max_chip_w + kTileW - 1) / kTileW, (cv->max_chip_h + kTileH - 1) / kTileH, cv->n);
-    dim3 block(32, 8);
-    // canvas rows this context holds (band + halo; the whole canvas when it is not sharded): the only rows K7 feeds from
-    const int row0 = cv->banded ? cv->band_Y0 : 0, row1 = cv->banded ? cv->band_Y1 : cv->layout.canvas_h + 64;
-    k6_dist_map<<<grid, block, 0, ctx->stream>>>(cv->d_desc, cv->d_dist_max, cv->layout.dgx, cv->layout.dgy, (float)(cv->img_w - 1), (float)(cv->img_h - 1), row0, row1);
+    k6_init_bbox<<<(cv->n + 255) / 256, 256, 0, ctx->stream>>>(cv->d_own_bbox, cv->n);
     UAVM_CHECK_LAUNCH(ctx);
-    k6_normalize<<<grid, block, 0, ctx->stream>>>(cv->d_desc, cv->d_dist_max, row0, row1);
-    UAVM_CHECK_LAUNCH(ctx);
-    k6_owner<<<grid, block, 0, ctx->stream>>>(cv->d_desc, cv->d_nbr, row0, row1);
-    UAVM_CHECK_LAUNCH(ctx);
-    cv->seamed = true; cv->mask_plane_valid = true;
+    const float w1f = (float)(cv->img_w - 1), h1f = (float)(cv->img_h - 1);
+    {
+        dim3 grid((cv->max_chip_w + kTileW - 1) / kTileW, (cv->max_chip_h + kTileH - 1) / kTileH, cv->n);
+        k6_dist_max<<<grid, dim3(32, 8), 0, ctx->stream>>>(cv->d_desc, cv->d_dist_max, cv->layout.dgx, cv->layout.dgy, w1f, h1f);
+        UAVM_CHECK_LAUNCH(ctx);
+    }
+    {
+        // canvas pixels whose masks K7 can read: the whole canvas, or this context's rectangle + kShardMargin
+        int rx0 = 0, ry0 = 0, rx1 = cv->layout.canvas_w, ry1 = cv->layout.canvas_h;
+        if (cv->sharded) {
+            rx0 = cv->rect_x0 - uavm_canvas::kShardMargin > 0 ? cv->rect_x0 - uavm_canvas::kShardMargin : 0;
+            ry0 = cv->rect_y0 - uavm_canvas::kShardMargin > 0 ? cv->rect_y0 - uavm_canvas::kShardMargin : 0;
+            rx1 = cv->rect_x1 + uavm_canvas::kShardMargin < rx1 ? cv->rect_x1 + uavm_canvas::kShardMargin : rx1;
+            ry1 = cv->rect_y1 + uavm_canvas::kShardMargin < ry1 ? cv->rect_y1 + uavm_canvas::kShardMargin : ry1;
+        }
+        dim3 grid((rx1 - rx0 + kTileW - 1) / kTileW, (ry1 - ry0 + kTileH - 1) / kTileH);
+        if (grid.y > 65535) { UAVM_SET_ERR(ctx, "seam_masks: canvas rectangle too tall (%d rows): shard the canvas", ry1 - ry0); return UAVM_EINVAL; }
+        k6_owner<<<grid, dim3(32, 8), 0, ctx->stream>>>(cv->d_desc, cv->d_box, cv->d_dist_max, cv->n, cv->layout.dgx, cv->layout.dgy, w1f, h1f,
+                                                        rx0, ry0, rx1, ry1, cv->d_own_bbox);
+        UAVM_CHECK_LAUNCH(ctx);
+    }
+    cv->seamed = true; cv->mask_plane_valid = true; cv->own_bbox_valid = false;
     return UAVM_OK;
 }

@@ -74,3 +74,23 @@ def canvas_bands(canvas_h, world, align=32):
         y0 = u0 * align; y1 = min(u1 * align, canvas_h)
         out.append((y0, y1) if y1 > y0 else (0, 0))
     return out
+
+
+def canvas_grid(canvas_w, canvas_h, world, align=32):
+    """Split the canvas into `world` rectangles of a gx x gy grid (gx * gy == world, as square as the canvas allows:
+    SURVEY §8e's 4 x 2 grid for 8 GPUs) whose inner edges are multiples of `align`.  Returns [(x0, y0, x1, y1)] per rank,
+    row-major; a 2-D grid halves the chips a rank touches compared with full-width bands when chips are taller than a band."""
+    best = None
+    for gx in range(1, world + 1):
+        if world % gx:
+            continue
+        gy = world // gx
+        cost = abs(canvas_w / gx - canvas_h / gy)          # prefer square cells
+        if best is None or cost < best[0]:
+            best = (cost, gx, gy)
+    _, gx, gy = best
+    def cuts(n, g):
+        units = (n + align - 1) // align
+        return [min((units * k // g) * align, n) for k in range(g)] + [n]
+    xs, ys = cuts(canvas_w, gx), cuts(canvas_h, gy)
+    return [(xs[i], ys[j], xs[i + 1], ys[j + 1]) for j in range(gy) for i in range(gx)]

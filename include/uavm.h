@@ -146,9 +146,11 @@ int uavm_resample_by_overlap(const float* H, int n, int img_w, int img_h, float 
 int uavm_canvas_create(uavm_ctx* ctx, int n_images, int img_w, int img_h, const float* H, const int32_t* keep, uavm_canvas** out);
 void uavm_canvas_destroy(uavm_ctx* ctx, uavm_canvas* cv);
 int uavm_canvas_get_layout(uavm_canvas* cv, uavm_canvas_layout* canvas, uavm_chip_layout* chips);
-/* multi-GPU canvas sharding: this ctx computes only canvas rows [y0, y1) (multiples of 32; halo >= 128 rows of
- * redundant computation on each side make the band bit-identical to the untiled blend).  Chips that cannot touch
- * the band are deactivated (uavm_canvas_is_active == 0: no need to set their image). */
+/* multi-GPU canvas sharding: this ctx produces only the canvas rectangle [x0, x1) x [y0, y1) (even edges, or the canvas
+ * size).  The blend computes exactly the pyramid regions the rectangle depends on, so the assembled rectangles are
+ * bit-identical to the unsharded mosaic (at most 5 bands).  Chips that cannot contribute are deactivated
+ * (uavm_canvas_is_active == 0: no need to set their image).  uavm_canvas_set_band = full-width rectangle; `halo` is ignored. */
+int uavm_canvas_set_rect(uavm_ctx* ctx, uavm_canvas* cv, int x0, int y0, int x1, int y1);
 int uavm_canvas_set_band(uavm_ctx* ctx, uavm_canvas* cv, int y0, int y1, int halo);
 int uavm_canvas_is_active(uavm_canvas* cv, int image);
 /* source frame n (BGR u8 interleaved, `step` bytes per row); is_device != 0: device pointer */
@@ -171,6 +173,8 @@ int uavm_canvas_get_result(uavm_ctx* ctx, uavm_canvas* cv, uint8_t* bgr, int ste
 /* rows [y0, y1) of the result, dense (canvas_w * 3 bytes per row); is_device != 0: dst is device memory (stream-ordered
  * copy, e.g. the send buffer of the NCCL gather of canvas bands) */
 int uavm_canvas_copy_result_rows(uavm_ctx* ctx, uavm_canvas* cv, int y0, int y1, uint8_t* dst, int is_device);
+/* rectangle [x0, x1) x [y0, y1) of the result, dense ((x1 - x0) * 3 bytes per row) */
+int uavm_canvas_copy_result_rect(uavm_ctx* ctx, uavm_canvas* cv, int x0, int y0, int x1, int y1, uint8_t* dst, int is_device);
 
 /* ---- top-level shim with the shape of MosaicVavImages (M/MosaicWithoutPos.h:638-645,
  *      M/MosaicWithoutPos.cpp:10148-10214).  Features are supplied by the caller (SIFT extraction is

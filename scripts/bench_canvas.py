@@ -40,7 +40,7 @@ ctx = api.Context(local, torch.cuda.current_stream())
 lay, chips = api.canvas_layout(T, keep, W, H)
 cw, ch = lay.canvas_w, lay.canvas_h
 chip_px = sum(chips[k].chip_w * chips[k].chip_h for k in range(n) if chips[k].keep)
-need = n * W * H * 4 + chip_px * (4 + 1 + 4) + cw * ch * (12 * 4 / 3 + 4) + 2e9
+need = n * W * H * 4 + chip_px * (4 + 1 + 4) + cw * ch * (8 / 3 + 4) + 2e9      # sources, chips + masks + chip pyramids, final canvas levels + result
 free, total = torch.cuda.mem_get_info()
 if need > 0.92 * free:
     raise SystemExit(f"needs ~{need / 1e9:.0f} GB, {free / 1e9:.0f} GB free: use fewer tiles (--cols/--rows)")
@@ -48,7 +48,7 @@ cv = api.Canvas(ctx, T, W, H, keep)
 bands = D.canvas_bands(ch, world)
 y0, y1 = bands[rank]
 if world > 1:
-    cv.set_band(y0, y1, 128)
+    cv.set_band(y0, y1)
 base = torch.from_numpy(synth.texture_image(rng, W, H, 6)).to(dev)
 n_active = 0
 for k in range(n):
