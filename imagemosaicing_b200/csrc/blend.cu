@@ -41,7 +41,7 @@ struct LevelArgs {
     int32_t level, n_chips;
     int32_t sx0, sy0, sx1, sy1;             // S_i: canvas level-i rectangle to produce
     short* fin; int32_t fin_x0, fin_y0, fin_pitch;                               // final level i (int16 x4), storage origin = S_i origin
-    const short* nxt; int32_t nxt_x0, nxt_y0, nxt_pitch, nxt_w, nxt_h;           // final level i+1 storage; nxt_w/h = full level size (border rules)
+    const short* nxt; int32_t nxt_x0, nxt_y0, nxt_pitch, nxt_rows, nxt_w, nxt_h;           // final level i+1 storage; nxt_w/h = full level size (border rules)
     uint8_t* out; uint8_t* out_mask; int32_t cw, ch;                             // level 0: mosaic (pitch cw pixels) and its mask
     int32_t ox0, oy0, ox1, oy1;                                                  // level 0: output rectangle
 };
@@ -100,6 +100,29 @@ k7_pyrdown(const BlendChip* __restrict__ chips, int sl)
     const int scx0 = L0 ? 0 : B.cx0[sl], scy0 = L0 ? 0 : B.cy0[sl], scw = L0 ? 0 : B.cw_[sl], sch = L0 ? 0 : B.ch_[sl];
     const short* __restrict__ src = L0 ? nullptr : B.pyr[sl];
     const float* __restrict__ wsrc = L0 ? nullptr : B.wp[sl];
+    // L0 fast path: the whole window lies inside the chip (hence inside the ROI): no border arithmetic, and when the chip
+    // sits at an even ROI column the (even, odd) pixel pair is one 8-byte load and its two mask bytes one 2-byte load
+    const bool interior = L0 && sx0 - B.left >= 0 && sx0 + kPdCols - B.left <= B.cw && sy0 - B.top >= 0 && sy0 + kPdRows - B.top <= B.ch;
+    if (L0 && interior) {
+        const int warp = tid >> 5, lane = tid & 31;
+        const bool even = (B.left & 1) == 0;
+        for (int r = warp; r < kPdRows; r += 8) {
+            const uint32_t* crow = B.chip + (size_t)(sy0 + r - B.top) * B.chip_step + (sx0 - B.left);
+            const uint8_t* mrow = B.mask + (size_t)(sy0 + r - B.top) * B.mask_step + (sx0 - B.left);
+            for (int j = lane; j < kPdCols / 2; j += 32) {
+                uint32_t c0, c1, m0, m1;
+                if (even) {
+                    const uint2 c = __ldg(reinterpret_cast<const uint2*>(crow + 2 * j));
+                    const uint32_t m = __ldg(reinterpret_cast<const unsigned short*>(mrow + 2 * j));
+                    c0 = c.x; c1 = c.y; m0 = m & 0xffu; m1 = m >> 8;
+                } else {
+                    c0 = __ldg(crow + 2 * j); c1 = __ldg(crow + 2 * j + 1); m0 = __ldg(mrow + 2 * j); m1 = __ldg(mrow + 2 * j + 1);
+                }
+                sE[r][j] = bgra_to_px(c0); sO[r][j] = bgra_to_px(c1);
+                wE[r][j] = (float)m0 * (float)(1. / 255.); wO[r][j] = (float)m1 * (float)(1. / 255.);
+            }
+        }
+    } else
     for (int e = tid; e < kPdRows * (kPdCols / 2); e += 256) {
         const int r = e / (kPdCols / 2), j = e - r * (kPdCols / 2);
         const int Y = reflect101(sy0 + r, h);
@@ -210,6 +233,47 @@ __device__ __forceinline__ void pyrup_2quads(const short* __restrict__ lo, int p
             }
 }
 
+// short(d / (wsum + 1e-5f)) (normalizeUsingWeightMap), with two exact shortcuts that remove most IEEE divisions:
+//   d == 0            -> 0
+//   wsum == 1.0f      -> d - sign(d): d / 1.00001f lies strictly between d - sign(d) and d for every int16 d (d * 1e-5 < 1 and
+//                        far above half an ulp of d), so the truncation drops exactly one unit — checked for all 65 536 values
+//                        of d in tests/test_cpu_blend.py.  With seam masks every owned level-0 pixel has wsum == 1.0f.
+__device__ __forceinline__ int norm_div(int d, float ws)
+{
+    if (d == 0) return 0;
+    if (ws == 1.0f) return d - (d > 0 ? 1 : -1);
+    return (short)__float2int_rz((float)d / (ws + 1e-5f));
+}
+
+// pyrUp for a 4 x 2 block from a staged coarse tile (border rules already applied while staging): st[r][c] holds the coarse
+// pixel (row r0 - 1 + r, column c0 - 1 + c); lc = local column of quad 0 (>= 1), lr = local row (>= 1)
+template <int PITCH>
+__device__ __forceinline__ void pyrup_2quads_smem(const int2 (*st)[PITCH], int lc, int lr, int up[2][4][3])
+{
+    int he[2][3][3], ho[2][3][3];
+#pragma unroll
+    for (int r = 0; r < 3; r++) {
+        int v[4][3];
+#pragma unroll
+        for (int j = 0; j < 4; j++) unpack3(st[lr - 1 + r][lc - 1 + j], v[j][0], v[j][1], v[j][2]);
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            he[0][r][k] = v[0][k] + 6 * v[1][k] + v[2][k]; ho[0][r][k] = 4 * (v[1][k] + v[2][k]);
+            he[1][r][k] = v[1][k] + 6 * v[2][k] + v[3][k]; ho[1][r][k] = 4 * (v[2][k] + v[3][k]);
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 2; q++)
+#pragma unroll
+        for (int dx = 0; dx < 2; dx++)
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                const int h0 = dx ? ho[q][0][k] : he[q][0][k], h1 = dx ? ho[q][1][k] : he[q][1][k], h2 = dx ? ho[q][2][k] : he[q][2][k];
+                up[0][2 * q + dx][k] = sat16((h0 + 6 * h1 + h2 + 32) >> 6);
+                up[1][2 * q + dx][k] = sat16((4 * (h1 + h2) + 32) >> 6);
+            }
+}
+
 // Sorted list of the chips whose contribution rectangle U_level intersects the CTA's tile, for chips [base, base + 256):
 // one candidate per thread, compacted in index order through warp ballots.  All 256 threads must call it.
 __device__ __forceinline__ int tile_chip_list(const BlendChip* __restrict__ chips, int n, int base, int level, int tx0, int ty0, int tx1, int ty1,
@@ -246,10 +310,21 @@ k7_level(const BlendChip* __restrict__ chips, const LevelArgs A)
 {
     __shared__ int list[256];
     __shared__ int wcount[8];
+    __shared__ int2 snx[10][68];                                                  // final level i+1 under this tile: 66 x 10 coarse pixels
     const int level = A.level;
     const int tx0 = (A.sx0 & ~3) + blockIdx.x * 128, ty0 = A.sy0 + blockIdx.y * 16;
     const int X = tx0 + 4 * threadIdx.x, Y = ty0 + 2 * threadIdx.y;               // this thread's block (canvas level coordinates)
     const bool live = X + 4 > A.sx0 && X < A.sx1 && Y < A.sy1;
+    // stage the coarse tile with pyrUp's border rules applied (reflect-101 at the near edge, replicate at the far edge);
+    // positions outside the stored rectangle S_{i+1} only feed pixels outside S_i and are clamped into it
+    for (int e = threadIdx.y * 32 + threadIdx.x; e < 10 * 66; e += 256) {
+        const int r = e / 66, c = e - r * 66;
+        int cx = (tx0 >> 1) - 1 + c, cy = (ty0 >> 1) - 1 + r;
+        cx = cx < 0 ? (A.nxt_w > 1 ? 1 : 0) : (cx > A.nxt_w - 1 ? A.nxt_w - 1 : cx);
+        cy = cy < 0 ? (A.nxt_h > 1 ? 1 : 0) : (cy > A.nxt_h - 1 ? A.nxt_h - 1 : cy);
+        const int lx = min(max(cx - A.nxt_x0, 0), A.nxt_pitch - 1), ly = min(max(cy - A.nxt_y0, 0), A.nxt_rows - 1);
+        snx[r][c] = *reinterpret_cast<const int2*>(A.nxt + ((size_t)ly * A.nxt_pitch + lx) * 4);
+    }
     int d[2][4][3];
     float ws[2][4];
 #pragma unroll
@@ -327,18 +402,18 @@ k7_level(const BlendChip* __restrict__ chips, const LevelArgs A)
         }
         __syncthreads();
     }
+    if (A.n_chips <= 0) __syncthreads();                                          // the staged tile (the chip loop synchronises otherwise)
     if (!live) return;
     int up[2][4][3];
-    pyrup_2quads(A.nxt, A.nxt_pitch, A.nxt_x0, A.nxt_y0, A.nxt_w, A.nxt_h, X >> 1, Y >> 1, up);
+    pyrup_2quads_smem<68>(snx, 1 + 2 * threadIdx.x, 1 + threadIdx.y, up);
 #pragma unroll
     for (int dy = 0; dy < 2; dy++) {
         const int yy = Y + dy;
         int v[4][3];
 #pragma unroll
         for (int p = 0; p < 4; p++) {
-            const float wv = ws[dy][p] + 1e-5f;
 #pragma unroll
-            for (int k = 0; k < 3; k++) v[p][k] = sat16(up[dy][p][k] + (short)__float2int_rz((float)d[dy][p][k] / wv));
+            for (int k = 0; k < 3; k++) v[p][k] = sat16(up[dy][p][k] + norm_div(d[dy][p][k], ws[dy][p]));
         }
         if (!L0) {
             if (yy >= A.sy1) break;
@@ -423,7 +498,7 @@ k7_level_top(const BlendChip* __restrict__ chips, const LevelArgs A)
     if (!live) return;
     int v[3];
 #pragma unroll
-    for (int k = 0; k < 3; k++) v[k] = (short)__float2int_rz((float)d[k] / (ws + 1e-5f));
+    for (int k = 0; k < 3; k++) v[k] = norm_div(d[k], ws);
     if (!L0) {
         *reinterpret_cast<int2*>(A.fin + ((ptrdiff_t)(Y - A.fin_y0) * A.fin_pitch + (X - A.fin_x0)) * 4) = pack3(v[0], v[1], v[2]);
     } else if (X >= A.ox0 && X < A.ox1 && Y >= A.oy0 && Y < A.oy1) {
@@ -549,7 +624,7 @@ extern "C" int uavm_canvas_blend(uavm_ctx* ctx, uavm_canvas* cv, int num_bands)
         A.sx0 = P.S[i].x0; A.sy0 = P.S[i].y0; A.sx1 = P.S[i].x1; A.sy1 = P.S[i].y1;
         if (A.sx1 <= A.sx0 || A.sy1 <= A.sy0) continue;
         if (i >= 1) { A.fin = ws->d_fin[i]; A.fin_x0 = P.S[i].x0; A.fin_y0 = P.S[i].y0; A.fin_pitch = P.S[i].x1 - P.S[i].x0; }
-        if (i < nb) { A.nxt = ws->d_fin[i + 1]; A.nxt_x0 = P.S[i + 1].x0; A.nxt_y0 = P.S[i + 1].y0; A.nxt_pitch = P.S[i + 1].x1 - P.S[i + 1].x0; A.nxt_w = P.lw[i + 1]; A.nxt_h = P.lh[i + 1]; }
+        if (i < nb) { A.nxt = ws->d_fin[i + 1]; A.nxt_x0 = P.S[i + 1].x0; A.nxt_y0 = P.S[i + 1].y0; A.nxt_pitch = P.S[i + 1].x1 - P.S[i + 1].x0; A.nxt_rows = P.S[i + 1].y1 - P.S[i + 1].y0; A.nxt_w = P.lw[i + 1]; A.nxt_h = P.lh[i + 1]; }
         if (i == 0) {
             A.out = cv->d_result; A.out_mask = cv->d_result_mask; A.cw = cw; A.ch = ch;
             A.ox0 = out.x0; A.oy0 = out.y0; A.ox1 = out.x1 < cw ? out.x1 : cw; A.oy1 = out.y1 < ch ? out.y1 : ch;

@@ -573,7 +573,7 @@ extern "C" void uavm_canvas_destroy(uavm_ctx* ctx, uavm_canvas* cv)
         if (cv->ev_free[s]) cudaEventDestroy(cv->ev_free[s]);
     }
     uavm_blend_free(cv);
-    cudaFree(cv->d_src); cudaFree(cv->d_chips); cudaFree(cv->d_masks); cudaFree(cv->d_dist_max); cudaFree(cv->d_box); cudaFree(cv->d_own_bbox);
+    cudaFree(cv->d_src); cudaFree(cv->d_chips); cudaFree(cv->d_masks); cudaFree(cv->d_dist_max); cudaFree(cv->d_k6); cudaFree(cv->d_mask_ptr); cudaFree(cv->d_mask_step); cudaFree(cv->d_own_bbox);
     cudaFree(cv->d_desc); cudaFree(cv->d_result); cudaFree(cv->d_result_mask);
     delete cv;
 }

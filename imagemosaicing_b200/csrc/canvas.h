@@ -21,7 +21,6 @@ struct ChipDesc {               // one per image, device-visible
                                                       // canvas (uavm_canvas_set_rect) can read from it
 };
 
-struct ChipBox { int32_t beg_x, beg_y, w, h; };       // compact per-image box for tile / chip intersection scans (w = 0: inactive)
 
 struct uavm_canvas {
     int n = 0, img_w = 0, img_h = 0, src_step_px = 0;
@@ -33,7 +32,9 @@ struct uavm_canvas {
     uint32_t* d_chips = nullptr;     // BGRA chips
     uint8_t* d_masks = nullptr;
     float* d_dist_max = nullptr;     // [n] per-image maximum of the distance map (as uint bits)
-    ChipBox* d_box = nullptr;        // [n]
+    void* d_k6 = nullptr;            // [n] K6Chip (masks.cu): packed per-chip constants of the distance evaluation
+    uint8_t** d_mask_ptr = nullptr;  // [n] mask plane of every chip
+    int32_t* d_mask_step = nullptr;  // [n]
     int32_t* d_own_bbox = nullptr;   // [n][4] K6: bounding box (min x, min y, max x, max y; chip coordinates) of the pixels a chip owns
     std::vector<int32_t> own_bbox;   // host copy, fetched by K7 (valid when own_bbox_valid)
     bool own_bbox_valid = false;

@@ -5,8 +5,9 @@
 // largest normalised distance (strict >, so the lowest image index wins ties and 0 never wins) and only
 // the owner's mask is 255.
 // Here no distance map is ever stored (the reference keeps an f32 map per chip):
-//   k6_dist_max   per chip pixel, compute only: validity from the warp's own coordinate chain (M/MosaicImage.cpp:2356-2362,
-//                 :2370), distance to the nearest edge, per-image maximum (atomicMax on the float bits);
+//   k6_dist_max   per chip, compute only: validity from the warp's own coordinate chain (M/MosaicImage.cpp:2356-2362, :2370),
+//                 distance to the nearest edge, per-image maximum (atomicMax on the float bits); tiles that provably cannot
+//                 hold the maximum are skipped (the distance is 1-Lipschitz), the maximum itself is exact;
 //   k6_owner      per CANVAS pixel: the normalised distance of every chip whose box covers the pixel is evaluated once, in
 //                 image index order with the reference's strict >; then each of those chips gets its mask byte (255 for the
 //                 owner, 0 for the others) and the bounding box of the pixels it owns (K7 only builds pyramids there).
@@ -19,43 +20,63 @@ namespace {
 
 constexpr int kTileW = 128, kTileH = 8;
 
-// distance of chip pixel (c, r) to the nearest quad edge; 0 when the pixel is outside the source frame (mask == 0)
-__device__ __forceinline__ float chip_min_dist(const ChipDesc& D, int c, int r, float dgx, float dgy, float w1f, float h1f)
+// Per-chip constants of the distance evaluation, packed so a thread fetches them with a few 16-byte loads and keeps them
+// in registers (reading the 200-byte ChipDesc field by field per pixel made the kernels LSU / issue bound).
+struct __align__(16) K6Chip {
+    float inv[8];                    // inv[0..7] of the chip (inv[8] below)
+    float inv8, sx, sy, fbx;         // fbx = (float)beg_x
+    float fby, pad0, pad1, pad2;     // fby = (float)beg_y
+    float A[4], B[4], C[4], I[4];    // quad edges A x + B y + C = 0 and 1 / sqrt(A^2 + B^2)
+    int32_t beg_x, beg_y, w, h;
+    int32_t affine, keep, pad3, pad4;
+};
+
+struct RowTerms { float ya, yb, yd, Br[4]; };       // row-invariant parts of the chain for one chip row
+
+__device__ __forceinline__ RowTerms row_terms(const K6Chip& D, int r, float dgy)
 {
-    const float yt = (float)r - dgy - D.sy + (float)D.beg_y;          // yTemp (:2357)
-    const float ya = yt * D.inv[1], yb = yt * D.inv[4];
-    const float xt = (float)c - dgx - D.sx + (float)D.beg_x;          // xTemp (:2356)
-    float xs = xt * D.inv[0] + ya + D.inv[2];
-    float ys = xt * D.inv[3] + yb + D.inv[5];
+    RowTerms t;
+    const float fr = (float)r;
+    const float yt = fr - dgy - D.sy + D.fby;                          // yTemp (:2357)
+    t.ya = yt * D.inv[1]; t.yb = yt * D.inv[4]; t.yd = yt * D.inv[7];
+#pragma unroll
+    for (int e = 0; e < 4; e++) t.Br[e] = D.B[e] * fr;
+    return t;
+}
+
+// distance of chip pixel (column fc = (float)c, row terms t) to the nearest quad edge; 0 when the pixel is outside the source
+// frame (mask == 0).  Same expressions, same order as the reference: xTemp (:2356), the inverse map (:2359-2362), the
+// validity test (:2370) and |A x + B y + C| * inv (:1789-1797).
+__device__ __forceinline__ float chip_min_dist(const K6Chip& D, const RowTerms& t, float fc, float dgx, float w1f, float h1f)
+{
+    const float xt = fc - dgx - D.sx + D.fbx;
+    float xs = xt * D.inv[0] + t.ya + D.inv[2];
+    float ys = xt * D.inv[3] + t.yb + D.inv[5];
     if (!D.affine) {
-        const float den = xt * D.inv[6] + yt * D.inv[7] + D.inv[8];
+        const float den = xt * D.inv[6] + t.yd + D.inv8;
         xs = xs / den; ys = ys / den;
     }
     if (!((xs >= 0.0f) && (xs < w1f) && (ys >= 0.0f) && (ys < h1f))) return 0.0f;
     float mind = 536870912.0f;                                         // float minDist = 1<<29
 #pragma unroll
     for (int e = 0; e < 4; e++) {
-        const float d = fabsf(D.lineA[e] * (float)c + D.lineB[e] * (float)r + D.lineC[e]) * D.lineInv[e];
+        const float d = fabsf(D.A[e] * fc + t.Br[e] + D.C[e]) * D.I[e];
         if (d < mind) mind = d;
     }
     return mind;
 }
 
-__global__ void __launch_bounds__(256)
-k6_dist_max(const ChipDesc* __restrict__ descs, float* __restrict__ dist_max, float dgx, float dgy, float w1f, float h1f)
+// geometric distance to the nearest edge line, validity ignored (1-Lipschitz in the pixel position)
+__device__ __forceinline__ float chip_edge_dist(const K6Chip& D, float fc, float fr)
 {
-    const ChipDesc& D = descs[blockIdx.z];
-    if (!D.keep) return;
-    if (blockIdx.x * kTileW >= D.chip_w || blockIdx.y * kTileH >= D.chip_h) return;
-    const int r = blockIdx.y * kTileH + threadIdx.y;
-    float mx = 0.0f;
-    if (r < D.chip_h) {
+    float mind = 536870912.0f;
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
-            const int c = blockIdx.x * kTileW + threadIdx.x + 32 * i;
-            if (c < D.chip_w) mx = fmaxf(mx, chip_min_dist(D, c, r, dgx, dgy, w1f, h1f));
-        }
-    }
+    for (int e = 0; e < 4; e++) mind = fminf(mind, fabsf(D.A[e] * fc + D.B[e] * fr + D.C[e]) * D.I[e]);
+    return mind;
+}
+
+__device__ __forceinline__ void block_max_to_global(float mx, float* slot)
+{
     // block max -> one atomic per block (distances are >= 0, so the uint order of the bits is the float order)
     __shared__ float smax[8];
     mx = __int_as_float(__reduce_max_sync(0xffffffffu, __float_as_int(mx)));
@@ -65,19 +86,54 @@ k6_dist_max(const ChipDesc* __restrict__ descs, float* __restrict__ dist_max, fl
         float m = smax[0];
 #pragma unroll
         for (int i = 1; i < 8; i++) m = fmaxf(m, smax[i]);
-        if (m > 0.0f && m > dist_max[blockIdx.z]) atomicMax(reinterpret_cast<unsigned int*>(dist_max + blockIdx.z), __float_as_uint(m));
+        if (m > 0.0f && m > *slot) atomicMax(reinterpret_cast<unsigned int*>(slot), __float_as_uint(m));
     }
 }
 
+// Per-image maximum of the distance map, two launches.  COARSE: every 8th pixel of every 8th row — a true value at a true
+// pixel, so a lower bound L of the maximum.  Fine: the distance is 1-Lipschitz in the pixel position, so a 128 x 32 tile whose
+// centre distance + half diagonal (+ 1 px of slack for float rounding) is below L cannot hold the maximum and is skipped;
+// the tiles along the quad's medial axis are evaluated at every pixel.  The result is the exact maximum over all pixels.
+constexpr int kMaxTileH = 32;
+template <bool COARSE>
+__global__ void __launch_bounds__(256)
+k6_dist_max(const K6Chip* __restrict__ chips, float* __restrict__ dist_max, float dgx, float dgy, float w1f, float h1f)
+{
+    const K6Chip D = chips[blockIdx.z];
+    if (!D.keep) return;
+    float mx = 0.0f;
+    if (COARSE) {
+        const int c = 8 * (blockIdx.x * 32 + threadIdx.x), r = 8 * (blockIdx.y * 8 + threadIdx.y);
+        if (8 * blockIdx.x * 32 >= D.w || 8 * blockIdx.y * 8 >= D.h) return;
+        if (c < D.w && r < D.h) mx = chip_min_dist(D, row_terms(D, r, dgy), (float)c, dgx, w1f, h1f);
+    } else {
+        const int c0 = blockIdx.x * kTileW, r0 = blockIdx.y * kMaxTileH;
+        if (c0 >= D.w || r0 >= D.h) return;
+        const float ub = chip_edge_dist(D, (float)c0 + 63.5f, (float)r0 + 15.5f) + 67.0f;      // half diagonal of 128 x 32 = 65.97
+        if (ub < dist_max[blockIdx.z]) return;
+#pragma unroll 1
+        for (int j = 0; j < kMaxTileH / 8; j++) {
+            const int r = r0 + 8 * j + threadIdx.y;
+            if (r >= D.h) break;
+            const RowTerms t = row_terms(D, r, dgy);
+            const float fc0 = (float)(c0 + threadIdx.x);
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+                if (c0 + threadIdx.x + 32 * i < D.w) mx = fmaxf(mx, chip_min_dist(D, t, fc0 + 32.0f * i, dgx, w1f, h1f));
+        }
+    }
+    block_max_to_global(mx, dist_max + blockIdx.z);
+}
+
 // chips [base, base + 256) whose boxes intersect the tile, compacted in index order (one candidate per thread)
-__device__ __forceinline__ int tile_box_list(const ChipBox* __restrict__ box, int n, int base, int tx0, int ty0, int tx1, int ty1, int* list, int* wcount)
+__device__ __forceinline__ int tile_box_list(const K6Chip* __restrict__ chips, int n, int base, int tx0, int ty0, int tx1, int ty1, int* list, int* wcount)
 {
     const int tid = threadIdx.y * 32 + threadIdx.x, lane = threadIdx.x, warp = threadIdx.y;
     const int c = base + tid;
     bool hit = false;
     if (c < n) {
-        const ChipBox b = box[c];
-        hit = b.w > 0 && b.beg_x < tx1 && b.beg_x + b.w > tx0 && b.beg_y < ty1 && b.beg_y + b.h > ty0;
+        const int4 b = *reinterpret_cast<const int4*>(&chips[c].beg_x);
+        hit = chips[c].keep && b.x < tx1 && b.x + b.z > tx0 && b.y < ty1 && b.y + b.w > ty0;
     }
     const unsigned m = __ballot_sync(0xffffffffu, hit);
     if (lane == 0) wcount[warp] = __popc(m);
@@ -92,48 +148,60 @@ __device__ __forceinline__ int tile_box_list(const ChipBox* __restrict__ box, in
 
 // canvas rectangle [rx0, rx1) x [ry0, ry1); a CTA covers 128 x 8 canvas pixels, a thread the pixels x + 32 k of one row
 __global__ void __launch_bounds__(256)
-k6_owner(const ChipDesc* __restrict__ descs, const ChipBox* __restrict__ box, const float* __restrict__ dist_max, int n,
-         float dgx, float dgy, float w1f, float h1f, int rx0, int ry0, int rx1, int ry1, int32_t* __restrict__ own_bbox)
+k6_owner(const K6Chip* __restrict__ chips, uint8_t* const* __restrict__ mask_ptr, const int32_t* __restrict__ mask_step,
+         const float* __restrict__ dist_max, int n, float dgx, float dgy, float w1f, float h1f, int rx0, int ry0, int rx1, int ry1,
+         int32_t* __restrict__ own_bbox)
 {
     __shared__ int list[256];
     __shared__ int wcount[8];
     __shared__ int sbb[256][4];
     const int tx0 = rx0 + blockIdx.x * kTileW, ty0 = ry0 + blockIdx.y * kTileH;
     const int gy = ty0 + threadIdx.y;
+    const int gx0 = tx0 + threadIdx.x;
     const int tid = threadIdx.y * 32 + threadIdx.x;
     float best[4] = {0.0f, 0.0f, 0.0f, 0.0f};                         // float maxDist = 0 (:1850)
     int owner[4] = {-1, -1, -1, -1};
     // pass 0: arg-max in image index order; pass 1: mask bytes + owned bounding boxes
     for (int pass = 0; pass < 2; pass++) {
         for (int base = 0; base < n; base += 256) {
-            const int total = tile_box_list(box, n, base, tx0, ty0, min(tx0 + kTileW, rx1), min(ty0 + kTileH, ry1), list, wcount);
+            const int total = tile_box_list(chips, n, base, tx0, ty0, min(tx0 + kTileW, rx1), min(ty0 + kTileH, ry1), list, wcount);
             if (pass == 1) {
                 if (tid < total) { sbb[tid][0] = 1 << 30; sbb[tid][1] = 1 << 30; sbb[tid][2] = -1; sbb[tid][3] = -1; }
                 __syncthreads();
             }
             for (int e = 0; e < total; e++) {
                 const int m = list[e];
-                const ChipDesc& D = descs[m];
-                const int r = gy - D.beg_y;
-                if (gy >= ry1 || r < 0 || r >= D.chip_h) continue;
                 if (pass == 0) {
+                    const int4 bx = *reinterpret_cast<const int4*>(&chips[m].beg_x);
+                    const int r = gy - bx.y;
+                    if (gy >= ry1 || r < 0 || r >= bx.w) continue;                            // warp uniform (a warp = one canvas row)
+                    if (tx0 + kTileW <= bx.x || tx0 >= bx.x + bx.z) continue;                     // this warp's 128 columns miss the box
+                    const K6Chip D = chips[m];
+                    const RowTerms t = row_terms(D, r, dgy);
                     const float mx = dist_max[m];
+                    // the IEEE division is only needed when the quotient can exceed the running maximum: md / mx > best
+                    // implies md > best * mx * (1 - 2^-22); the guard below is far more conservative than that
+                    const float mxg = mx * 0.99999f;
+                    const float fc0 = (float)(gx0 - D.beg_x);
 #pragma unroll
                     for (int k = 0; k < 4; k++) {
-                        const int gx = tx0 + threadIdx.x + 32 * k, c = gx - D.beg_x;
-                        if (gx >= rx1 || c < 0 || c >= D.chip_w) continue;
-                        const float md = chip_min_dist(D, c, r, dgx, dgy, w1f, h1f);
-                        if (md == 0.0f) continue;                         // invalid pixel: the map holds 0 there
+                        const int gx = gx0 + 32 * k, c = gx - D.beg_x;
+                        if (gx >= rx1 || c < 0 || c >= D.w) continue;
+                        const float md = chip_min_dist(D, t, fc0 + 32.0f * k, dgx, w1f, h1f);
+                        if (md == 0.0f || md < best[k] * mxg) continue;   // invalid pixel (the map holds 0 there), or cannot win
                         const float dn = md / mx;                         // pMapRow[c] /= maxDist (:1830)
                         if (dn > best[k]) { best[k] = dn; owner[k] = m; }
                     }
                 } else {
-                    uint8_t* mrow = D.mask + (size_t)r * D.mask_step;
+                    const int4 bx = *reinterpret_cast<const int4*>(&chips[m].beg_x);
+                    const int r = gy - bx.y;
+                    if (gy >= ry1 || r < 0 || r >= bx.w) continue;
+                    uint8_t* mrow = mask_ptr[m] + (size_t)r * mask_step[m];
                     int bx0 = 1 << 30, bx1 = -1;
 #pragma unroll
                     for (int k = 0; k < 4; k++) {
-                        const int gx = tx0 + threadIdx.x + 32 * k, c = gx - D.beg_x;
-                        if (gx >= rx1 || c < 0 || c >= D.chip_w) continue;
+                        const int gx = gx0 + 32 * k, c = gx - bx.x;
+                        if (gx >= rx1 || c < 0 || c >= bx.z) continue;
                         const bool mine = owner[k] == m;
                         mrow[c] = mine ? 255 : 0;
                         if (mine) { bx0 = min(bx0, c); bx1 = max(bx1, c); }
@@ -181,35 +249,48 @@ extern "C" int uavm_canvas_seam_masks(uavm_ctx* ctx, uavm_canvas* cv)
     UAVM_CUDA(ctx, cudaSetDevice(ctx->device));
     if (!cv->d_dist_max) {
         UAVM_CUDA(ctx, cudaMalloc(&cv->d_dist_max, (size_t)cv->n * sizeof(float)));
-        UAVM_CUDA(ctx, cudaMalloc(&cv->d_box, (size_t)cv->n * sizeof(ChipBox)));
+        UAVM_CUDA(ctx, cudaMalloc(&cv->d_k6, (size_t)cv->n * sizeof(K6Chip)));
+        UAVM_CUDA(ctx, cudaMalloc(&cv->d_mask_ptr, (size_t)cv->n * sizeof(uint8_t*)));
+        UAVM_CUDA(ctx, cudaMalloc(&cv->d_mask_step, (size_t)cv->n * sizeof(int32_t)));
         UAVM_CUDA(ctx, cudaMalloc(&cv->d_own_bbox, (size_t)cv->n * 4 * sizeof(int32_t)));
         cv->lines_dirty = true;
     }
     if (cv->lines_dirty) {
-        // edge lines of every active chip (:1783-1787) and the compact boxes of the tile scans
-        std::vector<ChipBox> boxes(cv->n);
+        // edge lines of every active chip (:1783-1787) and the packed per-chip constants
+        std::vector<K6Chip> kc(cv->n);
+        std::vector<uint8_t*> mp(cv->n); std::vector<int32_t> ms(cv->n);
         for (int k = 0; k < cv->n; k++) {
             ChipDesc& d = cv->desc[k];
-            boxes[k] = ChipBox{d.beg_x, d.beg_y, d.keep ? d.chip_w : 0, d.keep ? d.chip_h : 0};
+            K6Chip& q = kc[k]; memset(&q, 0, sizeof(q));
+            mp[k] = d.mask; ms[k] = d.mask_step;
+            q.beg_x = d.beg_x; q.beg_y = d.beg_y; q.w = d.keep ? d.chip_w : 0; q.h = d.keep ? d.chip_h : 0; q.keep = d.keep; q.affine = d.affine;
             if (!d.keep) continue;
             for (int e = 0; e < 4; e++) {
                 const int f = (e + 1) & 3;
                 line_of_2_points(d.lineA[e], d.lineB[e], d.lineC[e], d.quad[2 * e], d.quad[2 * e + 1], d.quad[2 * f], d.quad[2 * f + 1]);
                 d.lineInv[e] = 1 / sqrtf(d.lineA[e] * d.lineA[e] + d.lineB[e] * d.lineB[e]);
+                q.A[e] = d.lineA[e]; q.B[e] = d.lineB[e]; q.C[e] = d.lineC[e]; q.I[e] = d.lineInv[e];
             }
+            memcpy(q.inv, d.inv, 8 * sizeof(float)); q.inv8 = d.inv[8];
+            q.sx = d.sx; q.sy = d.sy; q.fbx = (float)d.beg_x; q.fby = (float)d.beg_y;
         }
-        UAVM_CUDA(ctx, cudaMemcpyAsync(cv->d_box, boxes.data(), boxes.size() * sizeof(ChipBox), cudaMemcpyHostToDevice, ctx->stream));
-        int rc = uavm_canvas_upload_desc(ctx, cv);          // synchronises: `boxes` may go out of scope
-        if (rc != UAVM_OK) return rc;
+        UAVM_CUDA(ctx, cudaMemcpyAsync(cv->d_k6, kc.data(), kc.size() * sizeof(K6Chip), cudaMemcpyHostToDevice, ctx->stream));
+        UAVM_CUDA(ctx, cudaMemcpyAsync(cv->d_mask_ptr, mp.data(), mp.size() * sizeof(uint8_t*), cudaMemcpyHostToDevice, ctx->stream));
+        UAVM_CUDA(ctx, cudaMemcpyAsync(cv->d_mask_step, ms.data(), ms.size() * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+        UAVM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));          // the host vectors go out of scope
         cv->lines_dirty = false;
     }
+    const K6Chip* k6 = (const K6Chip*)cv->d_k6;
     UAVM_CUDA(ctx, cudaMemsetAsync(cv->d_dist_max, 0, (size_t)cv->n * sizeof(float), ctx->stream));
     k6_init_bbox<<<(cv->n + 255) / 256, 256, 0, ctx->stream>>>(cv->d_own_bbox, cv->n);
     UAVM_CHECK_LAUNCH(ctx);
     const float w1f = (float)(cv->img_w - 1), h1f = (float)(cv->img_h - 1);
     {
-        dim3 grid((cv->max_chip_w + kTileW - 1) / kTileW, (cv->max_chip_h + kTileH - 1) / kTileH, cv->n);
-        k6_dist_max<<<grid, dim3(32, 8), 0, ctx->stream>>>(cv->d_desc, cv->d_dist_max, cv->layout.dgx, cv->layout.dgy, w1f, h1f);
+        dim3 gc((cv->max_chip_w + 255) / 256, (cv->max_chip_h + 63) / 64, cv->n);
+        k6_dist_max<true><<<gc, dim3(32, 8), 0, ctx->stream>>>(k6, cv->d_dist_max, cv->layout.dgx, cv->layout.dgy, w1f, h1f);
+        UAVM_CHECK_LAUNCH(ctx);
+        dim3 grid((cv->max_chip_w + kTileW - 1) / kTileW, (cv->max_chip_h + kMaxTileH - 1) / kMaxTileH, cv->n);
+        k6_dist_max<false><<<grid, dim3(32, 8), 0, ctx->stream>>>(k6, cv->d_dist_max, cv->layout.dgx, cv->layout.dgy, w1f, h1f);
         UAVM_CHECK_LAUNCH(ctx);
     }
     {
@@ -223,7 +304,7 @@ extern "C" int uavm_canvas_seam_masks(uavm_ctx* ctx, uavm_canvas* cv)
         }
         dim3 grid((rx1 - rx0 + kTileW - 1) / kTileW, (ry1 - ry0 + kTileH - 1) / kTileH);
         if (grid.y > 65535) { UAVM_SET_ERR(ctx, "seam_masks: canvas rectangle too tall (%d rows): shard the canvas", ry1 - ry0); return UAVM_EINVAL; }
-        k6_owner<<<grid, dim3(32, 8), 0, ctx->stream>>>(cv->d_desc, cv->d_box, cv->d_dist_max, cv->n, cv->layout.dgx, cv->layout.dgy, w1f, h1f,
+        k6_owner<<<grid, dim3(32, 8), 0, ctx->stream>>>(k6, cv->d_mask_ptr, cv->d_mask_step, cv->d_dist_max, cv->n, cv->layout.dgx, cv->layout.dgy, w1f, h1f,
                                                         rx0, ry0, rx1, ry1, cv->d_own_bbox);
         UAVM_CHECK_LAUNCH(ctx);
     }

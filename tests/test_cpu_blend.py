@@ -85,3 +85,14 @@ def test_blend_oracle_bit_exact_random_masks_and_bands(oracle):
         rs, rm = b.blend(None, None)
         assert np.array_equal(om, rm), trial
         assert np.array_equal(out, np.clip(rs, 0, 255).astype(np.uint8)), trial
+
+
+def test_normalise_shortcut_is_exact():
+    """K7 replaces short(d / (wsum + 1e-5f)) by d - sign(d) when wsum == 1.0f (and by 0 when d == 0): identical for every
+    int16 d in f32 arithmetic (csrc/blend.cu: norm_div)."""
+    d = np.arange(-32768, 32768, dtype=np.int32)
+    w = np.float32(1.0) + np.float32(1e-5)
+    v = np.trunc(d.astype(np.float32) / w).astype(np.int32)
+    assert np.array_equal(v, d - np.sign(d))
+    for ws in (np.float32(0.0), np.float32(0.37), np.float32(2.5)):
+        assert np.trunc(np.float32(0.0) / (ws + np.float32(1e-5))) == 0
