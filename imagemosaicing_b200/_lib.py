@@ -91,6 +91,11 @@ def lib():
         try:                                   # absent only in a host-only sanitizer build (UAVM_LIB_PATH)
             L.uavm_last_error.restype = C.c_char_p
             L.uavm_ctx_launch_count.restype = C.c_int64
+            L.uavm_dist_destroy.restype = None
+            L.uavm_dist_destroy.argtypes = [C.c_void_p, C.c_void_p]
+            L.uavm_pairbatch_allgather.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+            L.uavm_canvas_gather.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+            L.uavm_dist_broadcast.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int]
         except AttributeError:
             if not os.environ.get("UAVM_LIB_PATH"):
                 raise

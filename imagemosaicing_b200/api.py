@@ -199,6 +199,80 @@ class PairBatch:
             pass
 
 
+class Dist:
+    """NCCL communicator of this rank behind the C ABI (uavm_dist; csrc/dist.cu).  `Dist.from_torch(ctx)` bootstraps it in a
+    torchrun job (rank 0 creates the NCCL id, torch.distributed carries it to the other ranks); a C++ host hands the id
+    around by its own means.  world == 1 needs no peers."""
+
+    ID_BYTES = 128
+
+    @staticmethod
+    def _one_nccl_per_process():
+        """The library picks up an NCCL that is already loaded; a Python process that will also import torch must load torch's
+        bundled NCCL first (torch's libraries are linked against that version)."""
+        try:
+            import torch  # noqa: F401
+        except Exception:
+            pass
+
+    def __init__(self, ctx, rank, world, unique_id):
+        self._one_nccl_per_process()
+        self.ctx = ctx; self.rank = int(rank); self.world = int(world)
+        idb = (C.c_uint8 * self.ID_BYTES).from_buffer_copy(bytes(unique_id))
+        self._h = C.c_void_p()
+        ctx.check(L.lib().uavm_dist_init(ctx._h, self.rank, self.world, idb, self.ID_BYTES, C.byref(self._h)))
+
+    @staticmethod
+    def unique_id():
+        Dist._one_nccl_per_process()
+        idb = (C.c_uint8 * Dist.ID_BYTES)()
+        rc = L.lib().uavm_dist_unique_id(idb, Dist.ID_BYTES)
+        if rc != 0:
+            raise UavmError(f"uavm_dist_unique_id failed with {rc} (libnccl.so.2 missing?)")
+        return bytes(idb)
+
+    @staticmethod
+    def from_torch(ctx):
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized()):
+            return Dist(ctx, 0, 1, Dist.unique_id())
+        rank, world = dist.get_rank(), dist.get_world_size()
+        box = [Dist.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        return Dist(ctx, rank, world, box[0])
+
+    def allgather_matches(self, pb, n_pairs_global, min_inner_points=30):
+        """-> (MatchPointPairs array of ALL pairs in global pair order, n, n_accepted_pairs); identical on every rank."""
+        h = pb._h if pb is not None else None
+        n = C.c_int(0); acc = C.c_int(0)
+        self.ctx.check(L.lib().uavm_pairbatch_allgather(self.ctx._h, self._h, h, int(n_pairs_global), int(min_inner_points), None, 0, C.byref(n), C.byref(acc)))
+        out = (MatchPointPairs * max(n.value, 1))()
+        self.ctx.check(L.lib().uavm_pairbatch_allgather(self.ctx._h, self._h, h, int(n_pairs_global), int(min_inner_points), out, n.value, C.byref(n), C.byref(acc)))
+        return out, n.value, acc.value
+
+    def gather_canvas(self, cv, rects, root=0):
+        """rects: (world, 4) int32 (x0, y0, x1, y1) per rank; afterwards root's canvas result is the whole mosaic."""
+        r = np.ascontiguousarray(rects, np.int32).reshape(-1, 4)
+        assert len(r) == self.world
+        self.ctx.check(L.lib().uavm_canvas_gather(self.ctx._h, self._h, cv._h, _ptr(r, i32p), int(root)))
+
+    def broadcast(self, tensor, root=0):
+        """torch CUDA tensor, replicated from root in place (ncclBroadcast on the ctx stream)."""
+        assert _is_torch_cuda(tensor) and tensor.is_contiguous()
+        self.ctx.check(L.lib().uavm_dist_broadcast(self.ctx._h, self._h, C.c_void_p(tensor.data_ptr()), C.c_int64(tensor.numel() * tensor.element_size()), int(root)))
+
+    def close(self):
+        if self._h:
+            L.lib().uavm_dist_destroy(self.ctx._h, self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 # ---- single-pair seams (host buffers in, host buffers out) -------------------------------------
 def match(ctx, desc1, desc2):
     """Exact L2 1-NN of every row of desc1 in desc2 -> structured array (queryIdx, trainIdx, imgIdx, distance)."""

@@ -589,6 +589,7 @@ extern "C" int uavm_canvas_get_layout(uavm_canvas* cv, uavm_canvas_layout* canva
 extern "C" int uavm_canvas_set_image(uavm_ctx* ctx, uavm_canvas* cv, int image, const uint8_t* bgr, int step, int is_device)
 {
     if (!ctx || !cv || image < 0 || image >= cv->n || !bgr || step < cv->img_w * 3) return UAVM_EINVAL;
+    UAVM_CUDA(ctx, cudaSetDevice(ctx->device));
     const uint8_t* src = bgr; int sstep = step;
     int slot = -1;
     if (!is_device) {
@@ -622,6 +623,7 @@ extern "C" int uavm_canvas_warp_range(uavm_ctx* ctx, uavm_canvas* cv, int first,
 {
     if (!ctx || !cv || first < 0 || count < 0 || first + count > cv->n) return UAVM_EINVAL;
     if (cv->max_chip_w <= 0 || count == 0) return UAVM_OK;
+    UAVM_CUDA(ctx, cudaSetDevice(ctx->device));
     dim3 grid((cv->max_chip_w + kWarpTileW - 1) / kWarpTileW, (cv->max_chip_h + kWarpTileH - 1) / kWarpTileH, count);
     dim3 block(32, kWarpsY);
     bool any_affine = false, any_proj = false;

@@ -18,7 +18,9 @@ struct uavm_ctx {
     cudaEvent_t ev_fork = nullptr, ev_side = nullptr;
     bool forked = false, side_pending = false;
     int64_t launches = 0;
-    bool k5_attr_set = false;          // per-device function attributes of the K5 kernel applied
+    bool k5_attr_set = false;          // per-device function attributes applied through THIS context (attributes are per device,
+    bool k2_attr_set = false, k4_fin_attr_set = false;   // contexts are per device: a process-wide flag would skip the opt-in on a second GPU)
+    size_t k4_eval_attr_smem = 0;
     char err[512] = {0};
 };
 

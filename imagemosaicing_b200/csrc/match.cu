@@ -198,10 +198,10 @@ k2_match_tcgen05(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
 int uavm_launch_match(uavm_ctx* ctx, uavm_pairbatch* pb)
 {
     if (pb->n_items == 0) return UAVM_OK;
-    static bool attr_set = false;
-    if (!attr_set) {
+    UAVM_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (!ctx->k2_attr_set) {                              // function attributes are per device: tracked per context
         UAVM_CUDA(ctx, cudaFuncSetAttribute(k2_match_tcgen05, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-        attr_set = true;
+        ctx->k2_attr_set = true;
     }
     int grid = pb->n_items < ctx->sm_count ? pb->n_items : ctx->sm_count;
     k2_match_tcgen05<<<grid, kThreads, kSmemBytes, ctx->stream>>>(pb->fs->tmap_q, pb->fs->tmap_t, pb->fs->d_ckey,

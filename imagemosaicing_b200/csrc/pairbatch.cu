@@ -107,9 +107,18 @@ extern "C" int uavm_pairbatch_ransac(uavm_ctx* ctx, uavm_pairbatch* pb, float ra
 // ------------------------------------------------------------------------------------------------
 // results -> host
 // ------------------------------------------------------------------------------------------------
+// A caller that ran a stage on the side stream (fork ... unfork) and fetches results before uavm_ctx_join would read
+// them while the kernels still run: the getters join first.
+static int join_side(uavm_ctx* ctx)
+{
+    if (ctx->forked) { UAVM_SET_ERR(ctx, "results requested between fork and unfork"); return UAVM_EINVAL; }
+    return ctx->side_pending ? uavm_ctx_join(ctx) : UAVM_OK;
+}
+
 extern "C" int uavm_pairbatch_get_matches(uavm_ctx* ctx, uavm_pairbatch* pb, int pair, uavm_dmatch* out, int cap, int* n_out)
 {
     if (!ctx || !pb || pair < 0 || pair >= pb->n_pairs || !out) return UAVM_EINVAL;
+    { int rcj = join_side(ctx); if (rcj != UAVM_OK) return rcj; }
     const PairDesc& d = pb->pairs[pair];
     if (cap < d.nq) return UAVM_EINVAL;
     std::vector<int32_t> ti(d.nq > 0 ? d.nq : 1), dd(d.nq > 0 ? d.nq : 1);
@@ -129,6 +138,7 @@ extern "C" int uavm_pairbatch_get_matches(uavm_ctx* ctx, uavm_pairbatch* pb, int
 extern "C" int uavm_pairbatch_get_candidates(uavm_ctx* ctx, uavm_pairbatch* pb, int pair, uavm_sfpoint* pts1, uavm_sfpoint* pts2, int cap, int* n_out)
 {
     if (!ctx || !pb || pair < 0 || pair >= pb->n_pairs || !pts1 || !pts2 || !n_out) return UAVM_EINVAL;
+    { int rcj = join_side(ctx); if (rcj != UAVM_OK) return rcj; }
     int n = 0;
     UAVM_CUDA(ctx, cudaMemcpyAsync(&n, pb->d_cand_n + pair, 4, cudaMemcpyDeviceToHost, ctx->stream));
     UAVM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -154,6 +164,7 @@ extern "C" int uavm_pairbatch_get_candidates(uavm_ctx* ctx, uavm_pairbatch* pb, 
 extern "C" int uavm_pairbatch_get_ransac(uavm_ctx* ctx, uavm_pairbatch* pb, int pair, uint8_t* inlier_mask, int cap, uavm_ransac_result* res)
 {
     if (!ctx || !pb || pair < 0 || pair >= pb->n_pairs || !res) return UAVM_EINVAL;
+    { int rcj = join_side(ctx); if (rcj != UAVM_OK) return rcj; }
     if (!pb->ransacked) { UAVM_SET_ERR(ctx, "get_ransac before ransac"); return UAVM_EINVAL; }
     int n = 0;
     UAVM_CUDA(ctx, cudaMemcpyAsync(&n, pb->d_cand_n + pair, 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -173,6 +184,7 @@ extern "C" int uavm_pairbatch_get_ransac(uavm_ctx* ctx, uavm_pairbatch* pb, int 
 extern "C" int uavm_pairbatch_collect(uavm_ctx* ctx, uavm_pairbatch* pb, int min_inner_points, uavm_matchpointpairs* out, int cap, int* n_out, int* n_accepted_pairs)
 {
     if (!ctx || !pb || !n_out) return UAVM_EINVAL;
+    { int rcj = join_side(ctx); if (rcj != UAVM_OK) return rcj; }
     if (!pb->ransacked) { UAVM_SET_ERR(ctx, "collect before ransac"); return UAVM_EINVAL; }
     size_t np = (size_t)pb->n_pairs;
     std::vector<uavm_ransac_result> res(np);

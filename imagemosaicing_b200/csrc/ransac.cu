@@ -468,10 +468,10 @@ int uavm_launch_ransac(uavm_ctx* ctx, uavm_pairbatch* pb, float dist, int sample
     if (groups > UAVM_RANSAC_MAX_TUPLES_FIRST) groups = UAVM_RANSAC_MAX_TUPLES_FIRST;
     groups = ((groups + kGroupsPerBlock - 1) / kGroupsPerBlock) * kGroupsPerBlock;
     if (groups > UAVM_RANSAC_MAX_TUPLES_FIRST) groups = UAVM_RANSAC_MAX_TUPLES_FIRST;
-    static bool attr_set = false;
-    if (!attr_set) {
+    UAVM_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (!ctx->k4_fin_attr_set) {                          // function attributes are per device: tracked per context
         UAVM_CUDA(ctx, cudaFuncSetAttribute(k4_ransac_finalize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFinSmemBytes));
-        attr_set = true;
+        ctx->k4_fin_attr_set = true;
     }
     if (groups > 0) {
         dim3 grid(groups / kGroupsPerBlock, pb->n_pairs);
@@ -482,10 +482,9 @@ int uavm_launch_ransac(uavm_ctx* ctx, uavm_pairbatch* pb, float dist, int sample
         int bpsm = 3;
         if (getenv("UAVM_RANSAC_EVAL_BPSM")) bpsm = atoi(getenv("UAVM_RANSAC_EVAL_BPSM"));
         if (bpsm == 1) pad_smem = 100 * 1024; else if (bpsm == 2) pad_smem = 60 * 1024;
-        static size_t attr_smem = 0;
-        if (pad_smem > attr_smem) {
+        if (pad_smem > ctx->k4_eval_attr_smem) {
             UAVM_CUDA(ctx, cudaFuncSetAttribute(k4_ransac_eval, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pad_smem));
-            attr_smem = pad_smem;
+            ctx->k4_eval_attr_smem = pad_smem;
         }
         k4_ransac_eval<<<grid, kEvalThreads, pad_smem, ctx->stream>>>(pb->d_pairs, pb->d_cand_xy1, pb->d_cand_xy2, pb->d_cand_n,
                                                                thr2, groups, pb->d_tuple_res, pb->d_tuple_h);

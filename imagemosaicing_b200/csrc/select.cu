@@ -49,6 +49,9 @@ k3_select(const PairDesc* __restrict__ pairs, const int32_t* __restrict__ train_
     const PairDesc pd = pairs[blockIdx.x];
     const int n = pd.nq;
     const int tid = threadIdx.x;
+    // an empty train image has no matches (trainIdx stays -1): the reference's matcher returns an empty list and the pair
+    // yields no candidates (M/MosaicWithoutPos.cpp:5108-5111)
+    if (pd.nt <= 0 || n <= 0) { if (tid == 0) cand_n[blockIdx.x] = 0; return; }
     const int32_t* tix = train_idx + pd.match_off;
     const int32_t* dd = d2 + pd.match_off;
     const float* kp1 = kp + (size_t)pd.q_row * 2;

@@ -176,6 +176,28 @@ int uavm_canvas_copy_result_rows(uavm_ctx* ctx, uavm_canvas* cv, int y0, int y1,
 /* rectangle [x0, x1) x [y0, y1) of the result, dense ((x1 - x0) * 3 bytes per row) */
 int uavm_canvas_copy_result_rect(uavm_ctx* ctx, uavm_canvas* cv, int x0, int y0, int x1, int y1, uint8_t* dst, int is_device);
 
+/* ---- multi-GPU (csrc/dist.cu): one uavm_ctx per GPU / rank, NCCL over NVLink, loaded at run time (libnccl.so.2).
+ *      Replaces the worker fan-out of GetMatchedPairsOneToAllSIFT_MultiThread + PushMatchPairs
+ *      (M/MosaicWithoutPos.cpp:5244-5295, :10137-10145): image pairs are sharded round-robin (pair p on rank p % world, local
+ *      index p / world), ranks compute independently, one collective merges the results.  A multi-threaded C++ host calls
+ *      uavm_dist_init from each of its GPU threads with the same id; torchrun ranks exchange the id over their store. */
+typedef struct uavm_dist uavm_dist;
+#define UAVM_DIST_ID_BYTES 128
+int uavm_dist_unique_id(uint8_t* id_out, int id_bytes);                       /* rank 0: ncclGetUniqueId */
+int uavm_dist_init(uavm_ctx* ctx, int rank, int world, const uint8_t* id, int id_bytes, uavm_dist** out);
+void uavm_dist_destroy(uavm_ctx* ctx, uavm_dist* d);
+int uavm_dist_rank(const uavm_dist* d);
+int uavm_dist_world(const uavm_dist* d);
+/* all ranks: merged MatchPointPairs list of ALL n_pairs_global pairs (accepted pairs in global pair order) — identical on
+ * every rank and identical to uavm_pairbatch_collect of one context holding every pair.  Device-side pack, ncclAllGather of
+ * fixed-size per-pair records, device-side compaction, one device-to-host copy of the dense list.  out == NULL: counts only. */
+int uavm_pairbatch_allgather(uavm_ctx* ctx, uavm_dist* d, uavm_pairbatch* pb, int n_pairs_global, int min_inner_points,
+                             uavm_matchpointpairs* out, int cap, int* n_out, int* n_accepted_pairs);
+/* rects: world x 4 (x0, y0, x1, y1), rank r blended rects[r] (uavm_canvas_set_rect); afterwards root's result is the whole
+ * mosaic.  Stream ordered (grouped ncclSend / ncclRecv); synchronise with uavm_ctx_sync. */
+int uavm_canvas_gather(uavm_ctx* ctx, uavm_dist* d, uavm_canvas* cv, const int32_t* rects, int root);
+int uavm_dist_broadcast(uavm_ctx* ctx, uavm_dist* d, void* device_buf, int64_t bytes, int root);
+
 /* ---- top-level shim with the shape of MosaicVavImages (M/MosaicWithoutPos.h:638-645,
  *      M/MosaicWithoutPos.cpp:10148-10214).  Features are supplied by the caller (SIFT extraction is
  *      upstream of this library): desc[i] n_kp[i] x 128 f32, kp_xy[i] n_kp[i] x 2.

@@ -210,3 +210,27 @@ def test_ransac_degenerate_inputs_generic_path(ctx, oracle):
     cases.append((z + 1.0, z))
     for k, (xy1, xy2) in enumerate(cases):
         _check_ransac(ctx, oracle, np.ascontiguousarray(xy1, np.float32), np.ascontiguousarray(xy2, np.float32), 4242 + k)
+
+
+def test_pair_with_empty_image_yields_no_candidates(ctx):
+    """An image without keypoints (allowed by uavm_mosaic_images) makes pairs with no matches: no candidates, RANSAC fails
+    cleanly, the pair is rejected — in either role (query or train)."""
+    rng = np.random.default_rng(8)
+    nk = [300, 0, 400]
+    descs = [rng.integers(0, 200, (n, 128)).astype(np.uint8) for n in nk]
+    kps = [synth.random_keypoints(rng, n, 1000, 750) if n else np.zeros((0, 2), np.float32) for n in nk]
+    fs = api.FeatureSet(ctx, nk)
+    for i in range(3):
+        if nk[i]:
+            fs.upload(i, descs[i], kps[i])
+    pb = api.PairBatch(ctx, fs, [[0, 1], [1, 2], [0, 2]])
+    pb.match(); pb.select(1000, 750); pb.ransac(2.5, 100, base_seed=1)
+    for p in (0, 1):
+        c1, c2 = pb.candidates(p)
+        assert len(c1) == 0 and len(c2) == 0
+        mask, res = pb.ransac_result(p)
+        assert res.n_inliers == 0 and res.ok == 0
+    c1, _ = pb.candidates(2)
+    assert len(c1) > 0
+    out, n, acc = pb.collect(30)
+    assert acc <= 1
