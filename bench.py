@@ -10,14 +10,20 @@ path over the strip: 49 x { 8192x8192x128 L2 1-NN match, candidate selection, Ra
 1000 counted hypotheses), one 4000x3000 frame warped into its chip + mask }.  With N GPUs every rank
 processes its own strip (weak scaling, no data-path collective: pairs are independent units).
 
-`value`  = pairs/s with inputs resident in HBM, timed with CUDA events on the launching stream.
+`value`  = pairs/s with inputs resident in HBM (u8 descriptors in the pool, frames as the BGR bytes a caller hands over),
+           timed with CUDA events on the launching stream.  Every kernel the BGR input needs is inside the timed region,
+           including the BGR -> BGRA pass of uavm_canvas_set_image (it runs next to the match kernel).
 `e2e`    = pairs/s through the host-buffer API: every step copies the strip's descriptors, keypoints and
-           frames from pinned host memory, runs the path and reads the inlier match list back.
+           frames from pinned host memory, runs the path and reads the inlier match list back (the warped chips stay
+           resident: they feed the seam masks and the blend).
+`block200` / `canvas500` = BASELINE configs[2] and configs[4], STRONG-scaled over the N GPUs through the C ABI's
+           multi-GPU entry points (uavm_pairbatch_allgather, uavm_canvas_set_rect + uavm_canvas_gather), with checksums
+           that must not depend on N.
 `roofline` = the dominant kernel of the step (K5 warp, k5_warp_affine_x2: reported against HBM; algorithmic 7 B per
              source pixel = frame read once + chip and mask written).
 `cpu_baseline` = the CPU oracle port timed on this box's host cores on a bounded sample of the same pairs.
---impl reference times the CPU path only (oracle port; RANSAC through the reference's own compiled
-Ransac2D when oracle/_ref is present).
+--impl reference times the CPU path only (oracle port; RANSAC and the chip warp through the reference's own compiled
+code when oracle/_ref is present) on all 49 pairs of the strip per step.
 """
 import argparse
 import json
@@ -36,6 +42,11 @@ W, H, NKP, NIMG = 4000, 3000, 8192, 50
 RANSAC_DIST, SAMPLE_TIMES = 2.5, 1000
 METRIC = "image-pairs/sec (match+RANSAC+warp)"
 UNIT = "pairs/s"
+# identical for both arms (the driver compares the dicts)
+CONFIG = {"workload": "configs[1]: 50-image strip 4000x3000, 8192 kp/image, sequential pairs (49 pair units per step per GPU)",
+          "pairs_per_step_per_gpu": NIMG - 1, "ransac": "396 candidates, 1000 counted hypotheses, ~50% inliers",
+          "l2": "per-step working set 5 GB (frames + chips) >> 126 MB L2; the warp pass evicts the 52 MB descriptor pool between match passes",
+          "parallelism": "pairs are independent units: one strip per GPU, no data-path collective"}
 
 
 def peaks():
@@ -117,32 +128,59 @@ def host_threads():
         return os.cpu_count() or 1
 
 
+def cpu_variants(descs, kps):
+    """What the reference itself pays per pair on top of the port: its matcher is OpenCV's FLANN kd-tree
+    (M/MosaicWithoutPos.cpp:5108-5110), and it re-parses the train image's descriptor XML for every pair (:5097-5103)."""
+    out = {}
+    try:
+        import cv2
+        cv2.setNumThreads(1)
+        a = descs[0].astype(np.float32); b = descs[1].astype(np.float32)
+        cv2.FlannBasedMatcher().match(a[:256], b)                      # warm
+        t0 = time.perf_counter(); m = cv2.FlannBasedMatcher().match(a, b); out["flann_match_ms_per_pair_1thread"] = (time.perf_counter() - t0) * 1e3
+        idx = np.array([x.trainIdx for x in m], np.int32)
+        from oracle import oracle as O
+        exact, _ = O.match_l2_fast(descs[0], descs[1])
+        out["flann_agrees_with_exact_1nn"] = float((idx == exact).mean())
+        from imagemosaicing_b200 import api
+        d = tempfile.mkdtemp()
+        xml = os.path.join(d, "discriptor_0.xml")
+        api.L.lib().uavm_descriptor_xml_write(xml.encode(), a.ctypes.data_as(api.f32p), a.shape[0], a.shape[1])
+        t0 = time.perf_counter(); fsr = cv2.FileStorage(xml, cv2.FILE_STORAGE_READ); mat = fsr.getNode("descriptor").mat(); fsr.release()
+        out["xml_reparse_ms_per_pair_1thread"] = (time.perf_counter() - t0) * 1e3
+        out["xml_bytes"] = os.path.getsize(xml)
+        assert mat.shape == a.shape
+        os.unlink(xml); os.rmdir(d)
+    except Exception as e:                                             # cv2 missing: the variants are informational
+        out["error"] = repr(e)
+    return out
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n_sample = max(4, min(48, host_threads()))      # pairs per step (bounded sample of the 49-pair workload): one per host thread
-    descs, kps, Hs, T, base = make_workload(0, n_img=n_sample + 1)
-    frames = [base] * (n_sample + 1)
-    pairs = [(i, i + 1) for i in range(n_sample)]
-    seeds = [1000 + p for p in range(n_sample)]
+    n_pairs = NIMG - 1                                  # the whole 49-pair step, like the GPU arm
+    descs, kps, Hs, T, base = make_workload(0)
+    frames = [base] * NIMG
+    pairs = [(i, i + 1) for i in range(n_pairs)]
+    seeds = [1000 + p for p in range(n_pairs)]
     from oracle import oracle as O
     O.lib()
-    for _ in range(max(args.warmup, 1) if args.warmup > 0 else 0):
-        cpu_pairs(descs, kps, T, frames, pairs[:1], seeds[:1])
+    for _ in range(1 if args.warmup > 0 else 0):
+        cpu_pairs(descs, kps, T, frames, pairs[:host_threads()], seeds[:host_threads()])
     t = 0.0
     for _ in range(args.steps):
         t += cpu_pairs(descs, kps, T, frames, pairs, seeds)
-    val = n_sample * args.steps / t
+    val = n_pairs * args.steps / t
     cores = host_threads()
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1000.0 * t / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8/int32 match, f32 RANSAC+warp", "data": "synthetic",
-        "config": {"workload": "configs[1]: 50-image strip 4000x3000, 8192 kp/image, sequential pairs",
-                   "pairs_per_step": n_sample},
+        "config": CONFIG,
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores,
-                         "kind": "port", "sample": cpu_sample_note(n_sample, O)},
+                         "kind": "port", "sample": cpu_sample_note(n_pairs, O), "variants": cpu_variants(descs, kps)},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -216,6 +254,171 @@ class ClockSampler:
         return out
 
 
+def crc_of(buf):
+    import zlib
+    return zlib.crc32(bytes(buf)) & 0xffffffff
+
+
+def run_block200(args, ctx, nd, rank, world, dev):
+    """BASELINE configs[2], strong scaling: a 200-image block (10 strips x 20 frames, shared world-point model), every pair
+    whose footprints overlap (1 692) sharded round-robin over the ranks; the timed region is match -> select -> RANSAC on the
+    shard, uavm_pairbatch_allgather (device pack, ncclAllGather, device compaction, one D2H of the dense list) and the host
+    stages on the merged list (connectivity + global affine alignment, uavm_global_align) — on every rank, replicas only."""
+    import ctypes as C
+    import torch
+    import torch.distributed as dist
+    from imagemosaicing_b200 import api, synth, dist as D, _lib as L
+    rows, cols = 10, 20
+    n = rows * cols
+    t0 = time.perf_counter()
+    descs, kps, poses, pairs = synth.make_block(rows, cols, W, H, NKP, seed=synth.SEED_BASE + 3)
+    t_synth = time.perf_counter() - t0
+    fs = api.FeatureSet(ctx, [NKP] * n)
+    for i in range(n):
+        fs.upload(i, descs[i], kps[i])                      # descriptors replicated on every rank (210 MB)
+    mine = D.shard_pairs(len(pairs), rank, world)
+    pb = api.PairBatch(ctx, fs, pairs[mine]) if len(mine) else None
+    seeds = (1000 + mine).astype(np.uint32)
+    cap = 1 << 19
+    out = (L.MatchPointPairs * cap)(); n_out = C.c_int(0); n_acc = C.c_int(0)
+    tr = (L.ImageTransform * n)(); label = (C.c_int32 * n)(); n_used = C.c_int(0)
+    lib = L.lib()
+
+    def step(ev=None):
+        if ev: ev[0].record()
+        if pb is not None:
+            pb.match(); pb.select(W, H); pb.ransac(RANSAC_DIST, SAMPLE_TIMES, seeds=seeds)
+        if ev: ev[1].record()
+        ctx.sync()                                           # stage attribution only: the gather is timed from a drained stream
+        t1 = time.perf_counter()
+        ctx.check(lib.uavm_pairbatch_allgather(ctx._h, nd._h, pb._h if pb is not None else None, len(pairs), 30, out, cap, C.byref(n_out), C.byref(n_acc)))
+        t2 = time.perf_counter()
+        rc = lib.uavm_global_align(out, n_out.value, n, tr, label, C.byref(n_used))
+        t3 = time.perf_counter()
+        return rc, (t2 - t1) * 1e3, (t3 - t2) * 1e3
+
+    for _ in range(2):
+        step()
+    torch.cuda.synchronize()
+    if world > 1: dist.barrier()
+    k = max(3, min(args.steps, 10))
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(k)]
+    gather_ms = align_ms = 0.0
+    t0 = time.perf_counter()
+    for s_ in range(k):
+        rc, g, a_ = step(evs[s_]); gather_ms += g; align_ms += a_
+    torch.cuda.synchronize()
+    total_ms = (time.perf_counter() - t0) * 1e3 / k
+    pair_ms = sum(e[0].elapsed_time(e[1]) for e in evs) / k
+    tt = torch.tensor([pair_ms, gather_ms / k, align_ms / k, total_ms], device=dev, dtype=torch.float64)
+    if world > 1: dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    res = None
+    if rank == 0:
+        # accuracy against the ground-truth poses + checksums that must not depend on N
+        corners = np.array([[0, 0], [W - 1, 0], [W - 1, H - 1], [0, H - 1]], np.float64)
+        err = []
+        for kk in range(n):
+            if not label[kk]: continue
+            G = np.linalg.inv(poses[0]) @ poses[kk]
+            Tm = np.array([tr[kk].h.m[t] for t in range(9)], np.float64).reshape(3, 3)
+            Tm[2] = [0, 0, 1]
+            err.append(float(np.abs(synth.apply_h(G, corners) - synth.apply_h(Tm, corners)).max()))
+        res = {"workload": f"configs[2]: {n}-image block ({rows} strips x {cols}), {W}x{H}, {NKP} kp/image, all {len(pairs)} pairs in overlap; strong scaling",
+               "n_gpus": world, "pairs": int(len(pairs)), "accepted_pairs": int(n_acc.value), "inlier_matches": int(n_out.value),
+               "pair_path_ms": float(tt[0]), "allgather_ms": float(tt[1]), "connectivity_plus_alignment_ms": float(tt[2]),
+               "total_ms": float(tt[3]), "pairs_per_s": len(pairs) / (float(tt[3]) / 1e3), "align_rc": int(rc),
+               "unknowns": 6 * (int(sum(label)) - 1), "connected_images": int(sum(label)),
+               "match_list_crc32": crc_of(C.string_at(out, n_out.value * 40)), "transforms_crc32": crc_of(C.string_at(tr, n * 40)),
+               "corner_error_px_max": max(err) if err else None, "corner_error_px_median": float(np.median(err)) if err else None,
+               "note": "timed: match+select+RANSAC on the shard (CUDA events), uavm_pairbatch_allgather and uavm_global_align (host clock), max over ranks; "
+                       "match_list_crc32 is taken after uavm_global_align compacted the list and set the fixed flags (the content of matchPairs.txt)",
+               "synth_s": t_synth}
+    if pb is not None: pb.close()
+    fs.close()
+    return res
+
+
+def run_canvas500(args, ctx, nd, rank, world, dev):
+    """BASELINE configs[4], strong scaling: 25 x 20 = 500 frames of 4000x3000 on a (1500, 1947) px pitch with +-2 deg / +-2 %
+    jitter -> one ~40000 x 40000 mosaic: K5 warp + K6 seam masks + K7 5-band blend, the canvas split into one rectangle per rank
+    (uavm_canvas_set_rect; exact, no halo exchange) and the finished rectangles moved to rank 0 with uavm_canvas_gather."""
+    import torch
+    import torch.distributed as dist
+    from imagemosaicing_b200 import api, synth, dist as D, _lib as L
+    cols, rows = 25, 20
+    n = cols * rows
+    rng = np.random.default_rng(20160308 + 5)
+    T = np.zeros((n, 9), np.float32)
+    for r in range(rows):
+        for c in range(cols):
+            k = r * cols + c
+            a = 0.0 if k == 0 else np.deg2rad(rng.uniform(-2, 2)); sc = 1.0 if k == 0 else rng.uniform(0.98, 1.02)
+            T[k] = [sc * np.cos(a), -sc * np.sin(a), c * 1500.0, sc * np.sin(a), sc * np.cos(a), r * 1947.0, 0, 0, 1]
+    keep = np.ones(n, np.int32)
+    L.lib().uavm_resample_by_overlap(T.ctypes.data_as(L.f32p), n, W, H, api.C.c_float(0.7), keep.ctypes.data_as(L.i32p))   # ResampleByOverlap (0.7)
+    lay, chips = api.canvas_layout(T, keep, W, H)
+    cw, ch = lay.canvas_w, lay.canvas_h
+    chip_px = sum(chips[k].chip_w * chips[k].chip_h for k in range(n) if chips[k].keep)
+    rects = D.canvas_grid(cw, ch, world)
+    # HBM needed on this rank (sources + chips + masks of the active frames, chip pyramids, final canvas levels, result)
+    frac = 1.0 if world == 1 else min(1.0, 2.2 / world)
+    need = frac * (n * W * H * 4 + chip_px * 9) + cw * ch * 4 + cw * ch * 3 / world + 3e9
+    free, total = torch.cuda.mem_get_info()
+    if need > 0.95 * free:
+        return {"skipped": f"needs ~{need / 1e9:.0f} GB of HBM, {free / 1e9:.0f} GB free"} if rank == 0 else None
+    cv = api.Canvas(ctx, T, W, H, keep)
+    if world > 1:
+        cv.set_rect(*rects[rank])
+    base = torch.from_numpy(synth.texture_image(rng, W, H, 6)).to(dev)
+    n_active = 0
+    for k in range(n):
+        if keep[k] and cv.is_active(k):
+            cv.set_image(k, torch.roll(base, shifts=(37 * k) % H, dims=0).contiguous()); n_active += 1
+    torch.cuda.synchronize()
+
+    def run():
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+        e[0].record(); cv.warp(); e[1].record(); cv.seam_masks(); e[2].record(); cv.blend(5); e[3].record()
+        if world > 1:
+            nd.gather_canvas(cv, rects, root=0)
+        e[4].record()
+        torch.cuda.synchronize()
+        return [e[i].elapsed_time(e[i + 1]) for i in range(4)] + [e[0].elapsed_time(e[4])]
+    run()                                            # warm-up (allocates the pyramids, sets the NCCL channels up)
+    if world > 1: dist.barrier()
+    t = np.min(np.array([run() for _ in range(2)]), axis=0)
+    tt = torch.tensor(list(t), device=dev, dtype=torch.float64)
+    if world > 1: dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    res = None
+    if rank == 0:
+        # checksum of the assembled mosaic on the device (must not depend on N)
+        chk = [0, 0]
+        rows_per = 2048
+        buf = torch.empty((rows_per, cw, 3), dtype=torch.uint8, device=dev)
+        wgt = (torch.arange(rows_per * cw * 3, device=dev, dtype=torch.int64) % 65521).reshape(rows_per, cw, 3)
+        for y0 in range(0, ch, rows_per):
+            y1 = min(y0 + rows_per, ch)
+            cv.copy_result_rows(y0, y1, buf[:y1 - y0])
+            v = buf[:y1 - y0].to(torch.int64)
+            chk[0] += int(v.sum()); chk[1] = (chk[1] + int((v * wgt[:y1 - y0]).sum()) * (1 + y0 // rows_per)) % (1 << 61)
+        del buf, wgt
+        warp_ms, seam_ms, blend_ms, gather_ms, total_ms = [float(x) for x in tt]
+        compulsory = int(keep.sum()) * W * H * 3 + cw * ch * 3
+        model = chip_px * 40 + cw * ch * 32        # SURVEY §8d multi-pass model: ~40 B per fed chip pixel + ~32 B per canvas pixel
+        pk = peaks()
+        res = {"workload": f"configs[4]: {int(keep.sum())} warped tiles of {W}x{H} -> {cw}x{ch} canvas, 5 bands; strong scaling, one canvas rectangle per GPU",
+               "n_gpus": world, "rects": [list(map(int, r)) for r in rects], "warp_ms": warp_ms, "seam_masks_ms": seam_ms, "blend_ms": blend_ms,
+               "gather_ms": gather_ms, "total_ms": total_ms, "canvas_mpx_per_s": cw * ch / 1e6 / (total_ms / 1e3),
+               "mosaic_checksum": [int(chk[0]), int(chk[1])], "fed_chip_mpx": chip_px / 1e6,
+               "compulsory_gb": compulsory / 1e9, "compulsory_ms_at_hbm_peak": compulsory / 1e9 / (pk["hbm_gbs"] * world) * 1e3,
+               "multipass_model_gb": model / 1e9, "multipass_model_ms_at_hbm_peak": model / 1e9 / (pk["hbm_gbs"] * world) * 1e3,
+               "frac_of_multipass_model_roofline": model / 1e9 / (pk["hbm_gbs"] * world) * 1e3 / total_ms,
+               "active_tiles_rank0": n_active, "hbm_used_gb_rank0": (total - torch.cuda.mem_get_info()[0]) / 1e9,
+               "note": "CUDA events, best of 2 after a warm-up, max over ranks; frames synthesised on the device"}
+    cv.close()
+    return res
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -226,6 +429,8 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local)
+    if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"                  # NCCL prints its version banner on stdout: this script prints ONE JSON line
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -250,29 +455,34 @@ def run_ours(args):
     pb = api.PairBatch(ctx, fs, pairs)
     cv = api.Canvas(ctx, T, W, H, keep)
 
-    def upload_all():
-        for k in range(NIMG):
-            fs.upload(k, h_desc[k], h_kp[k])
-        for k in range(1, NIMG):
-            cv.set_image(k, h_frames[k])
+    # device-resident inputs of `value`: descriptors in the pool, frames as BGR bytes (what a caller hands over)
+    for k in range(NIMG):
+        fs.upload(k, h_desc[k], h_kp[k])
+    d_frames = [None] + [h_frames[k].to(dev, non_blocking=True) for k in range(1, NIMG)]
+    torch.cuda.synchronize()
 
     def compute(ev=None, overlap=True):
-        """One step.  With overlap (the shipped configuration) the latency-bound RANSAC kernels run on the ctx's
-        high-priority side stream concurrently with the issue-bound warp; the serial variant times each stage
-        alone.  (Measured: also moving K2 to the side stream does not help — it owns every SM's registers.)"""
+        """One step from BGR frames.  With overlap (the shipped configuration) the pair path (match -> select -> RANSAC) runs
+        on the ctx's high-priority side stream while the frame path (BGR -> BGRA pass of set_image, then the warp) runs on
+        the main stream: the bandwidth-bound conversions sit next to the tensor-bound match, the latency-bound RANSAC next
+        to the issue-bound warp.  The serial variant times each stage alone."""
+        if overlap:
+            ctx.fork()
         if ev: ev[0].record()
         pb.match()
         if ev: ev[1].record()
         pb.select(W, H)
         if ev: ev[2].record()
-        if overlap:
-            ctx.fork()
         pb.ransac(RANSAC_DIST, SAMPLE_TIMES, base_seed=1000)
+        if ev: ev[3].record()
         if overlap:
             ctx.unfork()
-        if ev: ev[3].record()
-        cv.warp()
         if ev: ev[4].record()
+        for k in range(1, NIMG):
+            cv.set_image(k, d_frames[k])                   # device BGR -> the BGRA source pool (k5_bgr_to_bgra_x4)
+        if ev: ev[5].record()
+        cv.warp()
+        if ev: ev[6].record()
         if overlap:
             ctx.join()
 
@@ -281,41 +491,49 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    upload_all()
-    torch.cuda.synchronize()
-
+    # torch.cuda.Event records on torch's current stream; the side stream belongs to the library: stage events of the pair
+    # path are taken in the serial pass only
     # ---- device-resident timing ----
     for _ in range(args.warmup):
         compute()
     barrier()
     sampler = ClockSampler(local) if rank == 0 else None
-    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(args.steps)]
     l0 = ctx.launch_count
     t_start = torch.cuda.Event(enable_timing=True); t_end = torch.cuda.Event(enable_timing=True)
     barrier()
     t_start.record()
     for s in range(args.steps):
-        compute(evs[s])
+        compute()
     t_end.record()
     barrier()
     launches = ctx.launch_count - l0
     ms_total = t_start.elapsed_time(t_end)
-    stage_ms = np.zeros(4)                                   # inside the timed region (RANSAC overlaps the warp)
-    for s in range(args.steps):
-        for k in range(4):
-            stage_ms[k] += evs[s][k].elapsed_time(evs[s][k + 1])
-    stage_ms /= args.steps
+    # in-step stage times of the main stream (conversion, warp): a second timed pass with events (not part of `value`)
+    n_ev = 5
+    mev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(n_ev)]
+    for s in range(n_ev):
+        ctx.fork(); pb.match(); pb.select(W, H); pb.ransac(RANSAC_DIST, SAMPLE_TIMES, base_seed=1000); ctx.unfork()
+        mev[s][0].record()
+        for k in range(1, NIMG):
+            cv.set_image(k, d_frames[k])
+        mev[s][1].record()
+        cv.warp()
+        mev[s][2].record()
+        ctx.join()
+    barrier()
+    conv_ms = sum(e[0].elapsed_time(e[1]) for e in mev) / n_ev
+    warp_ms_instep = sum(e[1].elapsed_time(e[2]) for e in mev) / n_ev
     # serial pass (not part of `value`): every stage alone on the stream, for the per-kernel table
     n_ser = 3
-    sev = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(n_ser)]
+    sev = [[torch.cuda.Event(enable_timing=True) for _ in range(7)] for _ in range(n_ser)]
     for s in range(n_ser):
         compute(sev[s], overlap=False)
     barrier()
-    serial_ms = np.zeros(4)
+    serial_ms = np.zeros(6)
     for s in range(n_ser):
-        for k in range(4):
+        for k in range(6):
             serial_ms[k] += sev[s][k].elapsed_time(sev[s][k + 1])
-    serial_ms /= n_ser
+    serial_ms /= n_ser                                      # match, select, ransac, -, convert, warp
 
     # ---- end-to-end timing (host buffers in, inlier match list out) ----
     # API order of a streaming caller: descriptors first, match/select/RANSAC start while the frames are still
@@ -365,7 +583,7 @@ def run_ours(args):
     blend_info = None
     if rank == 0 and not args.no_blend:
         b0 = torch.cuda.Event(enable_timing=True); b1 = torch.cuda.Event(enable_timing=True); b2 = torch.cuda.Event(enable_timing=True)
-        cv.warp(); cv.seam_masks(); cv.blend(5)              # warm-up (allocates the canvas pyramid)
+        cv.warp(); cv.seam_masks(); cv.blend(5)              # warm-up (allocates the pyramids)
         torch.cuda.synchronize()
         cv.warp()
         b0.record(); cv.seam_masks(); b1.record(); cv.blend(5); b2.record()
@@ -376,10 +594,25 @@ def run_ours(args):
                       "k6_seam_masks_ms": b0.elapsed_time(b1), "k7_blend_ms": b1.elapsed_time(b2),
                       "canvas_mpx_per_s": cpx / 1e6 / (b1.elapsed_time(b2) / 1000.0), "bands": 5}
 
-    t = torch.tensor([ms_total, e2e_ms], device=dev, dtype=torch.float64)
+    t = torch.tensor([ms_total, e2e_ms, conv_ms, warp_ms_instep], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total, e2e_ms = float(t[0]), float(t[1])
+    ms_total, e2e_ms, conv_ms, warp_ms_instep = [float(x) for x in t]
+    warp_chips = [(cv.chips[k].chip_w, cv.chips[k].chip_h) for k in range(NIMG) if cv.chips[k].keep]
+    # free the strip before the larger workloads
+    cv.close(); pb.close(); fs.close()
+    del d_frames, h_frames, h_desc, h_kp
+    torch.cuda.empty_cache()
+
+    # ---- BASELINE configs[2] and configs[4], strong-scaled over the N GPUs through the C ABI ----
+    block_info = canvas_info = None
+    if not (args.no_block and args.no_canvas):
+        nd = api.Dist.from_torch(ctx)
+        if not args.no_block:
+            block_info = run_block200(args, ctx, nd, rank, world, dev)
+        if not args.no_canvas:
+            canvas_info = run_canvas500(args, ctx, nd, rank, world, dev)
+        nd.close()
 
     if rank == 0:
         pk = peaks()
@@ -389,51 +622,57 @@ def run_ours(args):
         h2d = NIMG * (NKP * 128 + NKP * 8) + n_pairs * W * H * 3
         d2h = int(n_match_pairs) * 40 + n_pairs * (4 * 16)
         # W*H*3 (source read once) + A_chip*(3+1) (chip + mask written) per warped frame
-        warp_bytes = float(sum(W * H * 3 + cv.chips[k].chip_w * cv.chips[k].chip_h * 4 for k in range(NIMG) if cv.chips[k].keep))
+        warp_bytes = float(sum(W * H * 3 + cw_ * ch_ * 4 for (cw_, ch_) in warp_chips))
         match_flop = 2.0 * NKP * NKP * 128 * n_pairs
-        warp_gbs = warp_bytes / (stage_ms[3] / 1000.0) / 1e9
+        warp_gbs = warp_bytes / (warp_ms_instep / 1000.0) / 1e9
         match_tf = match_flop / (serial_ms[0] / 1000.0) / 1e12
-        traffic = None
+        traffic = traffic_src = None
         try:                                                # dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["k5_warp_affine_x2"]["traffic"]
+            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["k5_warp_affine_x2"]
+            traffic = tj["traffic"]; traffic_src = "static: " + tj.get("src", "profiles/traffic.json") + " (one ncu --set full capture of this kernel on this workload; not measured in this run)"
         except Exception:
             pass
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8 x u8 -> s32 match (tcgen05 kind::i8), f32 RANSAC + warp", "data": "synthetic",
-            "config": {"workload": "configs[1]: 50-image strip 4000x3000, 8192 kp/image, sequential pairs (49 pair units per step per GPU)",
-                       "pairs_per_step_per_gpu": n_pairs, "ransac": "396 candidates, 1000 counted hypotheses, ~50% inliers",
-                       "l2": "per-step working set 5 GB (frames + chips) >> 126 MB L2; the warp pass evicts the 52 MB descriptor pool between match passes",
-                       "parallelism": f"pairs sharded over {world} GPU(s), no data-path collective"},
+            "config": CONFIG,
             "roofline": {"kernel": "k5_warp_affine_x2", "bound": "hbm", "achieved": warp_gbs, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                         "frac": warp_gbs / pk["hbm_gbs"], "traffic": traffic, "peak_src": pk["src"],
-                         "algorithmic_bytes_per_launch": warp_bytes, "ms_per_launch": float(stage_ms[3])},
-            "kernels": {"note": "timed region: k4 runs on the high-priority side stream concurrently with k5 on the main stream "
-                                "(k5 'ms' is measured there, with that interference); serial_ms: each stage alone, 3 extra untimed steps",
-                        "k2_match_tcgen05": {"ms": float(stage_ms[0]), "serial_ms": float(serial_ms[0]), "bound": "tensor", "achieved_tflops": match_tf,
+                         "frac": warp_gbs / pk["hbm_gbs"], "traffic": traffic, "traffic_src": traffic_src, "peak_src": pk["src"],
+                         "algorithmic_bytes_per_launch": warp_bytes, "ms_per_launch": float(warp_ms_instep),
+                         "note": "ms_per_launch: CUDA events around the warp on the main stream inside the overlapped step (RANSAC on the side stream), "
+                                 "5 extra steps after the timed region"},
+            "kernels": {"note": "value's step = pair path (k2, k3, k4) on the high-priority side stream || frame path (49 x k5_bgr_to_bgra_x4, then k5) "
+                                "on the main stream; serial_ms: each stage alone, 3 extra untimed steps",
+                        "k2_match_tcgen05": {"serial_ms": float(serial_ms[0]), "bound": "tensor", "achieved_tflops": match_tf,
                                              "peak_bf16_tflops": pk["bf16_tflops"], "frac_of_bf16_peak": match_tf / pk["bf16_tflops"]},
-                        "k3_select": {"ms": float(stage_ms[1]), "serial_ms": float(serial_ms[1])},
+                        "k3_select": {"serial_ms": float(serial_ms[1])},
                         "k4_ransac_eval+finalize": {"serial_ms": float(serial_ms[2]), "draw_groups_per_s": n_pairs * 2304 / (serial_ms[2] / 1000.0)},
-                        "k5_warp_affine_x2": {"ms": float(stage_ms[3]), "serial_ms": float(serial_ms[3]), "achieved_gbs": warp_gbs,
-                                          "serial_gbs": warp_bytes / (serial_ms[3] / 1000.0) / 1e9}},
+                        "k5_bgr_to_bgra_x4 (49 launches)": {"ms_in_step": float(conv_ms), "serial_ms": float(serial_ms[4]),
+                                                            "serial_gbs": n_pairs * W * H * 7 / (serial_ms[4] / 1000.0) / 1e9},
+                        "k5_warp_affine_x2": {"ms_in_step": float(warp_ms_instep), "serial_ms": float(serial_ms[5]), "achieved_gbs": warp_gbs,
+                                              "serial_gbs": warp_bytes / (serial_ms[5] / 1000.0) / 1e9}},
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": e_steps,
                     "ms_per_step": e2e_ms / e_steps, "pcie_h2d_probe_gbs": pcie_gbs, "host_numa_node_rank0": numa_node,
-                    "note": "PCIe bound: frames are copied on the library's copy stream while match/RANSAC/warp run"},
+                    "note": "inputs in (descriptors, keypoints, 49 BGR frames from pinned host memory), inlier match list out; the warped chips "
+                            "(2.6 GB) stay resident in HBM, where the seam masks and the blend consume them.  PCIe bound: frames are copied on the "
+                            "library's copy stream while match / RANSAC / warp run"},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "blend": blend_info,
+            "block200": block_info,
+            "canvas500": canvas_info,
         }
         # ---- CPU baseline on a bounded sample (rank 0, N=1 only) ----
         if world == 1 and not args.no_cpu:
+            from oracle import oracle as O
             n_sample = max(4, min(48, host_threads()))
-            frames = [h_frames[k].numpy() for k in range(n_sample + 1)]
+            frames = [np.roll(base, (37 * k) % H, axis=0) for k in range(n_sample + 1)]
             sp = [(i, i + 1) for i in range(n_sample)]
             cpu_pairs(descs, kps, T[:n_sample + 1], frames, sp[:1], [1000])       # warm
             t_cpu = cpu_pairs(descs, kps, T[:n_sample + 1], frames, sp, [1000 + p for p in range(n_sample)])
-            from oracle import oracle as O
             line["cpu_baseline"] = {"value": n_sample / t_cpu, "unit": UNIT, "cores": host_threads(), "kind": "port",
-                                    "sample": cpu_sample_note(n_sample, O)}
+                                    "sample": cpu_sample_note(n_sample, O), "variants": cpu_variants(descs, kps)}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -447,6 +686,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-blend", action="store_true", help="skip the separate seam-mask + multi-band blend measurement")
+    ap.add_argument("--no-block", action="store_true", help="skip BASELINE configs[2] (200-image block, strong scaling)")
+    ap.add_argument("--no-canvas", action="store_true", help="skip BASELINE configs[4] (500 tiles -> 40000^2 canvas, strong scaling)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -234,8 +234,8 @@ class Dist:
     @staticmethod
     def from_torch(ctx):
         import torch.distributed as dist
-        if not (dist.is_available() and dist.is_initialized()):
-            return Dist(ctx, 0, 1, Dist.unique_id())
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+            return Dist(ctx, 0, 1, bytes(Dist.ID_BYTES))            # a single rank needs no communicator
         rank, world = dist.get_rank(), dist.get_world_size()
         box = [Dist.unique_id() if rank == 0 else None]
         dist.broadcast_object_list(box, src=0)

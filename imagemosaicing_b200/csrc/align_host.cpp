@@ -64,7 +64,11 @@ extern "C" int uavm_connected_images(const uavm_matchpointpairs* pairs, int n_pa
 // of a strip or block couples an image only with nearby images, so rows are short (a 200-image block: 1194 unknowns, rows of
 // <= ~150 entries) and the factorisation costs n * row^2 instead of n^3 / 3.  Fill-in stays inside the envelope and every
 // skipped term is an exact zero, so the result is bit-identical to the full dense factorisation.
-static int cholesky_solve(std::vector<double>& N, std::vector<double>& b, int n)
+// The affine model decouples: x' = a x + b y + e and y' = c x + d y + f have the SAME normal matrix (built from the same
+// [x y 1] rows, M/MosaicWithoutPos.cpp:7035-7146) and no cross terms, so one factorisation of order 3 (N - 1) serves both
+// right-hand sides.  In the interleaved 6 (N - 1) system the cross entries are exact zeros and every non-zero term is
+// accumulated and eliminated in the same order, so this is again bit-identical — at a quarter of the work.
+static int cholesky_solve2(std::vector<double>& N, std::vector<double>& b1, std::vector<double>& b2, int n)
 {
     std::vector<int> first(n);
     for (int i = 0; i < n; i++) {
@@ -85,15 +89,18 @@ static int cholesky_solve(std::vector<double>& N, std::vector<double>& b, int n)
             N[(size_t)i * n + j] = t / l;
         }
     }
-    for (int i = 0; i < n; i++) {
-        double t = b[i];
-        for (int k = first[i]; k < i; k++) t -= N[(size_t)i * n + k] * b[k];
-        b[i] = t / N[(size_t)i * n + i];
-    }
-    for (int i = n - 1; i >= 0; i--) {
-        double t = b[i];
-        for (int k = i + 1; k < n; k++) if (first[k] <= i) t -= N[(size_t)k * n + i] * b[k];
-        b[i] = t / N[(size_t)i * n + i];
+    for (std::vector<double>* pb : {&b1, &b2}) {
+        std::vector<double>& b = *pb;
+        for (int i = 0; i < n; i++) {
+            double t = b[i];
+            for (int k = first[i]; k < i; k++) t -= N[(size_t)i * n + k] * b[k];
+            b[i] = t / N[(size_t)i * n + i];
+        }
+        for (int i = n - 1; i >= 0; i--) {
+            double t = b[i];
+            for (int k = i + 1; k < n; k++) if (first[k] <= i) t -= N[(size_t)k * n + i] * b[k];
+            b[i] = t / N[(size_t)i * n + i];
+        }
     }
     return 0;
 }
@@ -107,54 +114,51 @@ extern "C" int uavm_align_affine(const uavm_matchpointpairs* pairs, int n_pairs,
     int nf = 0;
     for (int i = 0; i < n_images; i++) { acc_fixed[i] = nf; if (init[i].fixed == 1) nf++; }
     if (n_fixed >= 0 && n_fixed != nf) return UAVM_EINVAL;
-    const int nu = 6 * (n_images - nf);
+    const int nu = 3 * (n_images - nf);                   // per coordinate: (a, b, e) resp. (c, d, f) of every free image
     if (nu <= 0) return UAVM_EFAIL;
     if (nu > 12000) return UAVM_EFAIL;                    // dense normal matrix limit (1.1 GB)
-    std::vector<double> N((size_t)nu * nu, 0.0), g(nu, 0.0);
-    // unknown order inside an image block: a b c d e f with x' = a x + b y + e, y' = c x + d y + f (:7035-7046)
-    static const int slot_x[3] = {0, 1, 4}, slot_y[3] = {2, 3, 5};
+    std::vector<double> N((size_t)nu * nu, 0.0), gx(nu, 0.0), gy(nu, 0.0);
     for (int n = 0; n < n_pairs; n++) {
         const uavm_matchpointpairs& m = pairs[n];
         if (m.ptA_i < 0 || m.ptA_i >= n_images || m.ptB_i < 0 || m.ptB_i >= n_images) return UAVM_EINVAL;
         int cols[6]; double vals[6]; int nc = 0; double rx = 0, ry = 0;
         const double xa = m.ptA.x, ya = m.ptA.y, xb = m.ptB.x, yb = m.ptB.y;
         if (m.ptA_Fixed == 0 && m.ptB_Fixed == 0) {
-            const int ca = 6 * (m.ptA_i - acc_fixed[m.ptA_i]), cb = 6 * (m.ptB_i - acc_fixed[m.ptB_i]);
+            const int ca = 3 * (m.ptA_i - acc_fixed[m.ptA_i]), cb = 3 * (m.ptB_i - acc_fixed[m.ptB_i]);
             cols[0] = ca; vals[0] = xa; cols[1] = ca; vals[1] = ya; cols[2] = ca; vals[2] = 1;
             cols[3] = cb; vals[3] = -xb; cols[4] = cb; vals[4] = -yb; cols[5] = cb; vals[5] = -1; nc = 6;
         } else if (m.ptA_Fixed == 1 && m.ptB_Fixed == 0) {
-            const int cb = 6 * (m.ptB_i - acc_fixed[m.ptB_i]);
+            const int cb = 3 * (m.ptB_i - acc_fixed[m.ptB_i]);
             cols[0] = cb; vals[0] = xb; cols[1] = cb; vals[1] = yb; cols[2] = cb; vals[2] = 1; nc = 3;
             double h[9]; for (int t = 0; t < 9; t++) h[t] = init[m.ptA_i].h.m[t];
             rx = (h[0] * xa + h[1] * ya + h[2]) / (h[6] * xa + h[7] * ya + h[8]);      // ApplyProject9 (M/MosaicWithoutPos.h:331-336)
             ry = (h[3] * xa + h[4] * ya + h[5]) / (h[6] * xa + h[7] * ya + h[8]);
         } else if (m.ptA_Fixed == 0 && m.ptB_Fixed == 1) {
-            const int ca = 6 * (m.ptA_i - acc_fixed[m.ptA_i]);
+            const int ca = 3 * (m.ptA_i - acc_fixed[m.ptA_i]);
             cols[0] = ca; vals[0] = xa; cols[1] = ca; vals[1] = ya; cols[2] = ca; vals[2] = 1; nc = 3;
             double h[9]; for (int t = 0; t < 9; t++) h[t] = init[m.ptB_i].h.m[t];
             rx = (h[0] * xb + h[1] * yb + h[2]) / (h[6] * xb + h[7] * yb + h[8]);
             ry = (h[3] * xb + h[4] * yb + h[5]) / (h[6] * xb + h[7] * yb + h[8]);
         } else continue;
         for (int a = 0; a < nc; a++) {
-            if (cols[a] < 0 || cols[a] + 5 >= nu) return UAVM_EINVAL;      // a "free" point on a fixed image
-            const int ax = cols[a] + slot_x[a % 3], ay = cols[a] + slot_y[a % 3];
+            if (cols[a] < 0 || cols[a] + 2 >= nu) return UAVM_EINVAL;      // a "free" point on a fixed image
+            const int ar = cols[a] + a % 3;
             for (int b = 0; b < nc; b++) {
-                N[(size_t)ax * nu + cols[b] + slot_x[b % 3]] += vals[a] * vals[b];
-                N[(size_t)ay * nu + cols[b] + slot_y[b % 3]] += vals[a] * vals[b];
+                const int bc = cols[b] + b % 3;
+                if (bc <= ar) N[(size_t)ar * nu + bc] += vals[a] * vals[b];       // the factorisation reads the lower triangle only
             }
-            g[ax] += vals[a] * rx;
-            g[ay] += vals[a] * ry;
+            gx[ar] += vals[a] * rx;
+            gy[ar] += vals[a] * ry;
         }
     }
-    if (cholesky_solve(N, g, nu) != 0) return UAVM_EFAIL;
+    if (cholesky_solve2(N, gx, gy, nu) != 0) return UAVM_EFAIL;
     int k = 0;
     for (int i = 0; i < n_images; i++) {
         if (init[i].fixed == 0) {
             uavm_imagetransform t; memset(&t, 0, sizeof(t));
             t.fixed = 0;
-            t.h.m[0] = (float)g[6 * k + 0]; t.h.m[1] = (float)g[6 * k + 1];
-            t.h.m[3] = (float)g[6 * k + 2]; t.h.m[4] = (float)g[6 * k + 3];
-            t.h.m[2] = (float)g[6 * k + 4]; t.h.m[5] = (float)g[6 * k + 5];
+            t.h.m[0] = (float)gx[3 * k + 0]; t.h.m[1] = (float)gx[3 * k + 1]; t.h.m[2] = (float)gx[3 * k + 2];
+            t.h.m[3] = (float)gy[3 * k + 0]; t.h.m[4] = (float)gy[3 * k + 1]; t.h.m[5] = (float)gy[3 * k + 2];
             t.h.m[6] = 0; t.h.m[7] = 0; t.h.m[8] = 1;
             out[i] = t; k++;
         } else out[i] = init[i];

@@ -178,6 +178,7 @@ struct uavm_dist {
 extern "C" int uavm_dist_unique_id(uint8_t* id_out, int id_bytes)
 {
     if (!id_out || id_bytes < (int)sizeof(ncclUniqueId)) return UAVM_EINVAL;
+    memset(id_out, 0, (size_t)id_bytes);
     if (load_nccl()) return UAVM_EFAIL;
     ncclUniqueId id;
     if (g_nccl.GetUniqueId(&id) != ncclSuccess) return UAVM_EFAIL;
@@ -189,10 +190,11 @@ extern "C" int uavm_dist_init(uavm_ctx* ctx, int rank, int world, const uint8_t*
 {
     if (!ctx || !out || world < 1 || rank < 0 || rank >= world || !id || id_bytes < (int)sizeof(ncclUniqueId)) return UAVM_EINVAL;
     *out = nullptr;
-    if (const char* e = load_nccl()) { UAVM_SET_ERR(ctx, "%s", e); return UAVM_EFAIL; }
     UAVM_CUDA(ctx, cudaSetDevice(ctx->device));
     uavm_dist* d = new uavm_dist();
     d->rank = rank; d->world = world; d->device = ctx->device;
+    if (world == 1) { *out = d; return UAVM_OK; }          // a single rank needs no communicator (and no NCCL in the process)
+    if (const char* e = load_nccl()) { UAVM_SET_ERR(ctx, "%s", e); delete d; return UAVM_EFAIL; }
     ncclUniqueId uid; memcpy(&uid, id, sizeof(uid));
     ncclResult_t r = g_nccl.CommInitRank(&d->comm, world, uid, rank);
     if (r != ncclSuccess) { UAVM_SET_ERR(ctx, "ncclCommInitRank -> %s", g_nccl.GetErrorString(r)); delete d; return UAVM_EFAIL; }
@@ -249,7 +251,8 @@ extern "C" int uavm_pairbatch_allgather(uavm_ctx* ctx, uavm_dist* d, uavm_pairba
                                                  pb ? pb->d_cand_xy1 : nullptr, pb ? pb->d_cand_xy2 : nullptr, pb ? pb->d_cand_id1 : nullptr, pb ? pb->d_cand_id2 : nullptr,
                                                  pb ? pb->d_res : nullptr, d->d_send);
     UAVM_CHECK_LAUNCH(ctx);
-    UAVM_NCCL(ctx, g_nccl.AllGather(d->d_send, d->d_recv, (size_t)n_slot * sizeof(PairRecord), ncclInt8, d->comm, ctx->stream));
+    if (world == 1) UAVM_CUDA(ctx, cudaMemcpyAsync(d->d_recv, d->d_send, (size_t)n_slot * sizeof(PairRecord), cudaMemcpyDeviceToDevice, ctx->stream));
+    else UAVM_NCCL(ctx, g_nccl.AllGather(d->d_send, d->d_recv, (size_t)n_slot * sizeof(PairRecord), ncclInt8, d->comm, ctx->stream));
     k_dist_offsets<<<1, 1024, 0, ctx->stream>>>(d->d_recv, n_pairs_global, world, n_slot, min_inner_points, d->d_offsets, d->d_nacc);
     UAVM_CHECK_LAUNCH(ctx);
     int32_t head[2] = {0, 0};

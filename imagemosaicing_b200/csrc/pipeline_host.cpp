@@ -94,6 +94,46 @@ extern "C" int uavm_mosaic_from_matches(uavm_ctx* ctx, const uavm_image* images,
     return mosaic_tail(ctx, images, n_images, matches, P, scale, result, num_mosaiced, transforms_out);
 }
 
+// Stages [B] and [C] of MosaicWithoutPose on a match list (M/MosaicWithoutPos.cpp:4501-4652): largest connected component of the
+// pair graph, matches touching unconnected images dropped (same removal order as :4512-4523), reference image 0 and its points
+// fixed (:4525-4556), BundleAdjustmentSparse (:4591), unconnected images flagged with m[8] = 0 (:4646-4652).  `pairs` is
+// modified in place (compacted, fixed flags set: exactly what the reference writes to matchPairs.txt); *n_used_out = matches
+// kept.  label_out (optional): 1 for images of the largest component.  Returns -2 when nothing was accepted, the reference
+// image is not in the largest component, or the normal equations are singular.
+extern "C" int uavm_global_align(uavm_matchpointpairs* pairs, int n_pairs, int n_images, uavm_imagetransform* transforms_out,
+                                 int32_t* label_out, int* n_used_out)
+{
+    if (n_images < 1 || n_pairs < 0 || (n_pairs > 0 && !pairs) || !transforms_out) return UAVM_EINVAL;
+    std::vector<int32_t> label(n_images, 0);
+    if (n_pairs > 0) { int rc = uavm_connected_images(pairs, n_pairs, n_images, label.data()); if (rc != UAVM_OK) return rc; }
+    int n = n_pairs;
+    for (int m = 0; m < n;) {                                          // same removal order as the reference (:4512-4523)
+        if (label[pairs[m].ptA_i] == 0 || label[pairs[m].ptB_i] == 0) { pairs[m] = pairs[n - 1]; n--; }
+        else m++;
+    }
+    const int ref = 0;
+    std::vector<uavm_imagetransform> init(n_images);
+    for (int i = 0; i < n_images; i++) {
+        memset(&init[i], 0, sizeof(init[i]));
+        init[i].h.m[0] = init[i].h.m[4] = init[i].h.m[8] = 1.0f;
+    }
+    for (int m = 0; m < n; m++) {
+        if (pairs[m].ptA_i == ref) pairs[m].ptA_Fixed = 1;
+        if (pairs[m].ptB_i == ref) pairs[m].ptB_Fixed = 1;
+    }
+    int n_fixed = 0;
+    for (int i = 0; i < n_images; i++) if (label[i] == 0) { init[i].fixed = 1; n_fixed++; }
+    if (label_out) memcpy(label_out, label.data(), sizeof(int32_t) * n_images);
+    if (n_used_out) *n_used_out = n;
+    if (init[ref].fixed == 0) { init[ref].fixed = 1; n_fixed++; }
+    else if (n > 0) return UAVM_EFAIL;                                 // reference image 0 is not in the largest connected component
+    if (n == 0) return UAVM_EFAIL;                                     // no image pair was accepted
+    int rc = uavm_align_affine(pairs, n, init.data(), n_images, n_fixed, transforms_out);
+    if (rc != UAVM_OK) return UAVM_EFAIL;
+    for (int i = 0; i < n_images; i++) if (label[i] == 0) transforms_out[i].h.m[8] = 0;      // "skip me" (:4646-4652)
+    return UAVM_OK;
+}
+
 // stages [B]-[D] of MosaicWithoutPose, shared by the matching path and the loadMatchPairs path
 static int mosaic_tail(uavm_ctx* ctx, const uavm_image* images, int n_images, std::vector<uavm_matchpointpairs>& matches, const uavm_param& P,
                        float scale, uavm_image* result, int* num_mosaiced, uavm_imagetransform* transforms_out)
@@ -102,34 +142,18 @@ static int mosaic_tail(uavm_ctx* ctx, const uavm_image* images, int n_images, st
     uavm_canvas* cv = nullptr;
     int rc = UAVM_OK;
 
-    // ---- [B] largest connected component, reference image 0 fixed (:4501-4571) ----
-    std::vector<int32_t> label(n_images, 0);
-    if (!matches.empty()) uavm_connected_images(matches.data(), (int)matches.size(), n_images, label.data());
-    for (size_t m = 0; m < matches.size();) {                          // same removal order as the reference (:4512-4523)
-        if (label[matches[m].ptA_i] == 0 || label[matches[m].ptB_i] == 0) { matches[m] = matches.back(); matches.pop_back(); }
-        else m++;
+    // ---- [B] + [C]: connectivity, reference image, global affine alignment ----
+    std::vector<uavm_imagetransform> refined(n_images);
+    {
+        std::vector<uavm_matchpointpairs> work(matches);
+        int n_used = 0;
+        rc = uavm_global_align(work.data(), (int)work.size(), n_images, refined.data(), nullptr, &n_used);
+        if (num_mosaiced) *num_mosaiced = n_images;                    // numMosaiced = nImages (:4621)
+        if (rc != UAVM_OK) {
+            UAVM_SET_ERR(ctx, matches.empty() ? "no image pair was accepted" : "global alignment failed (%d): reference image 0 outside the largest component or singular system", rc);
+            return UAVM_EFAIL;
+        }
     }
-    const int ref = 0;
-    std::vector<uavm_imagetransform> init(n_images), refined(n_images);
-    for (int i = 0; i < n_images; i++) {
-        memset(&init[i], 0, sizeof(init[i]));
-        init[i].h.m[0] = init[i].h.m[4] = init[i].h.m[8] = 1.0f;
-    }
-    for (size_t m = 0; m < matches.size(); m++) {
-        if (matches[m].ptA_i == ref) matches[m].ptA_Fixed = 1;
-        if (matches[m].ptB_i == ref) matches[m].ptB_Fixed = 1;
-    }
-    int n_fixed = 0;
-    for (int i = 0; i < n_images; i++) if (label[i] == 0) { init[i].fixed = 1; n_fixed++; }
-    if (init[ref].fixed == 0) { init[ref].fixed = 1; n_fixed++; }
-    else if (!matches.empty()) { UAVM_SET_ERR(ctx, "reference image 0 is not in the largest connected component"); return UAVM_EFAIL; }
-    if (num_mosaiced) *num_mosaiced = n_images;                        // numMosaiced = nImages (:4621)
-    if (matches.empty()) { UAVM_SET_ERR(ctx, "no image pair was accepted"); return UAVM_EFAIL; }
-
-    // ---- [C] global affine alignment: BundleAdjustmentSparse (:4591) ----
-    rc = uavm_align_affine(matches.data(), (int)matches.size(), init.data(), n_images, n_fixed, refined.data());
-    if (rc != UAVM_OK) { UAVM_SET_ERR(ctx, "global alignment failed (%d)", rc); return UAVM_EFAIL; }
-    for (int i = 0; i < n_images; i++) if (label[i] == 0) refined[i].h.m[8] = 0;          // "skip me" (:4646-4652)
     if (transforms_out) memcpy(transforms_out, refined.data(), sizeof(uavm_imagetransform) * n_images);
 
     // ---- [D] warp + blend: MergeImagesRefined -> LaplacianPyramidBlending(band = 5, scale) (:4663, :2180) ----

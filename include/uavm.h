@@ -129,6 +129,11 @@ int uavm_align_affine(const uavm_matchpointpairs* pairs, int n_pairs, const uavm
                       int n_fixed, uavm_imagetransform* out);
 /* largest connected component of the pair graph (Select_Connected_Matched_Images, :2754-2796) */
 int uavm_connected_images(const uavm_matchpointpairs* pairs, int n_pairs, int n_images, int32_t* label);
+/* stages [B] + [C] of MosaicWithoutPose on a match list (:4501-4652): connectivity, unconnected matches dropped, reference image 0
+ * fixed, BundleAdjustmentSparse, unconnected images flagged m[8] = 0.  pairs is compacted in place (*n_used_out kept, fixed
+ * flags set = the content of matchPairs.txt); label_out optional.  -2: nothing accepted / reference image unconnected. */
+int uavm_global_align(uavm_matchpointpairs* pairs, int n_pairs, int n_images, uavm_imagetransform* transforms_out,
+                      int32_t* label_out, int* n_used_out);
 
 /* ---- warp + seam masks + multi-band blend (replaces LaplacianPyramidBlending, M/MosaicImage.cpp:2205-2510) */
 typedef struct uavm_canvas uavm_canvas;
