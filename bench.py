@@ -429,7 +429,7 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local)
-    if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
         os.environ["NCCL_DEBUG"] = "WARN"                  # NCCL prints its version banner on stdout: this script prints ONE JSON line
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")

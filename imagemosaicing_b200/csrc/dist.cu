@@ -167,7 +167,7 @@ struct uavm_dist {
     ncclComm_t comm = nullptr;
     int rank = 0, world = 1, device = 0;
     // pair gather workspace
-    PairRecord* d_send = nullptr; PairRecord* d_recv = nullptr; size_t slot_cap = 0;
+    PairRecord* d_send = nullptr; PairRecord* d_recv = nullptr; size_t send_cap = 0, recv_cap = 0;
     int32_t* d_offsets = nullptr; size_t off_cap = 0;
     int32_t* d_nacc = nullptr;
     uavm_matchpointpairs* d_dense = nullptr; size_t dense_cap = 0;
@@ -240,10 +240,8 @@ extern "C" int uavm_pairbatch_allgather(uavm_ctx* ctx, uavm_dist* d, uavm_pairba
     const int n_slot = (n_pairs_global + world - 1) / world;                         // records per rank, padded
     if (n_slot == 0) { *n_out = 0; if (n_accepted_pairs) *n_accepted_pairs = 0; return UAVM_OK; }
     {
-        size_t cap1 = d->slot_cap, cap2 = d->slot_cap;
-        int rc = grow(ctx, (void**)&d->d_send, &cap1, (size_t)n_slot * sizeof(PairRecord)); if (rc != UAVM_OK) return rc;
-        rc = grow(ctx, (void**)&d->d_recv, &cap2, (size_t)n_slot * world * sizeof(PairRecord)); if (rc != UAVM_OK) return rc;
-        d->slot_cap = cap1 < cap2 ? cap1 : cap2;
+        int rc = grow(ctx, (void**)&d->d_send, &d->send_cap, (size_t)n_slot * sizeof(PairRecord)); if (rc != UAVM_OK) return rc;
+        rc = grow(ctx, (void**)&d->d_recv, &d->recv_cap, (size_t)n_slot * world * sizeof(PairRecord)); if (rc != UAVM_OK) return rc;
         rc = grow(ctx, (void**)&d->d_offsets, &d->off_cap, ((size_t)n_pairs_global + 1) * sizeof(int32_t)); if (rc != UAVM_OK) return rc;
         if (!d->d_nacc) UAVM_CUDA(ctx, cudaMalloc(&d->d_nacc, sizeof(int32_t)));
     }
