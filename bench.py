@@ -455,11 +455,19 @@ def run_ours(args):
     pb = api.PairBatch(ctx, fs, pairs)
     cv = api.Canvas(ctx, T, W, H, keep)
 
-    # device-resident inputs of `value`: descriptors in the pool, frames as BGR bytes (what a caller hands over)
+    # device-resident inputs of `value`: u8 descriptors in the feature pool, frames as the BGR bytes a caller hands over.
+    # With a BGR source pool (frame width % 16 == 0) uavm_canvas_set_image is a plain copy — the pool IS the resident BGR
+    # input and the step has nothing to convert.  Otherwise (BGRA pool) the BGR -> BGRA pass runs inside the timed step.
+    bgr_pool = cv.source_layout == 3
     for k in range(NIMG):
         fs.upload(k, h_desc[k], h_kp[k])
-    d_frames = [None] + [h_frames[k].to(dev, non_blocking=True) for k in range(1, NIMG)]
-    torch.cuda.synchronize()
+    d_frames = [None] * NIMG
+    for k in range(1, NIMG):
+        if bgr_pool:
+            cv.set_image(k, h_frames[k])
+        else:
+            d_frames[k] = h_frames[k].to(dev, non_blocking=True)
+    ctx.sync(); torch.cuda.synchronize()
 
     def compute(ev=None, overlap=True):
         """One step from BGR frames.  With overlap (the shipped configuration) the pair path (match -> select -> RANSAC) runs
@@ -478,8 +486,9 @@ def run_ours(args):
         if overlap:
             ctx.unfork()
         if ev: ev[4].record()
-        for k in range(1, NIMG):
-            cv.set_image(k, d_frames[k])                   # device BGR -> the BGRA source pool (k5_bgr_to_bgra_x4)
+        if not bgr_pool:
+            for k in range(1, NIMG):
+                cv.set_image(k, d_frames[k])               # device BGR -> the BGRA source pool (k5_bgr_to_bgra_x4)
         if ev: ev[5].record()
         cv.warp()
         if ev: ev[6].record()
@@ -514,8 +523,9 @@ def run_ours(args):
     for s in range(n_ev):
         ctx.fork(); pb.match(); pb.select(W, H); pb.ransac(RANSAC_DIST, SAMPLE_TIMES, base_seed=1000); ctx.unfork()
         mev[s][0].record()
-        for k in range(1, NIMG):
-            cv.set_image(k, d_frames[k])
+        if not bgr_pool:
+            for k in range(1, NIMG):
+                cv.set_image(k, d_frames[k])
         mev[s][1].record()
         cv.warp()
         mev[s][2].record()
@@ -642,13 +652,14 @@ def run_ours(args):
                          "algorithmic_bytes_per_launch": warp_bytes, "ms_per_launch": float(warp_ms_instep),
                          "note": "ms_per_launch: CUDA events around the warp on the main stream inside the overlapped step (RANSAC on the side stream), "
                                  "5 extra steps after the timed region"},
-            "kernels": {"note": "value's step = pair path (k2, k3, k4) on the high-priority side stream || frame path (49 x k5_bgr_to_bgra_x4, then k5) "
-                                "on the main stream; serial_ms: each stage alone, 3 extra untimed steps",
+            "kernels": {"note": "value's step = pair path (k2, k3, k4) on the high-priority side stream || frame path (k5 warp straight from the resident BGR "
+                                "frames; with a BGRA pool: 49 x k5_bgr_to_bgra_x4 first) on the main stream; serial_ms: each stage alone, 3 extra untimed steps",
+                        "source_pool": "BGR (3 B/px, frames kept as handed over; no conversion kernel)" if bgr_pool else "BGRA (4 B/px, conversion inside the step)",
                         "k2_match_tcgen05": {"serial_ms": float(serial_ms[0]), "bound": "tensor", "achieved_tflops": match_tf,
                                              "peak_bf16_tflops": pk["bf16_tflops"], "frac_of_bf16_peak": match_tf / pk["bf16_tflops"]},
                         "k3_select": {"serial_ms": float(serial_ms[1])},
                         "k4_ransac_eval+finalize": {"serial_ms": float(serial_ms[2]), "draw_groups_per_s": n_pairs * 2304 / (serial_ms[2] / 1000.0)},
-                        "k5_bgr_to_bgra_x4 (49 launches)": {"ms_in_step": float(conv_ms), "serial_ms": float(serial_ms[4]),
+                        "k5_bgr_to_bgra_x4 (49 launches)": None if bgr_pool else {"ms_in_step": float(conv_ms), "serial_ms": float(serial_ms[4]),
                                                             "serial_gbs": n_pairs * W * H * 7 / (serial_ms[4] / 1000.0) / 1e9},
                         "k5_warp_affine_x2": {"ms_in_step": float(warp_ms_instep), "serial_ms": float(serial_ms[5]), "achieved_gbs": warp_gbs,
                                               "serial_gbs": warp_bytes / (serial_ms[5] / 1000.0) / 1e9}},

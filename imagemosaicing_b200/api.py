@@ -121,7 +121,11 @@ class FeatureSet:
         else:
             rc = L.lib().uavm_featureset_upload_f32(self.ctx._h, self._h, int(image), _ptr(desc, f32p), kp_ptr, dev)
         self.ctx.check(rc)
-        self._keep = (desc, kp_xy)     # keep pageable sources alive until the stream has consumed them
+        # host sources are copied asynchronously (pinned memory: the DMA runs after this call returns): keep one reference PER
+        # IMAGE until that image is uploaded again or the object is closed, so a caller may pass temporaries
+        if not hasattr(self, "_keep"):
+            self._keep = {}
+        self._keep[int(image)] = (desc, kp_xy)
 
     def close(self):
         if self._h:
@@ -342,6 +346,11 @@ class Canvas:
         self.layout = CanvasLayout(); self.chips = (ChipLayout * self.n)()
         ctx.check(L.lib().uavm_canvas_get_layout(self._h, C.byref(self.layout), self.chips))
 
+    @property
+    def source_layout(self):
+        """3: frames stay BGR in HBM (no conversion pass), 4: BGRA pool."""
+        return int(L.lib().uavm_canvas_source_layout(self._h))
+
     def set_image(self, image, bgr):
         """bgr: (h, w, 3) uint8 numpy array (host) or torch CUDA tensor (device)."""
         bgr = _host(bgr)
@@ -352,7 +361,9 @@ class Canvas:
             bgr = np.ascontiguousarray(bgr, np.uint8); step = bgr.strides[0]
         assert bgr.shape[0] == self.img_h and bgr.shape[1] == self.img_w and bgr.shape[2] == 3
         self.ctx.check(L.lib().uavm_canvas_set_image(self.ctx._h, self._h, int(image), _ptr(bgr, u8p), int(step), dev))
-        self._keep = bgr
+        if not hasattr(self, "_keep"):
+            self._keep = {}
+        self._keep[int(image)] = bgr       # per image: the copy is asynchronous for pinned host frames (see FeatureSet.upload)
 
     def set_band(self, y0, y1, halo=0):
         """Multi-GPU canvas sharding: produce only canvas rows [y0, y1); see uavm_canvas_set_band (`halo` is ignored)."""

@@ -2,9 +2,11 @@
 //   K5  k5_warp_chips   bilinear inverse warp of every kept frame into its chip + validity mask (:2350-2448)
 // (K6 seam masks live in masks.cu, K7 multi-band blend in blend.cu.)
 //
-// HBM layout: source frames are stored as BGRA (uchar4) so that one 32-bit load returns a whole pixel
-// (a BGR triple straddles words; 12 byte loads per output pixel would make the kernel LSU-bound);
-// chips are BGRA words too (row step align4(chip_w) words): B, G, R = the warped pixel, alpha != 0 = the
+// HBM layout: source frames stay in the caller's BGR layout (3 bytes per pixel, all frames stacked in one pool) whenever the
+// frame width is a multiple of 16 — the packed affine kernel stages the BGR footprint of a chip tile with TMA and reads each
+// pair of horizontally adjacent taps as three aligned shared-memory words + two funnel shifts, so no conversion pass and no
+// 4th byte ever touch HBM.  Other widths use a BGRA (uchar4) pool filled by a conversion kernel (one 32-bit load per tap).
+// Chips are BGRA words (row step align4(chip_w) words): B, G, R = the warped pixel, alpha != 0 = the
 // reference's validity mask (:2443-2456) — the same 3 + 1 bytes per pixel as a BGR chip plus a mask plane,
 // written with one coalesced 32-bit store per pixel.  The u8 mask plane (row step align4(chip_w)) is K6's output.
 #include <stdlib.h>
@@ -85,11 +87,20 @@ constexpr int kWarpTileH = kWarpsY * kWarpRows;
 constexpr int kFpBoxW = 160, kFpBoxH = 16;        // TMA box (pixels): the staged footprint is up to kFpBoxes boxes stacked vertically
 constexpr int kFpBoxBytes = kFpBoxW * kFpBoxH * 4;
 constexpr int kFpBoxes = 4;                       // 160 x 64 px = 40 KB of dynamic shared memory per CTA (5 CTAs / SM)
+// BGR pool: a box is 176 px x 16 rows of packed BGR (528 bytes per row = 132 u32 tensor elements; the box origin must be 16-byte
+// aligned, i.e. a multiple of 16 pixels), 4 boxes = 33 KB
+constexpr int kFpBoxWBgr = 176, kFpPitchBgr = kFpBoxWBgr * 3, kFpBoxBytesBgr = kFpPitchBgr * kFpBoxH;
 
 // Generic (projective) warp, scalar.  AFFINE: inv[6] == inv[7] == 0 and inv[8] == 1, so the reference's denominator is
 // exactly 1.0f for every pixel and x / 1.0f == x: the two divides per coordinate (:2359-2362) are skipped without
 // changing a bit (kept as the A/B twin of the packed affine kernel below).
-template <bool AFFINE>
+// BGR: the source pool holds packed BGR rows of `src_step_px` BYTES; a tap is three byte loads (this kernel is the slow path).
+__device__ __forceinline__ uint32_t load_tap(const uint8_t* __restrict__ src8, size_t byte_off)
+{
+    return (uint32_t)__ldg(src8 + byte_off) | ((uint32_t)__ldg(src8 + byte_off + 1) << 8) | ((uint32_t)__ldg(src8 + byte_off + 2) << 16);
+}
+
+template <bool AFFINE, bool BGR>
 __global__ void __launch_bounds__(32 * kWarpsY)
 k5_warp_chips(const ChipDesc* __restrict__ descs, int img_w, int img_h, int src_step_px, float dgx, float dgy,
               uint32_t two23 /* = 0x4B000000, bits of 2^23: a kernel argument so PRMT takes the SELECTOR as its immediate */,
@@ -135,9 +146,16 @@ k5_warp_chips(const ChipDesc* __restrict__ descs, int img_w, int img_h, int src_
                 const float p = ys - (float)iy, q = xs - (float)ix;
                 const float omp = 1.0f - p, omq = 1.0f - q;
                 const float c_omp = -8388608.0f * omp, c_p = -8388608.0f * p;        // exact (power-of-two scale)
-                const uint32_t off = (uint32_t)(iy * src_step_px + ix);
-                const uint32_t t00 = __ldg(src + off), t01 = __ldg(src + off + 1u);
-                const uint32_t t10 = __ldg(src + off + (uint32_t)src_step_px), t11 = __ldg(src + off + (uint32_t)src_step_px + 1u);
+                uint32_t t00, t01, t10, t11;
+                if (BGR) {
+                    const uint8_t* s8 = reinterpret_cast<const uint8_t*>(D.src);
+                    const size_t o = (size_t)iy * (size_t)src_step_px + 3u * (size_t)ix;
+                    t00 = load_tap(s8, o); t01 = load_tap(s8, o + 3); t10 = load_tap(s8, o + src_step_px); t11 = load_tap(s8, o + src_step_px + 3);
+                } else {
+                    const uint32_t off = (uint32_t)(iy * src_step_px + ix);
+                    t00 = __ldg(src + off); t01 = __ldg(src + off + 1u);
+                    t10 = __ldg(src + off + (uint32_t)src_step_px); t11 = __ldg(src + off + (uint32_t)src_step_px + 1u);
+                }
                 const uint32_t b = bilinear_channel<0>(t00, t01, t10, t11, p, q, omp, omq, c_omp, c_p, two23);
                 const uint32_t g = bilinear_channel<1>(t00, t01, t10, t11, p, q, omp, omq, c_omp, c_p, two23);
                 const uint32_t r = bilinear_channel<2>(t00, t01, t10, t11, p, q, omp, omq, c_omp, c_p, two23);
@@ -187,6 +205,26 @@ __device__ __forceinline__ f32x2 bilinear_channel2(const uint32_t (&ta)[4], cons
     return add2_rz(s, T23);                                                    // 2^23 + int(v)
 }
 
+// BGR taps: f0 | f1 hold the 8 bytes that start at the first tap of a row (B0 G0 R0 B1 | G1 R1 ..), so the left tap's channel K
+// is byte K of f0 and the right tap's is byte K + 3 of the pair: still ONE PRMT per tap and channel.
+template <int K>
+__device__ __forceinline__ f32x2 bilinear_channel2_bgr(uint32_t f0a, uint32_t f1a, uint32_t g0a, uint32_t g1a, uint32_t f0b, uint32_t f1b, uint32_t g0b, uint32_t g1b,
+                                                       f32x2 P, f32x2 Q, f32x2 OMP, f32x2 OMQ, f32x2 C_OMP, f32x2 C_P, f32x2 ONE, f32x2 T23, uint32_t two23)
+{
+    constexpr uint32_t kSelR = 0x7540u | (K == 0 ? 3u : (uint32_t)(K - 1));      // right tap: byte K + 3 of (f0, f1)
+    const f32x2 G1 = pk2(__int_as_float(__byte_perm(f0a, two23, 0x7540 | K)), __int_as_float(__byte_perm(f0b, two23, 0x7540 | K)));
+    const f32x2 G2 = pk2(__int_as_float(__byte_perm(K == 0 ? f0a : f1a, two23, kSelR)), __int_as_float(__byte_perm(K == 0 ? f0b : f1b, two23, kSelR)));
+    const f32x2 G3 = pk2(__int_as_float(__byte_perm(g0a, two23, 0x7540 | K)), __int_as_float(__byte_perm(g0b, two23, 0x7540 | K)));
+    const f32x2 G4 = pk2(__int_as_float(__byte_perm(K == 0 ? g0a : g1a, two23, kSelR)), __int_as_float(__byte_perm(K == 0 ? g0b : g1b, two23, kSelR)));
+    const f32x2 a1 = fma2(G1, OMP, C_OMP), a2 = fma2(G2, OMP, C_OMP);
+    const f32x2 a3 = fma2(G3, P, C_P), a4 = fma2(G4, P, C_P);
+    f32x2 s = mul2(a1, OMQ);
+    s = fma2(mul2(a2, Q), ONE, s);
+    s = fma2(mul2(a3, OMQ), ONE, s);
+    s = fma2(mul2(a4, Q), ONE, s);
+    return add2_rz(s, T23);
+}
+
 // Source staging (SMEM = true).  The taps of a 128 x 32 chip tile fall into a small source rectangle (its footprint:
 // the image of the tile under the inverse transform, ~140 x 47 px for a UAV strip).  Fetching taps with per-thread
 // loads leaves every warp waiting on an L2/HBM round trip per pixel pair (ncu: ~90 % of resident warps stalled on the
@@ -200,14 +238,14 @@ __device__ __forceinline__ f32x2 bilinear_channel2(const uint32_t (&ta)[4], cons
 
 __device__ __forceinline__ uint32_t lds_u32(const uint8_t* base, uint32_t off) { return *reinterpret_cast<const uint32_t*>(base + off); }
 
-template <bool CHECK, bool SMEM>
+template <bool CHECK, bool SMEM, bool BGR>
 __device__ __forceinline__ void warp_affine_rows(const uint8_t* fp_base, const ChipDesc& D, const f32x2 (&MX)[2], const f32x2 (&MY)[2], int xl, int ybase, float dgy, float sy, float fby,
                                                  float iv1, float iv4, f32x2 IV2, f32x2 IV5, uint32_t step4, unsigned long long base_adj,
                                                  uint32_t sm_adj, float clampx, float clampy,
                                                  uint32_t one_u, uint32_t two23, float w1f, float h1f, f32x2 ONE)
 {
     const f32x2 T23 = pk2(8388608.0f, 8388608.0f), N23 = pk2(-8388608.0f, -8388608.0f), ONEI = pk2(1.0f, 1.0f);
-    constexpr uint32_t sm_pitch4 = kFpBoxW * 4u;
+    constexpr uint32_t sm_pitch4 = BGR ? (uint32_t)kFpPitchBgr : kFpBoxW * 4u;
 #pragma unroll
     for (int ry = 0; ry < kWarpRows; ry++) {
         const int yd = ybase + ry * kWarpsY;
@@ -236,6 +274,48 @@ __device__ __forceinline__ void warp_affine_rows(const uint8_t* fp_base, const C
             const f32x2 C_OMP = mul2(OMP, N23), C_P = mul2(P, N23);        // -2^23 * w, exact
             uint32_t ixa, ixb, iya, iyb;
             unpk2u(TX, ixa, ixb); unpk2u(TY, iya, iyb);
+            if (BGR) {
+                // byte offset of tap (ix, iy) = adj + iy_bits * pitch + ix_bits * 3; the 6 bytes of a tap pair come from three
+                // aligned words and two funnel shifts (pitches are multiples of 4, so both rows share the shift)
+                uint32_t f0a, f1a, g0a, g1a, f0b, f1b, g0b, g1b;
+                if (SMEM) {
+                    const uint32_t oa = iya * sm_pitch4 + (ixa * 3u + sm_adj), ob = iyb * sm_pitch4 + (ixb * 3u + sm_adj);
+                    const uint32_t ba = oa & ~3u, bb = ob & ~3u, sa = (oa & 3u) * 8u, sb = (ob & 3u) * 8u;
+                    const uint32_t a0 = lds_u32(fp_base, ba), a1 = lds_u32(fp_base, ba + 4u), a2 = lds_u32(fp_base, ba + 8u);
+                    const uint32_t a3 = lds_u32(fp_base, ba + sm_pitch4), a4 = lds_u32(fp_base, ba + sm_pitch4 + 4u), a5 = lds_u32(fp_base, ba + sm_pitch4 + 8u);
+                    const uint32_t b0 = lds_u32(fp_base, bb), b1 = lds_u32(fp_base, bb + 4u), b2 = lds_u32(fp_base, bb + 8u);
+                    const uint32_t b3 = lds_u32(fp_base, bb + sm_pitch4), b4 = lds_u32(fp_base, bb + sm_pitch4 + 4u), b5 = lds_u32(fp_base, bb + sm_pitch4 + 8u);
+                    f0a = __funnelshift_r(a0, a1, sa); f1a = __funnelshift_r(a1, a2, sa); g0a = __funnelshift_r(a3, a4, sa); g1a = __funnelshift_r(a4, a5, sa);
+                    f0b = __funnelshift_r(b0, b1, sb); f1b = __funnelshift_r(b1, b2, sb); g0b = __funnelshift_r(b3, b4, sb); g1b = __funnelshift_r(b4, b5, sb);
+                } else {
+                    const unsigned long long pa = base_adj + (unsigned long long)iya * step4 + (unsigned long long)ixa * 3u;
+                    const unsigned long long pb = base_adj + (unsigned long long)iyb * step4 + (unsigned long long)ixb * 3u;
+                    const unsigned long long qa = pa & ~3ull, qb = pb & ~3ull;
+                    const uint32_t sa = ((uint32_t)pa & 3u) * 8u, sb = ((uint32_t)pb & 3u) * 8u;
+                    const unsigned long long qa1 = qa + (unsigned long long)step4 * one_u, qb1 = qb + (unsigned long long)step4 * one_u;
+                    const uint32_t a0 = __ldg(reinterpret_cast<const uint32_t*>(qa)), a1 = __ldg(reinterpret_cast<const uint32_t*>(qa + 4)), a2 = __ldg(reinterpret_cast<const uint32_t*>(qa + 8));
+                    const uint32_t a3 = __ldg(reinterpret_cast<const uint32_t*>(qa1)), a4 = __ldg(reinterpret_cast<const uint32_t*>(qa1 + 4)), a5 = __ldg(reinterpret_cast<const uint32_t*>(qa1 + 8));
+                    const uint32_t b0 = __ldg(reinterpret_cast<const uint32_t*>(qb)), b1 = __ldg(reinterpret_cast<const uint32_t*>(qb + 4)), b2 = __ldg(reinterpret_cast<const uint32_t*>(qb + 8));
+                    const uint32_t b3 = __ldg(reinterpret_cast<const uint32_t*>(qb1)), b4 = __ldg(reinterpret_cast<const uint32_t*>(qb1 + 4)), b5 = __ldg(reinterpret_cast<const uint32_t*>(qb1 + 8));
+                    f0a = __funnelshift_r(a0, a1, sa); f1a = __funnelshift_r(a1, a2, sa); g0a = __funnelshift_r(a3, a4, sa); g1a = __funnelshift_r(a4, a5, sa);
+                    f0b = __funnelshift_r(b0, b1, sb); f1b = __funnelshift_r(b1, b2, sb); g0b = __funnelshift_r(b3, b4, sb); g1b = __funnelshift_r(b4, b5, sb);
+                }
+                uint32_t ba_, bb_, ga_, gb_, ra_, rb_;
+                unpk2u(bilinear_channel2_bgr<0>(f0a, f1a, g0a, g1a, f0b, f1b, g0b, g1b, P, Q, OMP, OMQ, C_OMP, C_P, ONE, T23, two23), ba_, bb_);
+                unpk2u(bilinear_channel2_bgr<1>(f0a, f1a, g0a, g1a, f0b, f1b, g0b, g1b, P, Q, OMP, OMQ, C_OMP, C_P, ONE, T23, two23), ga_, gb_);
+                unpk2u(bilinear_channel2_bgr<2>(f0a, f1a, g0a, g1a, f0b, f1b, g0b, g1b, P, Q, OMP, OMQ, C_OMP, C_P, ONE, T23, two23), ra_, rb_);
+                uint32_t wa = __byte_perm(__byte_perm(ba_, ga_, 0x0040), ra_, 0x7410);
+                uint32_t wb = __byte_perm(__byte_perm(bb_, gb_, 0x0040), rb_, 0x7410);
+                if (CHECK) {
+                    if (!va) wa = 0u;
+                    if (!vb) wb = 0u;
+                    if (xl + 64 * h < D.chip_w) crow[64 * h] = wa;
+                    if (xl + 64 * h + 32 < D.chip_w) crow[64 * h + 32] = wb;
+                } else {
+                    crow[64 * h] = wa; crow[64 * h + 32] = wb;
+                }
+                continue;
+            }
             uint32_t ta[4], tb[4];
             if (SMEM) {
                 // offset of tap (ix, iy) in the staged footprint = sm_adj + iy_bits * pitch + ix_bits * 4 (biases and footprint origin folded into sm_adj)
@@ -274,6 +354,7 @@ __device__ __forceinline__ void warp_affine_rows(const uint8_t* fp_base, const C
 // Footprint of chip tile (bx, by): the source rectangle its taps fall into.  xs, ys are monotone in the pixel column and
 // in the row (every rounding step is monotone), so their extremes over the tile are attained at its corner pixels.
 // Returns 0: use direct loads, 1: stage rows [y0, y0 + rows) x columns [x0, x0 + kFpBoxW), 2: tile entirely outside.
+template <bool BGR>
 __device__ __forceinline__ int tile_footprint(const ChipDesc& D, int bx, int by, int img_w, int img_h, float dgx, float dgy,
                                               float w1f, float h1f, int max_boxes, int& x0, int& y0, int& rows)
 {
@@ -290,19 +371,21 @@ __device__ __forceinline__ int tile_footprint(const ChipDesc& D, int bx, int by,
     }
     if (!(xmx >= 0.0f) || !(xmn < w1f) || !(ymx >= 0.0f) || !(ymn < h1f)) return 2;
     // valid samples have 0 <= xs < w-1: taps in columns int(xs), int(xs)+1 <= w-1 (same for rows)
-    x0 = ((int)fmaxf(xmn, 0.0f)) & ~3;                                         // 16-byte aligned box origin
+    x0 = ((int)fmaxf(xmn, 0.0f)) & (BGR ? ~15 : ~3);                           // 16-byte aligned box origin
     const int x1 = min((int)fminf(xmx, w1f) + 1, img_w - 1);
     y0 = (int)fmaxf(ymn, 0.0f);
     const int y1 = min((int)fminf(ymx, h1f) + 1, img_h - 1);
     rows = y1 - y0 + 1;
-    return (x1 - x0 + 1 <= kFpBoxW && rows <= max_boxes * kFpBoxH) ? 1 : 0;
+    // BGR: a tap pair reads the 12 bytes from the word holding its first byte, i.e. up to 2 pixels past the right tap
+    return (x1 - x0 + 1 + (BGR ? 2 : 0) <= (BGR ? kFpBoxWBgr : kFpBoxW) && rows <= max_boxes * kFpBoxH) ? 1 : 0;
 }
 
+template <bool BGR>
 __global__ void __launch_bounds__(32 * kWarpsY, 1024 / (32 * kWarpsY))
 k5_warp_affine_x2(const __grid_constant__ CUtensorMap tmap_src, const ChipDesc* __restrict__ descs, int img_w, int img_h, int src_step_px, float dgx, float dgy,
                   uint32_t two23, float w1f, float h1f, float one,
                   uint32_t one_u /* = 1, opaque: row-1 tap address = row-0 address + step4 * 1 as a single 64-bit IMAD */,
-                  unsigned long long bias /* = 0x4B000000 * (4 step + 4): the add.rz biases of iy and ix in byte-address units */,
+                  unsigned long long bias /* = 0x4B000000 * (row bytes + pixel bytes): the add.rz biases of iy and ix in byte-address units */,
                   int max_boxes /* TMA boxes of dynamic shared memory for the source footprint; 0 = always load taps directly */)
 {
     extern __shared__ __align__(128) uint8_t fp_smem[];
@@ -325,14 +408,15 @@ k5_warp_affine_x2(const __grid_constant__ CUtensorMap tmap_src, const ChipDesc* 
         int state = 0;                                // 0: direct loads, 1: staged, 2: tile entirely outside the source
         if (max_boxes > 0) {
             int x0, y0, rows;
-            state = tile_footprint(D, blockIdx.x, blockIdx.y, img_w, img_h, dgx, dgy, w1f, h1f, max_boxes, x0, y0, rows);
+            state = tile_footprint<BGR>(D, blockIdx.x, blockIdx.y, img_w, img_h, dgx, dgy, w1f, h1f, max_boxes, x0, y0, rows);
             if (state == 1) {
                 fp[0] = x0; fp[1] = y0; fp[2] = rows;
                 uavm::ptx::mbar_init(&fp_bar, 1); uavm::ptx::fence_mbar_init();
                 const int boxes = (rows + kFpBoxH - 1) / kFpBoxH;
-                uavm::ptx::mbar_arrive_expect_tx(&fp_bar, (uint32_t)(boxes * kFpBoxBytes));
-                for (int k = 0; k < boxes; k++)
-                    uavm::ptx::tma_load_2d(fp_smem + k * kFpBoxBytes, &tmap_src, &fp_bar, x0, D.src_row0 + y0 + k * kFpBoxH);
+                constexpr int box_bytes = BGR ? kFpBoxBytesBgr : kFpBoxBytes;
+                uavm::ptx::mbar_arrive_expect_tx(&fp_bar, (uint32_t)(boxes * box_bytes));
+                for (int k = 0; k < boxes; k++)       // BGR: the tensor's elements are u32 words of the packed rows (x0 is a multiple of 16 px = 12 words)
+                    uavm::ptx::tma_load_2d(fp_smem + k * box_bytes, &tmap_src, &fp_bar, BGR ? (x0 * 3) / 4 : x0, D.src_row0 + y0 + k * kFpBoxH);
             }
         }
         fp[3] = state;
@@ -340,7 +424,7 @@ k5_warp_affine_x2(const __grid_constant__ CUtensorMap tmap_src, const ChipDesc* 
     // per-thread set-up first: it overlaps thread 0's footprint plan and the flight of the TMA copies
     const f32x2 ONE = pk2(one, one);
     const f32x2 IV2 = pk2(iv2, iv2), IV5 = pk2(iv5, iv5);
-    const uint32_t step4 = 4u * (uint32_t)src_step_px;
+    const uint32_t step4 = BGR ? (uint32_t)src_step_px : 4u * (uint32_t)src_step_px;      // source row pitch in bytes (BGR: src_step_px is already bytes)
     // the raw add.rz results are 0x4B000000 + ix / + iy: fold both biases into the frame base (64-bit, wraps are harmless)
     const unsigned long long base_adj = reinterpret_cast<unsigned long long>(D.src) - bias;
     f32x2 MX[2], MY[2];                              // xTemp * inv[0], xTemp * inv[3] for the pixel pairs (k = 2h, 2h + 1): row invariant
@@ -375,21 +459,22 @@ k5_warp_affine_x2(const __grid_constant__ CUtensorMap tmap_src, const ChipDesc* 
         return;
     }
     uint32_t sm_adj = 0;
-    constexpr uint32_t sm_pitch4 = kFpBoxW * 4u;      // the boxes stack into rows of kFpBoxW words: a multiple of 32 banks
+    constexpr uint32_t sm_pitch4 = BGR ? (uint32_t)kFpPitchBgr : kFpBoxW * 4u;      // the boxes stack into rows of one pitch
+    constexpr uint32_t px_bytes = BGR ? 3u : 4u;
     float clampx = 0.0f, clampy = 0.0f;
     if (state == 1) {
         const int x0 = fp[0], y0 = fp[1];
-        sm_adj = 0u - (0x4B000000u * sm_pitch4 + 0x4B000000u * 4u) - ((uint32_t)y0 * sm_pitch4 + (uint32_t)x0 * 4u);   // offset from fp_smem
+        sm_adj = 0u - (0x4B000000u * sm_pitch4 + 0x4B000000u * px_bytes) - ((uint32_t)y0 * sm_pitch4 + (uint32_t)x0 * px_bytes);   // offset from fp_smem
         clampx = (float)x0; clampy = (float)y0;
     }
 #define K5_ROWS_ARGS fp_smem, D, MX, MY, xl, ybase, dgy, sy, fby, iv1, iv4, IV2, IV5, step4, base_adj, sm_adj, clampx, clampy, one_u, two23, w1f, h1f, ONE
     if (state == 1) {
         uavm::ptx::mbar_wait(&fp_bar, 0);             // footprint has landed in shared memory
-        if (inside) warp_affine_rows<false, true>(K5_ROWS_ARGS);
-        else        warp_affine_rows<true, true>(K5_ROWS_ARGS);
+        if (inside) warp_affine_rows<false, true, BGR>(K5_ROWS_ARGS);
+        else        warp_affine_rows<true, true, BGR>(K5_ROWS_ARGS);
     } else {
-        if (inside) warp_affine_rows<false, false>(K5_ROWS_ARGS);
-        else        warp_affine_rows<true, false>(K5_ROWS_ARGS);
+        if (inside) warp_affine_rows<false, false, BGR>(K5_ROWS_ARGS);
+        else        warp_affine_rows<true, false, BGR>(K5_ROWS_ARGS);
     }
 #undef K5_ROWS_ARGS
 }
@@ -434,7 +519,10 @@ extern "C" int uavm_canvas_create(uavm_ctx* ctx, int n_images, int img_w, int im
     if (!ctx || !out || n_images <= 0 || img_w < 2 || img_h < 2 || !H) return UAVM_EINVAL;
     *out = nullptr;
     uavm_canvas* cv = new uavm_canvas();
-    cv->n = n_images; cv->img_w = img_w; cv->img_h = img_h; cv->src_step_px = img_w;
+    cv->n = n_images; cv->img_w = img_w; cv->img_h = img_h;
+    cv->src_bgr = (img_w % 16 == 0) && getenv("UAVM_K5_BGRA") == nullptr;      // UAVM_K5_BGRA: force the BGRA pool (A/B measurements)
+    cv->src_step_px = cv->src_bgr ? 3 * img_w : img_w;                         // BGR pool: row pitch in BYTES
+    cv->last_warp_ev.assign(n_images, -1);
     cv->H.assign(H, H + (size_t)n_images * 9);
     cv->chips.resize(n_images);
     int rc = uavm_canvas_layout_compute(H, keep, n_images, img_w, img_h, &cv->layout, cv->chips.data());
@@ -469,7 +557,7 @@ extern "C" int uavm_canvas_create(uavm_ctx* ctx, int n_images, int img_w, int im
     }
     cv->chips_bytes = chip_off; cv->masks_bytes = mask_off;
     UAVM_CUDA(ctx, cudaSetDevice(ctx->device));
-    UAVM_CUDA(ctx, cudaMalloc(&cv->d_src, (size_t)n_images * img_h * cv->src_step_px * sizeof(uchar4)));
+    UAVM_CUDA(ctx, cudaMalloc(&cv->d_src, (size_t)n_images * img_h * cv->src_step_px * (cv->src_bgr ? 1 : sizeof(uchar4)) + 256));
     UAVM_CUDA(ctx, cudaMalloc(&cv->d_chips, chip_off + 256));
     UAVM_CUDA(ctx, cudaMalloc(&cv->d_masks, mask_off + 256));
     UAVM_CUDA(ctx, cudaMemsetAsync(cv->d_chips, 0, chip_off + 256, ctx->stream));       // row padding stays zero
@@ -478,20 +566,29 @@ extern "C" int uavm_canvas_create(uavm_ctx* ctx, int n_images, int img_w, int im
     cv->stage_pitch = (img_w * 3 + 15) & ~15;
     cv->stage_bytes = (size_t)img_h * cv->stage_pitch;
     for (int s = 0; s < uavm_canvas::kStageSlots; s++) {
-        UAVM_CUDA(ctx, cudaMalloc(&cv->d_stage[s], cv->stage_bytes));
+        if (!cv->src_bgr) UAVM_CUDA(ctx, cudaMalloc(&cv->d_stage[s], cv->stage_bytes));
         UAVM_CUDA(ctx, cudaEventCreateWithFlags(&cv->ev_copied[s], cudaEventDisableTiming));
         UAVM_CUDA(ctx, cudaEventCreateWithFlags(&cv->ev_free[s], cudaEventDisableTiming));
     }
+    if (cv->src_bgr)
+        for (int e = 0; e < uavm_canvas::kWarpEvents; e++) UAVM_CUDA(ctx, cudaEventCreateWithFlags(&cv->ev_warp[e], cudaEventDisableTiming));
     for (int k = 0; k < n_images; k++) {
         ChipDesc& d = cv->desc[k];
-        d.src = cv->d_src + (size_t)k * img_h * cv->src_step_px;
+        d.src = cv->src_bgr ? reinterpret_cast<const uchar4*>(reinterpret_cast<const uint8_t*>(cv->d_src) + (size_t)k * img_h * cv->src_step_px)
+                            : cv->d_src + (size_t)k * img_h * cv->src_step_px;
         d.src_row0 = k * img_h;
         if (!d.keep) continue;
         d.chip = cv->d_chips + coff[k] / 4; d.mask = cv->d_masks + moff[k];
     }
     // K5 stages the source footprint of a chip tile with TMA boxes of kFpBoxW x kFpBoxH pixels
     cv->tmap_src_ok = false;
-    if ((cv->src_step_px & 3) == 0 && (int64_t)n_images * img_h < ((int64_t)1 << 31) &&
+    if (cv->src_bgr) {
+        // packed BGR rows as a tensor of u32 words: 3 W / 4 words per row (W % 16 == 0), box = 132 words (176 px) x 16 rows
+        if ((int64_t)n_images * img_h < ((int64_t)1 << 31) &&
+            uavm_encode_tmap_2d(ctx, &cv->tmap_src, (int)CU_TENSOR_MAP_DATA_TYPE_UINT32, cv->d_src, (uint64_t)cv->src_step_px / 4, (uint64_t)n_images * img_h,
+                                (uint64_t)cv->src_step_px, kFpPitchBgr / 4, kFpBoxH, 0) == UAVM_OK)
+            cv->tmap_src_ok = true;
+    } else if ((cv->src_step_px & 3) == 0 && (int64_t)n_images * img_h < ((int64_t)1 << 31) &&
         uavm_encode_tmap_2d(ctx, &cv->tmap_src, (int)CU_TENSOR_MAP_DATA_TYPE_UINT32, cv->d_src, (uint64_t)cv->src_step_px, (uint64_t)n_images * img_h,
                             (uint64_t)cv->src_step_px * 4, kFpBoxW, kFpBoxH, 0) == UAVM_OK)
         cv->tmap_src_ok = true;
@@ -572,11 +669,15 @@ extern "C" void uavm_canvas_destroy(uavm_ctx* ctx, uavm_canvas* cv)
         if (cv->ev_copied[s]) cudaEventDestroy(cv->ev_copied[s]);
         if (cv->ev_free[s]) cudaEventDestroy(cv->ev_free[s]);
     }
+    for (int e = 0; e < uavm_canvas::kWarpEvents; e++) if (cv->ev_warp[e]) cudaEventDestroy(cv->ev_warp[e]);
     uavm_blend_free(cv);
     cudaFree(cv->d_src); cudaFree(cv->d_chips); cudaFree(cv->d_masks); cudaFree(cv->d_dist_max); cudaFree(cv->d_k6); cudaFree(cv->d_mask_ptr); cudaFree(cv->d_mask_step); cudaFree(cv->d_own_bbox);
     cudaFree(cv->d_desc); cudaFree(cv->d_result); cudaFree(cv->d_result_mask);
     delete cv;
 }
+
+// bytes per source pixel in HBM: 3 = the caller's BGR frames are kept as they are (width % 16 == 0), 4 = BGRA pool + conversion pass
+extern "C" int uavm_canvas_source_layout(const uavm_canvas* cv) { return cv ? (cv->src_bgr ? 3 : 4) : 0; }
 
 extern "C" int uavm_canvas_get_layout(uavm_canvas* cv, uavm_canvas_layout* canvas, uavm_chip_layout* chips)
 {
@@ -590,6 +691,22 @@ extern "C" int uavm_canvas_set_image(uavm_ctx* ctx, uavm_canvas* cv, int image, 
 {
     if (!ctx || !cv || image < 0 || image >= cv->n || !bgr || step < cv->img_w * 3) return UAVM_EINVAL;
     UAVM_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (cv->src_bgr) {
+        // the pool keeps the caller's BGR bytes: one copy straight into the frame's slot, no conversion.  Host frames travel on
+        // the copy stream (the compute stream only waits for THIS frame); the copy first waits for the last warp that read the slot.
+        uint8_t* dst8 = reinterpret_cast<uint8_t*>(cv->d_src) + (size_t)image * cv->img_h * cv->src_step_px;
+        cudaStream_t cs = is_device ? ctx->stream : ctx->copy_stream;
+        if (!is_device && cv->last_warp_ev[image] >= 0) UAVM_CUDA(ctx, cudaStreamWaitEvent(cs, cv->ev_warp[cv->last_warp_ev[image]], 0));
+        const cudaMemcpyKind kind = is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+        if (step == cv->src_step_px) UAVM_CUDA(ctx, cudaMemcpyAsync(dst8, bgr, (size_t)step * cv->img_h, kind, cs));
+        else UAVM_CUDA(ctx, cudaMemcpy2DAsync(dst8, (size_t)cv->src_step_px, bgr, (size_t)step, (size_t)cv->img_w * 3, cv->img_h, kind, cs));
+        if (!is_device) {
+            const int slot = cv->stage_next; cv->stage_next = (slot + 1) % uavm_canvas::kStageSlots;
+            UAVM_CUDA(ctx, cudaEventRecord(cv->ev_copied[slot], cs));
+            UAVM_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, cv->ev_copied[slot], 0));
+        }
+        return UAVM_OK;
+    }
     const uint8_t* src = bgr; int sstep = step;
     int slot = -1;
     if (!is_device) {
@@ -632,26 +749,44 @@ extern "C" int uavm_canvas_warp_range(uavm_ctx* ctx, uavm_canvas* cv, int first,
     if (any_affine) {
         static const bool scalar = getenv("UAVM_K5_SCALAR") != nullptr;       // A/B switch for profiling; both are bit-exact
         // the packed kernel derives tap offsets from 23-bit mantissas and 32-bit pixel offsets
-        if (!scalar && cv->img_w < (1 << 22) && cv->img_h < (1 << 22) && (int64_t)cv->img_h * cv->src_step_px < ((int64_t)1 << 31)) {
+        if (!scalar && cv->img_w < (1 << 22) && cv->img_h < (1 << 22) && (int64_t)cv->img_h * cv->src_step_px * (cv->src_bgr ? 1 : 4) < ((int64_t)1 << 32)) {
             static const int env_boxes = getenv("UAVM_K5_BOXES") ? atoi(getenv("UAVM_K5_BOXES")) : kFpBoxes;   // 0: direct tap loads (A/B)
             const int boxes = cv->tmap_src_ok ? env_boxes : 0;
             if (!ctx->k5_attr_set) {                      // function attributes are per device: once per context
-                cudaFuncSetAttribute(k5_warp_affine_x2, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+                cudaFuncSetAttribute(k5_warp_affine_x2<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+                cudaFuncSetAttribute(k5_warp_affine_x2<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
                 ctx->k5_attr_set = true;
             }
-            k5_warp_affine_x2<<<grid, block, boxes * kFpBoxBytes, ctx->stream>>>(
-                cv->tmap_src, cv->d_desc + first, cv->img_w, cv->img_h, cv->src_step_px, cv->layout.dgx, cv->layout.dgy, 0x4B000000u,
-                (float)(cv->img_w - 1), (float)(cv->img_h - 1), 1.0f, 1u, 0x4B000000ull * (4ull * (unsigned long long)cv->src_step_px + 4ull), boxes);
+            if (cv->src_bgr)
+                k5_warp_affine_x2<true><<<grid, block, boxes * kFpBoxBytesBgr, ctx->stream>>>(
+                    cv->tmap_src, cv->d_desc + first, cv->img_w, cv->img_h, cv->src_step_px, cv->layout.dgx, cv->layout.dgy, 0x4B000000u,
+                    (float)(cv->img_w - 1), (float)(cv->img_h - 1), 1.0f, 1u, 0x4B000000ull * ((unsigned long long)cv->src_step_px + 3ull), boxes);
+            else
+                k5_warp_affine_x2<false><<<grid, block, boxes * kFpBoxBytes, ctx->stream>>>(
+                    cv->tmap_src, cv->d_desc + first, cv->img_w, cv->img_h, cv->src_step_px, cv->layout.dgx, cv->layout.dgy, 0x4B000000u,
+                    (float)(cv->img_w - 1), (float)(cv->img_h - 1), 1.0f, 1u, 0x4B000000ull * (4ull * (unsigned long long)cv->src_step_px + 4ull), boxes);
         }
+        else if (cv->src_bgr)
+            k5_warp_chips<true, true><<<grid, block, 0, ctx->stream>>>(cv->d_desc + first, cv->img_w, cv->img_h, cv->src_step_px, cv->layout.dgx, cv->layout.dgy, 0x4B000000u,
+                                                                       (float)(cv->img_w - 1), (float)(cv->img_h - 1));
         else
-            k5_warp_chips<true><<<grid, block, 0, ctx->stream>>>(cv->d_desc + first, cv->img_w, cv->img_h, cv->src_step_px, cv->layout.dgx, cv->layout.dgy, 0x4B000000u,
-                                                                 (float)(cv->img_w - 1), (float)(cv->img_h - 1));
+            k5_warp_chips<true, false><<<grid, block, 0, ctx->stream>>>(cv->d_desc + first, cv->img_w, cv->img_h, cv->src_step_px, cv->layout.dgx, cv->layout.dgy, 0x4B000000u,
+                                                                        (float)(cv->img_w - 1), (float)(cv->img_h - 1));
         UAVM_CHECK_LAUNCH(ctx);
     }
     if (any_proj) {
-        k5_warp_chips<false><<<grid, block, 0, ctx->stream>>>(cv->d_desc + first, cv->img_w, cv->img_h, cv->src_step_px, cv->layout.dgx, cv->layout.dgy, 0x4B000000u,
-                                                             (float)(cv->img_w - 1), (float)(cv->img_h - 1));
+        if (cv->src_bgr)
+            k5_warp_chips<false, true><<<grid, block, 0, ctx->stream>>>(cv->d_desc + first, cv->img_w, cv->img_h, cv->src_step_px, cv->layout.dgx, cv->layout.dgy, 0x4B000000u,
+                                                                        (float)(cv->img_w - 1), (float)(cv->img_h - 1));
+        else
+            k5_warp_chips<false, false><<<grid, block, 0, ctx->stream>>>(cv->d_desc + first, cv->img_w, cv->img_h, cv->src_step_px, cv->layout.dgx, cv->layout.dgy, 0x4B000000u,
+                                                                         (float)(cv->img_w - 1), (float)(cv->img_h - 1));
         UAVM_CHECK_LAUNCH(ctx);
+    }
+    if (cv->src_bgr) {                                    // uploads into these frames' slots must wait for this launch
+        const int e = cv->ev_warp_next; cv->ev_warp_next = (e + 1) % uavm_canvas::kWarpEvents;
+        UAVM_CUDA(ctx, cudaEventRecord(cv->ev_warp[e], ctx->stream));
+        for (int k = first; k < first + count; k++) cv->last_warp_ev[k] = e;
     }
     cv->warped = true; cv->seamed = false; cv->mask_plane_valid = false;
     return UAVM_OK;

@@ -28,7 +28,12 @@ struct uavm_canvas {
     uavm_canvas_layout layout;
     std::vector<uavm_chip_layout> chips;
     std::vector<ChipDesc> desc;
-    uchar4* d_src = nullptr;
+    uchar4* d_src = nullptr;         // source pool: BGRA pixels, or (src_bgr) packed BGR rows of src_step_px BYTES
+    bool src_bgr = false;            // frames stay BGR in HBM (width % 16 == 0): no conversion pass, K5 reads BGR taps
+    static constexpr int kWarpEvents = 32;
+    cudaEvent_t ev_warp[kWarpEvents] = {nullptr};   // BGR pool: a frame is overwritten in place, so a new upload waits for the last warp that read it
+    int ev_warp_next = 0;
+    std::vector<int> last_warp_ev;   // per image: index into ev_warp of the last warp launch that read it (-1: none)
     uint32_t* d_chips = nullptr;     // BGRA chips
     uint8_t* d_masks = nullptr;
     float* d_dist_max = nullptr;     // [n] per-image maximum of the distance map (as uint bits)

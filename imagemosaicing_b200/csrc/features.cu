@@ -3,6 +3,7 @@
 // Replaces the reference's per-pair feature (de)serialisation (WriteSurfKeyPoints/LoadSurfKeyPoints,
 // M/MosaicWithoutPos.cpp:4682-4734, re-read for every pair at :5073-5103): descriptors are packed
 // once into a u8 pool in HBM and never leave it.
+#include <algorithm>
 #include "internal.h"
 
 // ------------------------------------------------------------------------------------------------
@@ -205,7 +206,10 @@ extern "C" int uavm_featureset_create(uavm_ctx* ctx, int n_images, const int32_t
 extern "C" void uavm_featureset_destroy(uavm_ctx* ctx, uavm_featureset* fs) {
     if (!fs) return;
     if (ctx) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
+    if (ctx && ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
     cudaFree(fs->d_desc); cudaFree(fs->d_norm); cudaFree(fs->d_ckey); cudaFree(fs->d_kp); cudaFree(fs->d_stage);
+    for (int e = 0; e < uavm_featureset::kUpEvents; e++) if (fs->ev_up[e]) cudaEventDestroy(fs->ev_up[e]);
+    if (fs->ev_read) cudaEventDestroy(fs->ev_read);
     delete fs;
 }
 
@@ -217,11 +221,32 @@ static int upload_impl(uavm_ctx* ctx, uavm_featureset* fs, int image, const T* d
     if (!desc) return UAVM_EINVAL;
     size_t r0 = (size_t)fs->row0[image];
     const T* src = desc;
+    UAVM_CUDA(ctx, cudaSetDevice(ctx->device));
+    bool kp_done = false;
     if (!is_device) {
         if (sizeof(T) == 1) {
             // u8 host descriptors land directly in their pool rows and are "packed" in place (each warp reads its row before
-            // writing it back): no staging buffer, so the copies of consecutive images queue back to back on the DMA engine
-            UAVM_CUDA(ctx, cudaMemcpyAsync(fs->d_desc + r0 * 128, desc, (size_t)n * 128, cudaMemcpyHostToDevice, ctx->stream));
+            // writing it back): no staging buffer.  The copies go to the ctx's copy stream, back to back and ahead of any frame
+            // copy queued later; the pack kernel on the compute stream waits for its own image only.
+            if (!fs->ev_read) {
+                UAVM_CUDA(ctx, cudaEventCreateWithFlags(&fs->ev_read, cudaEventDisableTiming));
+                for (int e = 0; e < uavm_featureset::kUpEvents; e++) UAVM_CUDA(ctx, cudaEventCreateWithFlags(&fs->ev_up[e], cudaEventDisableTiming));
+            }
+            // the rows may still be read or written by work queued earlier on the compute stream (a previous match, this image's
+            // previous pack): the copy stream waits for the compute stream once per round of uploads
+            if (fs->uploaded_since_wait.size() != (size_t)fs->n_images) fs->uploaded_since_wait.assign(fs->n_images, 0);
+            if (fs->pool_read_since_wait || fs->uploaded_since_wait[image]) {
+                UAVM_CUDA(ctx, cudaEventRecord(fs->ev_read, ctx->stream));
+                UAVM_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, fs->ev_read, 0));
+                fs->pool_read_since_wait = false;
+                std::fill(fs->uploaded_since_wait.begin(), fs->uploaded_since_wait.end(), 0);
+            }
+            fs->uploaded_since_wait[image] = 1;
+            UAVM_CUDA(ctx, cudaMemcpyAsync(fs->d_desc + r0 * 128, desc, (size_t)n * 128, cudaMemcpyHostToDevice, ctx->copy_stream));
+            if (kp_xy) { UAVM_CUDA(ctx, cudaMemcpyAsync(fs->d_kp + r0 * 2, kp_xy, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->copy_stream)); kp_done = true; }
+            const int e = fs->ev_up_next; fs->ev_up_next = (e + 1) % uavm_featureset::kUpEvents;
+            UAVM_CUDA(ctx, cudaEventRecord(fs->ev_up[e], ctx->copy_stream));
+            UAVM_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, fs->ev_up[e], 0));
             src = (const T*)(fs->d_desc + r0 * 128);
         } else {
             // stream-ordered: the staging buffer is reused only after the previous pack kernel (same stream)
@@ -231,7 +256,7 @@ static int upload_impl(uavm_ctx* ctx, uavm_featureset* fs, int image, const T* d
     }
     k1_pack_rows<T><<<(n * 32 + 255) / 256, 256, 0, ctx->stream>>>(src, n, fs->d_desc + r0 * 128, fs->d_norm + r0, fs->d_ckey + r0);
     UAVM_CHECK_LAUNCH(ctx);
-    if (kp_xy)
+    if (kp_xy && !kp_done)
         UAVM_CUDA(ctx, cudaMemcpyAsync(fs->d_kp + r0 * 2, kp_xy, (size_t)n * 8, is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream));
     return UAVM_OK;
 }

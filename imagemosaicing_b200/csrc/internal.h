@@ -63,6 +63,15 @@ struct uavm_featureset {
     float* d_kp = nullptr;       // [pool_rows][2] keypoint xy
     void* d_stage = nullptr;     // staging for f32 uploads
     size_t stage_bytes = 0;
+    // host uploads travel on the ctx's copy stream (FIFO with the frame copies of the canvas, so a step's descriptors are
+    // not overtaken by its 36 MB frames on the DMA engine); ev_up orders the pack kernel after the copy, ev_read orders a new
+    // upload after the last match kernel that read the pool
+    static constexpr int kUpEvents = 8;
+    cudaEvent_t ev_up[kUpEvents] = {nullptr};
+    int ev_up_next = 0;
+    cudaEvent_t ev_read = nullptr;
+    bool pool_read_since_wait = true;          // a match kernel was launched since the copy stream last waited for the compute stream
+    std::vector<uint8_t> uploaded_since_wait;  // per image: its rows were rewritten since that wait (a second rewrite must wait again)
     CUtensorMap tmap_q;          // box 256 rows x 128 B (query block)
     CUtensorMap tmap_t;          // box 128 rows x 128 B (train tile)
 };

@@ -208,5 +208,6 @@ int uavm_launch_match(uavm_ctx* ctx, uavm_pairbatch* pb)
                                                                    pb->fs->d_norm, pb->d_items, pb->n_items,
                                                                    pb->d_train_idx, pb->d_d2);
     UAVM_CHECK_LAUNCH(ctx);
+    pb->fs->pool_read_since_wait = true;                  // a later host upload into the pool has to wait for this launch
     return UAVM_OK;
 }

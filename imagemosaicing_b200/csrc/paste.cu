@@ -10,6 +10,7 @@ namespace {
 
 struct PasteDesc { float inv[9]; int beg_x, beg_y, end_x, end_y; };
 
+template <bool BGR>       // BGR: packed rows of src_step_px BYTES (canvas.h: src_bgr), else BGRA pixels
 __global__ void __launch_bounds__(256)
 k5_paste_image(const uchar4* __restrict__ src, int img_w, int img_h, int src_step_px, PasteDesc D, float dgx, float dgy,
                uint8_t* __restrict__ out, uint8_t* __restrict__ out_mask, int W, int H)
@@ -26,8 +27,16 @@ k5_paste_image(const uchar4* __restrict__ src, int img_w, int img_h, int src_ste
     const int ix = __float2int_rz(xs), iy = __float2int_rz(ys);
     const float p = ys - (float)iy, q = xs - (float)ix;
     const float omp = 1.0f - p, omq = 1.0f - q;
-    const uchar4* r0 = src + (size_t)iy * src_step_px + ix;
-    const uchar4 t00 = r0[0], t01 = r0[1], t10 = r0[src_step_px], t11 = r0[src_step_px + 1];
+    uchar4 t00, t01, t10, t11;
+    if (BGR) {
+        const uint8_t* r8 = reinterpret_cast<const uint8_t*>(src) + (size_t)iy * src_step_px + 3 * (size_t)ix;
+        t00 = make_uchar4(r8[0], r8[1], r8[2], 0); t01 = make_uchar4(r8[3], r8[4], r8[5], 0);
+        r8 += src_step_px;
+        t10 = make_uchar4(r8[0], r8[1], r8[2], 0); t11 = make_uchar4(r8[3], r8[4], r8[5], 0);
+    } else {
+        const uchar4* r0 = src + (size_t)iy * src_step_px + ix;
+        t00 = r0[0]; t01 = r0[1]; t10 = r0[src_step_px]; t11 = r0[src_step_px + 1];
+    }
     uint8_t* d = out + ((size_t)yd * W + xd) * 3;
     d[0] = (uint8_t)__float2int_rz((float)t00.x * omp * omq + (float)t01.x * omp * q + (float)t10.x * p * omq + (float)t11.x * p * q);
     d[1] = (uint8_t)__float2int_rz((float)t00.y * omp * omq + (float)t01.y * omp * q + (float)t10.y * p * omq + (float)t11.y * p * q);
@@ -119,8 +128,12 @@ extern "C" int uavm_canvas_paste(uavm_ctx* ctx, uavm_canvas* cv)
         D.beg_x = (int)(bminx - 0.5f); D.end_x = (int)(bmaxx + 0.5f);
         if (D.end_x < D.beg_x || D.end_y < D.beg_y) continue;
         dim3 grid((D.end_x - D.beg_x + 256) / 256, D.end_y - D.beg_y + 1);
-        k5_paste_image<<<grid, 256, 0, ctx->stream>>>(cv->d_src + (size_t)k * h * cv->src_step_px, w, h, cv->src_step_px, D, dgx, dgy,
-                                                       cv->d_result, cv->d_result_mask, W, H);
+        if (cv->src_bgr)
+            k5_paste_image<true><<<grid, 256, 0, ctx->stream>>>(reinterpret_cast<const uchar4*>(reinterpret_cast<const uint8_t*>(cv->d_src) + (size_t)k * h * cv->src_step_px),
+                                                                w, h, cv->src_step_px, D, dgx, dgy, cv->d_result, cv->d_result_mask, W, H);
+        else
+            k5_paste_image<false><<<grid, 256, 0, ctx->stream>>>(cv->d_src + (size_t)k * h * cv->src_step_px, w, h, cv->src_step_px, D, dgx, dgy,
+                                                                 cv->d_result, cv->d_result_mask, W, H);
         UAVM_CHECK_LAUNCH(ctx);
     }
     cv->blended = true;

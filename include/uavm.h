@@ -8,7 +8,9 @@
  * sm_100 device is available.
  *
  * Threading: one uavm_ctx per host thread / CUDA stream; objects created from a ctx are used
- * with that ctx.  All "host" pointers may be pageable; pinned memory makes uploads asynchronous.
+ * with that ctx.  All "host" pointers may be pageable; pinned memory makes uploads asynchronous:
+ * a pinned source buffer handed to uavm_featureset_upload_* / uavm_canvas_set_image must stay valid
+ * and unchanged until the next uavm_ctx_sync (or any result getter, which synchronises).
  */
 #ifndef UAVM_H
 #define UAVM_H
@@ -158,6 +160,9 @@ int uavm_canvas_get_layout(uavm_canvas* cv, uavm_canvas_layout* canvas, uavm_chi
 int uavm_canvas_set_rect(uavm_ctx* ctx, uavm_canvas* cv, int x0, int y0, int x1, int y1);
 int uavm_canvas_set_band(uavm_ctx* ctx, uavm_canvas* cv, int y0, int y1, int halo);
 int uavm_canvas_is_active(uavm_canvas* cv, int image);
+/* bytes per source pixel of the canvas' frame pool in HBM: 3 = frames are kept in the caller's BGR layout (width % 16 == 0: K5 reads
+ * BGR taps, uavm_canvas_set_image is a plain copy), 4 = BGRA pool filled by a conversion kernel */
+int uavm_canvas_source_layout(const uavm_canvas* cv);
 /* source frame n (BGR u8 interleaved, `step` bytes per row); is_device != 0: device pointer */
 int uavm_canvas_set_image(uavm_ctx* ctx, uavm_canvas* cv, int image, const uint8_t* bgr, int step, int is_device);
 /* K5: bilinear warp of every kept frame into its chip + validity mask (:2350-2448) */
