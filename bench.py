@@ -474,13 +474,16 @@ def run_ours(args):
         on the ctx's high-priority side stream while the frame path (BGR -> BGRA pass of set_image, then the warp) runs on
         the main stream: the bandwidth-bound conversions sit next to the tensor-bound match, the latency-bound RANSAC next
         to the issue-bound warp.  The serial variant times each stage alone."""
-        if overlap:
+        sched = os.environ.get("UAVM_BENCH_SCHED", "pair_path_side")     # experiment knob: which stages share the side stream
+        if overlap and sched == "pair_path_side":
             ctx.fork()
         if ev: ev[0].record()
         pb.match()
         if ev: ev[1].record()
         pb.select(W, H)
         if ev: ev[2].record()
+        if overlap and sched == "ransac_side":
+            ctx.fork()
         pb.ransac(RANSAC_DIST, SAMPLE_TIMES, base_seed=1000)
         if ev: ev[3].record()
         if overlap:

@@ -33,8 +33,8 @@ struct BlendChip {                          // device-visible plan of one active
     int32_t pw[kMaxBands + 1], ph[kMaxBands + 1];
     int32_t ux0[kMaxBands + 1], uy0[kMaxBands + 1], ux1[kMaxBands + 1], uy1[kMaxBands + 1];
     int32_t cx0[kMaxBands + 1], cy0[kMaxBands + 1], cw_[kMaxBands + 1], ch_[kMaxBands + 1];
-    short* pyr[kMaxBands + 1];              // levels >= 1: int16 x4 pixels of C_i, pitch cw_[i]
-    float* wp[kMaxBands + 1];
+    uint32_t* pyr[kMaxBands + 1];           // levels >= 1: Gaussian levels of C_i as B | G << 8 | R << 16 words (a Gaussian pyramid of
+    float* wp[kMaxBands + 1];               // u8 pixels stays in 0..255: (sum + 128) >> 8 of 256 weights), pitch cw_[i]
 };
 
 struct LevelArgs {
@@ -68,7 +68,10 @@ __device__ __forceinline__ int sat16(int v) { return max(-32768, min(32767, v));
 // Pyramid pixels are 4 x int16 (B, G, R, 0): one aligned 8-byte load / store per pixel
 __device__ __forceinline__ void unpack3(int2 v, int& a, int& b, int& c) { a = (short)(v.x & 0xffff); b = v.x >> 16; c = (short)(v.y & 0xffff); }
 __device__ __forceinline__ int2 pack3(int a, int b, int c) { return make_int2((a & 0xffff) | (b << 16), c & 0xffff); }
-__device__ __forceinline__ int2 bgra_to_px(uint32_t s) { return make_int2((int)((s & 0xffu) | ((s & 0xff00u) << 8)), (int)((s >> 16) & 0xffu)); }
+// Chip-side arithmetic is SIMD within a register: a pixel is expanded to (B | G << 16, R), two u8 channels as 16-bit lanes.
+// Every sum of the 5 x 5 binomial kernel (<= 256 * 255 = 65 280) and of pyrUp (<= 64 * 255 = 16 320) fits its lane, so lanes
+// never carry into each other and the packed results equal OpenCV's int arithmetic on CV_16S data bit for bit.
+__device__ __forceinline__ int2 px_expand(uint32_t s) { return make_int2((int)__byte_perm(s, 0u, 0x4140), (int)__byte_perm(s, 0u, 0x4442)); }
 
 // ---------------------------------------------------------------------------------------------------------------------
 // Tiled pyrDown of one pyramid level for every active chip (blockIdx.z).  A CTA produces a 64 x 8 tile of C_{l+1} from a
@@ -84,7 +87,7 @@ template <bool L0>
 __global__ void __launch_bounds__(256)
 k7_pyrdown(const BlendChip* __restrict__ chips, int sl)
 {
-    __shared__ int2 sE[kPdRows][kPdCols / 2], sO[kPdRows][kPdCols / 2];
+    __shared__ int2 sE[kPdRows][kPdCols / 2], sO[kPdRows][kPdCols / 2];          // expanded pixels (B | G << 16, R)
     __shared__ float wE[kPdRows][kPdCols / 2], wO[kPdRows][kPdCols / 2];
     const BlendChip& B = chips[blockIdx.z];
     const int dl = sl + 1;
@@ -95,31 +98,42 @@ k7_pyrdown(const BlendChip* __restrict__ chips, int sl)
     const int w = B.pw[sl], h = B.ph[sl];
     const int sx0 = 2 * ox0 - 2, sy0 = 2 * oy0 - 2;                              // window origin (even column)
     const int tid = threadIdx.y * kPdW + threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
     // source storage (levels >= 1): C_sl, origin (scx0, scy0), pitch scw; coordinates are clamped into it (window positions
     // that only feed outputs outside C_dl may fall outside C_sl)
     const int scx0 = L0 ? 0 : B.cx0[sl], scy0 = L0 ? 0 : B.cy0[sl], scw = L0 ? 0 : B.cw_[sl], sch = L0 ? 0 : B.ch_[sl];
-    const short* __restrict__ src = L0 ? nullptr : B.pyr[sl];
+    const uint32_t* __restrict__ src = L0 ? nullptr : B.pyr[sl];
     const float* __restrict__ wsrc = L0 ? nullptr : B.wp[sl];
-    // L0 fast path: the whole window lies inside the chip (hence inside the ROI): no border arithmetic, and when the chip
-    // sits at an even ROI column the (even, odd) pixel pair is one 8-byte load and its two mask bytes one 2-byte load
-    const bool interior = L0 && sx0 - B.left >= 0 && sx0 + kPdCols - B.left <= B.cw && sy0 - B.top >= 0 && sy0 + kPdRows - B.top <= B.ch;
-    if (L0 && interior) {
-        const int warp = tid >> 5, lane = tid & 31;
-        const bool even = (B.left & 1) == 0;
+    // fast path: the whole window lies inside the chip (L0) resp. inside C_sl and the ROI level (hence no border arithmetic);
+    // an (even, odd) pixel pair is one 8-byte load when it is 8-byte aligned, its two weights one load as well
+    const bool interior = L0 ? (sx0 - B.left >= 0 && sx0 + kPdCols - B.left <= B.cw && sy0 - B.top >= 0 && sy0 + kPdRows - B.top <= B.ch)
+                             : (sx0 >= 0 && sx0 + kPdCols <= w && sy0 >= 0 && sy0 + kPdRows <= h &&
+                                sx0 - scx0 >= 0 && sx0 + kPdCols - scx0 <= scw && sy0 - scy0 >= 0 && sy0 + kPdRows - scy0 <= sch);
+    if (interior) {
+        const bool even = L0 ? (B.left & 1) == 0 : true;                        // C origins below the top level are even
         for (int r = warp; r < kPdRows; r += 8) {
-            const uint32_t* crow = B.chip + (size_t)(sy0 + r - B.top) * B.chip_step + (sx0 - B.left);
-            const uint8_t* mrow = B.mask + (size_t)(sy0 + r - B.top) * B.mask_step + (sx0 - B.left);
+            const uint32_t* crow; const uint8_t* mrow = nullptr; const float* frow = nullptr;
+            if (L0) {
+                crow = B.chip + (size_t)(sy0 + r - B.top) * B.chip_step + (sx0 - B.left);
+                mrow = B.mask + (size_t)(sy0 + r - B.top) * B.mask_step + (sx0 - B.left);
+            } else {
+                crow = src + (size_t)(sy0 + r - scy0) * scw + (sx0 - scx0);
+                frow = wsrc + (size_t)(sy0 + r - scy0) * scw + (sx0 - scx0);
+            }
             for (int j = lane; j < kPdCols / 2; j += 32) {
-                uint32_t c0, c1, m0, m1;
-                if (even) {
-                    const uint2 c = __ldg(reinterpret_cast<const uint2*>(crow + 2 * j));
-                    const uint32_t m = __ldg(reinterpret_cast<const unsigned short*>(mrow + 2 * j));
-                    c0 = c.x; c1 = c.y; m0 = m & 0xffu; m1 = m >> 8;
+                uint32_t c0, c1; float f0, f1;
+                if (even) { const uint2 c = __ldg(reinterpret_cast<const uint2*>(crow + 2 * j)); c0 = c.x; c1 = c.y; }
+                else { c0 = __ldg(crow + 2 * j); c1 = __ldg(crow + 2 * j + 1); }
+                if (L0) {
+                    uint32_t m0, m1;
+                    if (even) { const uint32_t m = __ldg(reinterpret_cast<const unsigned short*>(mrow + 2 * j)); m0 = m & 0xffu; m1 = m >> 8; }
+                    else { m0 = __ldg(mrow + 2 * j); m1 = __ldg(mrow + 2 * j + 1); }
+                    f0 = (float)m0 * (float)(1. / 255.); f1 = (float)m1 * (float)(1. / 255.);
                 } else {
-                    c0 = __ldg(crow + 2 * j); c1 = __ldg(crow + 2 * j + 1); m0 = __ldg(mrow + 2 * j); m1 = __ldg(mrow + 2 * j + 1);
+                    const float2 f = __ldg(reinterpret_cast<const float2*>(frow + 2 * j)); f0 = f.x; f1 = f.y;
                 }
-                sE[r][j] = bgra_to_px(c0); sO[r][j] = bgra_to_px(c1);
-                wE[r][j] = (float)m0 * (float)(1. / 255.); wO[r][j] = (float)m1 * (float)(1. / 255.);
+                sE[r][j] = px_expand(c0); sO[r][j] = px_expand(c1);
+                wE[r][j] = f0; wO[r][j] = f1;
             }
         }
     } else
@@ -127,35 +141,20 @@ k7_pyrdown(const BlendChip* __restrict__ chips, int sl)
         const int r = e / (kPdCols / 2), j = e - r * (kPdCols / 2);
         const int Y = reflect101(sy0 + r, h);
         const int gx = sx0 + 2 * j;
-        if (L0) {
-            const int iy = Y - B.top, sy = reflect_edge(iy, B.ch);
-            const bool yin = iy >= 0 && iy < B.ch;
-            const uint32_t* crow = B.chip + (size_t)sy * B.chip_step;
-            const uint8_t* mrow = B.mask + (size_t)sy * B.mask_step;
 #pragma unroll
-            for (int o = 0; o < 2; o++) {
-                const int X = reflect101(gx + o, w);
+        for (int o = 0; o < 2; o++) {
+            const int X = reflect101(gx + o, w);
+            uint32_t c; float wv = 0.0f;
+            if (L0) {
+                const int iy = Y - B.top, sy = reflect_edge(iy, B.ch);
                 const int ix = X - B.left, sx = reflect_edge(ix, B.cw);
-                const int2 px = bgra_to_px(__ldg(crow + sx));
-                float wv = 0.0f;
-                if (yin && ix >= 0 && ix < B.cw) wv = (float)__ldg(mrow + ix) * (float)(1. / 255.);
-                if (o == 0) { sE[r][j] = px; wE[r][j] = wv; } else { sO[r][j] = px; wO[r][j] = wv; }
-            }
-        } else {
-            const int yy = min(max(Y - scy0, 0), sch - 1);
-            const int lx = gx - scx0;                                            // even (C origins below the top level are even)
-            if (gx >= 0 && gx + 1 < w && lx >= 0 && lx + 1 < scw) {
-                const size_t o = (size_t)yy * scw + lx;
-                const int4 v = *reinterpret_cast<const int4*>(src + o * 4);
-                sE[r][j] = make_int2(v.x, v.y); sO[r][j] = make_int2(v.z, v.w);
-                const float2 f = *reinterpret_cast<const float2*>(wsrc + o);
-                wE[r][j] = f.x; wO[r][j] = f.y;
+                c = __ldg(B.chip + (size_t)sy * B.chip_step + sx);
+                if (iy >= 0 && iy < B.ch && ix >= 0 && ix < B.cw) wv = (float)__ldg(B.mask + (size_t)iy * B.mask_step + ix) * (float)(1. / 255.);
             } else {
-                const int x0c = min(max(reflect101(gx, w) - scx0, 0), scw - 1), x1c = min(max(reflect101(gx + 1, w) - scx0, 0), scw - 1);
-                const size_t g0 = (size_t)yy * scw + x0c, g1 = (size_t)yy * scw + x1c;
-                sE[r][j] = *reinterpret_cast<const int2*>(src + g0 * 4); sO[r][j] = *reinterpret_cast<const int2*>(src + g1 * 4);
-                wE[r][j] = wsrc[g0]; wO[r][j] = wsrc[g1];
+                const size_t g = (size_t)min(max(Y - scy0, 0), sch - 1) * scw + min(max(X - scx0, 0), scw - 1);
+                c = __ldg(src + g); wv = __ldg(wsrc + g);
             }
+            if (o == 0) { sE[r][j] = px_expand(c); wE[r][j] = wv; } else { sO[r][j] = px_expand(c); wO[r][j] = wv; }
         }
     }
     __syncthreads();
@@ -167,70 +166,68 @@ k7_pyrdown(const BlendChip* __restrict__ chips, int sl)
     int width0 = (w - 3) / 2 + 1; if (w < 3) width0 = 0; if (width0 > dw) width0 = dw;
     const bool hvec = x >= 1 && x < 1 + 4 * ((width0 - 1 > 0 ? width0 - 1 : 0) / 4);
     const bool vvec = x < 4 * (dw / 4);
-    int acc[2][3] = {{0, 0, 0}, {0, 0, 0}};
+    uint32_t ax[2] = {0u, 0u}, ay[2] = {0u, 0u};                                // packed accumulators of the two outputs
     float F[7];
-    const int kw[5] = {1, 4, 6, 4, 1};
+    const uint32_t kw[5] = {1u, 4u, 6u, 4u, 1u};
 #pragma unroll
     for (int r = 0; r < 7; r++) {
         const int wr = 4 * ty + r;
         const int2 p0 = sE[wr][i], p1 = sO[wr][i], p2 = sE[wr][i + 1], p3 = sO[wr][i + 1], p4 = sE[wr][i + 2];
-        int hs[3];
-        hs[0] = (short)(p0.x & 0xffff) + (short)(p4.x & 0xffff) + 4 * ((short)(p1.x & 0xffff) + (short)(p3.x & 0xffff)) + 6 * (short)(p2.x & 0xffff);
-        hs[1] = (p0.x >> 16) + (p4.x >> 16) + 4 * ((p1.x >> 16) + (p3.x >> 16)) + 6 * (p2.x >> 16);
-        hs[2] = (short)(p0.y & 0xffff) + (short)(p4.y & 0xffff) + 4 * ((short)(p1.y & 0xffff) + (short)(p3.y & 0xffff)) + 6 * (short)(p2.y & 0xffff);
-#pragma unroll
-        for (int c = 0; c < 3; c++) {
-            if (r < 5) acc[0][c] += kw[r] * hs[c];
-            if (r >= 2) acc[1][c] += kw[r - 2] * hs[c];
-        }
+        const uint32_t hx = (uint32_t)p0.x + (uint32_t)p4.x + 4u * ((uint32_t)p1.x + (uint32_t)p3.x) + 6u * (uint32_t)p2.x;
+        const uint32_t hy = (uint32_t)p0.y + (uint32_t)p4.y + 4u * ((uint32_t)p1.y + (uint32_t)p3.y) + 6u * (uint32_t)p2.y;
+        if (r < 5) { ax[0] += kw[r] * hx; ay[0] += kw[r] * hy; }
+        if (r >= 2) { ax[1] += kw[r - 2] * hx; ay[1] += kw[r - 2] * hy; }
         const float s0 = wE[wr][i], s1 = wO[wr][i], s2 = wE[wr][i + 1], s3 = wO[wr][i + 1], s4 = wE[wr][i + 2];
         F[r] = hvec ? s2 * 6.0f + ((s1 + s3) * 4.0f + (s0 + s4)) : s2 * 6.0f + (s1 + s3) * 4.0f + s0 + s4;
     }
-    short* __restrict__ dst = B.pyr[dl];
+    uint32_t* __restrict__ dst = B.pyr[dl];
     float* __restrict__ wdst = B.wp[dl];
 #pragma unroll
     for (int o = 0; o < 2; o++) {
         const int ly = ty0 + 2 * ty + o;
         if (ly >= dch) break;
         const size_t di = (size_t)ly * dcw + lx;
-        *reinterpret_cast<int2*>(dst + di * 4) = pack3(sat16((acc[o][0] + 128) >> 8), sat16((acc[o][1] + 128) >> 8), sat16((acc[o][2] + 128) >> 8));
+        const uint32_t bg = ((ax[o] + 0x00800080u) >> 8) & 0x00ff00ffu, rr = ((ay[o] + 128u) >> 8) & 0xffu;      // (sum + 128) >> 8 per lane
+        dst[di] = __byte_perm(bg, rr, 0x7420);
         const float r0 = F[2 * o], r1 = F[1 + 2 * o], r2 = F[2 + 2 * o], r3 = F[3 + 2 * o], r4 = F[4 + 2 * o];
         const float v = vvec ? ((r1 + r3) + r2) * 4.0f + ((r0 + r4) + (r2 + r2)) : r2 * 6.0f + (r1 + r3) * 4.0f + r0 + r4;
         wdst[di] = v * (1.0f / 256.0f);
     }
 }
 
-// pyrUp of a coarser level for the 4 x 2 pixel block made of the quads (c0, cy) and (c0 + 1, cy): up[dy][px][channel].
-// Per axis: even sample s[i-1] + 6 s[i] + s[i+1], odd sample 4 (s[i] + s[i+1]); reflect-101 at the near edge, replicate at
-// the far edge; (sum + 32) >> 6, saturated.  lo: storage with origin (ox, oy) and `pitch` pixels per row; lw x lh = full level.
-__device__ __forceinline__ void pyrup_2quads(const short* __restrict__ lo, int pitch, int ox, int oy, int lw, int lh, int c0, int cy, int up[2][4][3])
+// pyrUp of a chip's Gaussian level (u8 words) for the 4 x 2 pixel block made of the quads (c0, cy) and (c0 + 1, cy), packed:
+// upx[dy][px] = (B | G << 16), upy[dy][px] = R.  Per axis: even sample s[i-1] + 6 s[i] + s[i+1], odd sample 4 (s[i] + s[i+1]);
+// reflect-101 at the near edge, replicate at the far edge; (sum + 32) >> 6.  lo: storage with origin (ox, oy) and `pitch`
+// pixels per row; lw x lh = full level size.
+__device__ __forceinline__ void pyrup_2quads_u8(const uint32_t* __restrict__ lo, int pitch, int ox, int oy, int lw, int lh, int c0, int cy,
+                                                uint32_t upx[2][4], uint32_t upy[2][4])
 {
     const int c1 = min(c0 + 1, lw - 1);
     const int cols[4] = {c0 == 0 ? (lw > 1 ? 1 : 0) : c0 - 1, c0, c1, c1 == lw - 1 ? lw - 1 : c1 + 1};
     const int rows[3] = {cy == 0 ? (lh > 1 ? 1 : 0) : cy - 1, cy, cy == lh - 1 ? lh - 1 : cy + 1};
-    int he[2][3][3], ho[2][3][3];                  // [quad][row][channel]: even-x sum a + 6 b + c, odd-x sum 4 (b + c)
+    uint32_t hex[2][3], hox[2][3], hey[2][3], hoy[2][3];           // [quad][row]: even-x sum a + 6 b + c, odd-x sum 4 (b + c)
 #pragma unroll
     for (int r = 0; r < 3; r++) {
-        const short* rowp = lo + ((ptrdiff_t)(rows[r] - oy) * pitch - ox) * 4;
-        int v[4][3];
+        const uint32_t* rowp = lo + (ptrdiff_t)(rows[r] - oy) * pitch - ox;
+        int2 v[4];
 #pragma unroll
-        for (int j = 0; j < 4; j++) unpack3(*reinterpret_cast<const int2*>(rowp + (ptrdiff_t)cols[j] * 4), v[j][0], v[j][1], v[j][2]);
-#pragma unroll
-        for (int k = 0; k < 3; k++) {
-            he[0][r][k] = v[0][k] + 6 * v[1][k] + v[2][k]; ho[0][r][k] = 4 * (v[1][k] + v[2][k]);
-            he[1][r][k] = v[1][k] + 6 * v[2][k] + v[3][k]; ho[1][r][k] = 4 * (v[2][k] + v[3][k]);
-        }
+        for (int j = 0; j < 4; j++) v[j] = px_expand(__ldg(rowp + cols[j]));
+        hex[0][r] = (uint32_t)v[0].x + 6u * (uint32_t)v[1].x + (uint32_t)v[2].x; hox[0][r] = 4u * ((uint32_t)v[1].x + (uint32_t)v[2].x);
+        hex[1][r] = (uint32_t)v[1].x + 6u * (uint32_t)v[2].x + (uint32_t)v[3].x; hox[1][r] = 4u * ((uint32_t)v[2].x + (uint32_t)v[3].x);
+        hey[0][r] = (uint32_t)v[0].y + 6u * (uint32_t)v[1].y + (uint32_t)v[2].y; hoy[0][r] = 4u * ((uint32_t)v[1].y + (uint32_t)v[2].y);
+        hey[1][r] = (uint32_t)v[1].y + 6u * (uint32_t)v[2].y + (uint32_t)v[3].y; hoy[1][r] = 4u * ((uint32_t)v[2].y + (uint32_t)v[3].y);
     }
 #pragma unroll
     for (int q = 0; q < 2; q++)
 #pragma unroll
-        for (int dx = 0; dx < 2; dx++)
-#pragma unroll
-            for (int k = 0; k < 3; k++) {
-                const int h0 = dx ? ho[q][0][k] : he[q][0][k], h1 = dx ? ho[q][1][k] : he[q][1][k], h2 = dx ? ho[q][2][k] : he[q][2][k];
-                up[0][2 * q + dx][k] = sat16((h0 + 6 * h1 + h2 + 32) >> 6);
-                up[1][2 * q + dx][k] = sat16((4 * (h1 + h2) + 32) >> 6);
-            }
+        for (int dx = 0; dx < 2; dx++) {
+            const uint32_t x0 = dx ? hox[q][0] : hex[q][0], x1 = dx ? hox[q][1] : hex[q][1], x2 = dx ? hox[q][2] : hex[q][2];
+            const uint32_t y0 = dx ? hoy[q][0] : hey[q][0], y1 = dx ? hoy[q][1] : hey[q][1], y2 = dx ? hoy[q][2] : hey[q][2];
+            upx[0][2 * q + dx] = ((x0 + 6u * x1 + x2 + 0x00200020u) >> 6) & 0x03ff03ffu;
+            upx[1][2 * q + dx] = ((4u * (x1 + x2) + 0x00200020u) >> 6) & 0x03ff03ffu;
+            upy[0][2 * q + dx] = (y0 + 6u * y1 + y2 + 32u) >> 6;
+            upy[1][2 * q + dx] = (4u * (y1 + y2) + 32u) >> 6;
+        }
 }
 
 // short(d / (wsum + 1e-5f)) (normalizeUsingWeightMap), with two exact shortcuts that remove most IEEE divisions:
@@ -315,15 +312,29 @@ k7_level(const BlendChip* __restrict__ chips, const LevelArgs A)
     const int tx0 = (A.sx0 & ~3) + blockIdx.x * 128, ty0 = A.sy0 + blockIdx.y * 16;
     const int X = tx0 + 4 * threadIdx.x, Y = ty0 + 2 * threadIdx.y;               // this thread's block (canvas level coordinates)
     const bool live = X + 4 > A.sx0 && X < A.sx1 && Y < A.sy1;
+    __shared__ int s_wide;                                                        // a staged value lies outside [-512, 511]
     // stage the coarse tile with pyrUp's border rules applied (reflect-101 at the near edge, replicate at the far edge);
-    // positions outside the stored rectangle S_{i+1} only feed pixels outside S_i and are clamped into it
-    for (int e = threadIdx.y * 32 + threadIdx.x; e < 10 * 66; e += 256) {
-        const int r = e / 66, c = e - r * 66;
-        int cx = (tx0 >> 1) - 1 + c, cy = (ty0 >> 1) - 1 + r;
-        cx = cx < 0 ? (A.nxt_w > 1 ? 1 : 0) : (cx > A.nxt_w - 1 ? A.nxt_w - 1 : cx);
-        cy = cy < 0 ? (A.nxt_h > 1 ? 1 : 0) : (cy > A.nxt_h - 1 ? A.nxt_h - 1 : cy);
-        const int lx = min(max(cx - A.nxt_x0, 0), A.nxt_pitch - 1), ly = min(max(cy - A.nxt_y0, 0), A.nxt_rows - 1);
-        snx[r][c] = *reinterpret_cast<const int2*>(A.nxt + ((size_t)ly * A.nxt_pitch + lx) * 4);
+    // positions outside the stored rectangle S_{i+1} only feed pixels outside S_i and are clamped into it.
+    // Values are staged BIASED and packed, (B + 512 | G + 512 << 16, R + 512): while every value of the tile lies in
+    // [-512, 511] (blended image data does) all pyrUp sums stay inside their 16-bit lanes (<= 64 * 1023) and
+    // ((sum' + 32) >> 6) = ((sum + 32) >> 6) + 512 exactly (the bias 64 * 512 is a multiple of 64).  A tile with a wider
+    // value is re-staged raw and takes the generic per-channel path.
+    if (threadIdx.x == 0 && threadIdx.y == 0) s_wide = 0;
+    __syncthreads();
+    {
+        int wide = 0;
+        for (int e = threadIdx.y * 32 + threadIdx.x; e < 10 * 66; e += 256) {
+            const int r = e / 66, c = e - r * 66;
+            int cx = (tx0 >> 1) - 1 + c, cy = (ty0 >> 1) - 1 + r;
+            cx = cx < 0 ? (A.nxt_w > 1 ? 1 : 0) : (cx > A.nxt_w - 1 ? A.nxt_w - 1 : cx);
+            cy = cy < 0 ? (A.nxt_h > 1 ? 1 : 0) : (cy > A.nxt_h - 1 ? A.nxt_h - 1 : cy);
+            const int lx = min(max(cx - A.nxt_x0, 0), A.nxt_pitch - 1), ly = min(max(cy - A.nxt_y0, 0), A.nxt_rows - 1);
+            int b3, g3, r3;
+            unpack3(*reinterpret_cast<const int2*>(A.nxt + ((size_t)ly * A.nxt_pitch + lx) * 4), b3, g3, r3);
+            wide |= ((unsigned)(b3 + 512) > 1023u) | ((unsigned)(g3 + 512) > 1023u) | ((unsigned)(r3 + 512) > 1023u);
+            snx[r][c] = make_int2((b3 + 512) | ((g3 + 512) << 16), r3 + 512);
+        }
+        if (wide) s_wide = 1;
     }
     int d[2][4][3];
     float ws[2][4];
@@ -376,36 +387,73 @@ k7_level(const BlendChip* __restrict__ chips, const LevelArgs A)
                 }
             }
             if (!any) continue;                                                   // dst + short(lap * 0) == dst, wsum + 0 == wsum
-            int up[2][4][3];
-            pyrup_2quads(B.pyr[level + 1], B.cw_[level + 1], B.cx0[level + 1], B.cy0[level + 1], B.pw[level + 1], B.ph[level + 1], x >> 1, y >> 1, up);
+            uint32_t upx[2][4], upy[2][4];                                        // pyrUp of the chip's coarser Gaussian level, packed
+            pyrup_2quads_u8(B.pyr[level + 1], B.cw_[level + 1], B.cx0[level + 1], B.cy0[level + 1], B.pw[level + 1], B.ph[level + 1], x >> 1, y >> 1, upx, upy);
 #pragma unroll
             for (int dy = 0; dy < 2; dy++)
 #pragma unroll
                 for (int p = 0; p < 4; p++) {
                     const float wv = w[dy][p];
                     if (wv == 0.0f) continue;
-                    int c3[3];
-                    if (L0) {
-                        const uint32_t s = __ldg(B.chip + (ptrdiff_t)(y + dy - B.top) * B.chip_step + (x + p - B.left));
-                        c3[0] = (int)(s & 0xffu); c3[1] = (int)((s >> 8) & 0xffu); c3[2] = (int)((s >> 16) & 0xffu);
-                    } else {
-                        unpack3(*reinterpret_cast<const int2*>(B.pyr[level] + ((ptrdiff_t)(y + dy - B.cy0[level]) * B.cw_[level] + (x + p - B.cx0[level])) * 4),
-                                c3[0], c3[1], c3[2]);
-                    }
+                    // the chip's pixel at this level: the chip itself (level 0), else its Gaussian level; both are u8 words
+                    const uint32_t s = L0 ? __ldg(B.chip + (ptrdiff_t)(y + dy - B.top) * B.chip_step + (x + p - B.left))
+                                          : __ldg(B.pyr[level] + (ptrdiff_t)(y + dy - B.cy0[level]) * B.cw_[level] + (x + p - B.cx0[level]));
+                    // Laplacian = pixel - pyrUp, in [-255, 255]: the saturating subtract never saturates
+                    const int lap[3] = {(int)(s & 0xffu) - (int)(upx[dy][p] & 0xffffu), (int)((s >> 8) & 0xffu) - (int)(upx[dy][p] >> 16),
+                                        (int)((s >> 16) & 0xffu) - (int)upy[dy][p]};
+                    // dst += short(lap * w): the int16 sums wrap, so they are kept as ints and truncated once at the end;
+                    // w == 1.0f (every owned level-0 pixel under seam masks) needs no float round trip
+                    if (wv == 1.0f) {
 #pragma unroll
-                    for (int k = 0; k < 3; k++) {
-                        const int lap = sat16(c3[k] - up[dy][p][k]);
-                        d[dy][p][k] = (short)(d[dy][p][k] + (short)__float2int_rz((float)lap * wv));
+                        for (int k = 0; k < 3; k++) d[dy][p][k] += lap[k];
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 3; k++) d[dy][p][k] += (short)__float2int_rz((float)lap[k] * wv);
                     }
                     ws[dy][p] += wv;
                 }
         }
         __syncthreads();
     }
-    if (A.n_chips <= 0) __syncthreads();                                          // the staged tile (the chip loop synchronises otherwise)
-    if (!live) return;
+    __syncthreads();                                                              // the staged tile and s_wide
     int up[2][4][3];
-    pyrup_2quads_smem<68>(snx, 1 + 2 * threadIdx.x, 1 + threadIdx.y, up);
+    if (s_wide) {                                                                 // uniform: re-stage raw values, generic per-channel pyrUp
+        __syncthreads();
+        for (int e = threadIdx.y * 32 + threadIdx.x; e < 10 * 66; e += 256) {
+            const int r = e / 66, c = e - r * 66;
+            int cx = (tx0 >> 1) - 1 + c, cy = (ty0 >> 1) - 1 + r;
+            cx = cx < 0 ? (A.nxt_w > 1 ? 1 : 0) : (cx > A.nxt_w - 1 ? A.nxt_w - 1 : cx);
+            cy = cy < 0 ? (A.nxt_h > 1 ? 1 : 0) : (cy > A.nxt_h - 1 ? A.nxt_h - 1 : cy);
+            const int lx = min(max(cx - A.nxt_x0, 0), A.nxt_pitch - 1), ly = min(max(cy - A.nxt_y0, 0), A.nxt_rows - 1);
+            snx[r][c] = *reinterpret_cast<const int2*>(A.nxt + ((size_t)ly * A.nxt_pitch + lx) * 4);
+        }
+        __syncthreads();
+        if (!live) return;
+        pyrup_2quads_smem<68>(snx, 1 + 2 * threadIdx.x, 1 + threadIdx.y, up);
+    } else {
+        if (!live) return;
+        const int lc = 1 + 2 * threadIdx.x, lr = 1 + threadIdx.y;
+        uint32_t hex[2][3], hox[2][3], hey[2][3], hoy[2][3];
+#pragma unroll
+        for (int r = 0; r < 3; r++) {
+            const int2 v0 = snx[lr - 1 + r][lc - 1], v1 = snx[lr - 1 + r][lc], v2 = snx[lr - 1 + r][lc + 1], v3 = snx[lr - 1 + r][lc + 2];
+            hex[0][r] = (uint32_t)v0.x + 6u * (uint32_t)v1.x + (uint32_t)v2.x; hox[0][r] = 4u * ((uint32_t)v1.x + (uint32_t)v2.x);
+            hex[1][r] = (uint32_t)v1.x + 6u * (uint32_t)v2.x + (uint32_t)v3.x; hox[1][r] = 4u * ((uint32_t)v2.x + (uint32_t)v3.x);
+            hey[0][r] = (uint32_t)v0.y + 6u * (uint32_t)v1.y + (uint32_t)v2.y; hoy[0][r] = 4u * ((uint32_t)v1.y + (uint32_t)v2.y);
+            hey[1][r] = (uint32_t)v1.y + 6u * (uint32_t)v2.y + (uint32_t)v3.y; hoy[1][r] = 4u * ((uint32_t)v2.y + (uint32_t)v3.y);
+        }
+#pragma unroll
+        for (int q = 0; q < 2; q++)
+#pragma unroll
+            for (int dx = 0; dx < 2; dx++) {
+                const uint32_t x0 = dx ? hox[q][0] : hex[q][0], x1 = dx ? hox[q][1] : hex[q][1], x2 = dx ? hox[q][2] : hex[q][2];
+                const uint32_t y0 = dx ? hoy[q][0] : hey[q][0], y1 = dx ? hoy[q][1] : hey[q][1], y2 = dx ? hoy[q][2] : hey[q][2];
+                const uint32_t ex = ((x0 + 6u * x1 + x2 + 0x00200020u) >> 6) & 0x03ff03ffu, ox_ = ((4u * (x1 + x2) + 0x00200020u) >> 6) & 0x03ff03ffu;
+                const uint32_t ey = (y0 + 6u * y1 + y2 + 32u) >> 6, oy_ = (4u * (y1 + y2) + 32u) >> 6;
+                up[0][2 * q + dx][0] = (int)(ex & 0xffffu) - 512; up[0][2 * q + dx][1] = (int)(ex >> 16) - 512; up[0][2 * q + dx][2] = (int)ey - 512;
+                up[1][2 * q + dx][0] = (int)(ox_ & 0xffffu) - 512; up[1][2 * q + dx][1] = (int)(ox_ >> 16) - 512; up[1][2 * q + dx][2] = (int)oy_ - 512;
+            }
+    }
 #pragma unroll
     for (int dy = 0; dy < 2; dy++) {
         const int yy = Y + dy;
@@ -413,7 +461,7 @@ k7_level(const BlendChip* __restrict__ chips, const LevelArgs A)
 #pragma unroll
         for (int p = 0; p < 4; p++) {
 #pragma unroll
-            for (int k = 0; k < 3; k++) v[p][k] = sat16(up[dy][p][k] + norm_div(d[dy][p][k], ws[dy][p]));
+            for (int k = 0; k < 3; k++) v[p][k] = sat16(up[dy][p][k] + norm_div((short)d[dy][p][k], ws[dy][p]));
         }
         if (!L0) {
             if (yy >= A.sy1) break;
@@ -487,7 +535,8 @@ k7_level_top(const BlendChip* __restrict__ chips, const LevelArgs A)
                 const ptrdiff_t o = (ptrdiff_t)(y - B.cy0[level]) * B.cw_[level] + (x - B.cx0[level]);
                 wv = B.wp[level][o];
                 if (wv == 0.0f) continue;
-                unpack3(*reinterpret_cast<const int2*>(B.pyr[level] + o * 4), c3[0], c3[1], c3[2]);
+                const uint32_t s = B.pyr[level][o];
+                c3[0] = (int)(s & 0xffu); c3[1] = (int)((s >> 8) & 0xffu); c3[2] = (int)((s >> 16) & 0xffu);
             }
 #pragma unroll
             for (int k = 0; k < 3; k++) d[k] = (short)(d[k] + (short)__float2int_rz((float)c3[k] * wv));
@@ -579,7 +628,7 @@ extern "C" int uavm_canvas_blend(uavm_ctx* ctx, uavm_canvas* cv, int num_bands)
             B.cx0[i] = c.C[i].x0; B.cy0[i] = c.C[i].y0; B.cw_[i] = c.C[i].x1 - c.C[i].x0; B.ch_[i] = c.C[i].y1 - c.C[i].y0;
             if (i >= 1) {
                 const size_t px = (size_t)B.cw_[i] * B.ch_[i];
-                B.pyr[i] = (short*)scratch; scratch += (px * 8 + 255) & ~(size_t)255;             // offsets for now, rebased below
+                B.pyr[i] = (uint32_t*)scratch; scratch += (px * 4 + 255) & ~(size_t)255;          // offsets for now, rebased below
                 B.wp[i] = (float*)scratch; scratch += (px * 4 + 255) & ~(size_t)255;
                 if (B.cw_[i] > max_cw[i]) max_cw[i] = B.cw_[i];
                 if (B.ch_[i] > max_ch[i]) max_ch[i] = B.ch_[i];
@@ -598,7 +647,7 @@ extern "C" int uavm_canvas_blend(uavm_ctx* ctx, uavm_canvas* cv, int num_bands)
         int rc = ensure_cap(ctx, (void**)&ws->d_fin[i], &ws->fin_cap[i], px * 8 + 256); if (rc != UAVM_OK) return rc;
     }
     for (auto& B : bc)
-        for (int i = 1; i <= nb; i++) { B.pyr[i] = (short*)(ws->d_scratch + (size_t)B.pyr[i]); B.wp[i] = (float*)(ws->d_scratch + (size_t)B.wp[i]); }
+        for (int i = 1; i <= nb; i++) { B.pyr[i] = (uint32_t*)(ws->d_scratch + (size_t)B.pyr[i]); B.wp[i] = (float*)(ws->d_scratch + (size_t)B.wp[i]); }
     if (n_act > 0) UAVM_CUDA(ctx, cudaMemcpyAsync(ws->d_chips, bc.data(), (size_t)n_act * sizeof(BlendChip), cudaMemcpyHostToDevice, ctx->stream));
     if (cv->result_w != cw || cv->result_h != ch) {
         cudaFree(cv->d_result); cudaFree(cv->d_result_mask); cv->d_result = nullptr; cv->d_result_mask = nullptr;

@@ -3,6 +3,7 @@
 // Replaces the reference's per-pair feature (de)serialisation (WriteSurfKeyPoints/LoadSurfKeyPoints,
 // M/MosaicWithoutPos.cpp:4682-4734, re-read for every pair at :5073-5103): descriptors are packed
 // once into a u8 pool in HBM and never leave it.
+#include <stdlib.h>
 #include <algorithm>
 #include "internal.h"
 
@@ -39,7 +40,8 @@ extern "C" int uavm_ctx_create(int device, uavm_ctx** out) {
     c->main_stream = c->stream;
     int prio_lo = 0, prio_hi = 0;
     cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);          // side stream = highest priority: its (latency-bound)
-    if (cudaStreamCreateWithPriority(&c->side_stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
+    const char* sp = getenv("UAVM_SIDE_PRIO");                     // experiment knob: "low" gives the side stream the lowest priority
+    if (cudaStreamCreateWithPriority(&c->side_stream, cudaStreamNonBlocking, (sp && sp[0] == 'l') ? prio_lo : prio_hi) != cudaSuccess ||
         cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||   // blocks are placed first
 
         cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
