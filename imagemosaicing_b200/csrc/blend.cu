@@ -18,6 +18,7 @@
 // S_i its output depends on; chip pyramids are computed in ROI coordinates exactly as in the unsharded case, so sharded
 // results are bit-identical by construction (no halo heuristics).
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 #include "canvas.h"
 #include "blend_plan.h"
@@ -301,8 +302,8 @@ __device__ __forceinline__ int tile_chip_list(const BlendChip* __restrict__ chip
 //   v = short(d / (wsum + 1e-5));  final = sat(pyrUp(final_{i+1}) + v)
 // L0: pyr_0 is the chip itself (a non-zero weight implies the pixel lies inside the chip), w = mask / 255, and the result is
 // written as the cropped u8 mosaic + mask (zero where wsum <= 1e-5; convertTo(CV_8U) saturates).
-template <bool L0>
-__global__ void __launch_bounds__(256)
+template <bool L0, int MINB>
+__global__ void __launch_bounds__(256, MINB)
 k7_level(const BlendChip* __restrict__ chips, const LevelArgs A)
 {
     __shared__ int list[256];
@@ -686,8 +687,10 @@ extern "C" int uavm_canvas_blend(uavm_ctx* ctx, uavm_canvas* cv, int num_bands)
         } else {
             dim3 grid((A.sx1 - (A.sx0 & ~3) + 127) / 128, (A.sy1 - A.sy0 + 15) / 16);
             if (grid.y > 65535) { UAVM_SET_ERR(ctx, "blend: canvas level %d too tall", i); return UAVM_EINVAL; }
-            if (i == 0) k7_level<true><<<grid, dim3(32, 8), 0, ctx->stream>>>(ws->d_chips, A);
-            else k7_level<false><<<grid, dim3(32, 8), 0, ctx->stream>>>(ws->d_chips, A);
+            static const int minb = getenv("UAVM_K7_MINB") ? atoi(getenv("UAVM_K7_MINB")) : 4;        // A/B knob: resident CTAs per SM the compiler targets
+            if (minb == 3) { if (i == 0) k7_level<true, 3><<<grid, dim3(32, 8), 0, ctx->stream>>>(ws->d_chips, A); else k7_level<false, 3><<<grid, dim3(32, 8), 0, ctx->stream>>>(ws->d_chips, A); }
+            else if (minb == 4) { if (i == 0) k7_level<true, 4><<<grid, dim3(32, 8), 0, ctx->stream>>>(ws->d_chips, A); else k7_level<false, 4><<<grid, dim3(32, 8), 0, ctx->stream>>>(ws->d_chips, A); }
+            else { if (i == 0) k7_level<true, 2><<<grid, dim3(32, 8), 0, ctx->stream>>>(ws->d_chips, A); else k7_level<false, 2><<<grid, dim3(32, 8), 0, ctx->stream>>>(ws->d_chips, A); }
         }
         UAVM_CHECK_LAUNCH(ctx);
     }

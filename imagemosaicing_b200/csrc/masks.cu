@@ -8,9 +8,10 @@
 //   k6_dist_max   per chip, compute only: validity from the warp's own coordinate chain (M/MosaicImage.cpp:2356-2362, :2370),
 //                 distance to the nearest edge, per-image maximum (atomicMax on the float bits); tiles that provably cannot
 //                 hold the maximum are skipped (the distance is 1-Lipschitz), the maximum itself is exact;
-//   k6_owner      per CANVAS pixel: the normalised distance of every chip whose box covers the pixel is evaluated once, in
-//                 image index order with the reference's strict >; then each of those chips gets its mask byte (255 for the
-//                 owner, 0 for the others) and the bounding box of the pixels it owns (K7 only builds pyramids there).
+//   k6_owner      per CANVAS pixel: the normalised distance of every chip that can own the pixel is evaluated once, in image
+//                 index order with the reference's strict > (chips that provably lose everywhere in the tile are pruned with
+//                 Lipschitz bounds); the owner's mask byte becomes 255 (the planes are zeroed first) and each chip gets the
+//                 bounding box of the pixels it owns (K7 only builds pyramids there).
 // The arithmetic per (chip, pixel) is exactly the reference's: same expressions, same order, IEEE division by the maximum.
 #include <math.h>
 #include <string.h>
@@ -125,16 +126,48 @@ k6_dist_max(const K6Chip* __restrict__ chips, float* __restrict__ dist_max, floa
     block_max_to_global(mx, dist_max + blockIdx.z);
 }
 
-// chips [base, base + 256) whose boxes intersect the tile, compacted in index order (one candidate per thread)
-__device__ __forceinline__ int tile_box_list(const K6Chip* __restrict__ chips, int n, int base, int tx0, int ty0, int tx1, int ty1, int* list, int* wcount)
+// Candidate chips of a canvas tile, for chips [base, base + 256): one chip per thread.  A chip is a candidate when its box
+// intersects the tile AND it can own a pixel of it.  The second test prunes with bounds that hold for every pixel of the tile:
+// the distance to the nearest edge line is 1-Lipschitz, so with R = half diagonal of the tile (+ slack)
+//     dn_m(p) <= (d_m(centre) + R) / max_m                                   for every chip m
+//     dn_b(p) >= (d_b(centre) - R) / max_b   if the disc of radius R + 2 around the centre is inside chip b's quad
+//                                            (then every pixel of the tile is valid in b)
+// A chip whose upper bound is below the best lower bound is never the arg-max inside the tile; the survivors are evaluated
+// exactly, in index order.  `lbmax` carries the best lower bound over the rounds.  All 256 threads must call this.
+__device__ __forceinline__ int tile_candidates(const K6Chip* __restrict__ chips, const float* __restrict__ dist_max, int n, int base,
+                                               int tx0, int ty0, int tx1, int ty1, float dgx, float dgy, float w1f, float h1f,
+                                               float& lbmax, int* list, int* wcount, float* s_lb)
 {
     const int tid = threadIdx.y * 32 + threadIdx.x, lane = threadIdx.x, warp = threadIdx.y;
     const int c = base + tid;
     bool hit = false;
+    float ub = 0.0f, lb = 0.0f;
     if (c < n) {
         const int4 b = *reinterpret_cast<const int4*>(&chips[c].beg_x);
         hit = chips[c].keep && b.x < tx1 && b.x + b.z > tx0 && b.y < ty1 && b.y + b.w > ty0;
+        if (hit) {
+            const K6Chip D = chips[c];
+            const float mx = dist_max[c];
+            const int pcx = (tx0 + tx1) >> 1, pcy = (ty0 + ty1) >> 1;                      // centre pixel of the tile
+            const float R = 0.5f * sqrtf((float)((tx1 - tx0) * (tx1 - tx0) + (ty1 - ty0) * (ty1 - ty0))) + 2.0f;
+            const float fc = (float)(pcx - D.beg_x), fr = (float)(pcy - D.beg_y);
+            const float dc = chip_edge_dist(D, fc, fr);
+            if (!(mx > 0.0f)) hit = false;                                                  // no valid pixel at all: never an owner
+            else {
+                ub = (dc + R) / mx * 1.0001f;
+                const bool centre_valid = pcx >= D.beg_x && pcx < D.beg_x + D.w && pcy >= D.beg_y && pcy < D.beg_y + D.h &&
+                                          chip_min_dist(D, row_terms(D, pcy - D.beg_y, dgy), fc, dgx, w1f, h1f) > 0.0f;
+                if (centre_valid && dc > R + 2.0f) lb = (dc - R) / mx * 0.9999f;
+            }
+        }
     }
+    // block maximum of the lower bounds
+    float wl = __int_as_float(__reduce_max_sync(0xffffffffu, __float_as_int(lb)));          // lb >= 0: int order == float order
+    if (lane == 0) s_lb[warp] = wl;
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 8; k++) lbmax = fmaxf(lbmax, s_lb[k]);
+    hit = hit && ub >= lbmax;
     const unsigned m = __ballot_sync(0xffffffffu, hit);
     if (lane == 0) wcount[warp] = __popc(m);
     __syncthreads();
@@ -146,7 +179,8 @@ __device__ __forceinline__ int tile_box_list(const K6Chip* __restrict__ chips, i
     return total;
 }
 
-// canvas rectangle [rx0, rx1) x [ry0, ry1); a CTA covers 128 x 8 canvas pixels, a thread the pixels x + 32 k of one row
+// canvas rectangle [rx0, rx1) x [ry0, ry1); a CTA covers 128 x 8 canvas pixels, a thread the pixels x + 32 k of one row.
+// The mask planes are zeroed beforehand; the kernel stores 255 at the owner's pixel only.
 __global__ void __launch_bounds__(256)
 k6_owner(const K6Chip* __restrict__ chips, uint8_t* const* __restrict__ mask_ptr, const int32_t* __restrict__ mask_step,
          const float* __restrict__ dist_max, int n, float dgx, float dgy, float w1f, float h1f, int rx0, int ry0, int rx1, int ry1,
@@ -154,74 +188,58 @@ k6_owner(const K6Chip* __restrict__ chips, uint8_t* const* __restrict__ mask_ptr
 {
     __shared__ int list[256];
     __shared__ int wcount[8];
-    __shared__ int sbb[256][4];
+    __shared__ float s_lb[8];
     const int tx0 = rx0 + blockIdx.x * kTileW, ty0 = ry0 + blockIdx.y * kTileH;
+    const int tx1 = min(tx0 + kTileW, rx1), ty1 = min(ty0 + kTileH, ry1);
     const int gy = ty0 + threadIdx.y;
     const int gx0 = tx0 + threadIdx.x;
-    const int tid = threadIdx.y * 32 + threadIdx.x;
     float best[4] = {0.0f, 0.0f, 0.0f, 0.0f};                         // float maxDist = 0 (:1850)
     int owner[4] = {-1, -1, -1, -1};
-    // pass 0: arg-max in image index order; pass 1: mask bytes + owned bounding boxes
-    for (int pass = 0; pass < 2; pass++) {
-        for (int base = 0; base < n; base += 256) {
-            const int total = tile_box_list(chips, n, base, tx0, ty0, min(tx0 + kTileW, rx1), min(ty0 + kTileH, ry1), list, wcount);
-            if (pass == 1) {
-                if (tid < total) { sbb[tid][0] = 1 << 30; sbb[tid][1] = 1 << 30; sbb[tid][2] = -1; sbb[tid][3] = -1; }
-                __syncthreads();
-            }
-            for (int e = 0; e < total; e++) {
-                const int m = list[e];
-                if (pass == 0) {
-                    const int4 bx = *reinterpret_cast<const int4*>(&chips[m].beg_x);
-                    const int r = gy - bx.y;
-                    if (gy >= ry1 || r < 0 || r >= bx.w) continue;                            // warp uniform (a warp = one canvas row)
-                    if (tx0 + kTileW <= bx.x || tx0 >= bx.x + bx.z) continue;                     // this warp's 128 columns miss the box
-                    const K6Chip D = chips[m];
-                    const RowTerms t = row_terms(D, r, dgy);
-                    const float mx = dist_max[m];
-                    // the IEEE division is only needed when the quotient can exceed the running maximum: md / mx > best
-                    // implies md > best * mx * (1 - 2^-22); the guard below is far more conservative than that
-                    const float mxg = mx * 0.99999f;
-                    const float fc0 = (float)(gx0 - D.beg_x);
+    float lbmax = 0.0f;
+    for (int base = 0; base < n; base += 256) {
+        const int total = tile_candidates(chips, dist_max, n, base, tx0, ty0, tx1, ty1, dgx, dgy, w1f, h1f, lbmax, list, wcount, s_lb);
+        for (int e = 0; e < total; e++) {
+            const int m = list[e];
+            const int4 bx = *reinterpret_cast<const int4*>(&chips[m].beg_x);
+            const int r = gy - bx.y;
+            if (gy >= ry1 || r < 0 || r >= bx.w) continue;                                // warp uniform (a warp = one canvas row)
+            const K6Chip D = chips[m];
+            const RowTerms t = row_terms(D, r, dgy);
+            const float mx = dist_max[m];
+            // the IEEE division is only needed when the quotient can exceed the running maximum: md / mx > best
+            // implies md > best * mx * (1 - 2^-22); the guard below is far more conservative than that
+            const float mxg = mx * 0.99999f;
+            const float fc0 = (float)(gx0 - D.beg_x);
 #pragma unroll
-                    for (int k = 0; k < 4; k++) {
-                        const int gx = gx0 + 32 * k, c = gx - D.beg_x;
-                        if (gx >= rx1 || c < 0 || c >= D.w) continue;
-                        const float md = chip_min_dist(D, t, fc0 + 32.0f * k, dgx, w1f, h1f);
-                        if (md == 0.0f || md < best[k] * mxg) continue;   // invalid pixel (the map holds 0 there), or cannot win
-                        const float dn = md / mx;                         // pMapRow[c] /= maxDist (:1830)
-                        if (dn > best[k]) { best[k] = dn; owner[k] = m; }
-                    }
-                } else {
-                    const int4 bx = *reinterpret_cast<const int4*>(&chips[m].beg_x);
-                    const int r = gy - bx.y;
-                    if (gy >= ry1 || r < 0 || r >= bx.w) continue;
-                    uint8_t* mrow = mask_ptr[m] + (size_t)r * mask_step[m];
-                    int bx0 = 1 << 30, bx1 = -1;
+            for (int k = 0; k < 4; k++) {
+                const int gx = gx0 + 32 * k, c = gx - D.beg_x;
+                if (gx >= rx1 || c < 0 || c >= D.w) continue;
+                const float md = chip_min_dist(D, t, fc0 + 32.0f * k, dgx, w1f, h1f);
+                if (md == 0.0f || md < best[k] * mxg) continue;           // invalid pixel (the map holds 0 there), or cannot win
+                const float dn = md / mx;                                 // pMapRow[c] /= maxDist (:1830)
+                if (dn > best[k]) { best[k] = dn; owner[k] = m; }
+            }
+        }
+        __syncthreads();
+    }
+    // the owner's mask byte, and the bounding box of what each chip owns (lanes with the same owner reduce together)
 #pragma unroll
-                    for (int k = 0; k < 4; k++) {
-                        const int gx = gx0 + 32 * k, c = gx - bx.x;
-                        if (gx >= rx1 || c < 0 || c >= bx.z) continue;
-                        const bool mine = owner[k] == m;
-                        mrow[c] = mine ? 255 : 0;
-                        if (mine) { bx0 = min(bx0, c); bx1 = max(bx1, c); }
-                    }
-                    const int wx0 = __reduce_min_sync(0xffffffffu, bx0), wx1 = __reduce_max_sync(0xffffffffu, bx1);
-                    if (threadIdx.x == 0 && wx1 >= 0) {
-                        atomicMin(&sbb[e][0], wx0); atomicMax(&sbb[e][2], wx1);
-                        atomicMin(&sbb[e][1], r); atomicMax(&sbb[e][3], r);
-                    }
-                }
-            }
-            __syncthreads();
-            if (pass == 1 && tid < total && sbb[tid][2] >= 0) {
-                int32_t* g = own_bbox + (size_t)list[tid] * 4;
-                if (sbb[tid][0] < g[0]) atomicMin(g + 0, sbb[tid][0]);
-                if (sbb[tid][1] < g[1]) atomicMin(g + 1, sbb[tid][1]);
-                if (sbb[tid][2] > g[2]) atomicMax(g + 2, sbb[tid][2]);
-                if (sbb[tid][3] > g[3]) atomicMax(g + 3, sbb[tid][3]);
-            }
-            __syncthreads();
+    for (int k = 0; k < 4; k++) {
+        const int m = owner[k];
+        int c = 0, r = 0;
+        if (m >= 0) {
+            const int4 bx = *reinterpret_cast<const int4*>(&chips[m].beg_x);
+            c = gx0 + 32 * k - bx.x; r = gy - bx.y;
+            mask_ptr[m][(size_t)r * mask_step[m] + c] = 255;
+        }
+        const unsigned grp = __match_any_sync(0xffffffffu, m);
+        const int c0 = __reduce_min_sync(grp, c), c1 = __reduce_max_sync(grp, c);
+        if (m >= 0 && threadIdx.x == (unsigned)(__ffs(grp) - 1)) {
+            int32_t* g = own_bbox + (size_t)m * 4;
+            if (c0 < g[0]) atomicMin(g + 0, c0);
+            if (r < g[1]) atomicMin(g + 1, r);
+            if (c1 > g[2]) atomicMax(g + 2, c1);
+            if (r > g[3]) atomicMax(g + 3, r);
         }
     }
 }
@@ -282,6 +300,7 @@ extern "C" int uavm_canvas_seam_masks(uavm_ctx* ctx, uavm_canvas* cv)
     }
     const K6Chip* k6 = (const K6Chip*)cv->d_k6;
     UAVM_CUDA(ctx, cudaMemsetAsync(cv->d_dist_max, 0, (size_t)cv->n * sizeof(float), ctx->stream));
+    UAVM_CUDA(ctx, cudaMemsetAsync(cv->d_masks, 0, cv->masks_bytes, ctx->stream));          // k6_owner stores 255 at owned pixels only
     k6_init_bbox<<<(cv->n + 255) / 256, 256, 0, ctx->stream>>>(cv->d_own_bbox, cv->n);
     UAVM_CHECK_LAUNCH(ctx);
     const float w1f = (float)(cv->img_w - 1), h1f = (float)(cv->img_h - 1);
