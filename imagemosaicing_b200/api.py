@@ -139,6 +139,42 @@ class FeatureSet:
             pass
 
 
+class Sift:
+    """SIFT detect + compute on the GPU (uavm_sift; replaces SiftExtraction_Thread's SIFT(2000, 3, 0.01, 20),
+    M/MosaicWithoutPos.cpp:4852-4872).  One object per image size."""
+
+    def __init__(self, ctx, img_w, img_h, nfeatures=2000, n_octave_layers=3, contrast_threshold=0.01, edge_threshold=20.0, sigma=1.6):
+        self.ctx = ctx; self.w = int(img_w); self.h = int(img_h)
+        self._h = C.c_void_p()
+        ctx.check(L.lib().uavm_sift_create(ctx._h, self.w, self.h, int(nfeatures), int(n_octave_layers), C.c_double(contrast_threshold),
+                                           C.c_double(edge_threshold), C.c_double(sigma), C.byref(self._h)))
+
+    def detect_and_compute(self, bgr, cap=1 << 17):
+        """bgr: (h, w, 3) uint8 numpy array or torch CUDA tensor -> (keypoints structured array, descriptors (n, 128) f32)."""
+        bgr = _host(bgr)
+        dev = 1 if _is_torch_cuda(bgr) else 0
+        if dev:
+            assert bgr.is_contiguous(); step = bgr.stride(0)
+        else:
+            bgr = np.ascontiguousarray(bgr, np.uint8); step = bgr.strides[0]
+        assert bgr.shape[0] == self.h and bgr.shape[1] == self.w and bgr.shape[2] == 3
+        kp = (L.KeyPoint * cap)(); desc = np.zeros((cap, 128), np.float32); n = C.c_int(0)
+        self.ctx.check(L.lib().uavm_sift_detect_and_compute(self.ctx._h, self._h, _ptr(bgr, u8p), int(step), dev, kp, _ptr(desc, f32p), cap, C.byref(n)))
+        dt = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"), ("octave", "<i4"), ("class_id", "<i4")])
+        return np.frombuffer(kp, dtype=dt)[:n.value].copy(), desc[:n.value].copy()
+
+    def close(self):
+        if self._h:
+            L.lib().uavm_sift_destroy(self.ctx._h, self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class PairBatch:
     """match -> select -> RANSAC for a list of (query image, train image) pairs (uavm_pairbatch)."""
 

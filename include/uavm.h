@@ -94,6 +94,16 @@ void uavm_featureset_destroy(uavm_ctx* ctx, uavm_featureset* fs);
 int uavm_featureset_upload_f32(uavm_ctx* ctx, uavm_featureset* fs, int image, const float* desc, const float* kp_xy, int is_device);
 int uavm_featureset_upload_u8(uavm_ctx* ctx, uavm_featureset* fs, int image, const uint8_t* desc, const float* kp_xy, int is_device);
 
+/* ---- SIFT on the GPU (csrc/sift.cu): replaces SiftExtraction_Thread's SIFT(2000, 3, 0.01, 20) detect + compute
+ *      (M/MosaicWithoutPos.cpp:4852-4872).  One object per image size; kp_out are cv::KeyPoint records, desc_out n x 128 floats
+ *      (integer valued 0..255, OpenCV's descriptor format).  nfeatures = 0 keeps every keypoint. */
+typedef struct uavm_sift uavm_sift;
+int uavm_sift_create(uavm_ctx* ctx, int img_w, int img_h, int nfeatures, int n_octave_layers, double contrast_threshold,
+                     double edge_threshold, double sigma, uavm_sift** out);
+void uavm_sift_destroy(uavm_ctx* ctx, uavm_sift* s);
+int uavm_sift_detect_and_compute(uavm_ctx* ctx, uavm_sift* s, const uint8_t* bgr, int step, int is_device,
+                                 uavm_keypoint* kp_out, float* desc_out, int cap, int* n_out);
+
 /* ---- batched pair pipeline: match -> select -> RANSAC ------------------------------------------ */
 typedef struct uavm_pairbatch uavm_pairbatch;
 /* pair_ij: n_pairs x 2 (query image i, train image j), host memory. */
