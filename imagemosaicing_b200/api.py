@@ -520,6 +520,24 @@ def mosaic_images(ctx, images, descs, kps, param=None, scale=1.0, return_matches
     return out + (matches,) if return_matches else out
 
 
+def mosaic_images_sift(ctx, images, param=None, scale=1.0):
+    """MosaicVavImages' own shape (uavm_mosaic_images_sift): images in, (mosaic, transforms, fixed, matches) out; SIFT runs on
+    the GPU with the reference's parameters."""
+    n = len(images)
+    ims, arr = _image_array(images)
+    P = _param(param)
+    res = L.Image(); nm = C.c_int(0); tr = (ImageTransform * n)()
+    pp = C.POINTER(MatchPointPairs)(); npairs = C.c_int(0)
+    rc = L.lib().uavm_mosaic_images_sift(ctx._h, arr, n, C.byref(P), C.c_float(scale), C.byref(res), C.byref(nm), tr, C.byref(pp), C.byref(npairs))
+    matches = None
+    if npairs.value > 0:
+        matches = (MatchPointPairs * npairs.value)()
+        C.memmove(matches, pp, C.sizeof(MatchPointPairs) * npairs.value)
+        L.lib().uavm_free(C.cast(pp, C.c_void_p))
+    ctx.check(rc)
+    return _take_result(res, tr, n) + (matches,)
+
+
 def mosaic_from_matches(ctx, images, matches, param=None, scale=1.0):
     """The loadMatchPairs = 1 path (M/MosaicWithoutPos.cpp:4465-4477) without the stdin prompt: `matches` (a ctypes array of
     MatchPointPairs, e.g. from read_match_file) replaces feature matching."""

@@ -78,6 +78,42 @@ extern "C" int uavm_mosaic_images(uavm_ctx* ctx, const uavm_image* images, int n
     return uavm_mosaic_images_ex(ctx, images, n_images, desc, kp_xy, n_kp, param_in, scale, result, num_mosaiced, transforms_out, nullptr, nullptr);
 }
 
+// MosaicVavImages' own signature (M/MosaicWithoutPos.h:638-645): images in, mosaic out.  Features come from the GPU SIFT
+// (csrc/sift.cu) with the reference's parameters SIFT(2000, 3, 0.01, 20) (M/MosaicWithoutPos.cpp:4852), one image after the other
+// like SiftExtraction_Thread (:4832-4887) but without the round trip through keypoint_%d.key / discriptor_%d.xml.
+extern "C" int uavm_mosaic_images_sift(uavm_ctx* ctx, const uavm_image* images, int n_images, const uavm_param* param_in, float scale,
+                                       uavm_image* result, int* num_mosaiced, uavm_imagetransform* transforms_out,
+                                       uavm_matchpointpairs** pairs_out, int* n_pairs_out)
+{
+    if (!ctx || !images || n_images < 2 || !result) return UAVM_EINVAL;
+    memset(result, 0, sizeof(*result));
+    if (check_images(images, n_images) != UAVM_OK) return UAVM_EINVAL;
+    const int w = images[0].width, h = images[0].height;
+    uavm_sift* sift = nullptr;
+    int rc = uavm_sift_create(ctx, w, h, 2000, 3, 0.01, 20.0, 1.6, &sift);
+    if (rc != UAVM_OK) return UAVM_EFAIL;
+    const int cap = 1 << 16;
+    std::vector<std::vector<float>> desc(n_images), kp(n_images);
+    std::vector<int32_t> n_kp(n_images, 0);
+    std::vector<uavm_keypoint> kbuf(cap);
+    std::vector<float> dbuf((size_t)cap * 128);
+    for (int i = 0; rc == UAVM_OK && i < n_images; i++) {
+        int n = 0;
+        rc = uavm_sift_detect_and_compute(ctx, sift, images[i].imageData, images[i].widthStep, 0, kbuf.data(), dbuf.data(), cap, &n);
+        if (rc != UAVM_OK) break;
+        n_kp[i] = n;
+        desc[i].assign(dbuf.begin(), dbuf.begin() + (size_t)n * 128);
+        kp[i].resize((size_t)n * 2);
+        for (int k = 0; k < n; k++) { kp[i][2 * k] = kbuf[k].x; kp[i][2 * k + 1] = kbuf[k].y; }
+    }
+    uavm_sift_destroy(ctx, sift);
+    if (rc != UAVM_OK) return UAVM_EFAIL;
+    std::vector<const float*> dp(n_images), kpp(n_images);
+    for (int i = 0; i < n_images; i++) { dp[i] = desc[i].data(); kpp[i] = kp[i].data(); }
+    return uavm_mosaic_images_ex(ctx, images, n_images, dp.data(), kpp.data(), n_kp.data(), param_in, scale, result, num_mosaiced, transforms_out,
+                                 pairs_out, n_pairs_out);
+}
+
 extern "C" int uavm_mosaic_from_matches(uavm_ctx* ctx, const uavm_image* images, int n_images,
                                         const uavm_matchpointpairs* pairs, int n_pairs, const uavm_param* param_in, float scale,
                                         uavm_image* result, int* num_mosaiced, uavm_imagetransform* transforms_out)

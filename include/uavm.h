@@ -226,6 +226,11 @@ int uavm_mosaic_images(uavm_ctx* ctx, const uavm_image* images, int n_images,
                        const float* const* desc, const float* const* kp_xy, const int32_t* n_kp,
                        const uavm_param* param, float scale,
                        uavm_image* result, int* num_mosaiced, uavm_imagetransform* transforms_out);
+/* MosaicVavImages' own signature (M/MosaicWithoutPos.h:638-645): images in, mosaic out; features from the GPU SIFT with the
+ * reference's parameters SIFT(2000, 3, 0.01, 20).  pairs_out / n_pairs_out optional (uavm_free). */
+int uavm_mosaic_images_sift(uavm_ctx* ctx, const uavm_image* images, int n_images, const uavm_param* param, float scale,
+                            uavm_image* result, int* num_mosaiced, uavm_imagetransform* transforms_out,
+                            uavm_matchpointpairs** pairs_out, int* n_pairs_out);
 /* the loadMatchPairs = 1 path of MosaicWithoutPose (M/MosaicWithoutPos.cpp:4465-4477), without the stdin prompt: the match
  * list (e.g. uavm_match_file_read of a matchPairs.match written by the original tool or by uavm_match_file_write) replaces
  * feature matching; connectivity -> global alignment -> warp / blend run as in uavm_mosaic_images. */
