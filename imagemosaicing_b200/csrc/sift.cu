@@ -351,6 +351,20 @@ ks_describe(const Kp* __restrict__ kps, int n, const OctaveGauss* __restrict__ o
     desc[(size_t)blockIdx.x * 128 + t] = (float)max(0, min(255, q));
 }
 
+// retainBest keeps the nfeatures strongest keypoints; a dense 12 Mpx frame yields over a million.  Instead of moving and sorting
+// them all on the host, a histogram over the top 16 bits of the responses (positive floats: integer order == float order) gives
+// a conservative cut, only the keypoints above it travel, and the exact filter runs on those.
+__global__ void __launch_bounds__(256) ks_resp_hist(const Kp* __restrict__ kps, int n, int* __restrict__ hist)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) atomicAdd(&hist[__float_as_uint(kps[i].response) >> 16], 1);
+}
+__global__ void __launch_bounds__(256) ks_resp_select(const Kp* __restrict__ kps, int n, unsigned int min_bin, Kp* __restrict__ out, int* __restrict__ n_out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && (__float_as_uint(kps[i].response) >> 16) >= min_bin) out[atomicAdd(n_out, 1)] = kps[i];
+}
+
 }  // namespace
 
 struct uavm_sift {
@@ -364,7 +378,8 @@ struct uavm_sift {
     uint8_t* d_img = nullptr;                // staged host image
     OctaveGauss* d_octs = nullptr;
     Cand* d_cand = nullptr; Kp* d_kp = nullptr; Kp* d_kp_final = nullptr; float* d_desc = nullptr; int* d_counts = nullptr;
-    int cap = 1 << 19, desc_cap = 1 << 17;
+    int cap = 1 << 22, desc_cap = 1 << 17;
+    int* d_hist = nullptr;                   // 65536 bins over the top 16 bits of the (positive) responses
     float taps[kMaxLayers + 3][kMaxTaps]; int radius[kMaxLayers + 3];
 };
 
@@ -418,8 +433,8 @@ extern "C" int uavm_sift_create(uavm_ctx* ctx, int img_w, int img_h, int nfeatur
     bool fail = cudaMalloc(&s->d_img, (size_t)img_w * img_h * 3) != cudaSuccess || cudaMalloc(&s->d_octs, sizeof(OctaveGauss) * kMaxOctaves) != cudaSuccess ||
                 cudaMalloc(&s->d_cand, sizeof(Cand) * s->cap) != cudaSuccess || cudaMalloc(&s->d_kp, sizeof(Kp) * s->cap) != cudaSuccess ||
                 cudaMalloc(&s->d_kp_final, sizeof(Kp) * s->cap) != cudaSuccess || cudaMalloc(&s->d_desc, sizeof(float) * 128 * (size_t)s->desc_cap) != cudaSuccess ||
-                cudaMalloc(&s->d_counts, 2 * sizeof(int)) != cudaSuccess;
-    if (fail) { cudaGetLastError(); cudaFree(s->d_pool); cudaFree(s->d_img); cudaFree(s->d_octs); cudaFree(s->d_cand); cudaFree(s->d_kp); cudaFree(s->d_kp_final); cudaFree(s->d_desc); cudaFree(s->d_counts); delete s; return UAVM_EFAIL; }
+                cudaMalloc(&s->d_counts, 4 * sizeof(int)) != cudaSuccess || cudaMalloc(&s->d_hist, 65536 * sizeof(int)) != cudaSuccess;
+    if (fail) { cudaGetLastError(); cudaFree(s->d_pool); cudaFree(s->d_img); cudaFree(s->d_octs); cudaFree(s->d_cand); cudaFree(s->d_kp); cudaFree(s->d_kp_final); cudaFree(s->d_desc); cudaFree(s->d_counts); cudaFree(s->d_hist); delete s; return UAVM_EFAIL; }
     std::vector<OctaveGauss> og(kMaxOctaves);
     for (int o = 0; o < n_oct; o++) { og[o].w = s->ow[o]; og[o].h = s->oh[o]; for (int i = 0; i < s->nl + 3; i++) og[o].g[i] = s->gauss[o][i]; }
     UAVM_CUDA(ctx, cudaMemcpy(s->d_octs, og.data(), sizeof(OctaveGauss) * kMaxOctaves, cudaMemcpyHostToDevice));
@@ -431,7 +446,7 @@ extern "C" void uavm_sift_destroy(uavm_ctx* ctx, uavm_sift* s)
 {
     if (!s) return;
     if (ctx) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
-    cudaFree(s->d_pool); cudaFree(s->d_img); cudaFree(s->d_octs); cudaFree(s->d_cand); cudaFree(s->d_kp); cudaFree(s->d_kp_final); cudaFree(s->d_desc); cudaFree(s->d_counts);
+    cudaFree(s->d_pool); cudaFree(s->d_img); cudaFree(s->d_octs); cudaFree(s->d_cand); cudaFree(s->d_kp); cudaFree(s->d_kp_final); cudaFree(s->d_desc); cudaFree(s->d_counts); cudaFree(s->d_hist);
     delete s;
 }
 
@@ -484,7 +499,7 @@ extern "C" int uavm_sift_detect_and_compute(uavm_ctx* ctx, uavm_sift* s, const u
     }
     UAVM_CUDA(ctx, cudaMemcpyToSymbolAsync(c_taps, s->taps, sizeof(s->taps), 0, cudaMemcpyHostToDevice, st));
     UAVM_CUDA(ctx, cudaMemcpyToSymbolAsync(c_radius, s->radius, sizeof(s->radius), 0, cudaMemcpyHostToDevice, st));
-    UAVM_CUDA(ctx, cudaMemsetAsync(s->d_counts, 0, 2 * sizeof(int), st));
+    UAVM_CUDA(ctx, cudaMemsetAsync(s->d_counts, 0, 4 * sizeof(int), st));
     const int bw = s->ow[0], bh = s->oh[0];
     float* base_pre = s->d_tmp + (size_t)bw * bh;
     auto grid2 = [](int w, int h) { return dim3((w + 255) / 256, h); };
@@ -515,17 +530,47 @@ extern "C" int uavm_sift_detect_and_compute(uavm_ctx* ctx, uavm_sift* s, const u
     int counts[2] = {0, 0};
     UAVM_CUDA(ctx, cudaMemcpyAsync(counts, s->d_counts, sizeof(int), cudaMemcpyDeviceToHost, st));
     UAVM_CUDA(ctx, cudaStreamSynchronize(st));
-    int n_cand = std::min(counts[0], s->cap);
+    if (counts[0] > s->cap) { UAVM_SET_ERR(ctx, "sift: %d extrema exceed the candidate buffer (%d)", counts[0], s->cap); return UAVM_EFAIL; }
+    int n_cand = counts[0];
     if (n_cand > 0) {
         ks_orient<<<(n_cand * 32 + 255) / 256, 256, 0, st>>>(s->d_cand, n_cand, s->d_octs, s->d_kp, s->d_counts + 1, s->cap);
         UAVM_CHECK_LAUNCH(ctx);
     }
     UAVM_CUDA(ctx, cudaMemcpyAsync(counts, s->d_counts, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
     UAVM_CUDA(ctx, cudaStreamSynchronize(st));
-    const int n_kp = std::min(counts[1], s->cap);
-    std::vector<Kp> v(n_kp);
-    if (n_kp > 0) UAVM_CUDA(ctx, cudaMemcpy(v.data(), s->d_kp, sizeof(Kp) * n_kp, cudaMemcpyDeviceToHost));
-    filter_keypoints(v, s->nfeatures);
+    if (counts[1] > s->cap) { UAVM_SET_ERR(ctx, "sift: %d keypoints exceed the keypoint buffer (%d)", counts[1], s->cap); return UAVM_EFAIL; }
+    const int n_kp = counts[1];
+    std::vector<Kp> v;
+    const int want = s->nfeatures > 0 ? s->nfeatures + s->nfeatures / 4 + 256 : 0;       // slack for duplicates removed before retainBest
+    if (s->nfeatures > 0 && n_kp > 2 * want) {
+        UAVM_CUDA(ctx, cudaMemsetAsync(s->d_hist, 0, 65536 * sizeof(int), st));
+        ks_resp_hist<<<(n_kp + 255) / 256, 256, 0, st>>>(s->d_kp, n_kp, s->d_hist);
+        UAVM_CHECK_LAUNCH(ctx);
+        std::vector<int> hist(65536);
+        UAVM_CUDA(ctx, cudaMemcpyAsync(hist.data(), s->d_hist, 65536 * sizeof(int), cudaMemcpyDeviceToHost, st));
+        UAVM_CUDA(ctx, cudaStreamSynchronize(st));
+        int bin = 65535, acc = 0;
+        for (; bin > 0; bin--) { acc += hist[bin]; if (acc >= want) break; }
+        ks_resp_select<<<(n_kp + 255) / 256, 256, 0, st>>>(s->d_kp, n_kp, (unsigned)bin, s->d_kp_final, s->d_counts + 2);
+        UAVM_CHECK_LAUNCH(ctx);
+        int n_sel = 0;
+        UAVM_CUDA(ctx, cudaMemcpyAsync(&n_sel, s->d_counts + 2, sizeof(int), cudaMemcpyDeviceToHost, st));
+        UAVM_CUDA(ctx, cudaStreamSynchronize(st));
+        v.resize(n_sel);
+        if (n_sel > 0) UAVM_CUDA(ctx, cudaMemcpy(v.data(), s->d_kp_final, sizeof(Kp) * n_sel, cudaMemcpyDeviceToHost));
+        std::vector<Kp> probe(v);
+        filter_keypoints(probe, s->nfeatures);
+        if ((int)probe.size() >= s->nfeatures) v.swap(probe);
+        else {                                                            // more duplicates than slack: exact filter on everything
+            v.resize(n_kp);
+            UAVM_CUDA(ctx, cudaMemcpy(v.data(), s->d_kp, sizeof(Kp) * n_kp, cudaMemcpyDeviceToHost));
+            filter_keypoints(v, s->nfeatures);
+        }
+    } else {
+        v.resize(n_kp);
+        if (n_kp > 0) UAVM_CUDA(ctx, cudaMemcpy(v.data(), s->d_kp, sizeof(Kp) * n_kp, cudaMemcpyDeviceToHost));
+        filter_keypoints(v, s->nfeatures);
+    }
     const int n = (int)v.size();
     *n_out = n;
     if (n > cap) return UAVM_EINVAL;
