@@ -580,6 +580,50 @@ def run_ours(args):
     e1.record()
     barrier()
     e2e_ms = e0.elapsed_time(e1)
+    # ---- the same step with the frames handed over as JPEG bytes (f4): decoded on the device by nvJPEG straight into the source
+    # pool.  Informational: at 4000x3000 the step becomes decode bound (the raw frames cross PCIe at ~18 Gpx/s).
+    enc_info = None
+    if rank == 0 and not args.no_jpeg:
+        try:
+            import cv2
+            t0 = time.perf_counter()
+            encs = [None] + [cv2.imencode(".jpg", h_frames[k].numpy(), [cv2.IMWRITE_JPEG_QUALITY, 90])[1] for k in range(1, NIMG)]
+            t_enc = time.perf_counter() - t0
+            t0 = time.perf_counter(); cv2.imdecode(encs[1], cv2.IMREAD_COLOR); host_dec_ms = (time.perf_counter() - t0) * 1e3
+            best = None
+            for backend in (2, 0):
+                try:
+                    jp = api.Jpeg(ctx, backend)
+                except api.UavmError:
+                    continue
+                def enc_step():
+                    for k in range(NIMG):
+                        fs.upload(k, h_desc[k], h_kp[k])
+                    ctx.fork(); pb.match(); pb.select(W, H); pb.ransac(RANSAC_DIST, SAMPLE_TIMES, base_seed=1000); ctx.unfork()
+                    for g0 in range(1, NIMG, GROUP):
+                        g1 = min(g0 + GROUP, NIMG)
+                        for k in range(g0, g1):
+                            jp.set_canvas_image(cv, k, encs[k])
+                        cv.warp(g0, g1 - g0)
+                    ctx.join()
+                    return pb.collect(30)
+                enc_step(); torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                for _ in range(2):
+                    enc_step()
+                torch.cuda.synchronize()
+                ms = (time.perf_counter() - t0) / 2 * 1e3
+                jp.close()
+                if best is None or ms < best[0]:
+                    best = (ms, backend)
+            if best is not None:
+                enc_info = {"value": n_pairs / (best[0] / 1e3), "unit": UNIT, "ms_per_step": best[0], "nvjpeg_backend": best[1],
+                            "jpeg_bytes_per_step": int(sum(len(e) for e in encs[1:])), "jpeg_quality": 90,
+                            "host_libjpeg_turbo_decode_ms_per_frame_1thread": host_dec_ms,
+                            "note": "49 JPEG frames (4000x3000) decoded by nvJPEG into the BGR source pool inside the step, host clock; decode bound"}
+            del encs
+        except Exception as e:
+            enc_info = {"error": repr(e)}
     # PCIe ceiling for context: the same frames copied back to back with nothing else running
     probe = torch.empty((H, W, 3), dtype=torch.uint8, device=dev)
     p0 = torch.cuda.Event(enable_timing=True); p1 = torch.cuda.Event(enable_timing=True)
@@ -671,6 +715,7 @@ def run_ours(args):
                     "note": "inputs in (descriptors, keypoints, 49 BGR frames from pinned host memory), inlier match list out; the warped chips "
                             "(2.6 GB) stay resident in HBM, where the seam masks and the blend consume them.  PCIe bound: frames are copied on the "
                             "library's copy stream while match / RANSAC / warp run"},
+            "e2e_encoded": enc_info,
             "gpu_launches": int(launches),
             "clocks": clocks,
             "blend": blend_info,
@@ -700,6 +745,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-blend", action="store_true", help="skip the separate seam-mask + multi-band blend measurement")
+    ap.add_argument("--no-jpeg", action="store_true", help="skip the JPEG-input variant of the end-to-end step (nvJPEG decode on the device)")
     ap.add_argument("--no-block", action="store_true", help="skip BASELINE configs[2] (200-image block, strong scaling)")
     ap.add_argument("--no-canvas", action="store_true", help="skip BASELINE configs[4] (500 tiles -> 40000^2 canvas, strong scaling)")
     args = ap.parse_args()

@@ -91,6 +91,10 @@ def lib():
         try:                                   # absent only in a host-only sanitizer build (UAVM_LIB_PATH)
             L.uavm_last_error.restype = C.c_char_p
             L.uavm_ctx_launch_count.restype = C.c_int64
+            L.uavm_jpeg_decode_bgr.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_int, C.c_int]
+            L.uavm_canvas_set_image_jpeg.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int64]
+            L.uavm_jpeg_destroy.restype = None
+            L.uavm_jpeg_destroy.argtypes = [C.c_void_p, C.c_void_p]
             L.uavm_dist_destroy.restype = None
             L.uavm_dist_destroy.argtypes = [C.c_void_p, C.c_void_p]
             L.uavm_pairbatch_allgather.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]

@@ -175,6 +175,37 @@ class Sift:
             pass
 
 
+class Jpeg:
+    """nvJPEG decoder handle (uavm_jpeg): JPEG bytes in, BGR pixels in HBM out."""
+
+    def __init__(self, ctx, backend=0):
+        self.ctx = ctx
+        self._h = C.c_void_p()
+        ctx.check(L.lib().uavm_jpeg_create(ctx._h, int(backend), C.byref(self._h)))
+
+    def decode(self, data, out):
+        """data: bytes / uint8 numpy array with the JPEG stream; out: torch CUDA uint8 tensor (h, w, 3), contiguous."""
+        buf = np.frombuffer(data, np.uint8) if isinstance(data, (bytes, bytearray)) else np.ascontiguousarray(data, np.uint8)
+        assert _is_torch_cuda(out) and out.is_contiguous()
+        self.ctx.check(L.lib().uavm_jpeg_decode_bgr(self.ctx._h, self._h, _ptr(buf, u8p), C.c_int64(buf.size), C.c_void_p(out.data_ptr()),
+                                                    int(out.stride(0)), int(out.shape[1]), int(out.shape[0])))
+
+    def set_canvas_image(self, cv, image, data):
+        buf = np.frombuffer(data, np.uint8) if isinstance(data, (bytes, bytearray)) else np.ascontiguousarray(data, np.uint8)
+        self.ctx.check(L.lib().uavm_canvas_set_image_jpeg(self.ctx._h, cv._h, self._h, int(image), _ptr(buf, u8p), C.c_int64(buf.size)))
+
+    def close(self):
+        if self._h:
+            L.lib().uavm_jpeg_destroy(self.ctx._h, self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class PairBatch:
     """match -> select -> RANSAC for a list of (query image, train image) pairs (uavm_pairbatch)."""
 

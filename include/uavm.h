@@ -175,6 +175,17 @@ int uavm_canvas_is_active(uavm_canvas* cv, int image);
 int uavm_canvas_source_layout(const uavm_canvas* cv);
 /* source frame n (BGR u8 interleaved, `step` bytes per row); is_device != 0: device pointer */
 int uavm_canvas_set_image(uavm_ctx* ctx, uavm_canvas* cv, int image, const uint8_t* bgr, int step, int is_device);
+/* ---- JPEG frames decoded on the device (csrc/decode.cu; nvJPEG loaded at run time) — replaces the callers' cvLoadImage
+ *      (M/mosaicing.cpp:51-100, M/MosaicWithoutPos.cpp:10224-10308).  backend: 0 default, 1 hybrid, 2 GPU hybrid. */
+typedef struct uavm_jpeg uavm_jpeg;
+int uavm_jpeg_create(uavm_ctx* ctx, int backend, uavm_jpeg** out);
+void uavm_jpeg_destroy(uavm_ctx* ctx, uavm_jpeg* j);
+int uavm_jpeg_info(uavm_ctx* ctx, uavm_jpeg* j, const uint8_t* jpeg, int64_t n_bytes, int* width, int* height);
+int uavm_jpeg_decode_bgr(uavm_ctx* ctx, uavm_jpeg* j, const uint8_t* jpeg, int64_t n_bytes, uint8_t* d_bgr, int step, int width, int height);
+/* source frame `image` from JPEG bytes: decoded straight into the canvas' BGR pool slot */
+int uavm_canvas_set_image_jpeg(uavm_ctx* ctx, uavm_canvas* cv, uavm_jpeg* j, int image, const uint8_t* jpeg, int64_t n_bytes);
+/* device address of a source frame in a BGR pool (e.g. to run uavm_sift_detect_and_compute on it with is_device = 1) */
+int uavm_canvas_image_ptr(uavm_canvas* cv, int image, const uint8_t** d_bgr, int* step);
 /* K5: bilinear warp of every kept frame into its chip + validity mask (:2350-2448) */
 int uavm_canvas_warp(uavm_ctx* ctx, uavm_canvas* cv);
 /* same for images [first, first + count) only: a caller that streams frames in (uavm_canvas_set_image copies host
