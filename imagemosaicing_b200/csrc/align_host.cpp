@@ -5,7 +5,12 @@
 // The reference solves x = (A^T A)^-1 A^T b with CHOLMOD in double; here the normal equations are
 // accumulated directly (double) and solved with a dense Cholesky — same system, same precision class.
 #include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
+#include <algorithm>
+#include <chrono>
+#include <thread>
 #include <vector>
 #include "internal.h"
 
@@ -117,41 +122,102 @@ extern "C" int uavm_align_affine(const uavm_matchpointpairs* pairs, int n_pairs,
     const int nu = 3 * (n_images - nf);                   // per coordinate: (a, b, e) resp. (c, d, f) of every free image
     if (nu <= 0) return UAVM_EFAIL;
     if (nu > 12000) return UAVM_EFAIL;                    // dense normal matrix limit (1.1 GB)
+    const auto t_begin = std::chrono::steady_clock::now();
     std::vector<double> N((size_t)nu * nu, 0.0), gx(nu, 0.0), gy(nu, 0.0);
-    for (int n = 0; n < n_pairs; n++) {
-        const uavm_matchpointpairs& m = pairs[n];
-        if (m.ptA_i < 0 || m.ptA_i >= n_images || m.ptB_i < 0 || m.ptB_i >= n_images) return UAVM_EINVAL;
-        int cols[6]; double vals[6]; int nc = 0; double rx = 0, ry = 0;
-        const double xa = m.ptA.x, ya = m.ptA.y, xb = m.ptB.x, yb = m.ptB.y;
+    // The matches of one image pair arrive as a run (uavm_pairbatch_collect / _allgather emit pair after pair) and all touch the
+    // same <= 6 x 6 block of N.  Runs are independent: each is summed (match by match, in order) into 21 + 12 local accumulators,
+    // several runs at a time on host threads, and the blocks are then added to N in run order — the result does not depend on
+    // the number of threads.  Summation order differs from adding match by match into N, so the result equals the dense oracle
+    // to rounding (1e-12 relative), not bit for bit.
+    struct Run { int begin, end, nc; int cols[6]; double loc[6][6], gx[6], gy[6]; };
+    auto classify = [&](const uavm_matchpointpairs& m, int* cols) -> int {       // columns of the match's unknown blocks; -1: contributes nothing
         if (m.ptA_Fixed == 0 && m.ptB_Fixed == 0) {
             const int ca = 3 * (m.ptA_i - acc_fixed[m.ptA_i]), cb = 3 * (m.ptB_i - acc_fixed[m.ptB_i]);
-            cols[0] = ca; vals[0] = xa; cols[1] = ca; vals[1] = ya; cols[2] = ca; vals[2] = 1;
-            cols[3] = cb; vals[3] = -xb; cols[4] = cb; vals[4] = -yb; cols[5] = cb; vals[5] = -1; nc = 6;
-        } else if (m.ptA_Fixed == 1 && m.ptB_Fixed == 0) {
-            const int cb = 3 * (m.ptB_i - acc_fixed[m.ptB_i]);
-            cols[0] = cb; vals[0] = xb; cols[1] = cb; vals[1] = yb; cols[2] = cb; vals[2] = 1; nc = 3;
-            double h[9]; for (int t = 0; t < 9; t++) h[t] = init[m.ptA_i].h.m[t];
-            rx = (h[0] * xa + h[1] * ya + h[2]) / (h[6] * xa + h[7] * ya + h[8]);      // ApplyProject9 (M/MosaicWithoutPos.h:331-336)
-            ry = (h[3] * xa + h[4] * ya + h[5]) / (h[6] * xa + h[7] * ya + h[8]);
-        } else if (m.ptA_Fixed == 0 && m.ptB_Fixed == 1) {
-            const int ca = 3 * (m.ptA_i - acc_fixed[m.ptA_i]);
-            cols[0] = ca; vals[0] = xa; cols[1] = ca; vals[1] = ya; cols[2] = ca; vals[2] = 1; nc = 3;
-            double h[9]; for (int t = 0; t < 9; t++) h[t] = init[m.ptB_i].h.m[t];
-            rx = (h[0] * xb + h[1] * yb + h[2]) / (h[6] * xb + h[7] * yb + h[8]);
-            ry = (h[3] * xb + h[4] * yb + h[5]) / (h[6] * xb + h[7] * yb + h[8]);
-        } else continue;
-        for (int a = 0; a < nc; a++) {
-            if (cols[a] < 0 || cols[a] + 2 >= nu) return UAVM_EINVAL;      // a "free" point on a fixed image
-            const int ar = cols[a] + a % 3;
-            for (int b = 0; b < nc; b++) {
-                const int bc = cols[b] + b % 3;
-                if (bc <= ar) N[(size_t)ar * nu + bc] += vals[a] * vals[b];       // the factorisation reads the lower triangle only
+            cols[0] = cols[1] = cols[2] = ca; cols[3] = cols[4] = cols[5] = cb; return 6;
+        }
+        if (m.ptA_Fixed == 1 && m.ptB_Fixed == 0) { cols[0] = cols[1] = cols[2] = 3 * (m.ptB_i - acc_fixed[m.ptB_i]); return 3; }
+        if (m.ptA_Fixed == 0 && m.ptB_Fixed == 1) { cols[0] = cols[1] = cols[2] = 3 * (m.ptA_i - acc_fixed[m.ptA_i]); return 3; }
+        return -1;
+    };
+    // fixed chunks of the match list (a run that crosses a chunk edge is summed as two blocks — at the same places whatever the
+    // number of threads), one pass per chunk: find the runs and sum them
+    const auto t_alloc = std::chrono::steady_clock::now();
+    constexpr int kChunk = 8192;
+    const int n_chunks = (n_pairs + kChunk - 1) / kChunk;
+    std::vector<std::vector<Run>> chunk_runs(n_chunks);
+    std::vector<int> chunk_bad(n_chunks, 0);
+    auto do_chunk = [&](int c) {
+        std::vector<Run>& runs = chunk_runs[c];
+        const int n0 = c * kChunk, n1 = std::min(n_pairs, n0 + kChunk);
+        for (int n = n0; n < n1; n++) {
+            const uavm_matchpointpairs& m = pairs[n];
+            if (m.ptA_i < 0 || m.ptA_i >= n_images || m.ptB_i < 0 || m.ptB_i >= n_images) { chunk_bad[c] = 1; return; }
+            int cols[6] = {0, 0, 0, 0, 0, 0};
+            const int nc = classify(m, cols);
+            if (nc < 0) continue;
+            for (int a = 0; a < nc; a++)
+                if (cols[a] < 0 || cols[a] + 2 >= nu) { chunk_bad[c] = 1; return; }      // a "free" point on a fixed image
+            bool same = false;
+            if (!runs.empty()) {
+                const Run& r = runs.back();
+                const uavm_matchpointpairs& p = pairs[r.begin];
+                same = r.end == n && r.nc == nc && p.ptA_i == m.ptA_i && p.ptB_i == m.ptB_i && p.ptA_Fixed == m.ptA_Fixed && p.ptB_Fixed == m.ptB_Fixed;
             }
-            gx[ar] += vals[a] * rx;
-            gy[ar] += vals[a] * ry;
+            if (!same) {
+                Run r; memset(&r, 0, sizeof(r));
+                r.begin = n; r.nc = nc; memcpy(r.cols, cols, sizeof(cols));
+                runs.push_back(r);
+            }
+            Run& r = runs.back();
+            r.end = n + 1;
+            double vals[6]; double rx = 0, ry = 0;
+            const double xa = m.ptA.x, ya = m.ptA.y, xb = m.ptB.x, yb = m.ptB.y;
+            if (nc == 6) { vals[0] = xa; vals[1] = ya; vals[2] = 1; vals[3] = -xb; vals[4] = -yb; vals[5] = -1; }
+            else if (m.ptA_Fixed == 1) {
+                vals[0] = xb; vals[1] = yb; vals[2] = 1;
+                double h[9]; for (int t = 0; t < 9; t++) h[t] = init[m.ptA_i].h.m[t];
+                rx = (h[0] * xa + h[1] * ya + h[2]) / (h[6] * xa + h[7] * ya + h[8]);      // ApplyProject9 (M/MosaicWithoutPos.h:331-336)
+                ry = (h[3] * xa + h[4] * ya + h[5]) / (h[6] * xa + h[7] * ya + h[8]);
+            } else {
+                vals[0] = xa; vals[1] = ya; vals[2] = 1;
+                double h[9]; for (int t = 0; t < 9; t++) h[t] = init[m.ptB_i].h.m[t];
+                rx = (h[0] * xb + h[1] * yb + h[2]) / (h[6] * xb + h[7] * yb + h[8]);
+                ry = (h[3] * xb + h[4] * yb + h[5]) / (h[6] * xb + h[7] * yb + h[8]);
+            }
+            for (int a = 0; a < nc; a++) {
+                for (int b = 0; b <= a; b++) r.loc[a][b] += vals[a] * vals[b];          // symmetric: lower triangle of the block only
+                r.gx[a] += vals[a] * rx;
+                r.gy[a] += vals[a] * ry;
+            }
+        }
+    };
+    {
+        unsigned hw = std::thread::hardware_concurrency();
+        int T = std::min<int>(std::min<unsigned>(hw ? hw : 1, 8), n_chunks);
+        if (getenv("UAVM_ALIGN_THREADS")) T = std::max(1, std::min(atoi(getenv("UAVM_ALIGN_THREADS")), n_chunks));
+        if (T <= 1) { for (int c = 0; c < n_chunks; c++) do_chunk(c); }
+        else {
+            std::vector<std::thread> th;
+            for (int t = 0; t < T; t++)
+                th.emplace_back([&, t]() { for (int c = t; c < n_chunks; c += T) do_chunk(c); });
+            for (auto& x : th) x.join();
         }
     }
+    const auto t_par = std::chrono::steady_clock::now();
+    for (int c = 0; c < n_chunks; c++) if (chunk_bad[c]) return UAVM_EINVAL;
+    for (int c = 0; c < n_chunks; c++)                                            // blocks into N in list order: independent of T
+        for (const Run& r : chunk_runs[c])
+            for (int a = 0; a < r.nc; a++) {
+                const int ar = r.cols[a] + a % 3;
+                for (int b = 0; b < r.nc; b++) {
+                    const int bc = r.cols[b] + b % 3;
+                    if (bc <= ar) N[(size_t)ar * nu + bc] += b <= a ? r.loc[a][b] : r.loc[b][a];   // the factorisation reads the lower triangle only
+                }
+                gx[ar] += r.gx[a]; gy[ar] += r.gy[a];
+            }
+    const auto t_acc = std::chrono::steady_clock::now();
     if (cholesky_solve2(N, gx, gy, nu) != 0) return UAVM_EFAIL;
+    if (getenv("UAVM_ALIGN_TIMING")) fprintf(stderr, "align: alloc %.3f ms, runs %.3f ms, accumulate %.3f ms, solve %.3f ms (nu = %d)\n", std::chrono::duration<double, std::milli>(t_alloc - t_begin).count(), std::chrono::duration<double, std::milli>(t_par - t_alloc).count(), std::chrono::duration<double, std::milli>(t_acc - t_begin).count(), std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_acc).count(), nu);
     int k = 0;
     for (int i = 0; i < n_images; i++) {
         if (init[i].fixed == 0) {

@@ -556,22 +556,22 @@ extern "C" int uavm_canvas_create(uavm_ctx* ctx, int n_images, int img_w, int im
         if (c.chip_h > cv->max_chip_h) cv->max_chip_h = c.chip_h;
     }
     cv->chips_bytes = chip_off; cv->masks_bytes = mask_off;
-    UAVM_CUDA(ctx, cudaSetDevice(ctx->device));
-    UAVM_CUDA(ctx, cudaMalloc(&cv->d_src, (size_t)n_images * img_h * cv->src_step_px * (cv->src_bgr ? 1 : sizeof(uchar4)) + 256));
-    UAVM_CUDA(ctx, cudaMalloc(&cv->d_chips, chip_off + 256));
-    UAVM_CUDA(ctx, cudaMalloc(&cv->d_masks, mask_off + 256));
-    UAVM_CUDA(ctx, cudaMemsetAsync(cv->d_chips, 0, chip_off + 256, ctx->stream));       // row padding stays zero
-    UAVM_CUDA(ctx, cudaMemsetAsync(cv->d_masks, 0, mask_off + 256, ctx->stream));
-    UAVM_CUDA(ctx, cudaMalloc(&cv->d_desc, (size_t)n_images * sizeof(ChipDesc)));
+    UAVM_CUDA_OR(ctx, cudaSetDevice(ctx->device), uavm_canvas_destroy(ctx, cv));
+    UAVM_CUDA_OR(ctx, cudaMalloc(&cv->d_src, (size_t)n_images * img_h * cv->src_step_px * (cv->src_bgr ? 1 : sizeof(uchar4)) + 256), uavm_canvas_destroy(ctx, cv));
+    UAVM_CUDA_OR(ctx, cudaMalloc(&cv->d_chips, chip_off + 256), uavm_canvas_destroy(ctx, cv));
+    UAVM_CUDA_OR(ctx, cudaMalloc(&cv->d_masks, mask_off + 256), uavm_canvas_destroy(ctx, cv));
+    UAVM_CUDA_OR(ctx, cudaMemsetAsync(cv->d_chips, 0, chip_off + 256, ctx->stream), uavm_canvas_destroy(ctx, cv));       // row padding stays zero
+    UAVM_CUDA_OR(ctx, cudaMemsetAsync(cv->d_masks, 0, mask_off + 256, ctx->stream), uavm_canvas_destroy(ctx, cv));
+    UAVM_CUDA_OR(ctx, cudaMalloc(&cv->d_desc, (size_t)n_images * sizeof(ChipDesc)), uavm_canvas_destroy(ctx, cv));
     cv->stage_pitch = (img_w * 3 + 15) & ~15;
     cv->stage_bytes = (size_t)img_h * cv->stage_pitch;
     for (int s = 0; s < uavm_canvas::kStageSlots; s++) {
-        if (!cv->src_bgr) UAVM_CUDA(ctx, cudaMalloc(&cv->d_stage[s], cv->stage_bytes));
-        UAVM_CUDA(ctx, cudaEventCreateWithFlags(&cv->ev_copied[s], cudaEventDisableTiming));
-        UAVM_CUDA(ctx, cudaEventCreateWithFlags(&cv->ev_free[s], cudaEventDisableTiming));
+        if (!cv->src_bgr) UAVM_CUDA_OR(ctx, cudaMalloc(&cv->d_stage[s], cv->stage_bytes), uavm_canvas_destroy(ctx, cv));
+        UAVM_CUDA_OR(ctx, cudaEventCreateWithFlags(&cv->ev_copied[s], cudaEventDisableTiming), uavm_canvas_destroy(ctx, cv));
+        UAVM_CUDA_OR(ctx, cudaEventCreateWithFlags(&cv->ev_free[s], cudaEventDisableTiming), uavm_canvas_destroy(ctx, cv));
     }
     if (cv->src_bgr)
-        for (int e = 0; e < uavm_canvas::kWarpEvents; e++) UAVM_CUDA(ctx, cudaEventCreateWithFlags(&cv->ev_warp[e], cudaEventDisableTiming));
+        for (int e = 0; e < uavm_canvas::kWarpEvents; e++) UAVM_CUDA_OR(ctx, cudaEventCreateWithFlags(&cv->ev_warp[e], cudaEventDisableTiming), uavm_canvas_destroy(ctx, cv));
     for (int k = 0; k < n_images; k++) {
         ChipDesc& d = cv->desc[k];
         d.src = cv->src_bgr ? reinterpret_cast<const uchar4*>(reinterpret_cast<const uint8_t*>(cv->d_src) + (size_t)k * img_h * cv->src_step_px)

@@ -187,15 +187,15 @@ extern "C" int uavm_featureset_create(uavm_ctx* ctx, int n_images, const int32_t
     }
     if (rows > 0x7fffff00LL) { delete fs; UAVM_SET_ERR(ctx, "feature pool too large"); return UAVM_EINVAL; }
     fs->pool_rows = rows;
-    UAVM_CUDA(ctx, cudaSetDevice(ctx->device));
-    UAVM_CUDA(ctx, cudaMalloc(&fs->d_desc, (size_t)rows * 128));
-    UAVM_CUDA(ctx, cudaMalloc(&fs->d_norm, (size_t)rows * 4));
-    UAVM_CUDA(ctx, cudaMalloc(&fs->d_ckey, (size_t)rows * 4));
-    UAVM_CUDA(ctx, cudaMalloc(&fs->d_kp, (size_t)rows * 8));
+    UAVM_CUDA_OR(ctx, cudaSetDevice(ctx->device), uavm_featureset_destroy(ctx, fs));
+    UAVM_CUDA_OR(ctx, cudaMalloc(&fs->d_desc, (size_t)rows * 128), uavm_featureset_destroy(ctx, fs));
+    UAVM_CUDA_OR(ctx, cudaMalloc(&fs->d_norm, (size_t)rows * 4), uavm_featureset_destroy(ctx, fs));
+    UAVM_CUDA_OR(ctx, cudaMalloc(&fs->d_ckey, (size_t)rows * 4), uavm_featureset_destroy(ctx, fs));
+    UAVM_CUDA_OR(ctx, cudaMalloc(&fs->d_kp, (size_t)rows * 8), uavm_featureset_destroy(ctx, fs));
     fs->stage_bytes = (size_t)(max_n > 0 ? max_n : 1) * 128 * sizeof(float);
-    UAVM_CUDA(ctx, cudaMalloc(&fs->d_stage, fs->stage_bytes));
-    UAVM_CUDA(ctx, cudaMemsetAsync(fs->d_desc, 0, (size_t)rows * 128, ctx->stream));
-    UAVM_CUDA(ctx, cudaMemsetAsync(fs->d_kp, 0, (size_t)rows * 8, ctx->stream));
+    UAVM_CUDA_OR(ctx, cudaMalloc(&fs->d_stage, fs->stage_bytes), uavm_featureset_destroy(ctx, fs));
+    UAVM_CUDA_OR(ctx, cudaMemsetAsync(fs->d_desc, 0, (size_t)rows * 128, ctx->stream), uavm_featureset_destroy(ctx, fs));
+    UAVM_CUDA_OR(ctx, cudaMemsetAsync(fs->d_kp, 0, (size_t)rows * 8, ctx->stream), uavm_featureset_destroy(ctx, fs));
     k1_fill_sentinel<<<(unsigned)((rows + 255) / 256), 256, 0, ctx->stream>>>(fs->d_ckey, fs->d_norm, rows);
     UAVM_CHECK_LAUNCH(ctx);
     int rc = make_tmap(ctx, &fs->tmap_q, fs->d_desc, rows, 256);

@@ -38,6 +38,18 @@ struct uavm_ctx {
         }                                                                                        \
     } while (0)
 
+// same, but runs `cleanup` before returning (allocation paths: an OOM must not leak what was already allocated)
+#define UAVM_CUDA_OR(ctx, call, cleanup)                                                         \
+    do {                                                                                         \
+        cudaError_t e__ = (call);                                                                \
+        if (e__ != cudaSuccess) {                                                                \
+            UAVM_SET_ERR(ctx, "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+            cudaGetLastError();                                                                  \
+            cleanup;                                                                             \
+            return UAVM_EFAIL;                                                                   \
+        }                                                                                        \
+    } while (0)
+
 #define UAVM_CHECK_LAUNCH(ctx)                                                             \
     do {                                                                                   \
         cudaError_t e__ = cudaGetLastError();                                              \

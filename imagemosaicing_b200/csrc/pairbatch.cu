@@ -34,29 +34,29 @@ extern "C" int uavm_pairbatch_create(uavm_ctx* ctx, uavm_featureset* fs, int n_p
     }
     if (off > 0x7fffffffLL) { delete pb; return UAVM_EINVAL; }
     pb->total_q = off; pb->n_items = (int)items.size();
-    UAVM_CUDA(ctx, cudaSetDevice(ctx->device));
+    UAVM_CUDA_OR(ctx, cudaSetDevice(ctx->device), uavm_pairbatch_destroy(ctx, pb));
     size_t np = (size_t)n_pairs;
-    UAVM_CUDA(ctx, cudaMalloc(&pb->d_pairs, np * sizeof(PairDesc)));
-    UAVM_CUDA(ctx, cudaMalloc(&pb->d_items, (items.size() + 1) * sizeof(MatchItem)));
-    UAVM_CUDA(ctx, cudaMalloc(&pb->d_train_idx, (size_t)(off + 1) * 4));
-    UAVM_CUDA(ctx, cudaMalloc(&pb->d_d2, (size_t)(off + 1) * 4));
-    UAVM_CUDA(ctx, cudaMalloc(&pb->d_cand_xy1, np * UAVM_CAND_SLOTS * 8));
-    UAVM_CUDA(ctx, cudaMalloc(&pb->d_cand_xy2, np * UAVM_CAND_SLOTS * 8));
-    UAVM_CUDA(ctx, cudaMalloc(&pb->d_cand_id1, np * UAVM_CAND_SLOTS * 4));
-    UAVM_CUDA(ctx, cudaMalloc(&pb->d_cand_id2, np * UAVM_CAND_SLOTS * 4));
-    UAVM_CUDA(ctx, cudaMalloc(&pb->d_cand_n, np * 4));
-    UAVM_CUDA(ctx, cudaMalloc(&pb->d_tuple_res, np * UAVM_RANSAC_MAX_TUPLES_FIRST * 4));
-    UAVM_CUDA(ctx, cudaMalloc(&pb->d_tuple_h, np * UAVM_RANSAC_MAX_TUPLES_FIRST * 9 * 4));
-    UAVM_CUDA(ctx, cudaMalloc(&pb->d_inlier, np * UAVM_CAND_SLOTS));
-    UAVM_CUDA(ctx, cudaMalloc(&pb->d_res, np * sizeof(uavm_ransac_result)));
-    UAVM_CUDA(ctx, cudaMemcpyAsync(pb->d_pairs, pb->pairs.data(), np * sizeof(PairDesc), cudaMemcpyHostToDevice, ctx->stream));
+    UAVM_CUDA_OR(ctx, cudaMalloc(&pb->d_pairs, np * sizeof(PairDesc)), uavm_pairbatch_destroy(ctx, pb));
+    UAVM_CUDA_OR(ctx, cudaMalloc(&pb->d_items, (items.size() + 1) * sizeof(MatchItem)), uavm_pairbatch_destroy(ctx, pb));
+    UAVM_CUDA_OR(ctx, cudaMalloc(&pb->d_train_idx, (size_t)(off + 1) * 4), uavm_pairbatch_destroy(ctx, pb));
+    UAVM_CUDA_OR(ctx, cudaMalloc(&pb->d_d2, (size_t)(off + 1) * 4), uavm_pairbatch_destroy(ctx, pb));
+    UAVM_CUDA_OR(ctx, cudaMalloc(&pb->d_cand_xy1, np * UAVM_CAND_SLOTS * 8), uavm_pairbatch_destroy(ctx, pb));
+    UAVM_CUDA_OR(ctx, cudaMalloc(&pb->d_cand_xy2, np * UAVM_CAND_SLOTS * 8), uavm_pairbatch_destroy(ctx, pb));
+    UAVM_CUDA_OR(ctx, cudaMalloc(&pb->d_cand_id1, np * UAVM_CAND_SLOTS * 4), uavm_pairbatch_destroy(ctx, pb));
+    UAVM_CUDA_OR(ctx, cudaMalloc(&pb->d_cand_id2, np * UAVM_CAND_SLOTS * 4), uavm_pairbatch_destroy(ctx, pb));
+    UAVM_CUDA_OR(ctx, cudaMalloc(&pb->d_cand_n, np * 4), uavm_pairbatch_destroy(ctx, pb));
+    UAVM_CUDA_OR(ctx, cudaMalloc(&pb->d_tuple_res, np * UAVM_RANSAC_MAX_TUPLES_FIRST * 4), uavm_pairbatch_destroy(ctx, pb));
+    UAVM_CUDA_OR(ctx, cudaMalloc(&pb->d_tuple_h, np * UAVM_RANSAC_MAX_TUPLES_FIRST * 9 * 4), uavm_pairbatch_destroy(ctx, pb));
+    UAVM_CUDA_OR(ctx, cudaMalloc(&pb->d_inlier, np * UAVM_CAND_SLOTS), uavm_pairbatch_destroy(ctx, pb));
+    UAVM_CUDA_OR(ctx, cudaMalloc(&pb->d_res, np * sizeof(uavm_ransac_result)), uavm_pairbatch_destroy(ctx, pb));
+    UAVM_CUDA_OR(ctx, cudaMemcpyAsync(pb->d_pairs, pb->pairs.data(), np * sizeof(PairDesc), cudaMemcpyHostToDevice, ctx->stream), uavm_pairbatch_destroy(ctx, pb));
     if (!items.empty())
-        UAVM_CUDA(ctx, cudaMemcpyAsync(pb->d_items, items.data(), items.size() * sizeof(MatchItem), cudaMemcpyHostToDevice, ctx->stream));
+        UAVM_CUDA_OR(ctx, cudaMemcpyAsync(pb->d_items, items.data(), items.size() * sizeof(MatchItem), cudaMemcpyHostToDevice, ctx->stream), uavm_pairbatch_destroy(ctx, pb));
     // pairs with an empty train image have no match: trainIdx = -1
-    UAVM_CUDA(ctx, cudaMemsetAsync(pb->d_train_idx, 0xff, (size_t)(off + 1) * 4, ctx->stream));
-    UAVM_CUDA(ctx, cudaMemsetAsync(pb->d_d2, 0, (size_t)(off + 1) * 4, ctx->stream));
-    UAVM_CUDA(ctx, cudaMemsetAsync(pb->d_cand_n, 0, np * 4, ctx->stream));
-    UAVM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));     // host vectors go out of scope
+    UAVM_CUDA_OR(ctx, cudaMemsetAsync(pb->d_train_idx, 0xff, (size_t)(off + 1) * 4, ctx->stream), uavm_pairbatch_destroy(ctx, pb));
+    UAVM_CUDA_OR(ctx, cudaMemsetAsync(pb->d_d2, 0, (size_t)(off + 1) * 4, ctx->stream), uavm_pairbatch_destroy(ctx, pb));
+    UAVM_CUDA_OR(ctx, cudaMemsetAsync(pb->d_cand_n, 0, np * 4, ctx->stream), uavm_pairbatch_destroy(ctx, pb));
+    UAVM_CUDA_OR(ctx, cudaStreamSynchronize(ctx->stream), uavm_pairbatch_destroy(ctx, pb));     // host vectors go out of scope
     *out = pb;
     return UAVM_OK;
 }
@@ -263,8 +263,8 @@ extern "C" int uavm_select(uavm_ctx* ctx, const uavm_dmatch* matches, int n_matc
     int rc = uavm_featureset_create(ctx, 2, n, &fs);
     if (rc != UAVM_OK) return rc;
     int32_t ij[2] = {0, 1};
-    UAVM_CUDA(ctx, cudaMemcpyAsync(fs->d_kp + (size_t)fs->row0[0] * 2, kp1_xy, (size_t)n1 * 8, cudaMemcpyHostToDevice, ctx->stream));
-    UAVM_CUDA(ctx, cudaMemcpyAsync(fs->d_kp + (size_t)fs->row0[1] * 2, kp2_xy, (size_t)n2 * 8, cudaMemcpyHostToDevice, ctx->stream));
+    UAVM_CUDA_OR(ctx, cudaMemcpyAsync(fs->d_kp + (size_t)fs->row0[0] * 2, kp1_xy, (size_t)n1 * 8, cudaMemcpyHostToDevice, ctx->stream), uavm_featureset_destroy(ctx, fs));
+    UAVM_CUDA_OR(ctx, cudaMemcpyAsync(fs->d_kp + (size_t)fs->row0[1] * 2, kp2_xy, (size_t)n2 * 8, cudaMemcpyHostToDevice, ctx->stream), uavm_featureset_destroy(ctx, fs));
     rc = uavm_pairbatch_create(ctx, fs, 1, ij, &pb);
     if (rc == UAVM_OK) {
         cudaMemcpyAsync(pb->d_train_idx, ti.data(), (size_t)n1 * 4, cudaMemcpyHostToDevice, ctx->stream);
