@@ -323,6 +323,26 @@ def run_block200(args, ctx, nd, rank, world, dev):
             Tm = np.array([tr[kk].h.m[t] for t in range(9)], np.float64).reshape(3, 3)
             Tm[2] = [0, 0, 1]
             err.append(float(np.abs(synth.apply_h(G, corners) - synth.apply_h(Tm, corners)).max()))
+        # f3 (informational, untimed part of the step): the paper's rotation-constrained refinement on the same match list
+        rot = None
+        try:
+            init = (L.ImageTransform * n)(); tr2 = (L.ImageTransform * n)()
+            for i in range(n):
+                for t in range(9):
+                    init[i].h.m[t] = 1.0 if t in (0, 4, 8) else 0.0
+                init[i].fixed = 1 if (i == 0 or not label[i]) else 0
+            t0 = time.perf_counter()
+            rc2 = lib.uavm_align_affine_rot(out, n_used.value, init, n, int(sum(1 for i in range(n) if init[i].fixed)), C.c_float(100.0), 10, tr2)
+            rot_ms = (time.perf_counter() - t0) * 1e3
+            err2 = []
+            for kk in range(n):
+                if not label[kk]: continue
+                G = np.linalg.inv(poses[0]) @ poses[kk]
+                Tm = np.array([tr2[kk].h.m[t] for t in range(9)], np.float64).reshape(3, 3); Tm[2] = [0, 0, 1]
+                err2.append(float(np.abs(synth.apply_h(G, corners) - synth.apply_h(Tm, corners)).max()))
+            rot = {"rc": int(rc2), "ms_host": rot_ms, "weight": 100.0, "iterations": 10, "corner_error_px_max": max(err2), "corner_error_px_median": float(np.median(err2))}
+        except Exception as e:
+            rot = {"error": repr(e)}
         res = {"workload": f"configs[2]: {n}-image block ({rows} strips x {cols}), {W}x{H}, {NKP} kp/image, all {len(pairs)} pairs in overlap; strong scaling",
                "n_gpus": world, "pairs": int(len(pairs)), "accepted_pairs": int(n_acc.value), "inlier_matches": int(n_out.value),
                "pair_path_ms": float(tt[0]), "allgather_ms": float(tt[1]), "connectivity_plus_alignment_ms": float(tt[2]),
@@ -330,6 +350,7 @@ def run_block200(args, ctx, nd, rank, world, dev):
                "unknowns": 6 * (int(sum(label)) - 1), "connected_images": int(sum(label)),
                "match_list_crc32": crc_of(C.string_at(out, n_out.value * 40)), "transforms_crc32": crc_of(C.string_at(tr, n * 40)),
                "corner_error_px_max": max(err) if err else None, "corner_error_px_median": float(np.median(err)) if err else None,
+               "rot_constrained_refinement": rot,
                "note": "timed: match+select+RANSAC on the shard (CUDA events), uavm_pairbatch_allgather and uavm_global_align (host clock), max over ranks; "
                        "match_list_crc32 is taken after uavm_global_align compacted the list and set the fixed flags (the content of matchPairs.txt)",
                "synth_s": t_synth}

@@ -383,6 +383,20 @@ def ransac2d(ctx, xy1, xy2, ransac_dist=2.5, sample_times=1000, seed=1):
     return res.ok, mask, np.array(list(res.H), np.float32), res
 
 
+def align_affine_rot(matches, n_matches, n_images, fixed, weight=100.0, iterations=10):
+    """f3: SparseAffineRotConstraint (M/MosaicWithoutPos.cpp:6302-6808) on a MatchPointPairs ctypes array whose fixed flags are
+    set; `fixed`: (n_images,) 0/1.  Returns (n_images, 9) float32 transforms."""
+    init = (ImageTransform * n_images)(); out = (ImageTransform * n_images)()
+    for i in range(n_images):
+        for t in range(9):
+            init[i].h.m[t] = 1.0 if t in (0, 4, 8) else 0.0
+        init[i].fixed = int(fixed[i])
+    rc = L.lib().uavm_align_affine_rot(matches, int(n_matches), init, int(n_images), int(sum(int(f) for f in fixed)), C.c_float(weight), int(iterations), out)
+    if rc != 0:
+        raise UavmError(f"uavm_align_affine_rot failed with {rc}")
+    return np.array([[out[i].h.m[t] for t in range(9)] for i in range(n_images)], np.float32)
+
+
 # ---- warp / seam masks / blend --------------------------------------------------------------------
 def canvas_layout(H, keep, img_w, img_h):
     """Canvas sizing + chip boxes (M/MosaicImage.cpp:2233-2348), host side."""

@@ -231,3 +231,165 @@ extern "C" int uavm_align_affine(const uavm_matchpointpairs* pairs, int n_pairs,
     }
     return UAVM_OK;
 }
+
+
+// ------------------------------------------------------------------------------------------------------------------------------
+// f3: the constrained variants of the global alignment (dead code in the shipped reference — `methodType = 0`,
+// M/MosaicWithoutPos.cpp:4588 — but part of the paper's method and of SURVEY §8 f3):
+//   uavm_align_affine_constrained  <- BundleAdjustmentSparseConstraint (:6032-6300): the affine least squares plus, per free image,
+//                                     the soft similarity constraints nC (a - d) = 0 and nC (b + c) = 0, nC = number of its
+//                                     non-fixed match points (the reference pushes the same row nC times, which sums to nC)
+//   uavm_align_affine_rot          <- SparseAffineRotConstraint (:6302-6808): starts from the result above and runs 10 Gauss-Newton
+//                                     steps on the match residuals plus, per free image, w (a b + c d), w (a^2 + c^2 - 1),
+//                                     w (b^2 + d^2 - 1) with w = int(nC * weight) (Jacobian rows and residuals both scaled by w,
+//                                     as in the reference), each step one sparse Cholesky solve (SolveSparseSystem2).
+// Unknown order per free image: a b c d e f with x' = a x + b y + e, y' = c x + d y + f (:6390-6400).  The systems couple a..d, so
+// the x / y decoupling of uavm_align_affine does not apply; the envelope Cholesky above is used on 6 (N - nFixed) unknowns.
+namespace {
+
+struct MatchSystem {
+    int nu = 0;
+    std::vector<double> N, g;            // A^T A (full symmetric storage) and A^T b of the match rows
+    std::vector<int> acc_fixed, freq;    // images fixed before i; non-fixed match points per image
+};
+
+int build_match_system(const uavm_matchpointpairs* pairs, int n_pairs, const uavm_imagetransform* init, int n_images, int n_fixed, MatchSystem& S)
+{
+    S.acc_fixed.assign(n_images, 0); S.freq.assign(n_images, 0);
+    int nf = 0;
+    for (int i = 0; i < n_images; i++) { S.acc_fixed[i] = nf; if (init[i].fixed == 1) nf++; }
+    if (n_fixed >= 0 && n_fixed != nf) return UAVM_EINVAL;
+    S.nu = 6 * (n_images - nf);
+    if (S.nu <= 0 || S.nu > 12000) return UAVM_EFAIL;
+    const int nu = S.nu;
+    S.N.assign((size_t)nu * nu, 0.0); S.g.assign(nu, 0.0);
+    static const int slot_x[3] = {0, 1, 4}, slot_y[3] = {2, 3, 5};
+    for (int n = 0; n < n_pairs; n++) {
+        const uavm_matchpointpairs& m = pairs[n];
+        if (m.ptA_i < 0 || m.ptA_i >= n_images || m.ptB_i < 0 || m.ptB_i >= n_images) return UAVM_EINVAL;
+        if (m.ptA_Fixed == 0) S.freq[m.ptA_i]++;
+        if (m.ptB_Fixed == 0) S.freq[m.ptB_i]++;
+        int cols[6]; double vals[6]; int nc = 0; double rx = 0, ry = 0;
+        const double xa = m.ptA.x, ya = m.ptA.y, xb = m.ptB.x, yb = m.ptB.y;
+        if (m.ptA_Fixed == 0 && m.ptB_Fixed == 0) {
+            const int ca = 6 * (m.ptA_i - S.acc_fixed[m.ptA_i]), cb = 6 * (m.ptB_i - S.acc_fixed[m.ptB_i]);
+            cols[0] = cols[1] = cols[2] = ca; vals[0] = xa; vals[1] = ya; vals[2] = 1;
+            cols[3] = cols[4] = cols[5] = cb; vals[3] = -xb; vals[4] = -yb; vals[5] = -1; nc = 6;
+        } else if (m.ptA_Fixed == 1 && m.ptB_Fixed == 0) {
+            const int cb = 6 * (m.ptB_i - S.acc_fixed[m.ptB_i]);
+            cols[0] = cols[1] = cols[2] = cb; vals[0] = xb; vals[1] = yb; vals[2] = 1; nc = 3;
+            double h[9]; for (int t = 0; t < 9; t++) h[t] = init[m.ptA_i].h.m[t];
+            rx = (h[0] * xa + h[1] * ya + h[2]) / (h[6] * xa + h[7] * ya + h[8]);
+            ry = (h[3] * xa + h[4] * ya + h[5]) / (h[6] * xa + h[7] * ya + h[8]);
+        } else if (m.ptA_Fixed == 0 && m.ptB_Fixed == 1) {
+            const int ca = 6 * (m.ptA_i - S.acc_fixed[m.ptA_i]);
+            cols[0] = cols[1] = cols[2] = ca; vals[0] = xa; vals[1] = ya; vals[2] = 1; nc = 3;
+            double h[9]; for (int t = 0; t < 9; t++) h[t] = init[m.ptB_i].h.m[t];
+            rx = (h[0] * xb + h[1] * yb + h[2]) / (h[6] * xb + h[7] * yb + h[8]);
+            ry = (h[3] * xb + h[4] * yb + h[5]) / (h[6] * xb + h[7] * yb + h[8]);
+        } else continue;
+        for (int a = 0; a < nc; a++) {
+            if (cols[a] < 0 || cols[a] + 5 >= nu) return UAVM_EINVAL;
+            const int ax = cols[a] + slot_x[a % 3], ay = cols[a] + slot_y[a % 3];
+            for (int b = 0; b < nc; b++) {
+                S.N[(size_t)ax * nu + cols[b] + slot_x[b % 3]] += vals[a] * vals[b];
+                S.N[(size_t)ay * nu + cols[b] + slot_y[b % 3]] += vals[a] * vals[b];
+            }
+            S.g[ax] += vals[a] * rx;
+            S.g[ay] += vals[a] * ry;
+        }
+    }
+    return UAVM_OK;
+}
+
+void unpack6(const std::vector<double>& x, const uavm_imagetransform* init, int n_images, uavm_imagetransform* out)
+{
+    int k = 0;
+    for (int i = 0; i < n_images; i++) {
+        if (init[i].fixed == 0) {
+            uavm_imagetransform t; memset(&t, 0, sizeof(t));
+            t.h.m[0] = (float)x[6 * k + 0]; t.h.m[1] = (float)x[6 * k + 1]; t.h.m[3] = (float)x[6 * k + 2]; t.h.m[4] = (float)x[6 * k + 3];
+            t.h.m[2] = (float)x[6 * k + 4]; t.h.m[5] = (float)x[6 * k + 5]; t.h.m[8] = 1;
+            out[i] = t; k++;
+        } else out[i] = init[i];
+    }
+}
+
+int solve_sym(std::vector<double>& N, std::vector<double>& b, int n)
+{
+    std::vector<double> dummy(n, 0.0);
+    return cholesky_solve2(N, b, dummy, n);
+}
+
+}  // namespace
+
+extern "C" int uavm_align_affine_constrained(const uavm_matchpointpairs* pairs, int n_pairs, const uavm_imagetransform* init, int n_images,
+                                             int n_fixed, uavm_imagetransform* out)
+{
+    if (!pairs || n_pairs <= 0 || !init || !out) return UAVM_EINVAL;
+    if (n_images <= 1) return UAVM_EFAIL;
+    MatchSystem S;
+    int rc = build_match_system(pairs, n_pairs, init, n_images, n_fixed, S);
+    if (rc != UAVM_OK) return rc;
+    const int nu = S.nu;
+    for (int i = 0; i < n_images; i++) {                  // nC (a - d) = 0, nC (b + c) = 0 (:6228-6241)
+        if (init[i].fixed == 1) continue;
+        const int u = 6 * (i - S.acc_fixed[i]);
+        const double w2 = (double)S.freq[i] * (double)S.freq[i];
+        S.N[(size_t)(u + 0) * nu + u + 0] += w2; S.N[(size_t)(u + 3) * nu + u + 3] += w2;
+        S.N[(size_t)(u + 0) * nu + u + 3] -= w2; S.N[(size_t)(u + 3) * nu + u + 0] -= w2;
+        S.N[(size_t)(u + 1) * nu + u + 1] += w2; S.N[(size_t)(u + 2) * nu + u + 2] += w2;
+        S.N[(size_t)(u + 1) * nu + u + 2] += w2; S.N[(size_t)(u + 2) * nu + u + 1] += w2;
+    }
+    std::vector<double> x(S.g);
+    if (solve_sym(S.N, x, nu) != 0) return UAVM_EFAIL;
+    unpack6(x, init, n_images, out);
+    return UAVM_OK;
+}
+
+extern "C" int uavm_align_affine_rot(const uavm_matchpointpairs* pairs, int n_pairs, const uavm_imagetransform* init, int n_images,
+                                     int n_fixed, float weight, int iterations, uavm_imagetransform* out)
+{
+    if (!pairs || n_pairs <= 0 || !init || !out || iterations < 0) return UAVM_EINVAL;
+    if (n_images <= 1) return UAVM_EFAIL;
+    int rc = uavm_align_affine_constrained(pairs, n_pairs, init, n_images, n_fixed, out);        // initial value (:6374)
+    if (rc != UAVM_OK) return rc;
+    MatchSystem S;
+    rc = build_match_system(pairs, n_pairs, init, n_images, n_fixed, S);
+    if (rc != UAVM_OK) return rc;
+    const int nu = S.nu;
+    std::vector<double> X(nu, 0.0);
+    std::vector<int> img_of(nu / 6, 0);
+    for (int i = 0, k = 0; i < n_images; i++)
+        if (init[i].fixed == 0) {                          // pX from the float transforms (:6380-6393)
+            X[6 * k + 0] = out[i].h.m[0]; X[6 * k + 1] = out[i].h.m[1]; X[6 * k + 2] = out[i].h.m[3]; X[6 * k + 3] = out[i].h.m[4];
+            X[6 * k + 4] = out[i].h.m[2]; X[6 * k + 5] = out[i].h.m[5];
+            img_of[k++] = i;
+        }
+    std::vector<double> Nt, rhs(nu);
+    for (int it = 0; it < iterations; it++) {              // MAX_ITER = 10 (:6404), no convergence test
+        Nt = S.N;
+        for (int r = 0; r < nu; r++) {                     // A^T (A X - b)
+            double acc = -S.g[r];
+            const double* row = &S.N[(size_t)r * nu];
+            for (int c = 0; c < nu; c++) acc += row[c] * X[c];
+            rhs[r] = acc;
+        }
+        for (int k = 0; k < nu / 6; k++) {
+            const int u = 6 * k;
+            const double a = X[u], b = X[u + 1], c = X[u + 2], d = X[u + 3];
+            const double w = (double)(int)((float)S.freq[img_of[k]] * weight);            // freqMatch[n] *= weight (int), wRot = nC (:6334-6338, :6637)
+            const double J[3][4] = {{w * b, w * a, w * d, w * c}, {w * 2 * a, 0, w * 2 * c, 0}, {0, w * 2 * b, 0, w * 2 * d}};
+            const double res[3] = {w * (a * b + c * d), w * (a * a + c * c - 1), w * (b * b + d * d - 1)};
+            for (int q = 0; q < 3; q++)
+                for (int i = 0; i < 4; i++) {
+                    rhs[u + i] += J[q][i] * res[q];
+                    for (int j = 0; j < 4; j++) Nt[(size_t)(u + i) * nu + u + j] += J[q][i] * J[q][j];
+                }
+        }
+        if (solve_sym(Nt, rhs, nu) != 0) return UAVM_EFAIL;
+        for (int r = 0; r < nu; r++) X[r] -= rhs[r];       // pX = pX - pDX (:6655-6656)
+    }
+    unpack6(X, init, n_images, out);
+    return UAVM_OK;
+}

@@ -139,6 +139,14 @@ int uavm_ransac2d(uavm_ctx* ctx, const uavm_sfpoint* pts1, const uavm_sfpoint* p
 /* ---- K8 global affine alignment (host; replaces BundleAdjustmentSparse, :6971-7202) ----------- */
 int uavm_align_affine(const uavm_matchpointpairs* pairs, int n_pairs, const uavm_imagetransform* init, int n_images,
                       int n_fixed, uavm_imagetransform* out);
+/* f3, the constrained variants (dead code in the shipped reference, methodType = 0 at :4588): the affine least squares with the
+ * soft similarity constraints nC (a - d) = 0, nC (b + c) = 0 per free image (BundleAdjustmentSparseConstraint, :6032-6300), and the
+ * rotation-constrained Gauss-Newton refinement that starts from it (SparseAffineRotConstraint, :6302-6808; the reference runs
+ * 10 iterations; `weight` scales the per-image constraint weight int(nC * weight)). */
+int uavm_align_affine_constrained(const uavm_matchpointpairs* pairs, int n_pairs, const uavm_imagetransform* init, int n_images,
+                                  int n_fixed, uavm_imagetransform* out);
+int uavm_align_affine_rot(const uavm_matchpointpairs* pairs, int n_pairs, const uavm_imagetransform* init, int n_images,
+                          int n_fixed, float weight, int iterations, uavm_imagetransform* out);
 /* largest connected component of the pair graph (Select_Connected_Matched_Images, :2754-2796) */
 int uavm_connected_images(const uavm_matchpointpairs* pairs, int n_pairs, int n_images, int32_t* label);
 /* stages [B] + [C] of MosaicWithoutPose on a match list (:4501-4652): connectivity, unconnected matches dropped, reference image 0

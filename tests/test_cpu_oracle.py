@@ -448,3 +448,60 @@ def test_header_is_c99_and_links_from_c(tmp_path):
     assert r.returncode == 0, r.stdout
     r = subprocess.run([exe], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     assert r.returncode == 0 and "c consumer ok" in r.stdout, r.stdout
+
+
+def test_constrained_alignment_variants_vs_oracle():
+    """f3: uavm_align_affine_constrained / uavm_align_affine_rot (host C++) against the numpy restatement of
+    BundleAdjustmentSparseConstraint / SparseAffineRotConstraint; and the point of the variants: on a chain of images the
+    rotation-constrained solution is a near-similarity while the unconstrained affine fit drifts in scale / shear."""
+    from imagemosaicing_b200 import synth, _lib
+    from oracle import oracle_align as OA
+    rng = np.random.default_rng(12)
+    n, w, h = 8, 1000, 750
+    poses = [np.eye(3)]
+    for k in range(1, n):
+        a = np.deg2rad(rng.uniform(-4, 4))
+        poses.append(poses[-1] @ np.array([[np.cos(a), -np.sin(a), 420 + rng.uniform(-20, 20)], [np.sin(a), np.cos(a), rng.uniform(-30, 30)], [0, 0, 1]]))
+    rows = []
+    for i in range(n - 1):
+        for j in range(i + 1, min(n, i + 3)):
+            wp = synth.apply_h(poses[j], np.stack([rng.uniform(0, w - 1, 60), rng.uniform(0, h - 1, 60)], 1))
+            pi = synth.apply_h(np.linalg.inv(poses[i]), wp); pj = synth.apply_h(np.linalg.inv(poses[j]), wp)
+            ok = (pi[:, 0] >= 0) & (pi[:, 0] <= w - 1) & (pi[:, 1] >= 0) & (pi[:, 1] <= h - 1)
+            pi = pi[ok] + rng.normal(0, 0.7, (int(ok.sum()), 2)); pj = pj[ok]
+            for k in range(len(pi)):
+                rows.append([i, np.float32(pi[k, 0]), np.float32(pi[k, 1]), 1 if i == 0 else 0, j, np.float32(pj[k, 0]), np.float32(pj[k, 1]), 0])
+    m = np.array(rows, np.float64); fixed = np.zeros(n, np.int32); fixed[0] = 1
+    T0 = np.tile(np.eye(3, dtype=np.float32).reshape(1, 9), (n, 1))
+    arr = (_lib.MatchPointPairs * len(m))()
+    for k, p in enumerate(m):
+        arr[k].ptA.x, arr[k].ptA.y, arr[k].ptA_i, arr[k].ptA_Fixed = float(p[1]), float(p[2]), int(p[0]), int(p[3])
+        arr[k].ptB.x, arr[k].ptB.y, arr[k].ptB_i, arr[k].ptB_Fixed = float(p[5]), float(p[6]), int(p[4]), int(p[7])
+    init = (_lib.ImageTransform * n)(); out = (_lib.ImageTransform * n)()
+    for i in range(n):
+        for t in range(9):
+            init[i].h.m[t] = 1.0 if t in (0, 4, 8) else 0.0
+        init[i].fixed = int(fixed[i])
+    lib = _lib.lib()
+    get = lambda: np.array([[out[i].h.m[t] for t in range(9)] for i in range(n)], np.float32)
+    assert lib.uavm_align_affine_constrained(arr, len(m), init, n, 1, out) == 0
+    Tc = get()
+    assert np.allclose(Tc, OA.align_affine_constrained(m, fixed, T0), rtol=1e-5, atol=1e-3)
+    import ctypes as C
+    assert lib.uavm_align_affine_rot(arr, len(m), init, n, 1, C.c_float(1.0), 10, out) == 0
+    Tr = get()
+    assert np.allclose(Tr, OA.align_affine_rot(m, fixed, T0, 1.0, 10), rtol=1e-4, atol=5e-3)
+    assert lib.uavm_align_affine(arr, len(m), init, n, 1, out) == 0
+    Tu = get()
+    def nonsim(T):       # distance of the linear part from a rotation
+        a, b, c, d = T[1:, 0], T[1:, 1], T[1:, 3], T[1:, 4]
+        return np.max(np.abs(a * a + c * c - 1) + np.abs(b * b + d * d - 1) + np.abs(a * b + c * d))
+    corners = np.array([[0, 0], [w - 1, 0], [w - 1, h - 1], [0, h - 1]], np.float64)
+    err = lambda T: max(np.abs(synth.apply_h(poses[k], corners) - synth.apply_h(T[k].reshape(3, 3).astype(np.float64), corners)).max() for k in range(1, n))
+    # with a strong constraint weight the solution is a near-rotation and does not drift more than the free affine fit
+    assert lib.uavm_align_affine_rot(arr, len(m), init, n, 1, C.c_float(100.0), 10, out) == 0
+    Ts = get()
+    assert np.allclose(Ts, OA.align_affine_rot(m, fixed, T0, 100.0, 10), rtol=1e-4, atol=5e-3)
+    print("non-similarity: free", nonsim(Tu), "rot w=1", nonsim(Tr), "rot w=100", nonsim(Ts), "corner err", err(Tu), err(Tr), err(Ts))
+    assert nonsim(Ts) < 0.25 * nonsim(Tu)
+    assert err(Ts) < err(Tu) + 1.0
