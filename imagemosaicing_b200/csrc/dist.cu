@@ -31,6 +31,7 @@ struct NcclApi {
     decltype(&ncclGroupEnd) GroupEnd = nullptr;
     decltype(&ncclGetErrorString) GetErrorString = nullptr;
     decltype(&ncclBroadcast) Broadcast = nullptr;
+    decltype(&ncclAllReduce) AllReduce = nullptr;
 };
 NcclApi g_nccl;
 
@@ -47,7 +48,7 @@ const char* load_nccl()
 #define UAVM_SYM(field, name) g_nccl.field = (decltype(g_nccl.field))dlsym(h, name); if (!g_nccl.field) return "NCCL symbol " name " missing";
     UAVM_SYM(GetUniqueId, "ncclGetUniqueId") UAVM_SYM(CommInitRank, "ncclCommInitRank") UAVM_SYM(CommDestroy, "ncclCommDestroy")
     UAVM_SYM(AllGather, "ncclAllGather") UAVM_SYM(Send, "ncclSend") UAVM_SYM(Recv, "ncclRecv") UAVM_SYM(GroupStart, "ncclGroupStart")
-    UAVM_SYM(GroupEnd, "ncclGroupEnd") UAVM_SYM(GetErrorString, "ncclGetErrorString") UAVM_SYM(Broadcast, "ncclBroadcast")
+    UAVM_SYM(GroupEnd, "ncclGroupEnd") UAVM_SYM(GetErrorString, "ncclGetErrorString") UAVM_SYM(Broadcast, "ncclBroadcast") UAVM_SYM(AllReduce, "ncclAllReduce")
 #undef UAVM_SYM
     g_nccl.handle = h;
     return nullptr;
@@ -173,6 +174,9 @@ struct uavm_dist {
     uavm_matchpointpairs* d_dense = nullptr; size_t dense_cap = 0;
     // canvas gather workspace (root)
     uint8_t* d_tmp = nullptr; size_t tmp_cap = 0;
+    // direct gather: the root's result buffer mapped into this process (CUDA IPC), keyed by its handle
+    uint8_t* d_ipc = nullptr;                         // [64 handle bytes | 4-byte barrier word]
+    cudaIpcMemHandle_t peer_handle; void* peer_ptr = nullptr; bool peer_failed = false;
 };
 
 extern "C" int uavm_dist_unique_id(uint8_t* id_out, int id_bytes)
@@ -207,6 +211,8 @@ extern "C" void uavm_dist_destroy(uavm_ctx* ctx, uavm_dist* d)
     if (!d) return;
     if (ctx) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
     cudaFree(d->d_send); cudaFree(d->d_recv); cudaFree(d->d_offsets); cudaFree(d->d_nacc); cudaFree(d->d_dense); cudaFree(d->d_tmp);
+    if (d->peer_ptr) cudaIpcCloseMemHandle(d->peer_ptr);
+    cudaFree(d->d_ipc);
     if (d->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(d->comm);
     delete d;
 }
@@ -286,6 +292,50 @@ extern "C" int uavm_canvas_gather(uavm_ctx* ctx, uavm_dist* d, uavm_canvas* cv, 
     auto bytes = [&](int r) { const int32_t* q = rects + 4 * r; return (size_t)(q[2] - q[0]) * (size_t)(q[3] - q[1]) * 3; };
     auto full_width = [&](int r) { const int32_t* q = rects + 4 * r; return q[0] == 0 && q[2] == W; };
     if (d->world == 1) return UAVM_OK;
+    // Direct path: every rank writes its rectangle straight into the root's result buffer over NVLink (the buffer is mapped
+    // with CUDA IPC; one strided peer copy per rank, no packing, no staging on the root); a tiny all-reduce, stream-ordered
+    // after the copies, tells the root that every rectangle has landed.  Falls back to grouped ncclSend / ncclRecv when the
+    // mapping is not possible (all ranks in ONE process, or IPC unavailable).
+    if (!getenv("UAVM_GATHER_NCCL")) {
+        if (!d->d_ipc) UAVM_CUDA(ctx, cudaMalloc(&d->d_ipc, 128));
+        cudaIpcMemHandle_t h; memset(&h, 0, sizeof(h));
+        int ok_local = 1;
+        if (d->rank == root) {
+            if (cudaIpcGetMemHandle(&h, cv->d_result) != cudaSuccess) { cudaGetLastError(); ok_local = 0; memset(&h, 0, sizeof(h)); }
+            UAVM_CUDA(ctx, cudaMemcpyAsync(d->d_ipc, &h, sizeof(h), cudaMemcpyHostToDevice, ctx->stream));
+        }
+        UAVM_NCCL(ctx, g_nccl.Broadcast(d->d_ipc, d->d_ipc, sizeof(h), ncclInt8, root, d->comm, ctx->stream));
+        if (d->rank != root) {
+            UAVM_CUDA(ctx, cudaMemcpyAsync(&h, d->d_ipc, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+            UAVM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            bool zero = true;
+            for (size_t i = 0; i < sizeof(h); i++) if (((const char*)&h)[i]) { zero = false; break; }
+            if (zero || d->peer_failed) ok_local = 0;
+            else if (!d->peer_ptr || memcmp(&h, &d->peer_handle, sizeof(h)) != 0) {
+                if (d->peer_ptr) { cudaIpcCloseMemHandle(d->peer_ptr); d->peer_ptr = nullptr; }
+                if (cudaIpcOpenMemHandle(&d->peer_ptr, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); d->peer_ptr = nullptr; d->peer_failed = true; ok_local = 0; }
+                else d->peer_handle = h;
+            }
+        }
+        // agree on the path (all ranks must take the same one): sum of the "cannot" flags
+        int* d_flag = reinterpret_cast<int*>(d->d_ipc + 64);
+        const int cannot = ok_local ? 0 : 1;
+        UAVM_CUDA(ctx, cudaMemcpyAsync(d_flag, &cannot, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+        UAVM_NCCL(ctx, g_nccl.AllReduce(d_flag, d_flag, 1, ncclInt32, ncclSum, d->comm, ctx->stream));
+        int n_cannot = 0;
+        UAVM_CUDA(ctx, cudaMemcpyAsync(&n_cannot, d_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        UAVM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (n_cannot == 0) {
+            if (d->rank != root && bytes(d->rank) > 0) {
+                const int32_t* q = rects + 4 * d->rank;
+                const size_t off = ((size_t)q[1] * W + q[0]) * 3;
+                UAVM_CUDA(ctx, cudaMemcpy2DAsync(static_cast<uint8_t*>(d->peer_ptr) + off, (size_t)W * 3, cv->d_result + off, (size_t)W * 3,
+                                                 (size_t)(q[2] - q[0]) * 3, (size_t)(q[3] - q[1]), cudaMemcpyDeviceToDevice, ctx->stream));
+            }
+            UAVM_NCCL(ctx, g_nccl.AllReduce(d_flag, d_flag, 1, ncclInt32, ncclSum, d->comm, ctx->stream));     // completion barrier
+            return UAVM_OK;
+        }
+    }
     if (d->rank != root) {
         const int32_t* q = rects + 4 * d->rank;
         if (bytes(d->rank) == 0) return UAVM_OK;
