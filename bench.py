@@ -399,7 +399,8 @@ def run_canvas500(args, ctx, nd, rank, world, dev):
 
     def run():
         e = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
-        e[0].record(); cv.warp(); e[1].record(); cv.seam_masks(); e[2].record(); cv.blend(5); e[3].record()
+        # the pipeline's order (uavm_mosaic_images): K6 first (it needs no pixels), K5 only where the blend reads, K7
+        e[0].record(); cv.seam_masks(); e[1].record(); cv.warp_for_blend(); e[2].record(); cv.blend(5); e[3].record()
         if world > 1:
             nd.gather_canvas(cv, rects, root=0)
         e[4].record()
@@ -423,7 +424,7 @@ def run_canvas500(args, ctx, nd, rank, world, dev):
             v = buf[:y1 - y0].to(torch.int64)
             chk[0] += int(v.sum()); chk[1] = (chk[1] + int((v * wgt[:y1 - y0]).sum()) * (1 + y0 // rows_per)) % (1 << 61)
         del buf, wgt
-        warp_ms, seam_ms, blend_ms, gather_ms, total_ms = [float(x) for x in tt]
+        seam_ms, warp_ms, blend_ms, gather_ms, total_ms = [float(x) for x in tt]
         compulsory = int(keep.sum()) * W * H * 3 + cw * ch * 3
         model = chip_px * 40 + cw * ch * 32        # SURVEY §8d multi-pass model: ~40 B per fed chip pixel + ~32 B per canvas pixel
         pk = peaks()
@@ -435,7 +436,8 @@ def run_canvas500(args, ctx, nd, rank, world, dev):
                "multipass_model_gb": model / 1e9, "multipass_model_ms_at_hbm_peak": model / 1e9 / (pk["hbm_gbs"] * world) * 1e3,
                "frac_of_multipass_model_roofline": model / 1e9 / (pk["hbm_gbs"] * world) * 1e3 / total_ms,
                "active_tiles_rank0": n_active, "hbm_used_gb_rank0": (total - torch.cuda.mem_get_info()[0]) / 1e9,
-               "note": "CUDA events, best of 2 after a warm-up, max over ranks; frames synthesised on the device"}
+               "note": "order: seam masks, warp of the chip pixels the blend reads (uavm_canvas_warp_for_blend), blend, gather; CUDA events, best of 2 "
+                       "after a warm-up, max over ranks; frames synthesised on the device"}
     cv.close()
     return res
 

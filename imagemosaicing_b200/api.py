@@ -465,6 +465,10 @@ class Canvas:
         else:
             self.ctx.check(L.lib().uavm_canvas_warp_range(self.ctx._h, self._h, int(first), int(count)))
 
+    def warp_for_blend(self):
+        """K5 restricted to what the blend reads (needs seam_masks() first); uavm_canvas_warp_for_blend."""
+        self.ctx.check(L.lib().uavm_canvas_warp_for_blend(self.ctx._h, self._h))
+
     def seam_masks(self):
         self.ctx.check(L.lib().uavm_canvas_seam_masks(self.ctx._h, self._h))
 

@@ -593,6 +593,8 @@ extern "C" int uavm_canvas_create(uavm_ctx* ctx, int n_images, int img_w, int im
                             (uint64_t)cv->src_step_px * 4, kFpBoxW, kFpBoxH, 0) == UAVM_OK)
         cv->tmap_src_ok = true;
     cv->rect_x0 = 0; cv->rect_y0 = 0; cv->rect_x1 = cv->layout.canvas_w; cv->rect_y1 = cv->layout.canvas_h;
+    cv->need_base.resize((size_t)n_images * 4);
+    for (int k = 0; k < n_images; k++) { cv->need_base[4 * k] = cv->desc[k].need_x0; cv->need_base[4 * k + 1] = cv->desc[k].need_y0; cv->need_base[4 * k + 2] = cv->desc[k].need_x1; cv->need_base[4 * k + 3] = cv->desc[k].need_y1; }
     rc = uavm_canvas_upload_desc(ctx, cv);
     if (rc != UAVM_OK) { uavm_canvas_destroy(ctx, cv); return rc; }
     *out = cv;
@@ -644,6 +646,8 @@ extern "C" int uavm_canvas_set_rect(uavm_ctx* ctx, uavm_canvas* cv, int x0, int 
         if (d.keep) { if (c.chip_w > cv->max_chip_w) cv->max_chip_w = c.chip_w; if (c.chip_h > cv->max_chip_h) cv->max_chip_h = c.chip_h; }
     }
     cv->lines_dirty = true; cv->warped = false; cv->seamed = false; cv->blended = false; cv->mask_plane_valid = false; cv->own_bbox_valid = false;
+    for (int k = 0; k < cv->n; k++) { cv->need_base[4 * k] = cv->desc[k].need_x0; cv->need_base[4 * k + 1] = cv->desc[k].need_y0; cv->need_base[4 * k + 2] = cv->desc[k].need_x1; cv->need_base[4 * k + 3] = cv->desc[k].need_y1; }
+    cv->need_narrowed = false;
     return uavm_canvas_upload_desc(ctx, cv);
 }
 // horizontal band [y0, y1) of the canvas.  `halo` is accepted for source compatibility and ignored: K7 derives what a
@@ -741,6 +745,11 @@ extern "C" int uavm_canvas_warp_range(uavm_ctx* ctx, uavm_canvas* cv, int first,
     if (!ctx || !cv || first < 0 || count < 0 || first + count > cv->n) return UAVM_EINVAL;
     if (cv->max_chip_w <= 0 || count == 0) return UAVM_OK;
     UAVM_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (cv->need_narrowed && !cv->in_warp_for_blend) {         // a plain warp after uavm_canvas_warp_for_blend produces whole chips again
+        for (int k = 0; k < cv->n; k++) { cv->desc[k].need_x0 = cv->need_base[4 * k]; cv->desc[k].need_y0 = cv->need_base[4 * k + 1]; cv->desc[k].need_x1 = cv->need_base[4 * k + 2]; cv->desc[k].need_y1 = cv->need_base[4 * k + 3]; }
+        cv->need_narrowed = false;
+        int rcu = uavm_canvas_upload_desc(ctx, cv); if (rcu != UAVM_OK) return rcu;
+    }
     dim3 grid((cv->max_chip_w + kWarpTileW - 1) / kWarpTileW, (cv->max_chip_h + kWarpTileH - 1) / kWarpTileH, count);
     dim3 block(32, kWarpsY);
     bool any_affine = false, any_proj = false;
@@ -796,6 +805,59 @@ extern "C" int uavm_canvas_warp(uavm_ctx* ctx, uavm_canvas* cv)
 {
     if (!ctx || !cv) return UAVM_EINVAL;
     return uavm_canvas_warp_range(ctx, cv, 0, cv->n);
+}
+
+// K5 for a mosaic: warp only the chip pixels the blend can read.  With seam masks a chip contributes where it owns canvas pixels
+// (plus the support of the blender's pyramids), typically a third of its area; uavm_canvas_seam_masks does not need the chips
+// (validity is recomputed from the coordinates), so the pipeline runs K6 first, takes the bounding box of what each chip owns
+// and warps the rectangle a blend of up to 5 bands reads (blend_plan.h).  The mosaic is bit-identical; uavm_canvas_get_chip
+// afterwards returns a partly filled chip.  A plain uavm_canvas_warp restores whole chips.
+extern "C" int uavm_canvas_warp_for_blend(uavm_ctx* ctx, uavm_canvas* cv)
+{
+    if (!ctx || !cv) return UAVM_EINVAL;
+    if (!cv->seamed) { UAVM_SET_ERR(ctx, "warp_for_blend needs the seam masks (uavm_canvas_seam_masks) first"); return UAVM_EINVAL; }
+    UAVM_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (!cv->own_bbox_valid) {
+        cv->own_bbox.resize((size_t)cv->n * 4);
+        UAVM_CUDA(ctx, cudaMemcpyAsync(cv->own_bbox.data(), cv->d_own_bbox, (size_t)cv->n * 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        UAVM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        cv->own_bbox_valid = true;
+    }
+    using namespace uavm_plan;
+    const int cw = cv->layout.canvas_w, ch = cv->layout.canvas_h;
+    const double max_len = (double)(cw > ch ? cw : ch);
+    int nbmax = (int)ceil(log(max_len) / log(2.0)); if (nbmax > 5) nbmax = 5;
+    const IRect out = cv->sharded ? IRect{cv->rect_x0, cv->rect_y0, cv->rect_x1, cv->rect_y1} : IRect{0, 0, cw, ch};
+    for (int k = 0; k < cv->n; k++) {
+        ChipDesc& d = cv->desc[k];
+        if (!d.keep) continue;
+        const int32_t* b = &cv->own_bbox[(size_t)k * 4];
+        IRect need = make_empty();
+        if (!(b[2] < b[0] || b[3] < b[1])) {
+            const IRect a0{b[0], b[1], b[2] + 1, b[3] + 1};
+            for (int nb = 0; nb <= nbmax; nb++) {
+                const CanvasPlan P = plan_canvas(cw, ch, nb, out);
+                const ChipPlan cp = plan_chip(d.beg_x, d.beg_y, d.chip_w, d.chip_h, a0, P);
+                if (!cp.active) continue;
+                int lx, hx, ly, hy;
+                reflect_range(cp.C[0].x0 - cp.roi.left, cp.C[0].x1 - cp.roi.left, d.chip_w, lx, hx);
+                reflect_range(cp.C[0].y0 - cp.roi.top, cp.C[0].y1 - cp.roi.top, d.chip_h, ly, hy);
+                if (hx > lx && hy > ly) need = hull(need, IRect{lx, ly, hx, hy});
+            }
+        }
+        // never wider than what create / set_rect allowed
+        const IRect base{cv->need_base[4 * k], cv->need_base[4 * k + 1], cv->need_base[4 * k + 2], cv->need_base[4 * k + 3]};
+        need = isect(need, base);
+        d.need_x0 = need.x0; d.need_y0 = need.y0; d.need_x1 = need.x1; d.need_y1 = need.y1;      // empty: nothing of this chip is read
+    }
+    cv->need_narrowed = true;
+    int rc = uavm_canvas_upload_desc(ctx, cv);
+    if (rc != UAVM_OK) return rc;
+    cv->in_warp_for_blend = true;
+    rc = uavm_canvas_warp_range(ctx, cv, 0, cv->n);
+    cv->in_warp_for_blend = false;
+    cv->seamed = true; cv->mask_plane_valid = true;       // warp_range reset them: the seam masks are still the current ones
+    return rc;
 }
 
 // expands the validity masks (chip alpha) into the u8 mask plane unless the plane already holds them or K6's seam masks

@@ -28,6 +28,8 @@ struct uavm_canvas {
     uavm_canvas_layout layout;
     std::vector<uavm_chip_layout> chips;
     std::vector<ChipDesc> desc;
+    std::vector<int32_t> need_base;  // per image: the need rectangle (x0, y0, x1, y1) set by create / set_rect (uavm_canvas_warp_for_blend narrows desc's copy)
+    bool need_narrowed = false, in_warp_for_blend = false;
     uchar4* d_src = nullptr;         // source pool: BGRA pixels, or (src_bgr) packed BGR rows of src_step_px BYTES
     bool src_bgr = false;            // frames stay BGR in HBM (width % 16 == 0): no conversion pass, K5 reads BGR taps
     static constexpr int kWarpEvents = 32;

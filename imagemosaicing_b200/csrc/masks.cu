@@ -262,7 +262,7 @@ void line_of_2_points(float& a, float& b, float& c, float x1, float y1, float x2
 extern "C" int uavm_canvas_seam_masks(uavm_ctx* ctx, uavm_canvas* cv)
 {
     if (!ctx || !cv) return UAVM_EINVAL;
-    if (!cv->warped) { UAVM_SET_ERR(ctx, "seam_masks before warp"); return UAVM_EINVAL; }
+    // the chips are not needed: validity comes from the warp's coordinate chain, so K6 may run before K5 (uavm_canvas_warp_for_blend)
     if (cv->max_chip_w <= 0) return UAVM_OK;
     UAVM_CUDA(ctx, cudaSetDevice(ctx->device));
     if (!cv->d_dist_max) {

@@ -203,10 +203,12 @@ static int mosaic_tail(uavm_ctx* ctx, const uavm_image* images, int n_images, st
     rc = uavm_canvas_create(ctx, n_images, w, h, H.data(), keep.data(), &cv);
     for (int i = 0; rc == UAVM_OK && i < n_images; i++)
         if (keep[i] && H[(size_t)i * 9 + 8] != 0) rc = uavm_canvas_set_image(ctx, cv, i, images[i].imageData, images[i].widthStep, 0);
-    if (rc == UAVM_OK) rc = uavm_canvas_warp(ctx, cv);
     if (rc == UAVM_OK) {
         if (P.blending == 2) {
+            // K6 first (it needs no pixels), then K5 only where the blend reads, then K7
             rc = uavm_canvas_seam_masks(ctx, cv);
+            if (rc == UAVM_OK) rc = P.numBands <= 5 ? uavm_canvas_warp_for_blend(ctx, cv) : uavm_canvas_warp(ctx, cv);
+            if (rc == UAVM_OK && P.numBands > 5) rc = uavm_canvas_seam_masks(ctx, cv);
             if (rc == UAVM_OK) rc = uavm_canvas_blend(ctx, cv, P.numBands);
         } else rc = uavm_canvas_paste(ctx, cv);
     }

@@ -199,7 +199,11 @@ int uavm_canvas_warp(uavm_ctx* ctx, uavm_canvas* cv);
 /* same for images [first, first + count) only: a caller that streams frames in (uavm_canvas_set_image copies host
  * frames on an internal copy stream) warps each group as soon as it is set, overlapping PCIe with compute */
 int uavm_canvas_warp_range(uavm_ctx* ctx, uavm_canvas* cv, int first, int count);
-/* K6: FindMasksByDistMap (:1761-1881) */
+/* K5 for a mosaic: after uavm_canvas_seam_masks (which does not need the chips), warp only the chip pixels a blend of up to 5
+ * bands can read — about a third of the work under seam masks; the mosaic is bit-identical, uavm_canvas_get_chip then returns
+ * partly filled chips; a plain uavm_canvas_warp restores whole chips */
+int uavm_canvas_warp_for_blend(uavm_ctx* ctx, uavm_canvas* cv);
+/* K6: FindMasksByDistMap (:1761-1881); may run before the warp */
 int uavm_canvas_seam_masks(uavm_ctx* ctx, uavm_canvas* cv);
 /* K7: MultiBandBlender prepare/feed/blend + convertTo(CV_8U) (:2296-2299, :2476-2486) */
 int uavm_canvas_blend(uavm_ctx* ctx, uavm_canvas* cv, int num_bands);

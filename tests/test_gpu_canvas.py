@@ -304,3 +304,35 @@ def test_banded_blend_equals_untiled(ctx):
         assert np.array_equal(tiled_mask, full_mask)
         assert np.array_equal(tiled, full), f"world {world}: {(tiled != full).sum()} differing bytes"
         assert n_inactive > 0            # bands really skip chips that cannot touch them
+
+
+def test_warp_for_blend_equals_full_warp(ctx):
+    """K6 before K5: warping only what the blend reads gives the same mosaic byte for byte (unsharded and in a rectangle)."""
+    rng = np.random.default_rng(31)
+    w, h, cols, rows = 400, 300, 4, 3
+    H = _grid_transforms(rng, cols, rows, w, h); n = cols * rows
+    imgs = [synth.texture_image(rng, w, h, 5) for _ in range(3)]
+    a = api.Canvas(ctx, H, w, h)
+    for k in range(n):
+        a.set_image(k, imgs[k % 3])
+    a.warp(); a.seam_masks(); a.blend(5)
+    full, fm = a.result()
+    b = api.Canvas(ctx, H, w, h)
+    for k in range(n):
+        b.set_image(k, imgs[k % 3])
+    b.seam_masks(); b.warp_for_blend(); b.blend(5)
+    out, om = b.result()
+    assert np.array_equal(om, fm) and np.array_equal(out, full)
+    b.blend(3)                                            # fewer bands read less: still covered
+    a.blend(3)
+    assert np.array_equal(b.result()[0], a.result()[0])
+    cw, ch = b.layout.canvas_w, b.layout.canvas_h
+    x0, y0, x1, y1 = (cw // 3) & ~1, (ch // 4) & ~1, (2 * cw // 3) & ~1, ch
+    c = api.Canvas(ctx, H, w, h)
+    c.set_rect(x0, y0, x1, y1)
+    for k in range(n):
+        if c.is_active(k):
+            c.set_image(k, imgs[k % 3])
+    c.seam_masks(); c.warp_for_blend(); c.blend(5)
+    part, _ = c.result()
+    assert np.array_equal(part[y0:y1, x0:x1], full[y0:y1, x0:x1])
