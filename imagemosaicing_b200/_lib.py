@@ -93,6 +93,11 @@ def lib():
             L.uavm_ctx_launch_count.restype = C.c_int64
             L.uavm_jpeg_decode_bgr.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_int, C.c_int]
             L.uavm_canvas_set_image_jpeg.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int64]
+            L.uavm_canvas_set_images_jpeg.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+            L.uavm_jpeg_hw_engines.argtypes = [C.c_void_p]
+            L.uavm_jpeg_set_threads.argtypes = [C.c_void_p, C.c_int]
+            L.uavm_canvas_bind_root.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+            L.uavm_canvas_bound_root.argtypes = [C.c_void_p]
             L.uavm_jpeg_destroy.restype = None
             L.uavm_jpeg_destroy.argtypes = [C.c_void_p, C.c_void_p]
             L.uavm_dist_destroy.restype = None

@@ -45,6 +45,7 @@ class Context:
 
     def __init__(self, device=0, stream=None):
         self._h = C.c_void_p()
+        self.device = int(device)
         rc = L.lib().uavm_ctx_create(int(device), C.byref(self._h))
         if rc != 0:
             raise UavmError(f"uavm_ctx_create({device}) failed with {rc}: no sm_100 CUDA device (no CPU fallback)")
@@ -194,6 +195,22 @@ class Jpeg:
         buf = np.frombuffer(data, np.uint8) if isinstance(data, (bytes, bytearray)) else np.ascontiguousarray(data, np.uint8)
         self.ctx.check(L.lib().uavm_canvas_set_image_jpeg(self.ctx._h, cv._h, self._h, int(image), _ptr(buf, u8p), C.c_int64(buf.size)))
 
+    def set_canvas_images(self, cv, first, datas):
+        """uavm_canvas_set_images_jpeg: frames [first, first + len(datas)) decoded as ONE nvJPEG batch."""
+        bufs = [np.frombuffer(d, np.uint8) if isinstance(d, (bytes, bytearray)) else np.ascontiguousarray(d, np.uint8).reshape(-1) for d in datas]
+        ptrs = (C.c_void_p * len(bufs))(*[b.ctypes.data for b in bufs])
+        sizes = (C.c_int64 * len(bufs))(*[b.size for b in bufs])
+        self.ctx.check(L.lib().uavm_canvas_set_images_jpeg(self.ctx._h, cv._h, self._h, int(first), len(bufs), ptrs, sizes))
+        self._keep = bufs                      # the decoder reads the streams asynchronously
+
+    def set_threads(self, n):
+        """host threads of set_canvas_images: n >= 1, 0 = default, -1 = nvJPEG's own batched decoder."""
+        self.ctx.check(L.lib().uavm_jpeg_set_threads(self._h, int(n)))
+
+    @property
+    def hw_engines(self):
+        return int(L.lib().uavm_jpeg_hw_engines(self._h))
+
     def close(self):
         if self._h:
             L.lib().uavm_jpeg_destroy(self.ctx._h, self._h)
@@ -321,6 +338,12 @@ class Dist:
         self.ctx.check(L.lib().uavm_pairbatch_allgather(self.ctx._h, self._h, h, int(n_pairs_global), int(min_inner_points), out, n.value, C.byref(n), C.byref(acc)))
         return out, n.value, acc.value
 
+    def bind_canvas_root(self, cv, root=0):
+        """uavm_canvas_bind_root (collective, before blend): the blend's level-0 kernel of every other rank also writes its rectangle
+        into root's mosaic over NVLink; gather_canvas is then only the completion barrier."""
+        self.ctx.check(L.lib().uavm_canvas_bind_root(self.ctx._h, self._h, cv._h, int(root)))
+        return int(L.lib().uavm_canvas_bound_root(cv._h)) == int(root)
+
     def gather_canvas(self, cv, rects, root=0):
         """rects: (world, 4) int32 (x0, y0, x1, y1) per rank; afterwards root's canvas result is the whole mosaic."""
         r = np.ascontiguousarray(rects, np.int32).reshape(-1, 4)
@@ -431,6 +454,18 @@ class Canvas:
     def source_layout(self):
         """3: frames stay BGR in HBM (no conversion pass), 4: BGRA pool."""
         return int(L.lib().uavm_canvas_source_layout(self._h))
+
+    def source_frame(self, image):
+        """uavm_canvas_image_ptr: zero-copy torch view (h, w, 3) of source frame `image` in a BGR pool."""
+        import torch
+        p = C.c_void_p(); step = C.c_int()
+        self.ctx.check(L.lib().uavm_canvas_image_ptr(self._h, int(image), C.byref(p), C.byref(step)))
+        class _View:
+            pass
+        v = _View()
+        v.__cuda_array_interface__ = {"shape": (self.img_h, self.img_w, 3), "typestr": "|u1", "data": (int(p.value), False), "version": 2,
+                                      "strides": (int(step.value), 3, 1)}
+        return torch.as_tensor(v, device=f"cuda:{self.ctx.device}")
 
     def set_image(self, image, bgr):
         """bgr: (h, w, 3) uint8 numpy array (host) or torch CUDA tensor (device)."""

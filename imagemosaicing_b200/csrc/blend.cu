@@ -44,6 +44,7 @@ struct LevelArgs {
     short* fin; int32_t fin_x0, fin_y0, fin_pitch;                               // final level i (int16 x4), storage origin = S_i origin
     const short* nxt; int32_t nxt_x0, nxt_y0, nxt_pitch, nxt_rows, nxt_w, nxt_h;           // final level i+1 storage; nxt_w/h = full level size (border rules)
     uint8_t* out; uint8_t* out_mask; int32_t cw, ch;                             // level 0: mosaic (pitch cw pixels) and its mask
+    uint8_t* out_peer;                                                           // level 0: the root's mosaic over NVLink (uavm_canvas_bind_root), or null
     int32_t ox0, oy0, ox1, oy1;                                                  // level 0: output rectangle
 };
 
@@ -167,6 +168,8 @@ k7_pyrdown(const BlendChip* __restrict__ chips, int sl)
     int width0 = (w - 3) / 2 + 1; if (w < 3) width0 = 0; if (width0 > dw) width0 = dw;
     const bool hvec = x >= 1 && x < 1 + 4 * ((width0 - 1 > 0 ? width0 - 1 : 0) / 4);
     const bool vvec = x < 4 * (dw / 4);
+    const unsigned hv = __ballot_sync(__activemask(), hvec);
+    const int hmode = hv == __activemask() ? 1 : (hv == 0u ? 0 : 2);
     uint32_t ax[2] = {0u, 0u}, ay[2] = {0u, 0u};                                // packed accumulators of the two outputs
     float F[7];
     const uint32_t kw[5] = {1u, 4u, 6u, 4u, 1u};
@@ -179,7 +182,10 @@ k7_pyrdown(const BlendChip* __restrict__ chips, int sl)
         if (r < 5) { ax[0] += kw[r] * hx; ay[0] += kw[r] * hy; }
         if (r >= 2) { ax[1] += kw[r - 2] * hx; ay[1] += kw[r - 2] * hy; }
         const float s0 = wE[wr][i], s1 = wO[wr][i], s2 = wE[wr][i + 1], s3 = wO[wr][i + 1], s4 = wE[wr][i + 2];
-        F[r] = hvec ? s2 * 6.0f + ((s1 + s3) * 4.0f + (s0 + s4)) : s2 * 6.0f + (s1 + s3) * 4.0f + s0 + s4;
+        const float m6 = s2 * 6.0f, m4 = (s1 + s3) * 4.0f;
+        if (hmode == 1) F[r] = m6 + (m4 + (s0 + s4));                           // warp-uniform: one form per warp but at the borders
+        else if (hmode == 0) F[r] = m6 + m4 + s0 + s4;
+        else F[r] = hvec ? m6 + (m4 + (s0 + s4)) : m6 + m4 + s0 + s4;
     }
     uint32_t* __restrict__ dst = B.pyr[dl];
     float* __restrict__ wdst = B.wp[dl];
@@ -455,6 +461,28 @@ k7_level(const BlendChip* __restrict__ chips, const LevelArgs A)
                 up[1][2 * q + dx][0] = (int)(ox_ & 0xffffu) - 512; up[1][2 * q + dx][1] = (int)(ox_ >> 16) - 512; up[1][2 * q + dx][2] = (int)oy_ - 512;
             }
     }
+    // every weight sum of the block is 0 (nothing fed: d == 0) or exactly 1 (the rule under seam masks at level 0): the
+    // normalisation is d - sign(d) for all 24 values, no branches and no division
+    bool unit = true;
+#pragma unroll
+    for (int dy = 0; dy < 2; dy++)
+#pragma unroll
+        for (int p = 0; p < 4; p++) unit = unit && (ws[dy][p] == 1.0f || ws[dy][p] == 0.0f);
+    if (unit) {
+#pragma unroll
+        for (int dy = 0; dy < 2; dy++)
+#pragma unroll
+            for (int p = 0; p < 4; p++)
+#pragma unroll
+                for (int k = 0; k < 3; k++) { const int dd = (short)d[dy][p][k]; d[dy][p][k] = dd - (dd > 0) + (dd < 0); }
+    } else {
+#pragma unroll
+        for (int dy = 0; dy < 2; dy++)
+#pragma unroll
+            for (int p = 0; p < 4; p++)
+#pragma unroll
+                for (int k = 0; k < 3; k++) d[dy][p][k] = norm_div((short)d[dy][p][k], ws[dy][p]);
+    }
 #pragma unroll
     for (int dy = 0; dy < 2; dy++) {
         const int yy = Y + dy;
@@ -462,7 +490,7 @@ k7_level(const BlendChip* __restrict__ chips, const LevelArgs A)
 #pragma unroll
         for (int p = 0; p < 4; p++) {
 #pragma unroll
-            for (int k = 0; k < 3; k++) v[p][k] = sat16(up[dy][p][k] + norm_div((short)d[dy][p][k], ws[dy][p]));
+            for (int k = 0; k < 3; k++) v[p][k] = L0 ? up[dy][p][k] + d[dy][p][k] : sat16(up[dy][p][k] + d[dy][p][k]);   // level 0 clamps to [0, 255] below
         }
         if (!L0) {
             if (yy >= A.sy1) break;
@@ -490,15 +518,21 @@ k7_level(const BlendChip* __restrict__ chips, const LevelArgs A)
             }
             const size_t o = (size_t)yy * A.cw + X;
             if (X >= A.ox0 && X + 4 <= A.ox1 && (A.cw & 3) == 0) {                // 12 bytes = 3 aligned words (X and the row pitch are multiples of 4)
+                const uint32_t q0 = px[0] | (px[1] << 24), q1 = (px[1] >> 8) | (px[2] << 16), q2 = (px[2] >> 16) | (px[3] << 8);
                 uint32_t* o32 = reinterpret_cast<uint32_t*>(A.out + o * 3);
-                o32[0] = px[0] | (px[1] << 24); o32[1] = (px[1] >> 8) | (px[2] << 16); o32[2] = (px[2] >> 16) | (px[3] << 8);
+                o32[0] = q0; o32[1] = q1; o32[2] = q2;
                 *reinterpret_cast<uint32_t*>(A.out_mask + o) = mk;
+                if (A.out_peer) {                                                 // fused gather: the same 12 bytes straight into the root's mosaic (peer memory)
+                    uint32_t* r32 = reinterpret_cast<uint32_t*>(A.out_peer + o * 3);
+                    r32[0] = q0; r32[1] = q1; r32[2] = q2;
+                }
             } else {
 #pragma unroll
                 for (int p = 0; p < 4; p++) {
                     if (X + p < A.ox0 || X + p >= A.ox1) continue;
                     A.out[(o + p) * 3] = (uint8_t)px[p]; A.out[(o + p) * 3 + 1] = (uint8_t)(px[p] >> 8); A.out[(o + p) * 3 + 2] = (uint8_t)(px[p] >> 16);
                     A.out_mask[o + p] = (uint8_t)(mk >> (8 * p));
+                    if (A.out_peer) { A.out_peer[(o + p) * 3] = (uint8_t)px[p]; A.out_peer[(o + p) * 3 + 1] = (uint8_t)(px[p] >> 8); A.out_peer[(o + p) * 3 + 2] = (uint8_t)(px[p] >> 16); }
                 }
             }
         }
@@ -557,6 +591,11 @@ k7_level_top(const BlendChip* __restrict__ chips, const LevelArgs A)
 #pragma unroll
         for (int k = 0; k < 3; k++) o[k] = m ? (uint8_t)max(0, min(255, v[k])) : 0;
         A.out_mask[(size_t)Y * A.cw + X] = m ? 255 : 0;
+        if (A.out_peer) {
+            uint8_t* r = A.out_peer + ((size_t)Y * A.cw + X) * 3;
+#pragma unroll
+            for (int k = 0; k < 3; k++) r[k] = o[k];
+        }
     }
 }
 
@@ -582,6 +621,21 @@ static int ensure_cap(uavm_ctx* ctx, void** p, size_t* cap, size_t need)
     cudaFree(*p); *p = nullptr; *cap = 0;
     UAVM_CUDA(ctx, cudaMalloc(p, need));
     *cap = need;
+    return UAVM_OK;
+}
+
+// the mosaic buffers of the blend (canvas layout size), zeroed when (re)allocated
+int uavm_canvas_ensure_result(uavm_ctx* ctx, uavm_canvas* cv)
+{
+    const int cw = cv->layout.canvas_w, ch = cv->layout.canvas_h;
+    if (cv->result_w == cw && cv->result_h == ch && cv->d_result) return UAVM_OK;
+    cudaFree(cv->d_result); cudaFree(cv->d_result_mask); cv->d_result = nullptr; cv->d_result_mask = nullptr;
+    cv->result_w = cv->result_h = 0; cv->peer_result = nullptr;                   // a root binding refers to the old buffer
+    UAVM_CUDA(ctx, cudaMalloc(&cv->d_result, (size_t)cw * ch * 3));
+    UAVM_CUDA(ctx, cudaMalloc(&cv->d_result_mask, (size_t)cw * ch));
+    UAVM_CUDA(ctx, cudaMemsetAsync(cv->d_result, 0, (size_t)cw * ch * 3, ctx->stream));
+    UAVM_CUDA(ctx, cudaMemsetAsync(cv->d_result_mask, 0, (size_t)cw * ch, ctx->stream));
+    cv->result_w = cw; cv->result_h = ch;
     return UAVM_OK;
 }
 
@@ -650,14 +704,7 @@ extern "C" int uavm_canvas_blend(uavm_ctx* ctx, uavm_canvas* cv, int num_bands)
     for (auto& B : bc)
         for (int i = 1; i <= nb; i++) { B.pyr[i] = (uint32_t*)(ws->d_scratch + (size_t)B.pyr[i]); B.wp[i] = (float*)(ws->d_scratch + (size_t)B.wp[i]); }
     if (n_act > 0) UAVM_CUDA(ctx, cudaMemcpyAsync(ws->d_chips, bc.data(), (size_t)n_act * sizeof(BlendChip), cudaMemcpyHostToDevice, ctx->stream));
-    if (cv->result_w != cw || cv->result_h != ch) {
-        cudaFree(cv->d_result); cudaFree(cv->d_result_mask); cv->d_result = nullptr; cv->d_result_mask = nullptr;
-        UAVM_CUDA(ctx, cudaMalloc(&cv->d_result, (size_t)cw * ch * 3));
-        UAVM_CUDA(ctx, cudaMalloc(&cv->d_result_mask, (size_t)cw * ch));
-        UAVM_CUDA(ctx, cudaMemsetAsync(cv->d_result, 0, (size_t)cw * ch * 3, ctx->stream));
-        UAVM_CUDA(ctx, cudaMemsetAsync(cv->d_result_mask, 0, (size_t)cw * ch, ctx->stream));
-        cv->result_w = cw; cv->result_h = ch;
-    }
+    { int rc = uavm_canvas_ensure_result(ctx, cv); if (rc != UAVM_OK) return rc; }
     // 1. chip pyramids, all chips per launch
     for (int i = 0; i < nb && n_act > 0; i++) {
         if (max_cw[i + 1] <= 0 || max_ch[i + 1] <= 0) continue;
@@ -677,6 +724,7 @@ extern "C" int uavm_canvas_blend(uavm_ctx* ctx, uavm_canvas* cv, int num_bands)
         if (i < nb) { A.nxt = ws->d_fin[i + 1]; A.nxt_x0 = P.S[i + 1].x0; A.nxt_y0 = P.S[i + 1].y0; A.nxt_pitch = P.S[i + 1].x1 - P.S[i + 1].x0; A.nxt_rows = P.S[i + 1].y1 - P.S[i + 1].y0; A.nxt_w = P.lw[i + 1]; A.nxt_h = P.lh[i + 1]; }
         if (i == 0) {
             A.out = cv->d_result; A.out_mask = cv->d_result_mask; A.cw = cw; A.ch = ch;
+            A.out_peer = cv->peer_result;
             A.ox0 = out.x0; A.oy0 = out.y0; A.ox1 = out.x1 < cw ? out.x1 : cw; A.oy1 = out.y1 < ch ? out.y1 : ch;
         }
         if (i == nb) {
@@ -695,6 +743,7 @@ extern "C" int uavm_canvas_blend(uavm_ctx* ctx, uavm_canvas* cv, int num_bands)
         UAVM_CHECK_LAUNCH(ctx);
     }
     cv->blended = true;
+    cv->blend_bound_root = cv->bound_root;
     return UAVM_OK;
 }
 

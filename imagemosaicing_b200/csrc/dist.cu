@@ -275,6 +275,65 @@ extern "C" int uavm_pairbatch_allgather(uavm_ctx* ctx, uavm_dist* d, uavm_pairba
     return UAVM_OK;
 }
 
+// Maps the root's mosaic buffer into every other rank's address space (CUDA IPC; cached per handle) and agrees on the outcome:
+// *agreed = 1 when EVERY rank can write the root's buffer (all ranks must take the same path).  Collective; two small host
+// round trips.
+static int map_root_result(uavm_ctx* ctx, uavm_dist* d, uavm_canvas* cv, int root, int* agreed)
+{
+    *agreed = 0;
+    if (!d->d_ipc) UAVM_CUDA(ctx, cudaMalloc(&d->d_ipc, 128));
+    cudaIpcMemHandle_t h; memset(&h, 0, sizeof(h));
+    int ok_local = 1;
+    if (d->rank == root) {
+        if (cudaIpcGetMemHandle(&h, cv->d_result) != cudaSuccess) { cudaGetLastError(); ok_local = 0; memset(&h, 0, sizeof(h)); }
+        UAVM_CUDA(ctx, cudaMemcpyAsync(d->d_ipc, &h, sizeof(h), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    UAVM_NCCL(ctx, g_nccl.Broadcast(d->d_ipc, d->d_ipc, sizeof(h), ncclInt8, root, d->comm, ctx->stream));
+    if (d->rank != root) {
+        UAVM_CUDA(ctx, cudaMemcpyAsync(&h, d->d_ipc, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+        UAVM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        bool zero = true;
+        for (size_t i = 0; i < sizeof(h); i++) if (((const char*)&h)[i]) { zero = false; break; }
+        if (zero || d->peer_failed) ok_local = 0;
+        else if (!d->peer_ptr || memcmp(&h, &d->peer_handle, sizeof(h)) != 0) {
+            if (d->peer_ptr) { cudaIpcCloseMemHandle(d->peer_ptr); d->peer_ptr = nullptr; }
+            if (cudaIpcOpenMemHandle(&d->peer_ptr, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); d->peer_ptr = nullptr; d->peer_failed = true; ok_local = 0; }
+            else d->peer_handle = h;
+        }
+    }
+    int* d_flag = reinterpret_cast<int*>(d->d_ipc + 64);
+    const int cannot = ok_local ? 0 : 1;
+    UAVM_CUDA(ctx, cudaMemcpyAsync(d_flag, &cannot, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    UAVM_NCCL(ctx, g_nccl.AllReduce(d_flag, d_flag, 1, ncclInt32, ncclSum, d->comm, ctx->stream));
+    int n_cannot = 0;
+    UAVM_CUDA(ctx, cudaMemcpyAsync(&n_cannot, d_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    UAVM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *agreed = n_cannot == 0;
+    return UAVM_OK;
+}
+
+// Fused blend + gather: after this collective call the level-0 kernel of uavm_canvas_blend on every non-root rank stores its
+// mosaic rectangle ALSO into the root's mosaic buffer over NVLink (peer memory mapped with CUDA IPC), tile by tile as the
+// pixels are produced, so the transfer overlaps the blend and uavm_canvas_gather shrinks to its completion barrier.  Call it
+// once per canvas, on every rank, after uavm_canvas_set_rect and before uavm_canvas_blend.  When the mapping is not possible
+// (ranks sharing a process, IPC unavailable) nothing is bound and uavm_canvas_gather copies as before.  The binding refers to
+// `d`: keep the uavm_dist alive as long as the canvas blends.
+extern "C" int uavm_canvas_bind_root(uavm_ctx* ctx, uavm_dist* d, uavm_canvas* cv, int root)
+{
+    if (!ctx || !d || !cv || root < 0 || root >= d->world) return UAVM_EINVAL;
+    cv->bound_root = -1; cv->peer_result = nullptr;
+    if (d->world == 1 || getenv("UAVM_GATHER_NCCL") || getenv("UAVM_GATHER_COPY")) return UAVM_OK;
+    UAVM_CUDA(ctx, cudaSetDevice(ctx->device));
+    { const int rc = uavm_canvas_ensure_result(ctx, cv); if (rc != UAVM_OK) return rc; }
+    int agreed = 0;
+    { const int rc = map_root_result(ctx, d, cv, root, &agreed); if (rc != UAVM_OK) return rc; }
+    if (agreed) {
+        cv->bound_root = root;
+        if (d->rank != root) cv->peer_result = static_cast<uint8_t*>(d->peer_ptr);
+    }
+    return UAVM_OK;
+}
+
 // Gather the finished rectangles of a sharded canvas on `root`: rects = world x 4 (x0, y0, x1, y1), rank r blended rects[r]
 // (uavm_canvas_set_rect).  After the call the root's result holds the whole mosaic (uavm_canvas_get_result /
 // uavm_canvas_copy_result_rows).  Full-width rectangles travel straight between the result buffers; 2-D pieces are packed
@@ -292,40 +351,23 @@ extern "C" int uavm_canvas_gather(uavm_ctx* ctx, uavm_dist* d, uavm_canvas* cv, 
     auto bytes = [&](int r) { const int32_t* q = rects + 4 * r; return (size_t)(q[2] - q[0]) * (size_t)(q[3] - q[1]) * 3; };
     auto full_width = [&](int r) { const int32_t* q = rects + 4 * r; return q[0] == 0 && q[2] == W; };
     if (d->world == 1) return UAVM_OK;
+    int* d_flag = reinterpret_cast<int*>(d->d_ipc ? d->d_ipc + 64 : nullptr);
+    // Fused path: the blend's level-0 kernel already wrote this rank's rectangle into the root's mosaic (uavm_canvas_bind_root);
+    // what is left is the completion barrier, stream-ordered after the blend on every rank.
+    if (cv->blend_bound_root == root && d_flag) {
+        UAVM_CUDA(ctx, cudaMemsetAsync(d_flag, 0, sizeof(int), ctx->stream));
+        UAVM_NCCL(ctx, g_nccl.AllReduce(d_flag, d_flag, 1, ncclInt32, ncclSum, d->comm, ctx->stream));
+        return UAVM_OK;
+    }
     // Direct path: every rank writes its rectangle straight into the root's result buffer over NVLink (the buffer is mapped
     // with CUDA IPC; one strided peer copy per rank, no packing, no staging on the root); a tiny all-reduce, stream-ordered
     // after the copies, tells the root that every rectangle has landed.  Falls back to grouped ncclSend / ncclRecv when the
     // mapping is not possible (all ranks in ONE process, or IPC unavailable).
     if (!getenv("UAVM_GATHER_NCCL")) {
-        if (!d->d_ipc) UAVM_CUDA(ctx, cudaMalloc(&d->d_ipc, 128));
-        cudaIpcMemHandle_t h; memset(&h, 0, sizeof(h));
-        int ok_local = 1;
-        if (d->rank == root) {
-            if (cudaIpcGetMemHandle(&h, cv->d_result) != cudaSuccess) { cudaGetLastError(); ok_local = 0; memset(&h, 0, sizeof(h)); }
-            UAVM_CUDA(ctx, cudaMemcpyAsync(d->d_ipc, &h, sizeof(h), cudaMemcpyHostToDevice, ctx->stream));
-        }
-        UAVM_NCCL(ctx, g_nccl.Broadcast(d->d_ipc, d->d_ipc, sizeof(h), ncclInt8, root, d->comm, ctx->stream));
-        if (d->rank != root) {
-            UAVM_CUDA(ctx, cudaMemcpyAsync(&h, d->d_ipc, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
-            UAVM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-            bool zero = true;
-            for (size_t i = 0; i < sizeof(h); i++) if (((const char*)&h)[i]) { zero = false; break; }
-            if (zero || d->peer_failed) ok_local = 0;
-            else if (!d->peer_ptr || memcmp(&h, &d->peer_handle, sizeof(h)) != 0) {
-                if (d->peer_ptr) { cudaIpcCloseMemHandle(d->peer_ptr); d->peer_ptr = nullptr; }
-                if (cudaIpcOpenMemHandle(&d->peer_ptr, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); d->peer_ptr = nullptr; d->peer_failed = true; ok_local = 0; }
-                else d->peer_handle = h;
-            }
-        }
-        // agree on the path (all ranks must take the same one): sum of the "cannot" flags
-        int* d_flag = reinterpret_cast<int*>(d->d_ipc + 64);
-        const int cannot = ok_local ? 0 : 1;
-        UAVM_CUDA(ctx, cudaMemcpyAsync(d_flag, &cannot, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-        UAVM_NCCL(ctx, g_nccl.AllReduce(d_flag, d_flag, 1, ncclInt32, ncclSum, d->comm, ctx->stream));
-        int n_cannot = 0;
-        UAVM_CUDA(ctx, cudaMemcpyAsync(&n_cannot, d_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-        UAVM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        if (n_cannot == 0) {
+        int agreed = 0;
+        { const int rc = map_root_result(ctx, d, cv, root, &agreed); if (rc != UAVM_OK) return rc; }
+        d_flag = reinterpret_cast<int*>(d->d_ipc + 64);
+        if (agreed) {
             if (d->rank != root && bytes(d->rank) > 0) {
                 const int32_t* q = rects + 4 * d->rank;
                 const size_t off = ((size_t)q[1] * W + q[0]) * 3;
@@ -373,6 +415,9 @@ extern "C" int uavm_canvas_gather(uavm_ctx* ctx, uavm_dist* d, uavm_canvas* cv, 
     }
     return UAVM_OK;
 }
+
+// root of the canvas' binding (uavm_canvas_bind_root), -1 when nothing is bound
+extern "C" int uavm_canvas_bound_root(const uavm_canvas* cv) { return cv ? cv->bound_root : -1; }
 
 // replicate `bytes` of device memory from `root` to every rank (descriptor pools, transforms): ncclBroadcast on ctx's stream
 extern "C" int uavm_dist_broadcast(uavm_ctx* ctx, uavm_dist* d, void* device_buf, int64_t bytes, int root)

@@ -184,7 +184,8 @@ int uavm_canvas_source_layout(const uavm_canvas* cv);
 /* source frame n (BGR u8 interleaved, `step` bytes per row); is_device != 0: device pointer */
 int uavm_canvas_set_image(uavm_ctx* ctx, uavm_canvas* cv, int image, const uint8_t* bgr, int step, int is_device);
 /* ---- JPEG frames decoded on the device (csrc/decode.cu; nvJPEG loaded at run time) — replaces the callers' cvLoadImage
- *      (M/mosaicing.cpp:51-100, M/MosaicWithoutPos.cpp:10224-10308).  backend: 0 default, 1 hybrid, 2 GPU hybrid. */
+ *      (M/mosaicing.cpp:51-100, M/MosaicWithoutPos.cpp:10224-10308).  backend: 0 default, 1 hybrid, 2 GPU hybrid, 3 the GPU's
+ *      hardware JPEG engines (baseline single-scan streams, through the batched entry point). */
 typedef struct uavm_jpeg uavm_jpeg;
 int uavm_jpeg_create(uavm_ctx* ctx, int backend, uavm_jpeg** out);
 void uavm_jpeg_destroy(uavm_ctx* ctx, uavm_jpeg* j);
@@ -192,6 +193,13 @@ int uavm_jpeg_info(uavm_ctx* ctx, uavm_jpeg* j, const uint8_t* jpeg, int64_t n_b
 int uavm_jpeg_decode_bgr(uavm_ctx* ctx, uavm_jpeg* j, const uint8_t* jpeg, int64_t n_bytes, uint8_t* d_bgr, int step, int width, int height);
 /* source frame `image` from JPEG bytes: decoded straight into the canvas' BGR pool slot */
 int uavm_canvas_set_image_jpeg(uavm_ctx* ctx, uavm_canvas* cv, uavm_jpeg* j, int image, const uint8_t* jpeg, int64_t n_bytes);
+/* source frames [first, first + count) from JPEG bytes, decoded by several host threads at once (one nvJPEG decoder lane and CUDA
+ * stream per thread; JPEG's entropy stage is sequential per frame).  uavm_jpeg_set_threads: n >= 1 threads, 0 = default (the
+ * host's hardware threads, at most 16), -1 = nvJPEG's own batched decoder on the calling thread. */
+int uavm_jpeg_set_threads(uavm_jpeg* j, int n);
+int uavm_canvas_set_images_jpeg(uavm_ctx* ctx, uavm_canvas* cv, uavm_jpeg* j, int first, int count, const uint8_t* const* jpegs, const int64_t* n_bytes);
+/* hardware JPEG engines nvJPEG reports for the device (0: none) */
+int uavm_jpeg_hw_engines(uavm_jpeg* j);
 /* device address of a source frame in a BGR pool (e.g. to run uavm_sift_detect_and_compute on it with is_device = 1) */
 int uavm_canvas_image_ptr(uavm_canvas* cv, int image, const uint8_t** d_bgr, int* step);
 /* K5: bilinear warp of every kept frame into its chip + validity mask (:2350-2448) */
@@ -237,8 +245,15 @@ int uavm_dist_world(const uavm_dist* d);
 int uavm_pairbatch_allgather(uavm_ctx* ctx, uavm_dist* d, uavm_pairbatch* pb, int n_pairs_global, int min_inner_points,
                              uavm_matchpointpairs* out, int cap, int* n_out, int* n_accepted_pairs);
 /* rects: world x 4 (x0, y0, x1, y1), rank r blended rects[r] (uavm_canvas_set_rect); afterwards root's result is the whole
- * mosaic.  Stream ordered (grouped ncclSend / ncclRecv); synchronise with uavm_ctx_sync. */
+ * mosaic.  Each rank copies its rectangle straight into the root's mosaic buffer over NVLink (mapped with CUDA IPC; grouped
+ * ncclSend / ncclRecv when the ranks share a process or IPC is unavailable).  Stream ordered; synchronise with uavm_ctx_sync. */
 int uavm_canvas_gather(uavm_ctx* ctx, uavm_dist* d, uavm_canvas* cv, const int32_t* rects, int root);
+/* Fused blend + gather (collective; once per canvas, on every rank, after uavm_canvas_set_rect and before uavm_canvas_blend): the
+ * root's mosaic buffer is mapped into the other ranks (CUDA IPC) and the level-0 kernel of their blend stores its rectangle there
+ * as well, over NVLink, tile by tile while it computes; uavm_canvas_gather is then only the completion barrier.  If the mapping is
+ * not possible nothing is bound and uavm_canvas_gather copies as before.  Keep `d` alive while the canvas blends. */
+int uavm_canvas_bind_root(uavm_ctx* ctx, uavm_dist* d, uavm_canvas* cv, int root);
+int uavm_canvas_bound_root(const uavm_canvas* cv);      /* root of that binding, -1: none */
 int uavm_dist_broadcast(uavm_ctx* ctx, uavm_dist* d, void* device_buf, int64_t bytes, int root);
 
 /* ---- top-level shim with the shape of MosaicVavImages (M/MosaicWithoutPos.h:638-645,

@@ -5,8 +5,8 @@ them):
 
 Pairs are sharded round-robin and merged with uavm_pairbatch_allgather (device-side pack, ncclAllGather, device-side
 compaction); every rank warps / masks / blends only its rectangle of the mosaic canvas (row bands, then a 2-D grid), the
-finished rectangles are moved to rank 0 with uavm_canvas_gather (grouped ncclSend / ncclRecv over NVLink), and rank 0
-compares the match list and the assembled mosaics byte for byte with the single-GPU results."""
+finished rectangles are moved to rank 0 with uavm_canvas_gather (peer copies into rank 0's mosaic mapped with CUDA IPC, or written
+there by the blend itself after uavm_canvas_bind_root), and rank 0 compares the match list and the assembled mosaics byte for byte with the single-GPU results."""
 import os
 import sys
 import numpy as np
@@ -47,8 +47,10 @@ def main():
     all_pairs = np.frombuffer(out_all, dtype=D.MPP_DTYPE)[:n_all]
 
     # ---- canvas stage: one rectangle per rank (row bands, then a 2-D grid), gathered on rank 0 through the C ABI ----
+    # third pass: the 2-D grid again with the root bound (uavm_canvas_bind_root) — the blend's level-0 kernel writes the
+    # rectangles into rank 0's mosaic over NVLink itself and the gather is only the completion barrier; blended twice
     mosaics = []
-    for grid2d in (False, True):
+    for grid2d, bound in ((False, False), (True, False), (True, True)):
         cv = api.Canvas(ctx, H, w, h)
         cw, ch = cv.layout.canvas_w, cv.layout.canvas_h
         rects = D.canvas_grid(cw, ch, world) if grid2d else [(0, a, cw, b) for (a, b) in D.canvas_bands(ch, world)]
@@ -56,10 +58,15 @@ def main():
         for k in range(n):
             if cv.is_active(k):
                 cv.set_image(k, imgs[k])
-        cv.warp(); cv.seam_masks(); cv.blend(5)
-        nd.gather_canvas(cv, rects, root=0)
+        if bound:
+            nd.bind_canvas_root(cv, root=0)
+        cv.warp(); cv.seam_masks()
+        for _ in range(2 if bound else 1):
+            cv.blend(5)
+            nd.gather_canvas(cv, rects, root=0)
         ctx.sync()
         mosaics.append(cv.result()[0] if rank == 0 else None)
+        dist.barrier()                                  # rank 0 has read its mosaic before anybody unmaps / frees
         cv.close()
     ok = 1
     if rank == 0:
@@ -68,7 +75,7 @@ def main():
             ref.set_image(k, imgs[k])
         ref.warp(); ref.seam_masks(); ref.blend(5)
         full, _ = ref.result()
-        same = np.array_equal(mosaics[0], full) and np.array_equal(mosaics[1], full)
+        same = all(np.array_equal(m, full) for m in mosaics)
         # single-process pair results for comparison
         pb1 = api.PairBatch(ctx, fs, pairs)
         pb1.match(); pb1.select(w, h); pb1.ransac(2.5, 1000, seeds=(1000 + np.arange(len(pairs))).astype(np.uint32))

@@ -61,3 +61,44 @@ def test_canvas_from_jpeg_frames(ctx, oracle):
         o_px, o_mask = oracle.warp_chip(decoded[k], o_canvas, o_chips[k])
         assert np.array_equal(mask, o_mask) and np.array_equal(px, o_px)
     j.close()
+
+
+@pytest.mark.parametrize("threads", [3, -1])
+def test_jpeg_batch_equals_frame_by_frame(ctx, threads):
+    """uavm_canvas_set_images_jpeg (frames spread over host threads, one decoder lane and stream each; -1: nvJPEG's own batched
+    decoder) leaves the same pixels in the source pool as decoding frame after frame, back to back without a sync in between
+    (a decoder state is only reused after its previous decode has finished on the device)."""
+    rng = np.random.default_rng(3)
+    w, h, n = 640, 480, 7
+    H = np.tile(np.eye(3, dtype=np.float32).reshape(1, 9), (n, 1))
+    cv = api.Canvas(ctx, H, w, h)
+    encs = [cv2.imencode(".jpg", synth.texture_image(rng, w, h, 6), [cv2.IMWRITE_JPEG_QUALITY, 90])[1] for _ in range(n)]
+    j = api.Jpeg(ctx, 1)
+    for k in range(n):
+        j.set_canvas_image(cv, k, encs[k])
+    ctx.sync()
+    single = [cv.source_frame(k).cpu().numpy().copy() for k in range(n)]
+    for k in range(n):
+        host = cv2.imdecode(encs[k], cv2.IMREAD_COLOR)
+        d = np.abs(single[k].astype(np.int32) - host.astype(np.int32))
+        assert d.mean() < 1.5 and d.max() <= 12, (k, d.max(), d.mean())
+    for k in range(n):
+        cv.source_frame(k).zero_()
+    import torch
+    torch.cuda.synchronize()
+    j.set_threads(threads)
+    try:
+        j.set_canvas_images(cv, 0, encs)
+    except api.UavmError as e:
+        if threads == -1:
+            pytest.skip(f"nvJPEG batched decoder unavailable: {e}")
+        raise
+    ctx.sync()
+    for k in range(n):
+        got = cv.source_frame(k).cpu().numpy()
+        if threads == -1:                                  # nvJPEG's batched decoder may pick another backend: decoder tolerance
+            d = np.abs(got.astype(np.int32) - single[k].astype(np.int32))
+            assert d.max() <= 12, (k, d.max())
+        else:
+            assert np.array_equal(got, single[k]), k
+    j.close()
