@@ -619,7 +619,7 @@ def run_ours(args):
             t_enc = time.perf_counter() - t0
             t0 = time.perf_counter(); cv2.imdecode(encs[1], cv2.IMREAD_COLOR); host_dec_ms = (time.perf_counter() - t0) * 1e3
             best = None
-            GJ = 16                                     # frames per decode batch = host threads decoding at once
+            GJ = max(1, min(os.cpu_count() or 1, 32))   # frames per decode batch = host threads decoding at once
             for backend in (1, 0):
                 try:
                     jp = api.Jpeg(ctx, backend)
@@ -649,8 +649,8 @@ def run_ours(args):
                             "jpeg_bytes_per_step": int(sum(len(e) for e in encs[1:])), "jpeg_quality": 90,
                             "host_libjpeg_turbo_decode_ms_per_frame_1thread": host_dec_ms,
                             "host_threads": os.cpu_count(),
-                            "note": "49 JPEG frames (4000x3000) decoded by nvJPEG straight into the BGR source pool inside the step, batches of 16 frames "
-                                    "spread over the host threads (the entropy stage is sequential per frame and runs on the host: nvJPEG reports no "
+                            "note": "49 JPEG frames (4000x3000) decoded by nvJPEG straight into the BGR source pool inside the step, one frame per host thread and "
+                                    "batch (the entropy stage is sequential per frame and runs on the host: nvJPEG reports no "
                                     "hardware JPEG engine on this device); host clock; entropy-decode bound"}
             del encs
         except Exception as e:

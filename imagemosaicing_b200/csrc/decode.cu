@@ -185,7 +185,7 @@ extern "C" int uavm_canvas_set_image_jpeg(uavm_ctx* ctx, uavm_canvas* cv, uavm_j
 }
 
 // host threads a batch is decoded with: n >= 1 lanes (one nvJPEG state pair + CUDA stream each), 0 = default (the host's
-// hardware threads, at most 16), -1 = nvJPEG's own batched decoder (nvjpegDecodeBatched) on the calling thread
+// hardware threads, at most 32), -1 = nvJPEG's own batched decoder (nvjpegDecodeBatched) on the calling thread
 extern "C" int uavm_jpeg_set_threads(uavm_jpeg* j, int n)
 {
     if (!j || n < -1 || n > 64) return UAVM_EINVAL;
@@ -231,7 +231,7 @@ extern "C" int uavm_canvas_set_images_jpeg(uavm_ctx* ctx, uavm_canvas* cv, uavm_
         return UAVM_OK;
     }
     int nt = j->threads;
-    if (nt == 0) { nt = (int)std::thread::hardware_concurrency(); if (nt < 1) nt = 1; if (nt > 16) nt = 16; }
+    if (nt == 0) { nt = (int)std::thread::hardware_concurrency(); if (nt < 1) nt = 1; if (nt > 32) nt = 32; }
     if (nt > count) nt = count;
     while ((int)j->lanes.size() < 1 + nt) {                               // lanes 1..nt belong to the batch workers
         j->lanes.emplace_back();

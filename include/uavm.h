@@ -195,7 +195,7 @@ int uavm_jpeg_decode_bgr(uavm_ctx* ctx, uavm_jpeg* j, const uint8_t* jpeg, int64
 int uavm_canvas_set_image_jpeg(uavm_ctx* ctx, uavm_canvas* cv, uavm_jpeg* j, int image, const uint8_t* jpeg, int64_t n_bytes);
 /* source frames [first, first + count) from JPEG bytes, decoded by several host threads at once (one nvJPEG decoder lane and CUDA
  * stream per thread; JPEG's entropy stage is sequential per frame).  uavm_jpeg_set_threads: n >= 1 threads, 0 = default (the
- * host's hardware threads, at most 16), -1 = nvJPEG's own batched decoder on the calling thread. */
+ * host's hardware threads, at most 32), -1 = nvJPEG's own batched decoder on the calling thread. */
 int uavm_jpeg_set_threads(uavm_jpeg* j, int n);
 int uavm_canvas_set_images_jpeg(uavm_ctx* ctx, uavm_canvas* cv, uavm_jpeg* j, int first, int count, const uint8_t* const* jpegs, const int64_t* n_bytes);
 /* hardware JPEG engines nvJPEG reports for the device (0: none) */
