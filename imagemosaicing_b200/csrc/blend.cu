@@ -84,13 +84,51 @@ __device__ __forceinline__ int2 px_expand(uint32_t s) { return make_int2((int)__
 // f32 weights follow OpenCV's operation order (oracle_blend.c: vector form for columns [1, hvec_end) of the row pass and
 // [0, vvec_end) of the column pass, scalar form elsewhere), in ROI-level coordinates.
 constexpr int kPdW = 64, kPdH = 8, kPdCols = 2 * kPdW + 4, kPdRows = 2 * kPdH + 3;
+constexpr int kPdPairs = kPdCols / 2, kPdItems = kPdRows * kPdPairs, kPdPerThread = (kPdItems + 255) / 256;
+
+// interior staging: the window's (even, odd) pixel pairs are spread evenly over the 256 threads (item = row * 66 + pair), all
+// global loads of a thread are issued before the first conversion, and a pair lands in shared memory as one 16-byte store
+// (expanded pixels) + one 8-byte store (weights).  EVEN: the pair is 8-byte aligned in the source (one load).
+template <bool L0, bool EVEN>
+__device__ __forceinline__ void pyrdown_stage_interior(const BlendChip& B, int sl, int sx0, int sy0, int tid, int2 (*sP)[kPdCols], float (*sW)[kPdCols])
+{
+    uint32_t c0[kPdPerThread], c1[kPdPerThread], m[kPdPerThread];
+    float f0[kPdPerThread], f1[kPdPerThread];
+    const int scx0 = L0 ? 0 : B.cx0[sl], scy0 = L0 ? 0 : B.cy0[sl], scw = L0 ? 0 : B.cw_[sl];
+#pragma unroll
+    for (int k = 0; k < kPdPerThread; k++) {
+        const int e = tid + 256 * k;
+        if (e >= kPdItems) break;
+        const int r = e / kPdPairs, j = e - r * kPdPairs;
+        if (L0) {
+            const uint32_t* cp = B.chip + (ptrdiff_t)(sy0 + r - B.top) * B.chip_step + (sx0 - B.left + 2 * j);
+            const uint8_t* mp = B.mask + (ptrdiff_t)(sy0 + r - B.top) * B.mask_step + (sx0 - B.left + 2 * j);
+            if (EVEN) { const uint2 c = __ldg(reinterpret_cast<const uint2*>(cp)); c0[k] = c.x; c1[k] = c.y; m[k] = __ldg(reinterpret_cast<const unsigned short*>(mp)); }
+            else { c0[k] = __ldg(cp); c1[k] = __ldg(cp + 1); m[k] = (uint32_t)__ldg(mp) | ((uint32_t)__ldg(mp + 1) << 8); }
+        } else {
+            const ptrdiff_t g = (ptrdiff_t)(sy0 + r - scy0) * scw + (sx0 - scx0 + 2 * j);
+            const uint2 c = __ldg(reinterpret_cast<const uint2*>(B.pyr[sl] + g)); c0[k] = c.x; c1[k] = c.y;
+            const float2 f = __ldg(reinterpret_cast<const float2*>(B.wp[sl] + g)); f0[k] = f.x; f1[k] = f.y;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < kPdPerThread; k++) {
+        const int e = tid + 256 * k;
+        if (e >= kPdItems) break;
+        const int r = e / kPdPairs, j = e - r * kPdPairs;
+        if (L0) { f0[k] = (float)(m[k] & 0xffu) * (float)(1. / 255.); f1[k] = (float)(m[k] >> 8) * (float)(1. / 255.); }
+        const int2 a = px_expand(c0[k]), b = px_expand(c1[k]);
+        *reinterpret_cast<int4*>(&sP[r][2 * j]) = make_int4(a.x, a.y, b.x, b.y);
+        *reinterpret_cast<float2*>(&sW[r][2 * j]) = make_float2(f0[k], f1[k]);
+    }
+}
 
 template <bool L0>
 __global__ void __launch_bounds__(256)
 k7_pyrdown(const BlendChip* __restrict__ chips, int sl)
 {
-    __shared__ int2 sE[kPdRows][kPdCols / 2], sO[kPdRows][kPdCols / 2];          // expanded pixels (B | G << 16, R)
-    __shared__ float wE[kPdRows][kPdCols / 2], wO[kPdRows][kPdCols / 2];
+    __shared__ __align__(16) int2 sP[kPdRows][kPdCols];                           // expanded pixels (B | G << 16, R), window column order
+    __shared__ __align__(16) float sW[kPdRows][kPdCols];
     const BlendChip& B = chips[blockIdx.z];
     const int dl = sl + 1;
     const int dcw = B.cw_[dl], dch = B.ch_[dl];
@@ -100,47 +138,21 @@ k7_pyrdown(const BlendChip* __restrict__ chips, int sl)
     const int w = B.pw[sl], h = B.ph[sl];
     const int sx0 = 2 * ox0 - 2, sy0 = 2 * oy0 - 2;                              // window origin (even column)
     const int tid = threadIdx.y * kPdW + threadIdx.x;
-    const int warp = tid >> 5, lane = tid & 31;
     // source storage (levels >= 1): C_sl, origin (scx0, scy0), pitch scw; coordinates are clamped into it (window positions
     // that only feed outputs outside C_dl may fall outside C_sl)
     const int scx0 = L0 ? 0 : B.cx0[sl], scy0 = L0 ? 0 : B.cy0[sl], scw = L0 ? 0 : B.cw_[sl], sch = L0 ? 0 : B.ch_[sl];
     const uint32_t* __restrict__ src = L0 ? nullptr : B.pyr[sl];
     const float* __restrict__ wsrc = L0 ? nullptr : B.wp[sl];
-    // fast path: the whole window lies inside the chip (L0) resp. inside C_sl and the ROI level (hence no border arithmetic);
-    // an (even, odd) pixel pair is one 8-byte load when it is 8-byte aligned, its two weights one load as well
+    // fast path: the whole window lies inside the chip (L0) resp. inside C_sl and the ROI level (hence no border arithmetic)
     const bool interior = L0 ? (sx0 - B.left >= 0 && sx0 + kPdCols - B.left <= B.cw && sy0 - B.top >= 0 && sy0 + kPdRows - B.top <= B.ch)
                              : (sx0 >= 0 && sx0 + kPdCols <= w && sy0 >= 0 && sy0 + kPdRows <= h &&
                                 sx0 - scx0 >= 0 && sx0 + kPdCols - scx0 <= scw && sy0 - scy0 >= 0 && sy0 + kPdRows - scy0 <= sch);
     if (interior) {
-        const bool even = L0 ? (B.left & 1) == 0 : true;                        // C origins below the top level are even
-        for (int r = warp; r < kPdRows; r += 8) {
-            const uint32_t* crow; const uint8_t* mrow = nullptr; const float* frow = nullptr;
-            if (L0) {
-                crow = B.chip + (size_t)(sy0 + r - B.top) * B.chip_step + (sx0 - B.left);
-                mrow = B.mask + (size_t)(sy0 + r - B.top) * B.mask_step + (sx0 - B.left);
-            } else {
-                crow = src + (size_t)(sy0 + r - scy0) * scw + (sx0 - scx0);
-                frow = wsrc + (size_t)(sy0 + r - scy0) * scw + (sx0 - scx0);
-            }
-            for (int j = lane; j < kPdCols / 2; j += 32) {
-                uint32_t c0, c1; float f0, f1;
-                if (even) { const uint2 c = __ldg(reinterpret_cast<const uint2*>(crow + 2 * j)); c0 = c.x; c1 = c.y; }
-                else { c0 = __ldg(crow + 2 * j); c1 = __ldg(crow + 2 * j + 1); }
-                if (L0) {
-                    uint32_t m0, m1;
-                    if (even) { const uint32_t m = __ldg(reinterpret_cast<const unsigned short*>(mrow + 2 * j)); m0 = m & 0xffu; m1 = m >> 8; }
-                    else { m0 = __ldg(mrow + 2 * j); m1 = __ldg(mrow + 2 * j + 1); }
-                    f0 = (float)m0 * (float)(1. / 255.); f1 = (float)m1 * (float)(1. / 255.);
-                } else {
-                    const float2 f = __ldg(reinterpret_cast<const float2*>(frow + 2 * j)); f0 = f.x; f1 = f.y;
-                }
-                sE[r][j] = px_expand(c0); sO[r][j] = px_expand(c1);
-                wE[r][j] = f0; wO[r][j] = f1;
-            }
-        }
+        if (!L0 || (B.left & 1) == 0) pyrdown_stage_interior<L0, true>(B, sl, sx0, sy0, tid, sP, sW);     // C origins below the top level are even
+        else pyrdown_stage_interior<L0, false>(B, sl, sx0, sy0, tid, sP, sW);
     } else
-    for (int e = tid; e < kPdRows * (kPdCols / 2); e += 256) {
-        const int r = e / (kPdCols / 2), j = e - r * (kPdCols / 2);
+    for (int e = tid; e < kPdItems; e += 256) {
+        const int r = e / kPdPairs, j = e - r * kPdPairs;
         const int Y = reflect101(sy0 + r, h);
         const int gx = sx0 + 2 * j;
 #pragma unroll
@@ -156,34 +168,38 @@ k7_pyrdown(const BlendChip* __restrict__ chips, int sl)
                 const size_t g = (size_t)min(max(Y - scy0, 0), sch - 1) * scw + min(max(X - scx0, 0), scw - 1);
                 c = __ldg(src + g); wv = __ldg(wsrc + g);
             }
-            if (o == 0) { sE[r][j] = px_expand(c); wE[r][j] = wv; } else { sO[r][j] = px_expand(c); wO[r][j] = wv; }
+            sP[r][2 * j + o] = px_expand(c); sW[r][2 * j + o] = wv;
         }
     }
     __syncthreads();
     const int lx = tx0 + threadIdx.x;                                           // column inside C_dl
     if (lx >= dcw) return;
     const int x = ox0 + threadIdx.x, ty = threadIdx.y;                           // outputs (x, oy0 + 2 ty) and (x, oy0 + 2 ty + 1)
-    const int i = threadIdx.x;                                                   // window columns 2 i .. 2 i + 4 = E[i], O[i], E[i+1], O[i+1], E[i+2]
+    const int i = threadIdx.x;                                                   // window columns 2 i .. 2 i + 4
     const int dw = B.pw[dl];
     int width0 = (w - 3) / 2 + 1; if (w < 3) width0 = 0; if (width0 > dw) width0 = dw;
     const bool hvec = x >= 1 && x < 1 + 4 * ((width0 - 1 > 0 ? width0 - 1 : 0) / 4);
     const bool vvec = x < 4 * (dw / 4);
-    const unsigned hv = __ballot_sync(__activemask(), hvec);
-    const int hmode = hv == __activemask() ? 1 : (hv == 0u ? 0 : 2);
+    const unsigned act = __activemask();
+    const unsigned hv = __ballot_sync(act, hvec);
+    const int hmode = hv == act ? 1 : (hv == 0u ? 0 : 2);                       // warp-uniform: one form per warp but at the borders
     uint32_t ax[2] = {0u, 0u}, ay[2] = {0u, 0u};                                // packed accumulators of the two outputs
     float F[7];
     const uint32_t kw[5] = {1u, 4u, 6u, 4u, 1u};
 #pragma unroll
     for (int r = 0; r < 7; r++) {
         const int wr = 4 * ty + r;
-        const int2 p0 = sE[wr][i], p1 = sO[wr][i], p2 = sE[wr][i + 1], p3 = sO[wr][i + 1], p4 = sE[wr][i + 2];
-        const uint32_t hx = (uint32_t)p0.x + (uint32_t)p4.x + 4u * ((uint32_t)p1.x + (uint32_t)p3.x) + 6u * (uint32_t)p2.x;
-        const uint32_t hy = (uint32_t)p0.y + (uint32_t)p4.y + 4u * ((uint32_t)p1.y + (uint32_t)p3.y) + 6u * (uint32_t)p2.y;
+        // five consecutive window pixels = 40 bytes at a 16-byte aligned address: two 16-byte loads + one 8-byte load
+        const int4 q0 = *reinterpret_cast<const int4*>(&sP[wr][2 * i]), q1 = *reinterpret_cast<const int4*>(&sP[wr][2 * i + 2]);
+        const int2 p4 = sP[wr][2 * i + 4];
+        const uint32_t hx = (uint32_t)q0.x + (uint32_t)p4.x + 4u * ((uint32_t)q0.z + (uint32_t)q1.z) + 6u * (uint32_t)q1.x;
+        const uint32_t hy = (uint32_t)q0.y + (uint32_t)p4.y + 4u * ((uint32_t)q0.w + (uint32_t)q1.w) + 6u * (uint32_t)q1.y;
         if (r < 5) { ax[0] += kw[r] * hx; ay[0] += kw[r] * hy; }
         if (r >= 2) { ax[1] += kw[r - 2] * hx; ay[1] += kw[r - 2] * hy; }
-        const float s0 = wE[wr][i], s1 = wO[wr][i], s2 = wE[wr][i + 1], s3 = wO[wr][i + 1], s4 = wE[wr][i + 2];
+        const float2 w01 = *reinterpret_cast<const float2*>(&sW[wr][2 * i]), w23 = *reinterpret_cast<const float2*>(&sW[wr][2 * i + 2]);
+        const float s0 = w01.x, s1 = w01.y, s2 = w23.x, s3 = w23.y, s4 = sW[wr][2 * i + 4];
         const float m6 = s2 * 6.0f, m4 = (s1 + s3) * 4.0f;
-        if (hmode == 1) F[r] = m6 + (m4 + (s0 + s4));                           // warp-uniform: one form per warp but at the borders
+        if (hmode == 1) F[r] = m6 + (m4 + (s0 + s4));
         else if (hmode == 0) F[r] = m6 + m4 + s0 + s4;
         else F[r] = hvec ? m6 + (m4 + (s0 + s4)) : m6 + m4 + s0 + s4;
     }
@@ -330,12 +346,20 @@ k7_level(const BlendChip* __restrict__ chips, const LevelArgs A)
     __syncthreads();
     {
         int wide = 0;
+        // tile-uniform: the 66 x 10 coarse window lies inside the level and inside the stored rectangle (no border rules, no clamps)
+        const int cx_lo = (tx0 >> 1) - 1, cy_lo = (ty0 >> 1) - 1;
+        const bool st_in = cx_lo >= 0 && cx_lo >= A.nxt_x0 && cx_lo + 66 <= A.nxt_w && cx_lo + 66 <= A.nxt_x0 + A.nxt_pitch &&
+                           cy_lo >= 0 && cy_lo >= A.nxt_y0 && cy_lo + 10 <= A.nxt_h && cy_lo + 10 <= A.nxt_y0 + A.nxt_rows;
         for (int e = threadIdx.y * 32 + threadIdx.x; e < 10 * 66; e += 256) {
             const int r = e / 66, c = e - r * 66;
-            int cx = (tx0 >> 1) - 1 + c, cy = (ty0 >> 1) - 1 + r;
-            cx = cx < 0 ? (A.nxt_w > 1 ? 1 : 0) : (cx > A.nxt_w - 1 ? A.nxt_w - 1 : cx);
-            cy = cy < 0 ? (A.nxt_h > 1 ? 1 : 0) : (cy > A.nxt_h - 1 ? A.nxt_h - 1 : cy);
-            const int lx = min(max(cx - A.nxt_x0, 0), A.nxt_pitch - 1), ly = min(max(cy - A.nxt_y0, 0), A.nxt_rows - 1);
+            int lx, ly;
+            if (st_in) { lx = cx_lo + c - A.nxt_x0; ly = cy_lo + r - A.nxt_y0; }
+            else {
+                int cx = cx_lo + c, cy = cy_lo + r;
+                cx = cx < 0 ? (A.nxt_w > 1 ? 1 : 0) : (cx > A.nxt_w - 1 ? A.nxt_w - 1 : cx);
+                cy = cy < 0 ? (A.nxt_h > 1 ? 1 : 0) : (cy > A.nxt_h - 1 ? A.nxt_h - 1 : cy);
+                lx = min(max(cx - A.nxt_x0, 0), A.nxt_pitch - 1); ly = min(max(cy - A.nxt_y0, 0), A.nxt_rows - 1);
+            }
             int b3, g3, r3;
             unpack3(*reinterpret_cast<const int2*>(A.nxt + ((size_t)ly * A.nxt_pitch + lx) * 4), b3, g3, r3);
             wide |= ((unsigned)(b3 + 512) > 1023u) | ((unsigned)(g3 + 512) > 1023u) | ((unsigned)(r3 + 512) > 1023u);
@@ -359,6 +383,7 @@ k7_level(const BlendChip* __restrict__ chips, const LevelArgs A)
             if (!live || x + 4 <= ux0 || x >= ux1 || y + 2 <= uy0 || y >= uy1) continue;
             float w[2][4];
             bool any = false;
+            uint32_t m01[2] = {0u, 0u};
             if (L0) {
                 const int ix = x - B.left, iy = y - B.top;                        // chip coordinates
 #pragma unroll
@@ -376,9 +401,9 @@ k7_level(const BlendChip* __restrict__ chips, const LevelArgs A)
                             for (int p = 0; p < 4; p++) if (x + p >= ux0 && x + p < ux1) m |= (uint32_t)__ldg(mrow + ix + p) << (8 * p);
                         }
                     }
-#pragma unroll
-                    for (int p = 0; p < 4; p++) { w[dy][p] = (float)((m >> (8 * p)) & 0xffu) * (float)(1. / 255.); any = any || ((m >> (8 * p)) & 0xffu); }
+                    m01[dy] = m;
                 }
+                any = (m01[0] | m01[1]) != 0u;
             } else {
                 const float* __restrict__ wp = B.wp[level];
                 const int lx = x - B.cx0[level], ly = y - B.cy0[level], pitch = B.cw_[level];
@@ -396,6 +421,35 @@ k7_level(const BlendChip* __restrict__ chips, const LevelArgs A)
             if (!any) continue;                                                   // dst + short(lap * 0) == dst, wsum + 0 == wsum
             uint32_t upx[2][4], upy[2][4];                                        // pyrUp of the chip's coarser Gaussian level, packed
             pyrup_2quads_u8(B.pyr[level + 1], B.cw_[level + 1], B.cx0[level + 1], B.cy0[level + 1], B.pw[level + 1], B.ph[level + 1], x >> 1, y >> 1, upx, upy);
+            if (L0) {
+                if ((m01[0] & m01[1]) == 0xffffffffu) {
+                    // all eight weights are exactly 1 (the interior of what the chip owns): d += pixel - pyrUp, wsum += 1, no
+                    // per-pixel tests and no float round trip; four chip pixels are one 16-byte load when aligned
+                    const int ix = x - B.left;
+#pragma unroll
+                    for (int dy = 0; dy < 2; dy++) {
+                        const uint32_t* crow = B.chip + (ptrdiff_t)(y + dy - B.top) * B.chip_step + ix;
+                        uint32_t sp[4];
+                        if ((ix & 3) == 0) { const uint4 q = __ldg(reinterpret_cast<const uint4*>(crow)); sp[0] = q.x; sp[1] = q.y; sp[2] = q.z; sp[3] = q.w; }
+                        else {
+#pragma unroll
+                            for (int p = 0; p < 4; p++) sp[p] = __ldg(crow + p);
+                        }
+#pragma unroll
+                        for (int p = 0; p < 4; p++) {
+                            d[dy][p][0] += (int)(sp[p] & 0xffu) - (int)(upx[dy][p] & 0xffffu);
+                            d[dy][p][1] += (int)((sp[p] >> 8) & 0xffu) - (int)(upx[dy][p] >> 16);
+                            d[dy][p][2] += (int)((sp[p] >> 16) & 0xffu) - (int)upy[dy][p];
+                            ws[dy][p] += 1.0f;
+                        }
+                    }
+                    continue;
+                }
+#pragma unroll
+                for (int dy = 0; dy < 2; dy++)
+#pragma unroll
+                    for (int p = 0; p < 4; p++) w[dy][p] = (float)((m01[dy] >> (8 * p)) & 0xffu) * (float)(1. / 255.);
+            }
 #pragma unroll
             for (int dy = 0; dy < 2; dy++)
 #pragma unroll
