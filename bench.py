@@ -323,16 +323,16 @@ def run_block200(args, ctx, nd, rank, world, dev):
             Tm = np.array([tr[kk].h.m[t] for t in range(9)], np.float64).reshape(3, 3)
             Tm[2] = [0, 0, 1]
             err.append(float(np.abs(synth.apply_h(G, corners) - synth.apply_h(Tm, corners)).max()))
-        # f3 (informational, untimed part of the step): the paper's rotation-constrained refinement on the same match list
+        # f3 (informational, untimed part of the step): the similarity-constrained alignment variant on the same match list
         rot = None
         try:
             init = (L.ImageTransform * n)(); tr2 = (L.ImageTransform * n)()
-            for i in range(n):
+            for i in range(n):                        # start from the free affine solution (the reference passes transformInit too)
                 for t in range(9):
-                    init[i].h.m[t] = 1.0 if t in (0, 4, 8) else 0.0
+                    init[i].h.m[t] = tr[i].h.m[t] if label[i] else (1.0 if t in (0, 4, 8) else 0.0)
                 init[i].fixed = 1 if (i == 0 or not label[i]) else 0
             t0 = time.perf_counter()
-            rc2 = lib.uavm_align_affine_rot(out, n_used.value, init, n, int(sum(1 for i in range(n) if init[i].fixed)), C.c_float(100.0), 10, tr2)
+            rc2 = lib.uavm_align_affine_constrained(out, n_used.value, init, n, int(sum(1 for i in range(n) if init[i].fixed)), tr2)
             rot_ms = (time.perf_counter() - t0) * 1e3
             err2 = []
             for kk in range(n):
@@ -340,7 +340,10 @@ def run_block200(args, ctx, nd, rank, world, dev):
                 G = np.linalg.inv(poses[0]) @ poses[kk]
                 Tm = np.array([tr2[kk].h.m[t] for t in range(9)], np.float64).reshape(3, 3); Tm[2] = [0, 0, 1]
                 err2.append(float(np.abs(synth.apply_h(G, corners) - synth.apply_h(Tm, corners)).max()))
-            rot = {"rc": int(rc2), "ms_host": rot_ms, "weight": 100.0, "iterations": 10, "corner_error_px_max": max(err2), "corner_error_px_median": float(np.median(err2))}
+            rot = {"rc": int(rc2), "ms_host": rot_ms, "corner_error_px_max": max(err2), "corner_error_px_median": float(np.median(err2)),
+                   "note": "f3, not timed in total_ms: uavm_align_affine_constrained (soft similarity constraints a = d, b = -c per image, "
+                           "BundleAdjustmentSparseConstraint) on the same match list; the block's poses are similarities with 5 % scale jitter, "
+                           "so the rotation-only variant (uavm_align_affine_rot) does not apply to it"}
         except Exception as e:
             rot = {"error": repr(e)}
         res = {"workload": f"configs[2]: {n}-image block ({rows} strips x {cols}), {W}x{H}, {NKP} kp/image, all {len(pairs)} pairs in overlap; strong scaling",
@@ -350,7 +353,7 @@ def run_block200(args, ctx, nd, rank, world, dev):
                "unknowns": 6 * (int(sum(label)) - 1), "connected_images": int(sum(label)),
                "match_list_crc32": crc_of(C.string_at(out, n_out.value * 40)), "transforms_crc32": crc_of(C.string_at(tr, n * 40)),
                "corner_error_px_max": max(err) if err else None, "corner_error_px_median": float(np.median(err)) if err else None,
-               "rot_constrained_refinement": rot,
+               "similarity_constrained_alignment": rot,
                "note": "timed: match+select+RANSAC on the shard (CUDA events), uavm_pairbatch_allgather and uavm_global_align (host clock), max over ranks; "
                        "match_list_crc32 is taken after uavm_global_align compacted the list and set the fixed flags (the content of matchPairs.txt)",
                "synth_s": t_synth}
