@@ -263,7 +263,8 @@ def run_block200(args, ctx, nd, rank, world, dev):
     """BASELINE configs[2], strong scaling: a 200-image block (10 strips x 20 frames, shared world-point model), every pair
     whose footprints overlap (1 692) sharded round-robin over the ranks; the timed region is match -> select -> RANSAC on the
     shard, uavm_pairbatch_allgather (device pack, ncclAllGather, device compaction, one D2H of the dense list) and the host
-    stages on the merged list (connectivity + global affine alignment, uavm_global_align) — on every rank, replicas only."""
+    stages on the merged list (connectivity + global affine alignment, uavm_global_align) — on rank 0 with the host's threads, the
+    transforms broadcast to the other ranks (they share the host)."""
     import ctypes as C
     import torch
     import torch.distributed as dist
@@ -283,6 +284,8 @@ def run_block200(args, ctx, nd, rank, world, dev):
     out = (L.MatchPointPairs * cap)(); n_out = C.c_int(0); n_acc = C.c_int(0)
     tr = (L.ImageTransform * n)(); label = (C.c_int32 * n)(); n_used = C.c_int(0)
     lib = L.lib()
+    bbuf = torch.empty(n * 44 + 8, dtype=torch.uint8, device=dev)
+    assert C.sizeof(L.ImageTransform) == 40
 
     def step(ev=None):
         if ev: ev[0].record()
@@ -293,7 +296,20 @@ def run_block200(args, ctx, nd, rank, world, dev):
         t1 = time.perf_counter()
         ctx.check(lib.uavm_pairbatch_allgather(ctx._h, nd._h, pb._h if pb is not None else None, len(pairs), 30, out, cap, C.byref(n_out), C.byref(n_acc)))
         t2 = time.perf_counter()
-        rc = lib.uavm_global_align(out, n_out.value, n, tr, label, C.byref(n_used))
+        # host stages on the merged list.  One GPU: here.  N ranks share one host: rank 0 runs them with the host's threads and
+        # the result (200 transforms + labels, 9 KB) is broadcast — N replicas would only fight over the same cores.
+        rc = 0
+        if world == 1 or rank == 0:
+            rc = lib.uavm_global_align(out, n_out.value, n, tr, label, C.byref(n_used))
+        if world > 1:
+            if rank == 0:
+                pack = np.concatenate([np.frombuffer(tr, np.uint8), np.frombuffer(label, np.uint8), np.array([n_used.value, rc], np.int32).view(np.uint8)])
+                bbuf.copy_(torch.from_numpy(pack))
+            nd.broadcast(bbuf, 0)
+            host = bbuf.cpu().numpy()
+            if rank != 0:
+                C.memmove(tr, host[:n * 40].ctypes.data, n * 40); C.memmove(label, host[n * 40:n * 44].ctypes.data, n * 4)
+                tail = host[n * 44:n * 44 + 8].view(np.int32); n_used.value = int(tail[0]); rc = int(tail[1])
         t3 = time.perf_counter()
         return rc, (t2 - t1) * 1e3, (t3 - t2) * 1e3
 
@@ -354,7 +370,7 @@ def run_block200(args, ctx, nd, rank, world, dev):
                "match_list_crc32": crc_of(C.string_at(out, n_out.value * 40)), "transforms_crc32": crc_of(C.string_at(tr, n * 40)),
                "corner_error_px_max": max(err) if err else None, "corner_error_px_median": float(np.median(err)) if err else None,
                "similarity_constrained_alignment": rot,
-               "note": "timed: match+select+RANSAC on the shard (CUDA events), uavm_pairbatch_allgather and uavm_global_align (host clock), max over ranks; "
+               "note": "timed: match+select+RANSAC on the shard (CUDA events), uavm_pairbatch_allgather and uavm_global_align on rank 0 + broadcast of the transforms (host clock), max over ranks; "
                        "match_list_crc32 is taken after uavm_global_align compacted the list and set the fixed flags (the content of matchPairs.txt)",
                "synth_s": t_synth}
     if pb is not None: pb.close()
