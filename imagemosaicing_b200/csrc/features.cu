@@ -101,8 +101,8 @@ extern "C" void uavm_free(void* p) { free(p); }
 // ------------------------------------------------------------------------------------------------
 // K1: pack descriptors to u8, row norms and column keys.  One warp per descriptor row.
 //   norm[r] = sum_k d[r][k]^2                      (query-side constant of |a-b|^2)
-//   ckey[r] = 32*norm[r] + (local_row & 31)        (train-side key, low 5 bits carry the index so
-//                                                   one integer min yields min distance AND lowest index)
+//   ckey[r] = -(32*norm[r] + (local_row & 31))     (train-side key, NEGATED: K2 maximises 64 a.b + ckey — a shift-add, LEA — so
+//                                                   one integer max yields min distance AND, in the low 5 bits, lowest index)
 // ------------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(256) k1_pack_rows(const T* __restrict__ src, int n, uint8_t* __restrict__ dst,
@@ -128,14 +128,14 @@ __global__ void __launch_bounds__(256) k1_pack_rows(const T* __restrict__ src, i
     s = __reduce_add_sync(0xffffffffu, s);
     if (lane == 0) {
         norm[warp] = s;
-        ckey[warp] = s * 32 + (warp & 31);
+        ckey[warp] = -(s * 32 + (warp & 31));
     }
 }
 
 __global__ void k1_fill_sentinel(int32_t* __restrict__ ckey, int32_t* __restrict__ norm, int64_t rows) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < rows) {
-        ckey[i] = 0x7fffffe0 | (int32_t)(i & 31);   // key part (>>5) above any real key (<= 128*255^2)
+        ckey[i] = -(0x7fffffe0 | (int32_t)(i & 31));   // key part (>>5) above any real key (<= 128*255^2), negated like the rest
         norm[i] = 0;
     }
 }

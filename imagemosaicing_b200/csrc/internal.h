@@ -71,7 +71,7 @@ struct uavm_featureset {
     int64_t pool_rows = 0;
     uint8_t* d_desc = nullptr;   // [pool_rows][128] u8
     int32_t* d_norm = nullptr;   // [pool_rows] sum of squares (query side)
-    int32_t* d_ckey = nullptr;   // [pool_rows] 32*norm + (local_row & 31), sentinel on padding (train side)
+    int32_t* d_ckey = nullptr;   // [pool_rows] -(32*norm + (local_row & 31)), sentinel on padding (train side)
     float* d_kp = nullptr;       // [pool_rows][2] keypoint xy
     void* d_stage = nullptr;     // staging for f32 uploads
     size_t stage_bytes = 0;

@@ -6,25 +6,32 @@
 //   written anywhere: each epilogue thread owns one query row and keeps a running (min key, arg-min).
 //
 // Work item  = 256 query rows of one pair (two M=128 accumulator row blocks) x all train tiles (N=128).
-// CTA layout = 20 warps, persistent, one CTA per SM:
-//   warp 0      TMA producer  (A block once per item; B tiles through a kStages-deep smem ring, each with its 128 column keys)
+// CTA layout = 18 warps, persistent, one CTA per SM:
+//   warp 0      TMEM allocator (512 columns = 2 accumulator buffers x 2 row blocks x 128 columns), then TMA producer (A block once
+//               per item; B tiles through a kStages-deep smem ring, each with its 128 column keys)
 //   warp 1      MMA issuer    (one elected lane; 2 row blocks x 4 K-chunks of 32 per train tile)
-//   warp 2      TMEM allocator (512 columns = 2 accumulator buffers x 2 row blocks x 128 columns)
-//   warps 4-19  epilogue      (warp w reads TMEM lanes 32*(w%4).., row block ((w-4)/4)&1, column half (w-4)/8)
+//   warps 2-17  epilogue      (warp w reads TMEM lanes 32*(w%4).., 32 columns ((w-2)/4) of BOTH row blocks)
 // Pipelines: smem full/empty (TMA <-> MMA), TMEM full/empty (MMA <-> epilogue), A full/empty.
 //
-// What bounds it (scripts/microbench/ldtm.cu, profiles/r2_ldtm_microbench.txt): NOT the TMEM read port — tcgen05.ld.32x32b.x32
-// sustains 39 / 68 / 87 words per clock per SM from 4 / 8 / 16 warps, against the 16 words per clock this kernel needs at the
-// MMA rate.  The first version (8 epilogue warps, column keys fetched with 32 LDG.128 per tile and thread) ran at 2057 cycles per
-// 256 x 128 tile with the tensor pipe 28 % busy: two warps per scheduler cannot hide the latency chain wait -> tcgen05.ld ->
-// key loads -> min tree.  Now 16 epilogue warps (four per scheduler) each own 64 columns of a row block, and the column keys
-// arrive in shared memory with the B tile (cp.async.bulk on the same mbarrier), so the epilogue reads them with broadcast LDS:
-// 1429 cycles per tile, 0.51 ms per 49 pairs (was 0.70), 1.65 PFLOP/s.  Measured and rejected: handing the two row blocks of a
-// tile over separately (one mbarrier pair per row block: 0.199 vs 0.181 ms on the 32k x 32k case).
+// What bounds it — measured, in this order of discovery:
+//  * NOT the TMEM read port: tcgen05.ld.32x32b.x32 sustains 39 / 68 / 87 words per clock per SM from 4 / 8 / 16 warps
+//    (scripts/microbench/ldtm.cu, profiles/r2_ldtm_microbench.txt); the kernel needs 32 768 words per tile.
+//  * The tensor pipe, at HALF the rate the int8 data sheet figure suggests: with the epilogue reduced to "drain TMEM, hand the
+//    buffer back" (UAVM_K2_DBG=2) the TMA + MMA pipeline alone takes 0.354 ms per 49 pairs = 1 000 cycles per 256 x 128 x 128
+//    tile = 4 190 MAC / clk / SM — kind::i8 M=128 N=128 K=32 issues every ~125 cycles, the same MAC rate as kind::f16
+//    (2.38 Pop/s at 1.965 GHz).  That is the roofline of this kernel on this part; ncu's sm__pipe_tensor_cycles_active (40 %)
+//    counts half of it.
+//  * The epilogue on top of it: 16 warps (four per scheduler).  First version: one row block and 64 columns per warp, column
+//    keys fetched with LDG (2 057 cycles per tile); then keys delivered to shared memory with the B tile (cp.async.bulk on the
+//    same mbarrier): 1 429.  ncu then showed the LSU data pipe 80 % busy — a broadcast key costs one wavefront per key and
+//    warp — and the accumulator buffer held until the reduction was done.  Now a warp reads 32 columns of BOTH row blocks (half
+//    the key loads), hands the TMEM buffer back as soon as its tcgen05.ld has landed, prefetches the keys one step ahead and
+//    reduces with a 3-input max of 64 a.b + ckey (keys stored negated): 1 270 cycles per tile, 0.449 ms per 49 pairs (0.70 in
+//    round 1) = 1.87 PFLOP/s = 0.79 of the measured tensor floor; configs[3] 0.159 ms.
+//    Measured and rejected: one mbarrier pair per row block (0.199 vs 0.181 ms on configs[3]); 8- and 16-column software
+//    pipelines of the TMEM loads inside a warp (0.470 ms: they delay the buffer hand-over); 18 instead of 20 warps alone -5 %.
 //
-// Key trick: column key ckey[j] = 32*|b_j|^2 + (j & 31) (K1), packed = ckey[j] - 64*dot
-//          = 32*(|b_j|^2 - 2 dot) + (j & 31): ONE integer min over a 32-column chunk gives the minimum
-//   distance and, on ties, the lowest column; chunks/tiles are visited in ascending j with a strict <.
+#include <stdlib.h>
 #include "internal.h"
 #include "ptx.cuh"
 
@@ -36,14 +43,15 @@ constexpr int kStages = 6;            // B ring depth (16 KB per stage)
 constexpr int kTileN = 128;           // train rows per tile
 constexpr int kBlockM = 256;          // query rows per work item
 constexpr int kEpiWarps = 16;
-constexpr int kThreads = 128 + 32 * kEpiWarps;
+constexpr int kCtlWarps = 2;           // warp 0: TMEM allocator + TMA producer, warp 1: barrier init + MMA issuer
+constexpr int kThreads = 32 * (kCtlWarps + kEpiWarps);      // 576: 112 registers per thread (640 threads capped the epilogue at 96)
 constexpr uint32_t kABytes = kBlockM * 128;
 constexpr uint32_t kBBytes = kTileN * 128;
 constexpr uint32_t kKeyBytes = kTileN * 4;
 // The producer runs at most kStages tiles ahead of the MMA and the MMA at most 2 tiles (TMEM buffers) ahead of the epilogue:
 // a key ring of 16 tiles is never overwritten before the epilogue has read it.
 constexpr int kKeyStages = 16;
-constexpr size_t kSmemBytes = 1024 /*align slack*/ + kABytes + kStages * kBBytes + kKeyStages * kKeyBytes + 2 * kBlockM * 2 * 8 /*half results*/ + 256 /*barriers*/;
+constexpr size_t kSmemBytes = 1024 /*align slack*/ + kABytes + kStages * kBBytes + kKeyStages * kKeyBytes + 2 * kBlockM * 4 * 8 /*per-slice results*/ + 256 /*barriers*/;
 
 struct __align__(8) Barriers {
     uint64_t full[kStages];
@@ -59,7 +67,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 k2_match_tcgen05(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_t,
                  const int32_t* __restrict__ ckey, const int32_t* __restrict__ norm,
                  const MatchItem* __restrict__ items, int n_items,
-                 int32_t* __restrict__ out_idx, int32_t* __restrict__ out_d2)
+                 int32_t* __restrict__ out_idx, int32_t* __restrict__ out_d2, int dbg)
 {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -67,7 +75,7 @@ k2_match_tcgen05(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     uint8_t* smem_b = smem + kABytes;
     int32_t* smem_key = reinterpret_cast<int32_t*>(smem + kABytes + kStages * kBBytes);                   // [kKeyStages][128]
     int2* smem_res = reinterpret_cast<int2*>(smem + kABytes + kStages * kBBytes + kKeyStages * kKeyBytes); // [2 (item parity)][256 rows][2 halves]
-    Barriers* bar = reinterpret_cast<Barriers*>(smem + kABytes + kStages * kBBytes + kKeyStages * kKeyBytes + 2 * kBlockM * 2 * 8);
+    Barriers* bar = reinterpret_cast<Barriers*>(smem + kABytes + kStages * kBBytes + kKeyStages * kKeyBytes + 2 * kBlockM * 4 * 8);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -83,7 +91,8 @@ k2_match_tcgen05(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         for (int b = 0; b < 2; b++) { mbar_init(&bar->tmem_full[b], 1); mbar_init(&bar->tmem_empty[b], kEpiWarps); }
         fence_mbar_init();
     }
-    if (warp == 2) {
+    if (warp == 0) {
+        __syncwarp();
         tmem_alloc(&bar->tmem_base, 512);
         tmem_relinquish();
     }
@@ -144,73 +153,85 @@ k2_match_tcgen05(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             }
         }
         __syncwarp();
-    } else if (warp >= 4) {
+    } else if (warp >= kCtlWarps) {
         // ===================== epilogue: TMEM -> registers -> running arg-min =====================
-        const int ew = warp - 4;
-        const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
-        const int rb = (ew >> 2) & 1;                 // accumulator row block
-        const int ch = ew >> 3;                       // column half of the tile: columns [64 ch, 64 ch + 64)
-        const int row_in_block = rb * 128 + quarter * 32 + lane;
-        const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+        // This warp: TMEM lane quarter `quarter` (a warp may only read lanes 32 (warp % 4) ..), columns [32 cs, 32 cs + 32) of BOTH
+        // row blocks — one key load serves two accumulators (a broadcast key costs one LSU wavefront per key and warp: 80 % LSU
+        // utilisation when a warp owned one row block).
+        const int ew = warp - kCtlWarps;
+        const int quarter = warp & 3;
+        const int cs = ew >> 2;
+        const uint32_t col0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + cs * 32;
+        const uint32_t key_base = smem_u32(smem_key) + cs * 32 * 4;
+        const int r0 = quarter * 32 + lane;               // this thread's row inside a row block
         uint32_t acc = 0, it = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x, it++) {
             const MatchItem w = items[item];
-            int best_key = 0x7fffffff;
-            int best_j = 0;
+            int bk0 = 0x7fffffff, bj0 = 0, bk1 = 0x7fffffff, bj1 = 0;              // running (distance part, column) of row blocks 0 / 1
             for (int t = 0; t < w.n_tiles; t++, acc++) {
                 const uint32_t buf = acc & 1;
+                const uint32_t kaddr = key_base + (acc % kKeyStages) * kKeyBytes;
                 // the keys of this tile landed with its B tile (same mbarrier), which the MMA thread observed before it issued the
                 // MMAs whose completion tmem_full signals.  (Waiting on full[] here as well would be wrong: the producer may
                 // already have re-armed that stage twice, and a parity wait cannot tell phase k from phase k + 2.)
                 mbar_wait(&bar->tmem_full[buf], (acc >> 1) & 1);
                 tc_fence_after();
-                const uint32_t taddr = tmem_base + lane_addr + buf * 256 + rb * 128 + ch * 64;
                 uint32_t v0[32], v1[32];
-                tmem_ld_32x32b_x32(taddr, v0);
-                tmem_ld_32x32b_x32(taddr + 32, v1);
-                const int4* __restrict__ ck = reinterpret_cast<const int4*>(smem_key + (acc % kKeyStages) * kTileN + ch * 64);
-                tmem_ld_wait();
-                int m0 = 0x7fffffff, m1 = 0x7fffffff;
-#pragma unroll
-                for (int i = 0; i < 8; i++) {
-                    const int4 c0 = ck[i], c1 = ck[8 + i];                        // broadcast LDS.128
-                    const int p0 = c0.x - 64 * (int)v0[4 * i + 0];
-                    const int p1 = c0.y - 64 * (int)v0[4 * i + 1];
-                    const int p2 = c0.z - 64 * (int)v0[4 * i + 2];
-                    const int p3 = c0.w - 64 * (int)v0[4 * i + 3];
-                    m0 = __vimin3_s32(m0, p0, p1);
-                    m0 = __vimin3_s32(m0, p2, p3);
-                    const int q0 = c1.x - 64 * (int)v1[4 * i + 0];
-                    const int q1 = c1.y - 64 * (int)v1[4 * i + 1];
-                    const int q2 = c1.z - 64 * (int)v1[4 * i + 2];
-                    const int q3 = c1.w - 64 * (int)v1[4 * i + 3];
-                    m1 = __vimin3_s32(m1, q0, q1);
-                    m1 = __vimin3_s32(m1, q2, q3);
-                }
-                const int k0 = m0 >> 5, k1 = m1 >> 5;
-                if (k0 < best_key) { best_key = k0; best_j = t * kTileN + ch * 64 + (m0 & 31); }
-                if (k1 < best_key) { best_key = k1; best_j = t * kTileN + ch * 64 + 32 + (m1 & 31); }
+                tmem_ld_32x32b_x32(col0 + buf * 256, v0);                         // row block 0
+                tmem_ld_32x32b_x32(col0 + buf * 256 + 128, v1);                   // row block 1, same train columns
+                int4 kc = lds128(kaddr);                                          // first four keys while the loads fly
+                tmem_ld_wait_on(v0, v1);
+                // the accumulators are in registers: hand the buffer back BEFORE reducing them — the MMA of the tile after next
+                // needs it, and the tensor pipe is what this kernel has to keep busy
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&bar->tmem_empty[buf]);
+                pin_below(v0, v1);
+                if (dbg) { bk0 ^= (int)(v0[7] ^ v1[3]); continue; }                // timing experiments only (results are wrong)
+                // q = 64 a.b + ckey = -(32 (|b|^2 - 2 a.b) + (j & 31)): the maximum over the 32 columns is the nearest column and,
+                // among equals, the lowest one
+                int m0 = (int)0x80000000, m1 = (int)0x80000000;
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    const int4 c = kc;
+                    if (i < 7) kc = lds128(kaddr + 16 * (i + 1));                  // next four keys one step ahead of their use
+                    m0 = __vimax3_s32(m0, 64 * (int)v0[4 * i + 0] + c.x, 64 * (int)v0[4 * i + 1] + c.y);
+                    m1 = __vimax3_s32(m1, 64 * (int)v1[4 * i + 0] + c.x, 64 * (int)v1[4 * i + 1] + c.y);
+                    m0 = __vimax3_s32(m0, 64 * (int)v0[4 * i + 2] + c.z, 64 * (int)v0[4 * i + 3] + c.w);
+                    m1 = __vimax3_s32(m1, 64 * (int)v1[4 * i + 2] + c.z, 64 * (int)v1[4 * i + 3] + c.w);
+                }
+                // -m = 32 (|b|^2 - 2 a.b) + (j & 31) of the winning column: distance part and in-chunk index.  Strict <: an earlier
+                // tile keeps the row on equal distance.
+                const int P0 = -m0, P1 = -m1;
+                const int k0 = P0 >> 5, k1 = P1 >> 5;
+                if (k0 < bk0) { bk0 = k0; bj0 = t * kTileN + cs * 32 + (P0 & 31); }
+                if (k1 < bk1) { bk1 = k1; bj1 = t * kTileN + cs * 32 + (P1 & 31); }
             }
-            // merge the two column halves of a row: smaller key wins, equal keys keep the lower column (the halves visit
-            // disjoint columns, each in ascending order with a strict <)
-            int2* res = smem_res + (it & 1) * (kBlockM * 2);
-            res[row_in_block * 2 + ch] = make_int2(best_key, best_j);
+            // merge the four column slices of a row: smaller key wins, equal keys keep the lower column (the slices visit disjoint
+            // columns, each in ascending order with a strict <)
+            int2* res = smem_res + (it & 1) * (kBlockM * 4);
+            res[r0 * 4 + cs] = make_int2(bk0, bj0);
+            res[(128 + r0) * 4 + cs] = make_int2(bk1, bj1);
             named_bar_sync(1, 32 * kEpiWarps);
-            if (ch == 0 && row_in_block < w.q_valid) {
-                const int2 o = res[row_in_block * 2 + 1];
-                if (o.x < best_key || (o.x == best_key && o.y < best_j)) { best_key = o.x; best_j = o.y; }
-                out_idx[w.out_off + row_in_block] = best_j;
-                out_d2[w.out_off + row_in_block] = best_key + norm[w.q_row + row_in_block];
+            if (cs < 2) {
+                const int row = cs * 128 + r0;
+                if (row < w.q_valid) {
+                    int2 best = res[row * 4];
+#pragma unroll
+                    for (int q = 1; q < 4; q++) {
+                        const int2 o = res[row * 4 + q];
+                        if (o.x < best.x || (o.x == best.x && o.y < best.y)) best = o;
+                    }
+                    out_idx[w.out_off + row] = best.y;
+                    out_d2[w.out_off + row] = best.x + norm[w.q_row + row];
+                }
             }
         }
     }
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 2) {
+    if (warp == 0) {
         tc_fence_after();
         tmem_dealloc(tmem_base, 512);
     }
@@ -222,14 +243,16 @@ int uavm_launch_match(uavm_ctx* ctx, uavm_pairbatch* pb)
 {
     if (pb->n_items == 0) return UAVM_OK;
     UAVM_CUDA(ctx, cudaSetDevice(ctx->device));
+    // UAVM_K2_DBG != 0: timing experiment (wrong results) — the epilogue only drains TMEM and hands the buffers back, which leaves
+    // the TMA + MMA pipeline alone: 0.354 ms per 49 pairs = 1 000 cycles per 256 x 128 x 128 tile = 4 190 MAC / clk / SM
+    static const int dbg = getenv("UAVM_K2_DBG") ? atoi(getenv("UAVM_K2_DBG")) : 0;
     if (!ctx->k2_attr_set) {                              // function attributes are per device: tracked per context
         UAVM_CUDA(ctx, cudaFuncSetAttribute(k2_match_tcgen05, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
         ctx->k2_attr_set = true;
     }
     int grid = pb->n_items < ctx->sm_count ? pb->n_items : ctx->sm_count;
-    k2_match_tcgen05<<<grid, kThreads, kSmemBytes, ctx->stream>>>(pb->fs->tmap_q, pb->fs->tmap_t, pb->fs->d_ckey,
-                                                                   pb->fs->d_norm, pb->d_items, pb->n_items,
-                                                                   pb->d_train_idx, pb->d_d2);
+    k2_match_tcgen05<<<grid, kThreads, kSmemBytes, ctx->stream>>>(pb->fs->tmap_q, pb->fs->tmap_t, pb->fs->d_ckey, pb->fs->d_norm, pb->d_items, pb->n_items,
+                                                                   pb->d_train_idx, pb->d_d2, dbg);
     UAVM_CHECK_LAUNCH(ctx);
     pb->fs->pool_read_since_wait = true;                  // a later host upload into the pool has to wait for this launch
     return UAVM_OK;

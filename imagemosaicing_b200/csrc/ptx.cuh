@@ -131,6 +131,24 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&v)
 __device__ __forceinline__ void tmem_ld_wait() {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+// tcgen05.wait::ld with the loaded registers as in/out operands: arithmetic on them cannot be scheduled above the wait, and
+// what follows in the volatile-asm order (e.g. handing the TMEM buffer back) stays above that arithmetic only if pinned (below)
+#define UAVM_RW16(v, o) "+r"(v[o + 0]), "+r"(v[o + 1]), "+r"(v[o + 2]), "+r"(v[o + 3]), "+r"(v[o + 4]), "+r"(v[o + 5]), "+r"(v[o + 6]), "+r"(v[o + 7]), \
+                        "+r"(v[o + 8]), "+r"(v[o + 9]), "+r"(v[o + 10]), "+r"(v[o + 11]), "+r"(v[o + 12]), "+r"(v[o + 13]), "+r"(v[o + 14]), "+r"(v[o + 15])
+__device__ __forceinline__ void tmem_ld_wait_on(uint32_t (&a)[32], uint32_t (&b)[32]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;" : UAVM_RW16(a, 0), UAVM_RW16(a, 16), UAVM_RW16(b, 0), UAVM_RW16(b, 16) :: "memory");
+}
+// scheduling fence for the compiler: whatever is computed from a / b stays below this point of the volatile-asm order
+__device__ __forceinline__ void pin_below(uint32_t (&a)[32], uint32_t (&b)[32]) {
+    asm volatile("" : UAVM_RW16(a, 0), UAVM_RW16(a, 16), UAVM_RW16(b, 0), UAVM_RW16(b, 16));
+}
+#undef UAVM_RW16
+// 16-byte shared-memory load by shared-window address (a generic pointer makes the compiler emit LD.E instead of LDS)
+__device__ __forceinline__ int4 lds128(uint32_t saddr) {
+    int4 v;
+    asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr));
+    return v;
+}
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 "version 1" format):
 //   bits [0,14)  start address >> 4        bits [16,30) leading byte offset >> 4 (unused here)
