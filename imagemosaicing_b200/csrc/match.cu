@@ -16,18 +16,20 @@
 // What bounds it — measured, in this order of discovery:
 //  * NOT the TMEM read port: tcgen05.ld.32x32b.x32 sustains 39 / 68 / 87 words per clock per SM from 4 / 8 / 16 warps
 //    (scripts/microbench/ldtm.cu, profiles/r2_ldtm_microbench.txt); the kernel needs 32 768 words per tile.
-//  * The tensor pipe, at HALF the rate the int8 data sheet figure suggests: with the epilogue reduced to "drain TMEM, hand the
-//    buffer back" (UAVM_K2_DBG=2) the TMA + MMA pipeline alone takes 0.354 ms per 49 pairs = 1 000 cycles per 256 x 128 x 128
-//    tile = 4 190 MAC / clk / SM — kind::i8 M=128 N=128 K=32 issues every ~125 cycles, the same MAC rate as kind::f16
-//    (2.38 Pop/s at 1.965 GHz).  That is the roofline of this kernel on this part; ncu's sm__pipe_tensor_cycles_active (40 %)
-//    counts half of it.
+//  * The MMA pipeline of THIS configuration (cta_group::1, M=128 N=128 K=32, both operands from shared memory): with the epilogue
+//    reduced to "drain TMEM, hand the buffer back" (UAVM_K2_DBG=2) TMA + MMA alone take 0.354 ms per 49 pairs = 1 000 cycles per
+//    256 x 128 x 128 tile = 4 190 MAC / clk / SM = 2.38 Pop/s — one kind::i8 MMA every ~125 cycles, where the data-sheet int8
+//    rate would allow 64.  At that rate an SS-mode MMA reads 8 KB of operands per 64 cycles = the whole 128 B/clk of shared memory,
+//    next to the TMA writes; cuBLASLt's int8 GEMM (2-CTA MMA, operand sharing) reaches 2.83 Pop/s on the same box, bf16 1.60
+//    (scripts/microbench/int8_gemm_probe.py).  ncu's sm__pipe_tensor_cycles_active (40 %) does not show this.  Not pursued further:
+//    the epilogue below is the next limiter anyway.
 //  * The epilogue on top of it: 16 warps (four per scheduler).  First version: one row block and 64 columns per warp, column
 //    keys fetched with LDG (2 057 cycles per tile); then keys delivered to shared memory with the B tile (cp.async.bulk on the
 //    same mbarrier): 1 429.  ncu then showed the LSU data pipe 80 % busy — a broadcast key costs one wavefront per key and
 //    warp — and the accumulator buffer held until the reduction was done.  Now a warp reads 32 columns of BOTH row blocks (half
 //    the key loads), hands the TMEM buffer back as soon as its tcgen05.ld has landed, prefetches the keys one step ahead and
 //    reduces with a 3-input max of 64 a.b + ckey (keys stored negated): 1 270 cycles per tile, 0.449 ms per 49 pairs (0.70 in
-//    round 1) = 1.87 PFLOP/s = 0.79 of the measured tensor floor; configs[3] 0.159 ms.
+//    round 1) = 1.87 PFLOP/s = 0.79 of what the MMA pipeline above delivers alone; configs[3] 0.159 ms.
 //    Measured and rejected: one mbarrier pair per row block (0.199 vs 0.181 ms on configs[3]); 8- and 16-column software
 //    pipelines of the TMEM loads inside a warp (0.470 ms: they delay the buffer hand-over); 18 instead of 20 warps alone -5 %.
 //
@@ -244,7 +246,7 @@ int uavm_launch_match(uavm_ctx* ctx, uavm_pairbatch* pb)
     if (pb->n_items == 0) return UAVM_OK;
     UAVM_CUDA(ctx, cudaSetDevice(ctx->device));
     // UAVM_K2_DBG != 0: timing experiment (wrong results) — the epilogue only drains TMEM and hands the buffers back, which leaves
-    // the TMA + MMA pipeline alone: 0.354 ms per 49 pairs = 1 000 cycles per 256 x 128 x 128 tile = 4 190 MAC / clk / SM
+    // the TMA + MMA pipeline alone: 0.354 ms per 49 pairs = 1 000 cycles per 256 x 128 x 128 tile (see the header)
     static const int dbg = getenv("UAVM_K2_DBG") ? atoi(getenv("UAVM_K2_DBG")) : 0;
     if (!ctx->k2_attr_set) {                              // function attributes are per device: tracked per context
         UAVM_CUDA(ctx, cudaFuncSetAttribute(k2_match_tcgen05, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
