@@ -753,7 +753,11 @@ def run_ours(args):
                                 "frames; with a BGRA pool: 49 x k5_bgr_to_bgra_x4 first) on the main stream; serial_ms: each stage alone, 3 extra untimed steps",
                         "source_pool": "BGR (3 B/px, frames kept as handed over; no conversion kernel)" if bgr_pool else "BGRA (4 B/px, conversion inside the step)",
                         "k2_match_tcgen05": {"serial_ms": float(serial_ms[0]), "bound": "tensor", "achieved_tflops": match_tf,
-                                             "peak_bf16_tflops": pk["bf16_tflops"], "frac_of_bf16_peak": match_tf / pk["bf16_tflops"]},
+                                             "peak_bf16_tflops": pk["bf16_tflops"], "frac_of_bf16_peak": match_tf / pk["bf16_tflops"],
+                                             "static_context": {"mma_pipeline_alone_ms": 0.354, "mma_pipeline_alone_tops": 2380.0,
+                                                                "library_int8_gemm_tops": 2826.0, "tmem_drain_words_per_clk_per_sm_16_warps": 87.0,
+                                                                "src": "UAVM_K2_DBG=2 run of this bench, scripts/microbench/int8_gemm_probe.py and "
+                                                                       "ldtm.cu on a B200 of this pool (not measured in this run)"}},
                         "k3_select": {"serial_ms": float(serial_ms[1])},
                         "k4_ransac_eval+finalize": {"serial_ms": float(serial_ms[2]), "draw_groups_per_s": n_pairs * 2304 / (serial_ms[2] / 1000.0)},
                         "k5_bgr_to_bgra_x4 (49 launches)": None if bgr_pool else {"ms_in_step": float(conv_ms), "serial_ms": float(serial_ms[4]),
