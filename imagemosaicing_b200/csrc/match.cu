@@ -90,7 +90,7 @@ k2_match_tcgen05(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         for (int s = 0; s < kStages; s++) { mbar_init(&bar->full[s], 1); mbar_init(&bar->empty[s], 1); }
         mbar_init(&bar->a_full, 1);
         mbar_init(&bar->a_empty, 1);
-        for (int b = 0; b < 2; b++) { mbar_init(&bar->tmem_full[b], 1); mbar_init(&bar->tmem_empty[b], kEpiWarps); }
+        for (int b = 0; b < 2; b++) { mbar_init(&bar->tmem_full[b], 1); mbar_init(&bar->tmem_empty[b], kEpiWarps / 2); }
         fence_mbar_init();
     }
     if (warp == 0) {
@@ -157,66 +157,77 @@ k2_match_tcgen05(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         __syncwarp();
     } else if (warp >= kCtlWarps) {
         // ===================== epilogue: TMEM -> registers -> running arg-min =====================
-        // This warp: TMEM lane quarter `quarter` (a warp may only read lanes 32 (warp % 4) ..), columns [32 cs, 32 cs + 32) of BOTH
-        // row blocks — one key load serves two accumulators (a broadcast key costs one LSU wavefront per key and warp: 80 % LSU
-        // utilisation when a warp owned one row block).
+        // Two groups of 8 warps, one per TMEM buffer: group g reduces the tiles that land in buffer g (the MMA warp alternates
+        // buffers tile by tile, across items), so while one group drains its buffer the other one is computing on the previous tile; with all 16 warps in lockstep on one tile the TMEM drain (~380 cycles) and the
+        // reduction (~600) of every tile were serialised.
+        // This warp: TMEM lane quarter `quarter` (a warp may only read lanes 32 (warp % 4) ..), columns [64 half, 64 half + 64) of
+        // BOTH row blocks in two passes of 32 columns — one key load serves two accumulators (a broadcast key costs one LSU
+        // wavefront per key and warp: 80 % LSU utilisation when a warp owned one row block).
         const int ew = warp - kCtlWarps;
         const int quarter = warp & 3;
-        const int cs = ew >> 2;
-        const uint32_t col0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + cs * 32;
-        const uint32_t key_base = smem_u32(smem_key) + cs * 32 * 4;
+        const int g = ew >> 3;
+        const int half = (ew >> 2) & 1;
+        const int slice = 2 * g + half;
+        const uint32_t col0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + g * 256 + half * 64;
+        const uint32_t key_base = smem_u32(smem_key) + half * 64 * 4;
         const int r0 = quarter * 32 + lane;               // this thread's row inside a row block
-        uint32_t acc = 0, it = 0;
+        uint32_t use = 0, tile_base = 0, it = 0;          // uses of buffer g so far; tiles of earlier items (key ring position)
         for (int item = blockIdx.x; item < n_items; item += gridDim.x, it++) {
             const MatchItem w = items[item];
             int bk0 = 0x7fffffff, bj0 = 0, bk1 = 0x7fffffff, bj1 = 0;              // running (distance part, column) of row blocks 0 / 1
-            for (int t = 0; t < w.n_tiles; t++, acc++) {
-                const uint32_t buf = acc & 1;
-                const uint32_t kaddr = key_base + (acc % kKeyStages) * kKeyBytes;
+            for (int t = (g ^ (int)tile_base) & 1; t < w.n_tiles; t += 2, use++) {      // tile t of this item lands in buffer (tile_base + t) & 1
+                const uint32_t kaddr = key_base + ((tile_base + t) % kKeyStages) * kKeyBytes;
                 // the keys of this tile landed with its B tile (same mbarrier), which the MMA thread observed before it issued the
                 // MMAs whose completion tmem_full signals.  (Waiting on full[] here as well would be wrong: the producer may
                 // already have re-armed that stage twice, and a parity wait cannot tell phase k from phase k + 2.)
-                mbar_wait(&bar->tmem_full[buf], (acc >> 1) & 1);
+                mbar_wait(&bar->tmem_full[g], use & 1);
                 tc_fence_after();
-                uint32_t v0[32], v1[32];
-                tmem_ld_32x32b_x32(col0 + buf * 256, v0);                         // row block 0
-                tmem_ld_32x32b_x32(col0 + buf * 256 + 128, v1);                   // row block 1, same train columns
-                int4 kc = lds128(kaddr);                                          // first four keys while the loads fly
-                tmem_ld_wait_on(v0, v1);
-                // the accumulators are in registers: hand the buffer back BEFORE reducing them — the MMA of the tile after next
-                // needs it, and the tensor pipe is what this kernel has to keep busy
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&bar->tmem_empty[buf]);
-                pin_below(v0, v1);
-                if (dbg) { bk0 ^= (int)(v0[7] ^ v1[3]); continue; }                // timing experiments only (results are wrong)
-                // q = 64 a.b + ckey = -(32 (|b|^2 - 2 a.b) + (j & 31)): the maximum over the 32 columns is the nearest column and,
-                // among equals, the lowest one
-                int m0 = (int)0x80000000, m1 = (int)0x80000000;
 #pragma unroll
-                for (int i = 0; i < 8; i++) {
-                    const int4 c = kc;
-                    if (i < 7) kc = lds128(kaddr + 16 * (i + 1));                  // next four keys one step ahead of their use
-                    m0 = __vimax3_s32(m0, 64 * (int)v0[4 * i + 0] + c.x, 64 * (int)v0[4 * i + 1] + c.y);
-                    m1 = __vimax3_s32(m1, 64 * (int)v1[4 * i + 0] + c.x, 64 * (int)v1[4 * i + 1] + c.y);
-                    m0 = __vimax3_s32(m0, 64 * (int)v0[4 * i + 2] + c.z, 64 * (int)v0[4 * i + 3] + c.w);
-                    m1 = __vimax3_s32(m1, 64 * (int)v1[4 * i + 2] + c.z, 64 * (int)v1[4 * i + 3] + c.w);
+                for (int pass = 0; pass < 2; pass++) {
+                    uint32_t v0[32], v1[32];
+                    tmem_ld_32x32b_x32(col0 + 32 * pass, v0);                     // row block 0
+                    tmem_ld_32x32b_x32(col0 + 32 * pass + 128, v1);               // row block 1, same train columns
+                    int4 kc = lds128(kaddr + 128 * pass);                         // first four keys while the loads fly
+                    tmem_ld_wait_on(v0, v1);
+                    if (pass == 1) {
+                        // all of this warp's accumulators are in registers: hand the buffer back BEFORE reducing them — the MMA of
+                        // the tile after next needs it
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&bar->tmem_empty[g]);
+                    }
+                    pin_below(v0, v1);
+                    if (dbg) { bk0 ^= (int)(v0[7] ^ v1[3]); continue; }            // timing experiments only (results are wrong)
+                    // q = 64 a.b + ckey = -(32 (|b|^2 - 2 a.b) + (j & 31)): the maximum over the 32 columns is the nearest column
+                    // and, among equals, the lowest one
+                    int m0 = (int)0x80000000, m1 = (int)0x80000000;
+#pragma unroll
+                    for (int i = 0; i < 8; i++) {
+                        const int4 c = kc;
+                        if (i < 7) kc = lds128(kaddr + 128 * pass + 16 * (i + 1)); // next four keys one step ahead of their use
+                        m0 = __vimax3_s32(m0, 64 * (int)v0[4 * i + 0] + c.x, 64 * (int)v0[4 * i + 1] + c.y);
+                        m1 = __vimax3_s32(m1, 64 * (int)v1[4 * i + 0] + c.x, 64 * (int)v1[4 * i + 1] + c.y);
+                        m0 = __vimax3_s32(m0, 64 * (int)v0[4 * i + 2] + c.z, 64 * (int)v0[4 * i + 3] + c.w);
+                        m1 = __vimax3_s32(m1, 64 * (int)v1[4 * i + 2] + c.z, 64 * (int)v1[4 * i + 3] + c.w);
+                    }
+                    // -m = 32 (|b|^2 - 2 a.b) + (j & 31) of the winning column: distance part and in-chunk index.  Strict <: an
+                    // earlier chunk keeps the row on equal distance.
+                    const int P0 = -m0, P1 = -m1;
+                    const int k0 = P0 >> 5, k1 = P1 >> 5;
+                    const int jb = t * kTileN + half * 64 + 32 * pass;
+                    if (k0 < bk0) { bk0 = k0; bj0 = jb + (P0 & 31); }
+                    if (k1 < bk1) { bk1 = k1; bj1 = jb + (P1 & 31); }
                 }
-                // -m = 32 (|b|^2 - 2 a.b) + (j & 31) of the winning column: distance part and in-chunk index.  Strict <: an earlier
-                // tile keeps the row on equal distance.
-                const int P0 = -m0, P1 = -m1;
-                const int k0 = P0 >> 5, k1 = P1 >> 5;
-                if (k0 < bk0) { bk0 = k0; bj0 = t * kTileN + cs * 32 + (P0 & 31); }
-                if (k1 < bk1) { bk1 = k1; bj1 = t * kTileN + cs * 32 + (P1 & 31); }
             }
-            // merge the four column slices of a row: smaller key wins, equal keys keep the lower column (the slices visit disjoint
-            // columns, each in ascending order with a strict <)
+            tile_base += w.n_tiles;
+            // merge the four slices of a row (tile parity x column half): smaller key wins, equal keys keep the lower column (the
+            // slices visit disjoint columns, each in ascending order with a strict <)
             int2* res = smem_res + (it & 1) * (kBlockM * 4);
-            res[r0 * 4 + cs] = make_int2(bk0, bj0);
-            res[(128 + r0) * 4 + cs] = make_int2(bk1, bj1);
+            res[r0 * 4 + slice] = make_int2(bk0, bj0);
+            res[(128 + r0) * 4 + slice] = make_int2(bk1, bj1);
             named_bar_sync(1, 32 * kEpiWarps);
-            if (cs < 2) {
-                const int row = cs * 128 + r0;
+            if (slice < 2) {
+                const int row = slice * 128 + r0;
                 if (row < w.q_valid) {
                     int2 best = res[row * 4];
 #pragma unroll

@@ -42,6 +42,29 @@ def test_match_ties_duplicates_and_extremes(ctx, oracle):
     assert np.array_equal((m["distance"].astype(np.float64) ** 2).round().astype(np.int64), d2.astype(np.int64))
 
 
+def test_match_many_small_pairs_odd_tile_counts(ctx, oracle):
+    """More work items than SMs, train images of 1, 2 and 3 tiles of 128 rows: every persistent CTA walks several items and the
+    accumulator-buffer parity at the start of an item alternates (the two epilogue warp groups are bound to one TMEM buffer each)."""
+    rng = np.random.default_rng(23)
+    sizes = [100, 300, 129, 257, 384, 64, 200, 333]
+    descs = [_rand_desc(rng, n) for n in sizes]
+    descs[3][5] = descs[3][200]; descs[1][7] = descs[1][290]                       # duplicates across tiles: lowest index must win
+    fs = api.FeatureSet(ctx, sizes)
+    for i, d in enumerate(descs):
+        fs.upload(i, d)
+    pairs = [[i, j] for r in range(5) for i in range(len(sizes)) for j in range(len(sizes))]      # 320 pairs, ~450 work items
+    pb = api.PairBatch(ctx, fs, pairs)
+    pb.match()
+    ref = {}
+    for p, (i, j) in enumerate(pairs):
+        if (i, j) not in ref:
+            ref[(i, j)] = oracle.match_l2(descs[i], descs[j])
+        idx, d2 = ref[(i, j)]
+        m = pb.matches(p)
+        assert np.array_equal(m["trainIdx"], idx), (p, i, j)
+        assert np.array_equal(np.rint(m["distance"].astype(np.float64) ** 2).astype(np.int64), d2.astype(np.int64)), (p, i, j)
+
+
 def test_match_batched_pairs_full_size(ctx, oracle):
     """BASELINE config sizes: 8192 keypoints per image, several pairs in one launch; checked against the
     oracle on two pairs and by a size-independent property on the rest (d2 recomputed from the indices)."""
