@@ -10,7 +10,8 @@
 //   warp 0      TMEM allocator (512 columns = 2 accumulator buffers x 2 row blocks x 128 columns), then TMA producer (A block once
 //               per item; B tiles through a kStages-deep smem ring, each with its 128 column keys)
 //   warp 1      MMA issuer    (one elected lane; 2 row blocks x 4 K-chunks of 32 per train tile)
-//   warps 2-17  epilogue      (warp w reads TMEM lanes 32*(w%4).., 32 columns ((w-2)/4) of BOTH row blocks)
+//   warps 2-17  epilogue      (two groups of 8, one per TMEM buffer; warp w reads TMEM lanes 32*(w%4).., 64 columns of BOTH row
+//               blocks in two passes of 32)
 // Pipelines: smem full/empty (TMA <-> MMA), TMEM full/empty (MMA <-> epilogue), A full/empty.
 //
 // What bounds it — measured, in this order of discovery:
@@ -28,8 +29,10 @@
 //    same mbarrier): 1 429.  ncu then showed the LSU data pipe 80 % busy — a broadcast key costs one wavefront per key and
 //    warp — and the accumulator buffer held until the reduction was done.  Now a warp reads 32 columns of BOTH row blocks (half
 //    the key loads), hands the TMEM buffer back as soon as its tcgen05.ld has landed, prefetches the keys one step ahead and
-//    reduces with a 3-input max of 64 a.b + ckey (keys stored negated): 1 270 cycles per tile, 0.449 ms per 49 pairs (0.70 in
-//    round 1) = 1.87 PFLOP/s = 0.79 of what the MMA pipeline above delivers alone; configs[3] 0.159 ms.
+//    reduces with a 3-input max of 64 a.b + ckey (keys stored negated): 1 270 cycles per tile, 0.449 ms per 49 pairs.  With all
+//    16 warps in lockstep on one tile the TMEM drain (~380 cycles at 87 words/clk) and the reduction (~600, ALU pipe) of a tile
+//    are serialised; two groups of 8 warps, one per TMEM buffer, overlap them: 1 200 cycles per tile, 0.425 ms per 49 pairs
+//    (0.70 in round 1) = 1.98 PFLOP/s = 0.82 of what the MMA pipeline above delivers alone; configs[3] 0.154 ms.
 //    Measured and rejected: one mbarrier pair per row block (0.199 vs 0.181 ms on configs[3]); 8- and 16-column software
 //    pipelines of the TMEM loads inside a warp (0.470 ms: they delay the buffer hand-over); 18 instead of 20 warps alone -5 %.
 //
