@@ -581,19 +581,17 @@ def run_ours(args):
         mev[s][2].record()
         ctx.join()
     barrier()
-    conv_ms = sum(e[0].elapsed_time(e[1]) for e in mev) / n_ev
-    warp_ms_instep = sum(e[1].elapsed_time(e[2]) for e in mev) / n_ev
-    # serial pass (not part of `value`): every stage alone on the stream, for the per-kernel table
-    n_ser = 3
+    conv_ms = float(np.median([e[0].elapsed_time(e[1]) for e in mev]))
+    warp_ms_instep = float(np.median([e[1].elapsed_time(e[2]) for e in mev]))
+    # serial pass (not part of `value`): every stage alone on the stream, for the per-kernel table (median of 5: a concurrent
+    # nvidia-smi query of the clock sampler or a host hiccup can stretch a single sample by milliseconds)
+    n_ser = 5
     sev = [[torch.cuda.Event(enable_timing=True) for _ in range(7)] for _ in range(n_ser)]
     for s in range(n_ser):
         compute(sev[s], overlap=False)
     barrier()
-    serial_ms = np.zeros(6)
-    for s in range(n_ser):
-        for k in range(6):
-            serial_ms[k] += sev[s][k].elapsed_time(sev[s][k + 1])
-    serial_ms /= n_ser                                      # match, select, ransac, -, convert, warp
+    serial_ms = np.median(np.array([[sev[s][k].elapsed_time(sev[s][k + 1]) for k in range(6)] for s in range(n_ser)]), axis=0)
+    # match, select, ransac, -, convert, warp
 
     # ---- end-to-end timing (host buffers in, inlier match list out) ----
     # API order of a streaming caller: descriptors first, match/select/RANSAC start while the frames are still
@@ -748,9 +746,9 @@ def run_ours(args):
                          "frac": warp_gbs / pk["hbm_gbs"], "traffic": traffic, "traffic_src": traffic_src, "peak_src": pk["src"],
                          "algorithmic_bytes_per_launch": warp_bytes, "ms_per_launch": float(warp_ms_instep),
                          "note": "ms_per_launch: CUDA events around the warp on the main stream inside the overlapped step (RANSAC on the side stream), "
-                                 "5 extra steps after the timed region"},
+                                 "median of 5 extra steps after the timed region"},
             "kernels": {"note": "value's step = pair path (k2, k3, k4) on the high-priority side stream || frame path (k5 warp straight from the resident BGR "
-                                "frames; with a BGRA pool: 49 x k5_bgr_to_bgra_x4 first) on the main stream; serial_ms: each stage alone, 3 extra untimed steps",
+                                "frames; with a BGRA pool: 49 x k5_bgr_to_bgra_x4 first) on the main stream; serial_ms: each stage alone, median of 5 extra untimed steps",
                         "source_pool": "BGR (3 B/px, frames kept as handed over; no conversion kernel)" if bgr_pool else "BGRA (4 B/px, conversion inside the step)",
                         "k2_match_tcgen05": {"serial_ms": float(serial_ms[0]), "bound": "tensor", "achieved_tflops": match_tf,
                                              "peak_bf16_tflops": pk["bf16_tflops"], "frac_of_bf16_peak": match_tf / pk["bf16_tflops"],
