@@ -399,7 +399,11 @@ def run_canvas500(args, ctx, nd, rank, world, dev):
     lay, chips = api.canvas_layout(T, keep, W, H)
     cw, ch = lay.canvas_w, lay.canvas_h
     chip_px = sum(chips[k].chip_w * chips[k].chip_h for k in range(n) if chips[k].keep)
-    rects = D.canvas_grid(cw, ch, world)
+    # one rectangle per rank; the cuts equalise work (cells weighted by how many chips cover them), not area
+    if os.environ.get("UAVM_BENCH_GRID", "balanced") == "area":
+        rects = D.canvas_grid(cw, ch, world)
+    else:
+        rects = D.canvas_grid_balanced(cw, ch, world, [(chips[k].beg_x, chips[k].beg_y, chips[k].chip_w, chips[k].chip_h) for k in range(n) if chips[k].keep])
     # HBM needed on this rank (sources + chips + masks of the active frames, chip pyramids, final canvas levels, result)
     frac = 1.0 if world == 1 else min(1.0, 2.2 / world)
     need = frac * (n * W * H * 4 + chip_px * 9) + cw * ch * 4 + cw * ch * 3 / world + 3e9
@@ -432,7 +436,12 @@ def run_canvas500(args, ctx, nd, rank, world, dev):
     if world > 1: dist.barrier()
     t = np.min(np.array([run() for _ in range(2)]), axis=0)
     tt = torch.tensor(list(t), device=dev, dtype=torch.float64)
-    if world > 1: dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    per_rank = None
+    if world > 1:
+        allt = [torch.zeros_like(tt) for _ in range(world)]
+        dist.all_gather(allt, tt)
+        per_rank = [float(x[0] + x[1] + x[2]) for x in allt]          # seam + warp + blend of every rank (before the gather barrier)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     res = None
     if rank == 0:
         # checksum of the assembled mosaic on the device (must not depend on N)
@@ -453,6 +462,7 @@ def run_canvas500(args, ctx, nd, rank, world, dev):
         res = {"workload": f"configs[4]: {int(keep.sum())} warped tiles of {W}x{H} -> {cw}x{ch} canvas, 5 bands; strong scaling, one canvas rectangle per GPU",
                "n_gpus": world, "rects": [list(map(int, r)) for r in rects], "warp_ms": warp_ms, "seam_masks_ms": seam_ms, "blend_ms": blend_ms,
                "gather_ms": gather_ms, "total_ms": total_ms, "canvas_mpx_per_s": cw * ch / 1e6 / (total_ms / 1e3),
+               "per_rank_compute_ms": per_rank,
                "gather": ("fused: the blend's level-0 kernel stores every rank's rectangle into rank 0's mosaic over NVLink (uavm_canvas_bind_root); "
                           "gather_ms is the completion barrier" if bound else "uavm_canvas_gather after the blend" if world > 1 else "none (one GPU)"),
                "mosaic_checksum": [int(chk[0]), int(chk[1])], "fed_chip_mpx": chip_px / 1e6,

@@ -94,3 +94,47 @@ def canvas_grid(canvas_w, canvas_h, world, align=32):
         return [min((units * k // g) * align, n) for k in range(g)] + [n]
     xs, ys = cuts(canvas_w, gx), cuts(canvas_h, gy)
     return [(xs[i], ys[j], xs[i + 1], ys[j + 1]) for j in range(gy) for i in range(gx)]
+
+
+def canvas_grid_balanced(canvas_w, canvas_h, world, chip_boxes, align=32, base_cost=2.0):
+    """Like canvas_grid, but the cuts equalise WORK instead of area: a canvas cell costs base_cost + the number of chips covering
+    it (the seam masks evaluate every covering chip per pixel, the blend visits them, the warp and the pyramids follow what a
+    rectangle owns).  Column cuts first, then every column group gets its own row cuts, so the rectangles still partition the
+    canvas.  chip_boxes: iterable of (beg_x, beg_y, chip_w, chip_h) of the kept chips in canvas coordinates."""
+    import numpy as np
+    best = None
+    for gx in range(1, world + 1):
+        if world % gx:
+            continue
+        gy = world // gx
+        c = abs(canvas_w / gx - canvas_h / gy)
+        if best is None or c < best[0]:
+            best = (c, gx, gy)
+    _, gx, gy = best
+    wu, hu = (canvas_w + align - 1) // align, (canvas_h + align - 1) // align
+    cover = np.zeros((hu + 1, wu + 1), np.float64)                  # 2-D difference array of the chip boxes, in cells
+    for (bx, by, w, h) in chip_boxes:
+        x0, y0 = max(int(bx) // align, 0), max(int(by) // align, 0)
+        x1, y1 = min((int(bx) + int(w) + align - 1) // align, wu), min((int(by) + int(h) + align - 1) // align, hu)
+        if x1 <= x0 or y1 <= y0:
+            continue
+        cover[y0, x0] += 1; cover[y0, x1] -= 1; cover[y1, x0] -= 1; cover[y1, x1] += 1
+    cost = cover.cumsum(0).cumsum(1)[:hu, :wu] + base_cost
+
+    def cuts(weights, g, n):
+        cum = np.concatenate([[0.0], np.cumsum(weights)])
+        out = [0]
+        for k in range(1, g):
+            u = int(np.searchsorted(cum, cum[-1] * k / g))
+            u = min(max(u, out[-1] // align + 1), len(weights) - (g - k))      # strictly increasing, room for the rest
+            out.append(min(u * align, n))
+        return out + [n]
+
+    xs = cuts(cost.sum(0), gx, canvas_w)
+    rects = [None] * world
+    for i in range(gx):
+        c0, c1 = xs[i] // align, (xs[i + 1] + align - 1) // align
+        ys = cuts(cost[:, c0:c1].sum(1), gy, canvas_h)
+        for j in range(gy):
+            rects[j * gx + i] = (xs[i], ys[j], xs[i + 1], ys[j + 1])
+    return rects

@@ -66,3 +66,24 @@ def test_reference_pair_window():
     p = D.reference_pair_list(200, 182)
     assert len(p) == 19729                       # the reference rule on a 200-image block
     assert len(D.reference_pair_list(50, 2)) == 49
+
+
+def test_canvas_grid_balanced_partitions_the_canvas():
+    """The work-balanced grid is still a partition of the canvas into `world` rectangles with aligned inner edges."""
+    import numpy as np
+    from imagemosaicing_b200 import dist as D
+    rng = np.random.default_rng(4)
+    cw, ch = 10007, 7013
+    boxes = [(int(rng.integers(0, cw - 900)), int(rng.integers(0, ch - 700)), 900, 700) for _ in range(60)]
+    for world in (1, 2, 3, 4, 6, 8):
+        rects = D.canvas_grid_balanced(cw, ch, world, boxes)
+        assert len(rects) == world
+        cover = np.zeros((ch // 7 + 1, cw // 7 + 1), np.int32)       # sampled coverage count
+        area = 0
+        for (x0, y0, x1, y1) in rects:
+            assert 0 <= x0 < x1 <= cw and 0 <= y0 < y1 <= ch
+            assert x0 % 32 == 0 and y0 % 32 == 0 and (x1 % 32 == 0 or x1 == cw) and (y1 % 32 == 0 or y1 == ch)
+            area += (x1 - x0) * (y1 - y0)
+            ys = np.arange(0, ch, 7); xs = np.arange(0, cw, 7)
+            cover[np.ix_((ys >= y0) & (ys < y1), (xs >= x0) & (xs < x1))] += 1
+        assert area == cw * ch and cover[:len(np.arange(0, ch, 7)), :len(np.arange(0, cw, 7))].min() == 1 and cover.max() == 1
