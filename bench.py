@@ -527,16 +527,20 @@ def run_ours(args):
     ctx.sync(); torch.cuda.synchronize()
 
     def compute(ev=None, overlap=True):
-        """One step from BGR frames.  With overlap (the shipped configuration) the pair path (match -> select -> RANSAC) runs
-        on the ctx's high-priority side stream while the frame path (BGR -> BGRA pass of set_image, then the warp) runs on
-        the main stream: the bandwidth-bound conversions sit next to the tensor-bound match, the latency-bound RANSAC next
-        to the issue-bound warp.  The serial variant times each stage alone."""
-        sched = os.environ.get("UAVM_BENCH_SCHED", "pair_path_side")     # experiment knob: which stages share the side stream
+        """One step from BGR frames.  With overlap (the shipped configuration) K2 runs first on the main stream — its CTAs take every
+        SM's register file, nothing co-resides with it — then select -> RANSAC go to the ctx's high-priority side stream while the
+        frame path (BGR -> BGRA pass of set_image when the pool is BGRA, then the warp) follows K2 on the main stream: the
+        latency-bound RANSAC runs next to the issue-bound warp.  UAVM_BENCH_SCHED=pair_path_side forks before K2 instead (same
+        step time within 1 %, but the warp's events then also span the time it waits for K2's SMs).  The serial variant times each
+        stage alone."""
+        sched = os.environ.get("UAVM_BENCH_SCHED", "after_match")     # experiment knob: which stages share the side stream
         if overlap and sched == "pair_path_side":
             ctx.fork()
         if ev: ev[0].record()
         pb.match()
         if ev: ev[1].record()
+        if overlap and sched == "after_match":
+            ctx.fork()
         pb.select(W, H)
         if ev: ev[2].record()
         if overlap and sched == "ransac_side":
@@ -581,7 +585,10 @@ def run_ours(args):
     n_ev = 5
     mev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(n_ev)]
     for s in range(n_ev):
-        ctx.fork(); pb.match(); pb.select(W, H); pb.ransac(RANSAC_DIST, SAMPLE_TIMES, base_seed=1000); ctx.unfork()
+        if os.environ.get("UAVM_BENCH_SCHED", "after_match") == "after_match":
+            pb.match(); ctx.fork(); pb.select(W, H); pb.ransac(RANSAC_DIST, SAMPLE_TIMES, base_seed=1000); ctx.unfork()
+        else:
+            ctx.fork(); pb.match(); pb.select(W, H); pb.ransac(RANSAC_DIST, SAMPLE_TIMES, base_seed=1000); ctx.unfork()
         mev[s][0].record()
         if not bgr_pool:
             for k in range(1, NIMG):
@@ -755,9 +762,9 @@ def run_ours(args):
             "roofline": {"kernel": "k5_warp_affine_x2", "bound": "hbm", "achieved": warp_gbs, "peak": pk["hbm_gbs"], "unit": "GB/s",
                          "frac": warp_gbs / pk["hbm_gbs"], "traffic": traffic, "traffic_src": traffic_src, "peak_src": pk["src"],
                          "algorithmic_bytes_per_launch": warp_bytes, "ms_per_launch": float(warp_ms_instep),
-                         "note": "ms_per_launch: CUDA events around the warp on the main stream inside the overlapped step (RANSAC on the side stream), "
+                         "note": "ms_per_launch: CUDA events around the warp inside the overlapped step: it follows k2 on the main stream while select + RANSAC run beside it on the side stream; "
                                  "median of 5 extra steps after the timed region"},
-            "kernels": {"note": "value's step = pair path (k2, k3, k4) on the high-priority side stream || frame path (k5 warp straight from the resident BGR "
+            "kernels": {"note": "value's step = k2 on the main stream, then k3 + k4 on the high-priority side stream || frame path (k5 warp straight from the resident BGR "
                                 "frames; with a BGRA pool: 49 x k5_bgr_to_bgra_x4 first) on the main stream; serial_ms: each stage alone, median of 5 extra untimed steps",
                         "source_pool": "BGR (3 B/px, frames kept as handed over; no conversion kernel)" if bgr_pool else "BGRA (4 B/px, conversion inside the step)",
                         "k2_match_tcgen05": {"serial_ms": float(serial_ms[0]), "bound": "tensor", "achieved_tflops": match_tf,
