@@ -645,7 +645,8 @@ def run_ours(args):
     # ---- the same step with the frames handed over as JPEG bytes (f4): decoded on the device by nvJPEG straight into the source
     # pool.  Informational: at 4000x3000 the step becomes decode bound (the raw frames cross PCIe at ~18 Gpx/s).
     enc_info = None
-    if rank == 0 and not args.no_jpeg:
+    if rank == 0 and world == 1 and not args.no_jpeg:     # one GPU only: with N ranks the other ranks' host threads spin at the barrier
+        # and fight the decoder lanes for the cores
         try:
             import cv2
             t0 = time.perf_counter()
