@@ -676,6 +676,7 @@ extern "C" void uavm_canvas_destroy(uavm_ctx* ctx, uavm_canvas* cv)
     for (int e = 0; e < uavm_canvas::kWarpEvents; e++) if (cv->ev_warp[e]) cudaEventDestroy(cv->ev_warp[e]);
     uavm_blend_free(cv);
     cudaFree(cv->d_src); cudaFree(cv->d_chips); cudaFree(cv->d_masks); cudaFree(cv->d_dist_max); cudaFree(cv->d_k6); cudaFree(cv->d_mask_ptr); cudaFree(cv->d_mask_step); cudaFree(cv->d_own_bbox);
+    if (cv->bound_dist) uavm_dist_forget_canvas(cv->bound_dist, cv);
     cudaFree(cv->d_desc); cudaFree(cv->d_result); cudaFree(cv->d_result_mask);
     delete cv;
 }

@@ -63,6 +63,7 @@ struct uavm_canvas {
     uint8_t* peer_result = nullptr;  // the root's d_result mapped over NVLink (uavm_canvas_bind_root, non-root ranks): level 0 of the blend writes there too
     int bound_root = -1;             // root of that binding (-1: none), set on every rank
     int blend_bound_root = -1;       // binding the last blend ran under (uavm_canvas_gather: nothing left to copy)
+    void* bound_dist = nullptr;      // the uavm_dist that binding belongs to (it owns the peer mapping; one bound canvas per uavm_dist)
     // canvas rectangle owned by this context/rank (multi-GPU canvas sharding): output pixels [rect_x0, rect_x1) x
     // [rect_y0, rect_y1) (even edges); default = the whole canvas.  K6 produces seam masks on the rectangle grown by
     // kShardMargin (what K7's pyramids of the rectangle can depend on), K5 the chip pixels K7 can read.
@@ -78,4 +79,5 @@ struct uavm_canvas {
 int uavm_canvas_upload_desc(uavm_ctx* ctx, uavm_canvas* cv);
 int uavm_canvas_mask_plane(uavm_ctx* ctx, uavm_canvas* cv);   // makes sure d_masks is populated (validity masks if K6 has not run)
 void uavm_blend_free(uavm_canvas* cv);
+void uavm_dist_forget_canvas(void* dist, uavm_canvas* cv);     // canvas destroyed / rebound: the uavm_dist drops its pointer to it
 int uavm_canvas_ensure_result(uavm_ctx* ctx, uavm_canvas* cv); // allocates (and zeroes) the blend's mosaic buffers for the canvas layout

@@ -177,7 +177,22 @@ struct uavm_dist {
     // direct gather: the root's result buffer mapped into this process (CUDA IPC), keyed by its handle
     uint8_t* d_ipc = nullptr;                         // [64 handle bytes | 4-byte barrier word]
     cudaIpcMemHandle_t peer_handle; void* peer_ptr = nullptr; bool peer_failed = false;
+    uavm_canvas* bound_cv = nullptr;                  // the canvas whose blend writes through peer_ptr (uavm_canvas_bind_root), at most one
 };
+
+// the mapping in d->peer_ptr is about to change or go away: the canvas that writes through it must stop doing so
+static void unbind_current(uavm_dist* d)
+{
+    if (!d->bound_cv) return;
+    d->bound_cv->peer_result = nullptr; d->bound_cv->bound_root = -1; d->bound_cv->bound_dist = nullptr;
+    d->bound_cv = nullptr;
+}
+
+void uavm_dist_forget_canvas(void* dist, uavm_canvas* cv)
+{
+    uavm_dist* d = static_cast<uavm_dist*>(dist);
+    if (d && d->bound_cv == cv) d->bound_cv = nullptr;
+}
 
 extern "C" int uavm_dist_unique_id(uint8_t* id_out, int id_bytes)
 {
@@ -211,6 +226,7 @@ extern "C" void uavm_dist_destroy(uavm_ctx* ctx, uavm_dist* d)
     if (!d) return;
     if (ctx) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
     cudaFree(d->d_send); cudaFree(d->d_recv); cudaFree(d->d_offsets); cudaFree(d->d_nacc); cudaFree(d->d_dense); cudaFree(d->d_tmp);
+    unbind_current(d);
     if (d->peer_ptr) cudaIpcCloseMemHandle(d->peer_ptr);
     cudaFree(d->d_ipc);
     if (d->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(d->comm);
@@ -296,7 +312,7 @@ static int map_root_result(uavm_ctx* ctx, uavm_dist* d, uavm_canvas* cv, int roo
         for (size_t i = 0; i < sizeof(h); i++) if (((const char*)&h)[i]) { zero = false; break; }
         if (zero || d->peer_failed) ok_local = 0;
         else if (!d->peer_ptr || memcmp(&h, &d->peer_handle, sizeof(h)) != 0) {
-            if (d->peer_ptr) { cudaIpcCloseMemHandle(d->peer_ptr); d->peer_ptr = nullptr; }
+            if (d->peer_ptr) { unbind_current(d); cudaIpcCloseMemHandle(d->peer_ptr); d->peer_ptr = nullptr; }
             if (cudaIpcOpenMemHandle(&d->peer_ptr, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); d->peer_ptr = nullptr; d->peer_failed = true; ok_local = 0; }
             else d->peer_handle = h;
         }
@@ -321,14 +337,16 @@ static int map_root_result(uavm_ctx* ctx, uavm_dist* d, uavm_canvas* cv, int roo
 extern "C" int uavm_canvas_bind_root(uavm_ctx* ctx, uavm_dist* d, uavm_canvas* cv, int root)
 {
     if (!ctx || !d || !cv || root < 0 || root >= d->world) return UAVM_EINVAL;
-    cv->bound_root = -1; cv->peer_result = nullptr;
+    if (cv->bound_dist) uavm_dist_forget_canvas(cv->bound_dist, cv);
+    cv->bound_root = -1; cv->peer_result = nullptr; cv->bound_dist = nullptr;
     if (d->world == 1 || getenv("UAVM_GATHER_NCCL") || getenv("UAVM_GATHER_COPY")) return UAVM_OK;
     UAVM_CUDA(ctx, cudaSetDevice(ctx->device));
     { const int rc = uavm_canvas_ensure_result(ctx, cv); if (rc != UAVM_OK) return rc; }
     int agreed = 0;
     { const int rc = map_root_result(ctx, d, cv, root, &agreed); if (rc != UAVM_OK) return rc; }
     if (agreed) {
-        cv->bound_root = root;
+        if (d->bound_cv != cv) unbind_current(d);          // one bound canvas per uavm_dist: the mapping cache holds one buffer
+        cv->bound_root = root; cv->bound_dist = d; d->bound_cv = cv;
         if (d->rank != root) cv->peer_result = static_cast<uint8_t*>(d->peer_ptr);
     }
     return UAVM_OK;

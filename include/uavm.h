@@ -251,7 +251,8 @@ int uavm_canvas_gather(uavm_ctx* ctx, uavm_dist* d, uavm_canvas* cv, const int32
 /* Fused blend + gather (collective; once per canvas, on every rank, after uavm_canvas_set_rect and before uavm_canvas_blend): the
  * root's mosaic buffer is mapped into the other ranks (CUDA IPC) and the level-0 kernel of their blend stores its rectangle there
  * as well, over NVLink, tile by tile while it computes; uavm_canvas_gather is then only the completion barrier.  If the mapping is
- * not possible nothing is bound and uavm_canvas_gather copies as before.  Keep `d` alive while the canvas blends. */
+ * not possible nothing is bound and uavm_canvas_gather copies as before.  One canvas per uavm_dist is bound at a time: binding
+ * another one, or destroying the canvas or the uavm_dist, unbinds. */
 int uavm_canvas_bind_root(uavm_ctx* ctx, uavm_dist* d, uavm_canvas* cv, int root);
 int uavm_canvas_bound_root(const uavm_canvas* cv);      /* root of that binding, -1: none */
 int uavm_dist_broadcast(uavm_ctx* ctx, uavm_dist* d, void* device_buf, int64_t bytes, int root);
