@@ -450,6 +450,23 @@ def test_header_is_c99_and_links_from_c(tmp_path):
     assert r.returncode == 0 and "c consumer ok" in r.stdout, r.stdout
 
 
+def test_cpp_multi_gpu_host_compiles_and_links(tmp_path):
+    """INTEGRATION.md section 2c as a real program (tests/c_consumer/multi_gpu_host.cpp: one thread per GPU, uavm_dist_*,
+    uavm_pairbatch_allgather, uavm_global_align, uavm_canvas_set_rect / bind_root / gather): every call must match include/uavm.h
+    (-Wall -Wextra -Werror) and link against the library; without a GPU it reports so and exits 0 (no CPU fallback)."""
+    import subprocess
+    exe = str(tmp_path / "multi_gpu_host")
+    libdir = os.path.join(ROOT, "imagemosaicing_b200")
+    cmd = ["g++", "-std=c++17", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"),
+           os.path.join(ROOT, "tests", "c_consumer", "multi_gpu_host.cpp"), "-L", libdir, "-l:libuavmosaic.so", "-lpthread", "-Wl,-rpath," + libdir, "-o", exe]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, r.stdout
+    import torch
+    if not torch.cuda.is_available():
+        r = subprocess.run([exe, "2"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=60)
+        assert r.returncode == 0 and "no sm_100 device" in r.stdout, r.stdout
+
+
 def test_constrained_alignment_variants_vs_oracle():
     """f3: uavm_align_affine_constrained / uavm_align_affine_rot (host C++) against the numpy restatement of
     BundleAdjustmentSparseConstraint / SparseAffineRotConstraint; and the point of the variants: on a chain of images the
