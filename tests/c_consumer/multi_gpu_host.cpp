@@ -51,6 +51,7 @@ static void worker(Shared* S, int rank)
     std::vector<int32_t> label(S->n_images);
     int n_used = 0;
     if (rc == UAVM_OK) rc = uavm_global_align(list.data(), n_list, S->n_images, T.data(), label.data(), &n_used);
+    if (rc != UAVM_OK) fprintf(stderr, "rank %d: alignment failed (%d accepted pairs, %d matches)\n", rank, n_accepted, n_list);
 
     // ---- canvas: one rectangle per rank (here: row bands), exact, no halo exchange; fused blend + gather to rank 0 ----
     std::vector<float> H((size_t)S->n_images * 9);
@@ -83,7 +84,7 @@ static void worker(Shared* S, int rank)
         rc = uavm_canvas_get_result(ctx, cv, mosaic.data(), cw * 3, nullptr, 0);
         unsigned long long sum = 0;
         for (uint8_t v : mosaic) sum += v;
-        printf("multi_gpu_host: world %d, %d accepted pairs, %d matches, %d images aligned, mosaic %d x %d, byte sum %llu (bound root %d)\n",
+        printf("multi_gpu_host: world %d, %d accepted pairs, %d matches (%d used by the alignment), mosaic %d x %d, byte sum %llu (bound root %d)\n",
                S->world, n_accepted, n_list, n_used, cw, ch, sum, uavm_canvas_bound_root(cv));
     }
     if (rc != UAVM_OK) fprintf(stderr, "rank %d: rc %d: %s\n", rank, rc, uavm_last_error(ctx));
@@ -104,8 +105,8 @@ int main(int argc, char** argv)
         if (rc != UAVM_OK) { printf("multi_gpu_host: no sm_100 device (uavm_ctx_create -> %d), nothing to run\n", rc); return 0; }
         uavm_ctx_destroy(probe);
     }
-    // a synthetic strip: every frame shows the same texture shifted by 40 % of the width; keypoints on a jittered grid whose
-    // descriptors are a hash of the world position, so overlapping frames share true correspondences
+    // a synthetic strip: every frame shows the same texture shifted by 40 % of the width; keypoints on a grid whose descriptors
+    // are a hash of the world position, so consecutive frames share 1024 true correspondences (frames two apart share none)
     S.n_images = 6; S.w = 640; S.h = 480; S.n_kp = 2048;
     auto hash = [](uint32_t x) { x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16; return x; };
     const int step = (int)(0.4 * S.w);
@@ -114,7 +115,7 @@ int main(int argc, char** argv)
         S.desc[i].resize((size_t)S.n_kp * 128); S.kp[i].resize((size_t)S.n_kp * 2); S.frames[i].resize((size_t)S.w * S.h * 3);
         for (int k = 0; k < S.n_kp; k++) {
             const int gx = k % 64, gy = k / 64;                                   // 64 x 32 grid over the frame
-            const int wx = i * step + gx * 10 + 3, wy = gy * 15 + 4;              // world position
+            const int wx = i * step + gx * 8 + 3, wy = gy * 15 + 4;               // world position: the 256 px step is 32 grid columns
             S.kp[i][2 * k] = (float)(wx - i * step); S.kp[i][2 * k + 1] = (float)wy;
             for (int t = 0; t < 128; t++) S.desc[i][(size_t)k * 128 + t] = (uint8_t)(hash((uint32_t)(wx * 7919 + wy * 104729 + t * 31)) % 120);
         }
